@@ -1,0 +1,176 @@
+// fqz_api_front.cu — host orchestration of the compress front end + fqz_encode_streams.
+#include <string.h>
+
+#include <algorithm>
+
+#include "fqz_host.h"
+
+// boundaries of every fqz block inside the five scanned offset arrays
+__global__ void k_gather_bounds(const u32 *offs, u64 stride, u64 R, u32 nblocks, u32 *out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 per = nblocks + 1;
+    if (i >= 5 * per) return;
+    u32 a = i / per, b = i % per;
+    u64 r = min((u64)b * FQZ_BLOCK_RECORDS, R);
+    out[i] = offs[a * stride + r];
+}
+
+static const int kErrOfKind[5] = {0, FQZ_E_HEADER_AT, FQZ_E_PLUS, FQZ_E_LEN_MISMATCH, FQZ_E_LONG_N};
+
+int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out) {
+    out = FrontOut();
+    cudaStream_t s = c->stream;
+    if (n >= ((u64)1 << 32) - 65536) return FQZ_E_TOO_LARGE;
+    // ---- 1. count newlines per 16 KiB tile, scan, read the total
+    u32 ntiles = (u32)((n + FQZ_NL_TILE - 1) / FQZ_NL_TILE);
+    u32 *d_tiles = (u32 *)c->arena.alloc(((size_t)ntiles + 1) * sizeof(u32));
+    if (!d_tiles) {
+        c->err = "arena: out of device memory (tiles)";
+        return FQZ_E_CUDA;
+    }
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_tiles + ntiles, 0, sizeof(u32), s));
+    {
+        StageScope sc(c, ST_NL_COUNT, n);
+        fqz_launch_newline_count(d_text, n, d_tiles, ntiles, s);
+    }
+    {
+        StageScope sc(c, ST_SCAN, 0);
+        FQZ_TRY(fqz_scan_excl_u32(c, d_tiles, (u64)ntiles + 1, (u64)ntiles + 1, 1));
+    }
+    u32 *h = (u32 *)c->h_pin;
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_tiles + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    u64 nlines = h[0];
+    u64 R_all = nlines / 4;
+    u64 R = R_all;
+    u32 tail_lines = 0;
+    if (max_records && R > max_records) R = max_records;
+    if (!is_last) {
+        R = (R / FQZ_BLOCK_RECORDS) * FQZ_BLOCK_RECORDS;  // whole blocks only; the caller re-feeds the rest
+        if (R == 0) return FQZ_E_NEED_MORE;
+    } else if (R == R_all) {
+        tail_lines = (u32)(nlines - 4 * R_all);
+    }
+    out.R = R;
+    out.nblocks = (u32)((R + FQZ_BLOCK_RECORDS - 1) / FQZ_BLOCK_RECORDS);
+    // ---- 2. line_end[]
+    u64 want_lines = 4 * R + tail_lines;
+    u32 *d_line_end = (u32 *)c->arena.alloc((size_t)(want_lines + 4) * sizeof(u32));
+    if (!d_line_end) {
+        c->err = "arena: out of device memory (line_end)";
+        return FQZ_E_CUDA;
+    }
+    {
+        StageScope sc(c, ST_NL_INDEX, n + 4 * want_lines);
+        fqz_launch_newline_index(d_text, n, d_tiles, ntiles, d_line_end, (u32)want_lines, s);
+    }
+    // ---- 3. per-record sizes + validation + Phred min, then five scans
+    u64 stride = ((R + 1 + 63) / 64) * 64;
+    u32 *d_sizes = (u32 *)c->arena.alloc((size_t)(5 * stride) * sizeof(u32));
+    u32 *d_bounds = (u32 *)c->arena.alloc((size_t)(5 * (out.nblocks + 1)) * sizeof(u32));
+    if (!d_sizes || !d_bounds) {
+        c->err = "arena: out of device memory (sizes)";
+        return FQZ_E_CUDA;
+    }
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_sizes, 0, (size_t)(5 * stride) * sizeof(u32), s));
+    FqzWinStatus *hst = (FqzWinStatus *)(c->h_pin + 1024);
+    hst->err_key = ~0ull;
+    hst->qual_min = 255u;
+    hst->pad = 0;
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(c->d_status, hst, sizeof(FqzWinStatus), cudaMemcpyHostToDevice, s));
+    u64 phred_records = (phred_mode == -1) ? (u64)FQZ_BLOCK_RECORDS : 0;
+    {
+        StageScope sc(c, ST_RECORD_META, 0);
+        fqz_launch_record_meta(d_text, d_line_end, R, rec_base, tail_lines, d_sizes, stride, c->d_status, phred_records, s);
+    }
+    if (phred_mode == -1) {
+        fqz_launch_decide_phred(c->d_status, c->d_phred, s);
+    } else if (phred_mode >= 0) {
+        u32 *hv = (u32 *)(c->h_pin + 1280);
+        *hv = phred_mode ? 1u : 0u;
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(c->d_phred, hv, sizeof(u32), cudaMemcpyHostToDevice, s));
+    }
+    {
+        StageScope sc(c, ST_SCAN, 0);
+        FQZ_TRY(fqz_scan_excl_u32(c, d_sizes, R + 1, stride, 5));
+    }
+    u32 nb = 5 * (out.nblocks + 1);
+    FQZ_LAUNCH(k_gather_bounds, (nb + 127) / 128, 128, 0, s, d_sizes, stride, R, out.nblocks, d_bounds);
+    // ---- 4. one small readback: status, Phred flag, block boundaries, consumed offset
+    FQZ_TRY(fqz_pin_reserve(c, 4096 + (size_t)nb * sizeof(u32)));
+    h = (u32 *)c->h_pin;
+    FqzWinStatus *hst2 = (FqzWinStatus *)(c->h_pin + 1536);
+    u32 *hphred = (u32 *)(c->h_pin + 1600);
+    u32 *hcons = (u32 *)(c->h_pin + 1664);
+    u32 *hb = (u32 *)(c->h_pin + 2048);
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, c->d_status, sizeof(FqzWinStatus), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hphred, c->d_phred, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (R) FQZ_CUDA_TRY(c, cudaMemcpyAsync(hcons, d_line_end + 4 * R - 1, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hb, d_bounds, (size_t)nb * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (hst2->err_key != ~0ull) {
+        u32 kind = (u32)(hst2->err_key & 0xFF);
+        u64 rec = hst2->err_key >> 8;
+        char msg[160];
+        snprintf(msg, sizeof msg, "record %llu: %s", (unsigned long long)rec, fqz_strerror(kErrOfKind[kind < 5 ? kind : 0]));
+        c->err = msg;
+        out.consumed = rec;  // callers read the offending record index here
+        return kErrOfKind[kind < 5 ? kind : 0];
+    }
+    out.phred64 = *hphred;
+    out.consumed = R ? (u64)(*hcons) + 1 : (is_last ? n : 0);
+    if (is_last && R == R_all) out.consumed = n;  // an unterminated / partial last record is dropped
+    for (int a = 0; a < 5; a++) out.blk_off[a].assign(hb + a * (out.nblocks + 1), hb + (a + 1) * (out.nblocks + 1));
+    out.blk_off[5].resize(out.nblocks + 1);
+    out.orig.resize(out.nblocks);
+    for (u32 b = 0; b <= out.nblocks; b++) out.blk_off[5][b] = (u32)(4 * std::min<u64>((u64)b * FQZ_BLOCK_RECORDS, R));
+    for (u32 b = 0; b < out.nblocks; b++) out.orig[b] = out.blk_off[1][b + 1] - out.blk_off[1][b];
+    // ---- 5. carve the six streams and scatter
+    u64 total = 0;
+    for (int a = 0; a < 6; a++) {
+        size_t sz = out.blk_off[a][out.nblocks];
+        out.d_streams[a] = (u8 *)c->arena.alloc(sz + 16);
+        if (!out.d_streams[a]) {
+            c->err = "arena: out of device memory (streams)";
+            return FQZ_E_CUDA;
+        }
+        total += sz;
+    }
+    {
+        StageScope sc(c, ST_SCATTER, out.consumed + total);
+        fqz_launch_scatter(d_text, d_line_end, R, d_sizes, stride, c->d_phred, out.d_streams, s);
+    }
+    return FQZ_OK;
+}
+
+extern "C" int fqz_encode_streams(fqz_ctx *c, const uint8_t *fastq, size_t n, int phred64, uint8_t *const outp[6], const size_t cap[6],
+                                  size_t len[6], uint64_t info[6]) {
+    if (!c || (!fastq && n) || !len || !info) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->arena.reset();
+    c->err.clear();
+    for (int i = 0; i < 6; i++) info[i] = 0, len[i] = 0;
+    u8 *d_text = (u8 *)c->arena.alloc(n + 64);
+    if (!d_text) return FQZ_E_CUDA;
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_text + (n & ~(size_t)15), 0, 64, c->stream));  // defined bytes in the slack
+    if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_text, fastq, n, cudaMemcpyHostToDevice, c->stream));
+    FrontOut fo;
+    int rc = fqz_run_frontend(c, d_text, n, true, 0, phred64 < 0 ? -1 : (phred64 ? 1 : 0), FQZ_BLOCK_RECORDS, fo);
+    if (rc != FQZ_OK) {
+        info[5] = fo.consumed;
+        return rc;
+    }
+    info[0] = fo.R;
+    info[1] = fo.consumed;
+    info[2] = fo.phred64;
+    info[3] = fo.nblocks ? fo.orig[0] : 0;
+    info[4] = info[3];
+    for (int a = 0; a < 6; a++) len[a] = fo.nblocks ? fo.blk_off[a][1] : 0;
+    for (int a = 0; a < 6; a++)
+        if (len[a] > cap[a]) rc = FQZ_E_NOSPACE;
+    if (rc == FQZ_OK)
+        for (int a = 0; a < 6; a++)
+            if (len[a]) FQZ_CUDA_TRY(c, cudaMemcpyAsync(outp[a], fo.d_streams[a], len[a], cudaMemcpyDeviceToHost, c->stream));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return rc;
+}

@@ -1,0 +1,239 @@
+// fqz_ctx.cu — context, device arena, stage profiler, error strings.
+#include <stdio.h>
+#include <string.h>
+
+#include "fqz_host.h"
+
+unsigned long long g_fqz_launches = 0;
+
+// ---------------------------------------------------------------------------------- arena
+void *Arena::alloc(size_t bytes) {
+    size_t need = ((bytes + FQZ_PAD + 255) / 256) * 256;
+    for (auto &ch : chunks) {
+        if (ch.used + need <= ch.cap) {
+            void *p = ch.p + ch.used;
+            ch.used += need;
+            return p;
+        }
+    }
+    size_t cap = need > min_chunk ? need : min_chunk;
+    void *p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    chunks.push_back(Chunk{(u8 *)p, cap, need});
+    return p;
+}
+void Arena::reset() {
+    if (chunks.size() > 1) {  // coalesce so that the next window finds one large chunk
+        size_t total = 0;
+        for (auto &ch : chunks) total += ch.cap;
+        release();
+        void *p = nullptr;
+        size_t cap = total + total / 4;
+        if (cudaMalloc(&p, cap) == cudaSuccess) chunks.push_back(Chunk{(u8 *)p, cap, 0});
+        else cudaGetLastError();
+    }
+    for (auto &ch : chunks) ch.used = 0;
+}
+void Arena::release() {
+    for (auto &ch : chunks) cudaFree(ch.p);
+    chunks.clear();
+}
+size_t Arena::capacity() const {
+    size_t t = 0;
+    for (auto &ch : chunks) t += ch.cap;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------- profiler
+static const char *k_stage_names[ST_COUNT_] = {
+    "newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "xxh64",
+    "assemble", "zstd_dec_scan", "zstd_dec_literals", "zstd_dec_sequences", "zstd_dec_execute", "prefix_walk", "record_offsets",
+    "emit_fastq", "copy"};
+
+cudaEvent_t Profiler::get() {
+    if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void Profiler::collect() {
+    for (auto &r : open) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.stage] += t;
+        pool.push_back(r.a);
+        pool.push_back(r.b);
+    }
+    open.clear();
+}
+void Profiler::clear() {
+    collect();
+    for (int i = 0; i < ST_COUNT_; i++) {
+        ms[i] = 0;
+        launches[i] = 0;
+        bytes[i] = 0;
+    }
+}
+StageScope::StageScope(fqz_ctx *ctx, int st, u64 bytes) : c(ctx), stage(st), l0(g_fqz_launches) {
+    c->prof.bytes[st] += bytes;
+    if (c->prof.on) {
+        a = c->prof.get();
+        cudaEventRecord(a, c->stream);
+    }
+}
+StageScope::~StageScope() {
+    c->prof.launches[stage] += g_fqz_launches - l0;
+    if (a) {
+        cudaEvent_t b = c->prof.get();
+        cudaEventRecord(b, c->stream);
+        c->prof.open.push_back(Profiler::Rec{stage, a, b});
+    }
+}
+
+// ---------------------------------------------------------------------------------- context
+int fqz_pin_reserve(fqz_ctx *c, size_t bytes) {
+    if (bytes <= c->h_pin_cap) return FQZ_OK;
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr;
+    c->h_pin_cap = 0;
+    size_t cap = bytes < 65536 ? 65536 : bytes * 2;
+    FQZ_CUDA_TRY(c, cudaMallocHost((void **)&c->h_pin, cap));
+    c->h_pin_cap = cap;
+    return FQZ_OK;
+}
+int fqz_io_reserve(fqz_ctx *c, size_t bytes) {
+    if (bytes <= c->h_io_cap) return FQZ_OK;
+    if (c->h_io) cudaFreeHost(c->h_io);
+    c->h_io = nullptr;
+    c->h_io_cap = 0;
+    size_t cap = bytes + bytes / 8 + 4096;
+    FQZ_CUDA_TRY(c, cudaMallocHost((void **)&c->h_io, cap));
+    c->h_io_cap = cap;
+    return FQZ_OK;
+}
+
+extern "C" int fqz_abi_version(void) { return FQZ_ABI_VERSION; }
+
+extern "C" int fqz_init(int device, fqz_ctx **out) {
+    if (!out) return FQZ_E_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return FQZ_E_NO_DEVICE;  // no CPU fallback by design
+    }
+    if (device < 0 || device >= ndev) return FQZ_E_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return FQZ_E_NO_DEVICE;
+    fqz_ctx *c = new fqz_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void **)&c->d_status, 256) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_phred, 256) != cudaSuccess) {
+        delete c;
+        return FQZ_E_CUDA;
+    }
+    cudaMemset(c->d_phred, 0, 256);
+    if (fqz_pin_reserve(c, 65536) != FQZ_OK) {
+        delete c;
+        return FQZ_E_CUDA;
+    }
+    *out = c;
+    return FQZ_OK;
+}
+
+extern "C" void fqz_destroy(fqz_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->prof.collect();
+    for (auto e : c->prof.pool) cudaEventDestroy(e);
+    c->arena.release();
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->d_phred) cudaFree(c->d_phred);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_io) cudaFreeHost(c->h_io);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *fqz_last_error(const fqz_ctx *c) { return c ? c->err.c_str() : ""; }
+
+extern "C" const char *fqz_strerror(int code) {
+    switch (code) {
+    case FQZ_OK: return "ok";
+    case FQZ_E_HEADER_AT: return "invalid FASTQ: header line must start with @";
+    case FQZ_E_PLUS: return "invalid FASTQ: separator line must start with +";
+    case FQZ_E_LEN_MISMATCH: return "invalid FASTQ: sequence and quality lengths must match";
+    case FQZ_E_LONG_N: return "sequence has ambiguous bases beyond position 65536; N-position tracking is limited to 65536 bp";
+    case FQZ_E_MAGIC: return "invalid magic bytes: not an FQZ file";
+    case FQZ_E_VERSION: return "unsupported file version";
+    case FQZ_E_TRUNC_FILE: return "unexpected EOF";
+    case FQZ_E_ZSTD: return "zstd: invalid or corrupt frame";
+    case FQZ_E_TRUNC_HEADER: return "truncated header data";
+    case FQZ_E_TRUNC_PLUS: return "truncated plus-line payload data";
+    case FQZ_E_TRUNC_SEQ: return "truncated sequence data";
+    case FQZ_E_TRUNC_QUAL: return "truncated quality data";
+    case FQZ_E_TRUNC_LEN: return "truncated length data";
+    case FQZ_E_TRUNC_NPOS: return "truncated N position data";
+    case FQZ_E_NOSPACE: return "output buffer too small";
+    case FQZ_E_NPOS_RANGE: return "N position beyond sequence length";
+    case FQZ_E_CUDA: return "CUDA error";
+    case FQZ_E_NO_DEVICE: return "no CUDA device (libfqzgpu has no CPU fallback)";
+    case FQZ_E_INVALID_ARG: return "invalid argument";
+    case FQZ_E_NEED_MORE: return "window holds no complete block";
+    case FQZ_E_TOO_LARGE: return "input larger than one device window; use the streaming calls";
+    default: return "unknown error";
+    }
+}
+
+extern "C" void fqz_stats_reset(fqz_ctx *c) {
+    if (!c) return;
+    c->prof.clear();
+    c->launches_base = g_fqz_launches;
+}
+extern "C" void fqz_profile_enable(fqz_ctx *c, int on) {
+    if (c) c->prof.on = on != 0;
+}
+extern "C" int fqz_get_stats(fqz_ctx *c, fqz_stats *out) {
+    if (!c || !out) return FQZ_E_INVALID_ARG;
+    cudaStreamSynchronize(c->stream);
+    c->prof.collect();
+    memset(out, 0, sizeof *out);
+    out->launches = g_fqz_launches - c->launches_base;
+    out->n_stages = ST_COUNT_;
+    for (int i = 0; i < ST_COUNT_; i++) {
+        out->stage_name[i] = k_stage_names[i];
+        out->stage_ms[i] = c->prof.ms[i];
+        out->stage_launches[i] = c->prof.launches[i];
+        out->stage_bytes[i] = c->prof.bytes[i];
+    }
+    return FQZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- device-wide exclusive scan
+int fqz_scan_excl_u32(fqz_ctx *c, u32 *d, u64 n, u64 stride, u32 narr) {
+    if (n == 0) return FQZ_OK;
+    u32 ntiles = (u32)((n + FQZ_SCAN_TILE - 1) / FQZ_SCAN_TILE);
+    if (ntiles == 1) {
+        fqz_launch_scan_apply(d, n, stride, narr, nullptr, 1, c->stream);
+        return FQZ_OK;
+    }
+    u32 *sums = (u32 *)c->arena.alloc((size_t)narr * ntiles * sizeof(u32));
+    if (!sums) {
+        c->err = "arena: out of device memory (scan)";
+        return FQZ_E_CUDA;
+    }
+    fqz_launch_scan_partial(d, n, stride, narr, sums, ntiles, c->stream);
+    FQZ_TRY(fqz_scan_excl_u32(c, sums, ntiles, ntiles, narr));
+    fqz_launch_scan_apply(d, n, stride, narr, sums, ntiles, c->stream);
+    return FQZ_OK;
+}

@@ -1,0 +1,394 @@
+// fqz_frontend.cu — compress front end: FASTQ text -> six pre-entropy streams, bit-exact with
+// the reference's fqparser + encoder + per-record stream assembly.
+//
+//   k_newline_count / k_newline_index   warp-ballot-free SIMD-in-register '\n' scan -> line_end[]
+//                                       (replaces Parser.readLine, internal/fqparser/parser.go:209-243)
+//   k_record_meta                       validation + per-record stream sizes + Phred min
+//                                       (parser.go:136-184 nextInto, encoder/quality.go:22-49,
+//                                        compress.go:477-488 long-read guard)
+//   k_scan_*                            device-wide exclusive scans (stream offsets per record)
+//   k_scatter_streams                   TMA-staged record chunks -> seqPacked / quality / headers /
+//                                       plusLines / nPositions / seqLengths
+//                                       (compress.go:490-519, sequence.go:139-184, quality.go:53-103)
+//
+// All kernels are HBM-bound byte shuffling: algorithmic bytes = F (text) + S (streams).
+#include "fqz_common.cuh"
+#include "fqz_kernels.h"
+
+#define NL4 0x0a0a0a0au
+
+// ---------------------------------------------------------------------------------- newline scan
+// One CTA = one tile of FQZ_NL_TILE bytes; each thread owns 64 contiguous bytes (4 x 128-bit loads).
+__device__ __forceinline__ u32 nl_mask64(const u8 *text, u64 n, u64 pos, u64 &m_out) {
+    u64 m = 0;  // bit k set <=> text[pos+k] == '\n'
+    if (pos < n) {
+        const uint4 *v = (const uint4 *)(text + pos);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            u64 p = pos + 16u * q;
+            if (p >= n) break;
+            uint4 x = __ldg(v + q);
+            u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 e = __vcmpeq4(w[k], NL4) & 0x01010101u;
+                u32 bits = (e * 0x01020408u) >> 24;  // 4 flags -> 4 bits
+                m |= (u64)(bits & 0xFu) << (16 * q + 4 * k);
+            }
+        }
+        if (pos + 64 > n) m &= (~0ull) >> (64 - (n - pos));  // bytes past the end do not count
+    }
+    m_out = m;
+    return (u32)__popcll(m);
+}
+
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_count(const u8 *text, u64 n, u32 *tile_counts) {
+    __shared__ u32 ws[33];
+    u64 pos = (u64)blockIdx.x * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
+    u64 m;
+    u32 c = nl_mask64(text, n, pos, m);
+    u32 total;
+    block_excl_scan(c, ws, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+// tile_prefix = exclusive scan of tile_counts.  line_end[i] = byte offset of the i-th '\n'.
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_index(const u8 *text, u64 n, const u32 *tile_prefix, u32 *line_end, u32 max_lines) {
+    __shared__ u32 ws[33];
+    u64 pos = (u64)blockIdx.x * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
+    u64 m;
+    u32 c = nl_mask64(text, n, pos, m);
+    u32 ex = block_excl_scan(c, ws, nullptr);
+    u32 idx = tile_prefix[blockIdx.x] + ex;
+    while (m) {
+        int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (idx < max_lines) line_end[idx] = (u32)(pos + (u64)b);
+        idx++;
+    }
+}
+
+// ---------------------------------------------------------------------------------- device-wide exclusive scan (u32, in place)
+// data holds `narr` arrays of n elements, array a at data + a*stride.  2048 elements per CTA.
+__device__ __forceinline__ u32 scan_tile_load(const u32 *d, u64 n, u64 base, u32 v[FQZ_SCAN_PER_THREAD]) {
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < FQZ_SCAN_PER_THREAD; i++) {
+        u64 k = base + (u64)threadIdx.x * FQZ_SCAN_PER_THREAD + i;
+        v[i] = (k < n) ? d[k] : 0u;
+        s += v[i];
+    }
+    return s;
+}
+__global__ void __launch_bounds__(FQZ_SCAN_THREADS) k_scan_partial(const u32 *data, u64 n, u64 stride, u32 *sums, u32 ntiles) {
+    __shared__ u32 ws[33];
+    const u32 *d = data + (u64)blockIdx.y * stride;
+    u32 v[FQZ_SCAN_PER_THREAD];
+    u32 s = scan_tile_load(d, n, (u64)blockIdx.x * FQZ_SCAN_TILE, v);
+    u32 total;
+    block_excl_scan(s, ws, &total);
+    if (threadIdx.x == 0) sums[(u64)blockIdx.y * ntiles + blockIdx.x] = total;
+}
+// sums == nullptr: single-tile scan (tile offset 0)
+__global__ void __launch_bounds__(FQZ_SCAN_THREADS) k_scan_apply(u32 *data, u64 n, u64 stride, const u32 *sums, u32 ntiles) {
+    __shared__ u32 ws[33];
+    u32 *d = data + (u64)blockIdx.y * stride;
+    u32 v[FQZ_SCAN_PER_THREAD];
+    u64 base = (u64)blockIdx.x * FQZ_SCAN_TILE;
+    u32 s = scan_tile_load(d, n, base, v);
+    u32 ex = block_excl_scan(s, ws, nullptr);
+    u32 run = ex + (sums ? sums[(u64)blockIdx.y * ntiles + blockIdx.x] : 0u);
+#pragma unroll
+    for (int i = 0; i < FQZ_SCAN_PER_THREAD; i++) {
+        u64 k = base + (u64)threadIdx.x * FQZ_SCAN_PER_THREAD + i;
+        if (k < n) d[k] = run;
+        run += v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------- per-record metadata
+struct LineSpan {
+    u32 hs, he, ss, se, ps, pe, qs, qe;  // [start, end) of the four lines, '\n' and one '\r' stripped
+};
+// reference: parser.go:209-220 (strip '\n', then one trailing '\r')
+__device__ __forceinline__ u32 strip_cr(const u8 *text, u32 s, u32 e) { return (e > s && text[e - 1] == '\r') ? e - 1 : e; }
+__device__ __forceinline__ LineSpan record_lines(const u8 *text, const u32 *line_end, u64 r) {
+    LineSpan t;
+    u64 l = 4 * r;
+    u32 e0 = (l == 0) ? 0xFFFFFFFFu : line_end[l - 1];
+    u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
+    t.hs = e0 + 1u;
+    t.he = strip_cr(text, t.hs, e1);
+    t.ss = e1 + 1u;
+    t.se = strip_cr(text, t.ss, e2);
+    t.ps = e2 + 1u;
+    t.pe = strip_cr(text, t.ps, e3);
+    t.qs = e3 + 1u;
+    t.qe = strip_cr(text, t.qs, e4);
+    return t;
+}
+
+// Count bytes that are not ACGTacgt in text[a,b) with a group of `W` lanes (lane index g) using
+// aligned 32-bit words.  Returns the lane's partial count.
+template <int W>
+__device__ __forceinline__ u32 partial_count_n(const u8 *text, u32 a, u32 b, u32 g) {
+    u32 c = 0;
+    if (b > a) {
+        u32 w0 = a >> 2, w1 = (b - 1) >> 2;
+        for (u32 w = w0 + g; w <= w1; w += W) {
+            u32 x = *(const u32 *)(text + 4ull * w);
+            u32 nm = nonacgt_mask4(x) & range_mask4(4u * w, a, b);
+            c += (u32)__popc(nm & 0x01010101u);
+        }
+    }
+    return c;
+}
+template <int W>
+__device__ __forceinline__ u32 partial_min_byte(const u8 *text, u32 a, u32 b, u32 g) {
+    u32 mn = 0xFFFFFFFFu;
+    if (b > a) {
+        u32 w0 = a >> 2, w1 = (b - 1) >> 2;
+        for (u32 w = w0 + g; w <= w1; w += W) {
+            u32 x = *(const u32 *)(text + 4ull * w);
+            x |= ~range_mask4(4u * w, a, b);
+            mn = __vminu4(mn, x);
+        }
+    }
+    u32 m2 = min(mn & 0xFFu, (mn >> 8) & 0xFFu);
+    u32 m3 = min((mn >> 16) & 0xFFu, mn >> 24);
+    return min(m2, m3);
+}
+
+// sizes: 5 arrays of (R+1) u32 at stride `stride`: seq, qual, hdr, plus, npos bytes per record.
+// rec_base = index of this window's first record in the whole file (for error keys / Phred scope).
+// tail_lines: complete lines after the last whole record (only checked when is_last).
+__global__ void __launch_bounds__(FQZ_META_THREADS)
+k_record_meta(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, u32 *sizes, u64 stride, FqzWinStatus *st,
+              u64 phred_records /* records (file-global index <) taking part in Phred detection */) {
+    const int W = FQZ_META_GROUP;
+    u32 g = threadIdx.x & (W - 1);
+    u32 gm = group_mask(W);
+    u64 r = (u64)blockIdx.x * (FQZ_META_THREADS / W) + (threadIdx.x / W);
+    if (r > R) return;  // whole group leaves together
+    if (r == R) {
+        // trailing partial record: the reference still validates the lines it can read before it
+        // meets EOF (parser.go:138-166), e.g. a trailing blank line is a header error.
+        if (g == 0 && tail_lines > 0) {
+            u64 l = 4 * R;
+            u32 hs = (l == 0) ? 0u : line_end[l - 1] + 1u;
+            u32 he = strip_cr(text, hs, line_end[l]);
+            u32 kind = 0;
+            if (he == hs || text[hs] != '@') kind = FQZ_K_HEADER_AT;
+            else if (tail_lines >= 3) {
+                u32 ps = line_end[l + 1] + 1u;
+                u32 pe = strip_cr(text, ps, line_end[l + 2]);
+                if (pe == ps || text[ps] != '+') kind = FQZ_K_PLUS;
+            }
+            if (kind) atomicMin(&st->err_key, ((rec_base + R) << 8) | kind);
+        }
+        return;
+    }
+    LineSpan t = record_lines(text, line_end, r);
+    u32 L = t.se - t.ss;
+    u32 kind = 0;
+    if (t.he == t.hs || text[t.hs] != '@') kind = FQZ_K_HEADER_AT;
+    else if (t.pe == t.ps || text[t.ps] != '+') kind = FQZ_K_PLUS;
+    else if (L != t.qe - t.qs) kind = FQZ_K_LEN;
+    // N bases inside the tracked range, and the guard beyond it
+    u32 lim = t.ss + min(L, FQZ_MAX_SEQ_LEN);
+    u32 nn = group_sum(partial_count_n<W>(text, t.ss, lim, g), gm, W);
+    if (L > FQZ_MAX_SEQ_LEN) {
+        u32 beyond = group_sum(partial_count_n<W>(text, lim, t.se, g), gm, W);
+        if (beyond && !kind) kind = FQZ_K_LONG_N;
+    }
+    if (rec_base + r < phred_records) {
+        u32 mn = group_min(partial_min_byte<W>(text, t.qs, t.qe, g), gm, W);
+        if (g == 0 && mn < 255u) atomicMin(&st->qual_min, mn);
+    }
+    if (g == 0) {
+        if (kind) atomicMin(&st->err_key, ((rec_base + r) << 8) | kind);
+        u32 H = (kind == FQZ_K_HEADER_AT) ? 0u : (t.he - t.hs - 1u);
+        u32 P = (kind == FQZ_K_HEADER_AT || kind == FQZ_K_PLUS) ? 0u : (t.pe - t.ps - 1u);
+        sizes[0 * stride + r] = (L + 3u) >> 2;
+        sizes[1 * stride + r] = L;
+        sizes[2 * stride + r] = 2u + H;
+        sizes[3 * stride + r] = 2u + P;
+        sizes[4 * stride + r] = 2u + 2u * nn;
+    }
+}
+
+// Decide the file-global Phred flag from the min quality byte of block 0
+// (reference: quality.go:22-49: any byte < 59 -> 33; min >= 64 -> 64; none / 59..63 -> 33).
+__global__ void k_decide_phred(const FqzWinStatus *st, u32 *phred64) {
+    u32 m = st->qual_min;
+    *phred64 = (m != 255u && m >= 64u) ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------- stream scatter
+struct Src {  // text bytes, possibly served from a shared-memory copy of [bias, bias+len)
+    const u8 *p;
+    u32 bias;
+    __device__ __forceinline__ const u8 *at(u32 pos) const { return p + (pos - bias); }
+};
+
+// copy n bytes src->dst with a W-lane group: bytes up to dst alignment, aligned words, tail bytes
+template <int W>
+__device__ __forceinline__ void group_copy(u8 *dst, const u8 *src, u32 n, u32 g) {
+    u32 head = (u32)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > n) head = n;
+    if (g < head) dst[g] = src[g];
+    u32 nw = (n - head) >> 2;
+    for (u32 w = g; w < nw; w += W) *(u32 *)(dst + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
+    u32 t0 = head + 4u * nw;
+    if (g < n - t0) dst[t0 + g] = src[t0 + g];
+}
+
+__global__ void __launch_bounds__(FQZ_SC_THREADS)
+k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u64 stride, const u32 *phred64, u8 *s_seq, u8 *s_qual,
+                  u8 *s_hdr, u8 *s_plus, u8 *s_npos, u8 *s_len, u32 stage_cap) {
+    FQZ_DYN_SMEM(u8, smem);
+    const int W = FQZ_SC_GROUP;
+    u64 *bar = (u64 *)smem;
+    u8 *stage = smem + 128;
+    u64 r0 = (u64)blockIdx.x * FQZ_SC_RPC;
+    u64 r1 = min(r0 + (u64)FQZ_SC_RPC, R);
+    // contiguous text chunk of this CTA's records, widened to 16-byte boundaries for the bulk copy
+    u32 c0 = (r0 == 0) ? 0u : line_end[4 * r0 - 1] + 1u;
+    u32 c1 = line_end[4 * r1 - 1] + 1u;
+    u32 a0 = c0 & ~15u;
+    u32 a1 = (c1 + 15u) & ~15u;
+    Src src;
+    if (a1 - a0 + 16u <= stage_cap) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        cta_stage_bulk(stage, text + a0, a1 - a0, bar, 0);
+        src.p = stage;
+        src.bias = a0;
+    } else {  // chunk larger than the staging buffer (long reads): read HBM/L2 directly
+        src.p = text;
+        src.bias = 0;
+    }
+    const u8 off = *phred64 ? 64 : 33;
+    u32 g = threadIdx.x & (W - 1);
+    u32 gm = group_mask(W);
+    for (u64 r = r0 + threadIdx.x / W; r < r1; r += FQZ_SC_THREADS / W) {
+        // line_end holds window offsets; CR stripping must look at the same bytes the meta kernel saw
+        LineSpan t;
+        {
+            u64 l = 4 * r;
+            u32 e0 = (l == 0) ? 0xFFFFFFFFu : line_end[l - 1];
+            u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
+            t.hs = e0 + 1u;
+            t.he = (e1 > t.hs && *src.at(e1 - 1) == '\r') ? e1 - 1 : e1;
+            t.ss = e1 + 1u;
+            t.se = (e2 > t.ss && *src.at(e2 - 1) == '\r') ? e2 - 1 : e2;
+            t.ps = e2 + 1u;
+            t.pe = (e3 > t.ps && *src.at(e3 - 1) == '\r') ? e3 - 1 : e3;
+            t.qs = e3 + 1u;
+            t.qe = (e4 > t.qs && *src.at(e4 - 1) == '\r') ? e4 - 1 : e4;
+        }
+        u32 L = t.se - t.ss;
+        u32 H = t.he - t.hs - 1u, P = t.pe - t.ps - 1u;
+        u32 o_seq = offs[0 * stride + r], o_qual = offs[1 * stride + r], o_hdr = offs[2 * stride + r];
+        u32 o_plus = offs[3 * stride + r], o_npos = offs[4 * stride + r];
+        // seqLengths: u32 L (compress.go:501)
+        if (g == 0) *(u32 *)(s_len + 4ull * r) = L;
+        // headers / plusLines: u16 length prefix + bytes without the leading '@' / '+' (compress.go:514-519)
+        if (g == 0) st_u16_unaligned(s_hdr + o_hdr, H & 0xFFFFu);
+        group_copy<W>(s_hdr + o_hdr + 2, src.at(t.hs + 1u), H, g);
+        if (g == 0) st_u16_unaligned(s_plus + o_plus, P & 0xFFFFu);
+        group_copy<W>(s_plus + o_plus + 2, src.at(t.ps + 1u), P, g);
+        // seqPacked + nPositions (sequence.go:139-184): 16 bases per lane per round
+        u32 units = (L + 15u) >> 4, rounds = (units + W - 1) / W;
+        u32 nbase = 0;
+        for (u32 j = 0; j < rounds; j++) {
+            u32 u = j * W + g;
+            u32 nmask16 = 0;
+            if (u < units) {
+                const u8 *sp = src.at(t.ss + 16u * u);
+                u32 out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
+                    if (bp < L) {
+                        u32 x = ld_u32_unaligned(sp + 4 * k);
+                        u32 rm = range_mask4(bp, 0u, L);
+                        u32 nm = nonacgt_mask4(x) & rm;
+                        u32 codes = base_codes4(x, nm) & rm;
+                        out |= pack_codes4(codes) << (8 * k);
+                        nmask16 |= ((((nm & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+                    }
+                }
+                u32 vb = min(16u, L - 16u * u);
+                st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
+                if (16u * u >= FQZ_MAX_SEQ_LEN) nmask16 = 0;  // positions >= 65536 are not tracked
+            }
+            u32 cnt = (u32)__popc(nmask16);
+            u32 incl = group_incl_scan(cnt, gm, W);
+            u32 tot = __shfl_sync(gm, incl, W - 1, W);
+            u32 k = nbase + incl - cnt;
+            while (nmask16) {
+                int b = __ffs((int)nmask16) - 1;
+                nmask16 &= nmask16 - 1;
+                st_u16_unaligned(s_npos + o_npos + 2u + 2u * k, 16u * u + (u32)b);
+                k++;
+            }
+            nbase += tot;
+        }
+        if (g == 0) st_u16_unaligned(s_npos + o_npos, nbase & 0xFFFFu);  // compress.go:495 (silent u16 truncation)
+        // quality: normalise + per-record delta (compress.go:506-510; quality.go:53-103)
+        {
+            u8 *dq = s_qual + o_qual;
+            const u8 *sq = src.at(t.qs);
+            u32 head = (u32)((4u - ((uintptr_t)dq & 3u)) & 3u);
+            if (head == 0) head = 4;  // keeps every body word at index >= 1 so q[i-1] exists
+            if (head > L) head = L;
+            if (g < head) dq[g] = (u8)(sq[g] - (g ? sq[g - 1] : off));
+            u32 nw = (L - head) >> 2;
+            for (u32 w = g; w < nw; w += W) {
+                u32 i = head + 4u * w;
+                u32 cur = ld_u32_unaligned(sq + i);
+                u32 prv = ld_u32_unaligned(sq + i - 1);
+                *(u32 *)(dq + i) = __vsub4(cur, prv);
+            }
+            u32 t0 = head + 4u * nw;
+            if (g < L - t0) {
+                u32 i = t0 + g;
+                dq[i] = (u8)(sq[i] - (i ? sq[i - 1] : off));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- host launchers
+void fqz_launch_newline_count(const u8 *text, u64 n, u32 *tile_counts, u32 ntiles, cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_newline_count, ntiles, FQZ_NL_THREADS, 0, s, text, n, tile_counts);
+}
+void fqz_launch_newline_index(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_newline_index, ntiles, FQZ_NL_THREADS, 0, s, text, n, tile_prefix, line_end, max_lines);
+}
+void fqz_launch_scan_partial(const u32 *data, u64 n, u64 stride, u32 narr, u32 *sums, u32 ntiles, cudaStream_t s) {
+    FQZ_LAUNCH(k_scan_partial, dim3(ntiles, narr), FQZ_SCAN_THREADS, 0, s, data, n, stride, sums, ntiles);
+}
+void fqz_launch_scan_apply(u32 *data, u64 n, u64 stride, u32 narr, const u32 *sums, u32 ntiles, cudaStream_t s) {
+    FQZ_LAUNCH(k_scan_apply, dim3(ntiles, narr), FQZ_SCAN_THREADS, 0, s, data, n, stride, sums, ntiles);
+}
+void fqz_launch_record_meta(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, u32 *sizes, u64 stride,
+                            FqzWinStatus *st, u64 phred_records, cudaStream_t s) {
+    u32 per = FQZ_META_THREADS / FQZ_META_GROUP;
+    u32 grid = (u32)((R + 1 + per - 1) / per);
+    FQZ_LAUNCH(k_record_meta, grid, FQZ_META_THREADS, 0, s, text, line_end, R, rec_base, tail_lines, sizes, stride, st, phred_records);
+}
+void fqz_launch_decide_phred(const FqzWinStatus *st, u32 *phred64, cudaStream_t s) { FQZ_LAUNCH(k_decide_phred, 1, 1, 0, s, st, phred64); }
+void fqz_launch_scatter(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u64 stride, const u32 *phred64, u8 *const streams[6],
+                        cudaStream_t s) {
+    if (!R) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_scatter_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
+        attr_done = true;
+    }
+    u32 grid = (u32)((R + FQZ_SC_RPC - 1) / FQZ_SC_RPC);
+    FQZ_LAUNCH(k_scatter_streams, grid, FQZ_SC_THREADS, FQZ_SC_SMEM, s, text, line_end, R, offs, stride, phred64, streams[0], streams[1],
+               streams[2], streams[3], streams[4], streams[5], (u32)(FQZ_SC_SMEM - 128));
+}

@@ -1,0 +1,116 @@
+// fqz_host.h — host-side plumbing of libfqzgpu: context, device arena, stage profiler.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/fqzgpu.h"
+#include "fqz_kernels.h"
+
+#define FQZ_CUDA_TRY(ctx, expr)                                                      \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);         \
+            return FQZ_E_CUDA;                                                        \
+        }                                                                             \
+    } while (0)
+#define FQZ_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != FQZ_OK) return rc__; \
+    } while (0)
+
+// Bump allocator over a few large cudaMalloc chunks; reset between windows.
+struct Arena {
+    struct Chunk {
+        u8 *p;
+        size_t cap, used;
+    };
+    std::vector<Chunk> chunks;
+    size_t min_chunk = (size_t)64 << 20;
+    void *alloc(size_t bytes);  // 256-byte aligned, FQZ_PAD slack; nullptr on failure
+    void reset();               // keeps memory; coalesces several chunks into one
+    void release();
+    size_t capacity() const;
+};
+
+enum FqzStage {
+    ST_NL_COUNT = 0,
+    ST_NL_INDEX,
+    ST_SCAN,
+    ST_RECORD_META,
+    ST_SCATTER,
+    ST_ZENC_ENTROPY,
+    ST_ZENC_LZ,
+    ST_XXH64,
+    ST_ASSEMBLE,
+    ST_ZDEC_SCAN,
+    ST_ZDEC_LITERALS,
+    ST_ZDEC_SEQUENCES,
+    ST_ZDEC_EXECUTE,
+    ST_WALK,
+    ST_OFFSETS,
+    ST_EMIT,
+    ST_COPY,
+    ST_COUNT_
+};
+
+struct Profiler {
+    bool on = false;
+    struct Rec {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> open;
+    std::vector<cudaEvent_t> pool;
+    double ms[ST_COUNT_] = {0};
+    u64 launches[ST_COUNT_] = {0};
+    u64 bytes[ST_COUNT_] = {0};
+    cudaEvent_t get();
+    void collect();
+    void clear();
+};
+
+struct fqz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    Profiler prof;
+    std::string err;
+    FqzWinStatus *d_status = nullptr;  // device
+    u32 *d_phred = nullptr;            // device: file-global Phred flag
+    u8 *h_pin = nullptr;               // pinned host scratch for small readbacks / uploads
+    size_t h_pin_cap = 0;
+    u8 *h_io = nullptr;                // pinned staging for host-buffer entry points
+    size_t h_io_cap = 0;
+    int sm_count = 148;
+    u64 launches_base = 0;
+};
+
+// RAII stage marker: CUDA events around the launches of one pipeline stage when profiling is on
+struct StageScope {
+    fqz_ctx *c;
+    int stage;
+    u64 l0;
+    cudaEvent_t a = nullptr;
+    StageScope(fqz_ctx *ctx, int st, u64 bytes);
+    ~StageScope();
+};
+
+int fqz_pin_reserve(fqz_ctx *c, size_t bytes);
+int fqz_io_reserve(fqz_ctx *c, size_t bytes);
+int fqz_scan_excl_u32(fqz_ctx *c, u32 *d, u64 n, u64 stride, u32 narr);
+
+// ---- compress front end (fqz_api_front.cu)
+struct FrontOut {
+    u64 R = 0;          // records encoded from this window
+    u32 nblocks = 0;    // fqz blocks (100 000 records each, last one may be short)
+    u64 consumed = 0;   // bytes of text consumed
+    u32 phred64 = 0;
+    u8 *d_streams[6] = {0};
+    std::vector<u32> blk_off[6];  // nblocks+1 boundaries of each stream (bytes)
+    std::vector<u32> orig;        // per block: sum of sequence lengths (== quality lengths)
+};
+// phred_mode: -1 detect on the first block of the file (rec_base must be 0), -2 use c->d_phred as
+// already decided, 0/1 force.  max_records: cap on records taken (0 = all whole blocks / all).
+int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out);

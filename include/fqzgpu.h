@@ -1,0 +1,143 @@
+/*
+ * fqzgpu.h — C-ABI of libfqzgpu.so, the B200 (sm_100a) implementation of fqpack's block codec.
+ *
+ * This is the drop-in boundary for vertti/fastqpacker: the Go package internal/compress keeps its
+ * exported API (Compress / Decompress / Options / DecompressOptions, compress.go:70-82,125,558)
+ * and binds these entry points through cgo instead of running its CPU
+ * workers.  Plain pointers and sizes only; the library never keeps a caller pointer after a call
+ * returns (cgo rule), owns all device memory, pinned staging buffers and CUDA streams inside
+ * fqz_ctx, and has NO CPU fallback: without a CUDA device every call fails with FQZ_E_NO_DEVICE.
+ *
+ * Reference citations are file:line in vertti/fastqpacker.
+ */
+#ifndef FQZGPU_H
+#define FQZGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQZ_ABI_VERSION 1
+
+/* ---- result codes.  Negative codes map 1:1 onto the reference's error texts so that the Go shim
+ *      can return errors with the same wording. */
+#define FQZ_OK 0
+#define FQZ_E_HEADER_AT (-1)    /* "invalid FASTQ: header line must start with @"            internal/fqparser/parser.go:143 */
+#define FQZ_E_PLUS (-2)         /* "invalid FASTQ: separator line must start with +"         parser.go:164 */
+#define FQZ_E_LEN_MISMATCH (-3) /* "invalid FASTQ: sequence and quality lengths must match"  parser.go:180 */
+#define FQZ_E_LONG_N (-4)       /* "record %q: sequence length %d has ambiguous bases beyond position 65536; ..." internal/compress/compress.go:484 */
+#define FQZ_E_MAGIC (-5)        /* "invalid magic bytes: not an FQZ file"                    internal/fqformat/container.go:54 */
+#define FQZ_E_VERSION (-6)      /* "unsupported file version: %d"                            compress.go:572 */
+#define FQZ_E_TRUNC_FILE (-7)   /* "reading block header:" / "reading compressed data: unexpected EOF"  compress.go:727,732 */
+#define FQZ_E_ZSTD (-8)         /* "decompressing sequences|quality|headers|plus-line payload|N positions|lengths: ..." compress.go:787-813 */
+#define FQZ_E_TRUNC_HEADER (-9) /* "truncated header data"             compress.go:979 */
+#define FQZ_E_TRUNC_PLUS (-10)  /* "truncated plus-line payload data"  compress.go:1002 */
+#define FQZ_E_TRUNC_SEQ (-11)   /* "truncated sequence data"           compress.go:1020 */
+#define FQZ_E_TRUNC_QUAL (-12)  /* "truncated quality data"            compress.go:1033 */
+#define FQZ_E_TRUNC_LEN (-13)   /* "truncated length data"             compress.go:1048 */
+#define FQZ_E_TRUNC_NPOS (-14)  /* "truncated N position data"         compress.go:1057 */
+#define FQZ_E_NOSPACE (-15)     /* output buffer too small; *out_len = bytes required, nothing consumed */
+#define FQZ_E_NPOS_RANGE (-17)  /* N position >= sequence length (the reference panics: encoder/sequence.go:218-220) */
+#define FQZ_E_CUDA (-32)        /* CUDA runtime failure; text in fqz_last_error() */
+#define FQZ_E_NO_DEVICE (-33)   /* no usable CUDA device: there is no CPU fallback */
+#define FQZ_E_INVALID_ARG (-34)
+#define FQZ_E_NEED_MORE (-35)   /* streaming: window holds no complete block and is_last == 0 */
+#define FQZ_E_TOO_LARGE (-36)   /* single call larger than FQZ_MAX_WINDOW; use the streaming calls */
+
+#define FQZ_MAX_WINDOW ((size_t)3 << 30) /* bytes of FASTQ / .fqz handled by one device pass */
+#define FQZ_DEVICE_SLACK 64               /* readable bytes required after a caller-supplied DEVICE buffer */
+
+typedef struct fqz_ctx fqz_ctx;
+
+/* One context per process and GPU (reference: one zstd encoder/decoder per worker goroutine,
+ * compress.go:113-122,281,671).  Not thread-safe: one caller thread at a time per context. */
+int fqz_init(int device, fqz_ctx **out);
+void fqz_destroy(fqz_ctx *ctx);
+const char *fqz_strerror(int code);
+/* Detail of the last failure on this context (record index, CUDA error text, stream name). */
+const char *fqz_last_error(const fqz_ctx *ctx);
+int fqz_abi_version(void);
+
+/* ---- whole buffer, HOST memory: replaces the bodies of compress.Compress / compress.Decompress
+ *      (compress.go:125-192, 558-604).  Output = complete .fqz file (10-byte header + blocks of
+ *      100 000 records, F2) / complete FASTQ text.  header_block_size is echoed into the file
+ *      header only (0 -> 100000, compress.go:129-131). */
+size_t fqz_compress_bound(size_t fastq_bytes);
+int fqz_compress(fqz_ctx *ctx, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap, size_t *out_len);
+int fqz_decompress(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
+
+/* ---- streaming, HOST memory (Seam B): the Go producer feeds raw windows read from io.Reader and
+ *      writes what comes back to io.Writer in order (replaces produceCompressJobs / workers /
+ *      collectAndWriteResults, compress.go:240-403, and their decompress twins :630-719).
+ *      feed() consumes a whole number of blocks; the caller re-presents the unconsumed tail in
+ *      front of the next window.  The first compress feed also emits the file header; Phred is
+ *      decided on the first block only (compress.go:146-164). */
+typedef struct fqz_cstream fqz_cstream;
+typedef struct fqz_dstream fqz_dstream;
+int fqz_compress_begin(fqz_ctx *ctx, uint32_t header_block_size, fqz_cstream **s);
+int fqz_compress_feed(fqz_cstream *s, const uint8_t *fastq, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
+                      size_t *consumed);
+void fqz_compress_end(fqz_cstream *s);
+int fqz_decompress_begin(fqz_ctx *ctx, fqz_dstream **s);
+int fqz_decompress_feed(fqz_dstream *s, const uint8_t *fqz, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
+                        size_t *consumed);
+void fqz_decompress_end(fqz_dstream *s);
+
+/* ---- whole buffer, DEVICE memory (benchmarks, GPU pipelines): same semantics, pointers are
+ *      device pointers on the context's GPU, 16-byte aligned, with FQZ_DEVICE_SLACK readable bytes
+ *      after the input.  *out_len is returned on the host. */
+int fqz_compress_device(fqz_ctx *ctx, const void *d_fastq, size_t n, uint32_t header_block_size, void *d_out, size_t out_cap,
+                        size_t *out_len);
+int fqz_decompress_device(fqz_ctx *ctx, const void *d_fqz, size_t n, void *d_out, size_t out_cap, size_t *out_len);
+
+/* ---- block level (Seam A and the parity tests) -------------------------------------------------
+ * fqz_encode_streams: FASTQ chunk -> the six pre-entropy streams of its first block
+ *   (<= 100 000 records), byte-identical to what compressBlockWithBuffers builds before EncodeAll
+ *   (compress.go:474-520).  Stream order: 0 seqPacked, 1 quality, 2 headers, 3 plusLines,
+ *   4 nPositions, 5 seqLengths.  phred64: 0 / 1 forced, -1 = detect on these records
+ *   (encoder/quality.go:22-49).  info: [0] records [1] bytes consumed [2] phred64 used
+ *   [3] OriginalSeqSize [4] OriginalQualSize [5] index of the offending record on error.
+ * fqz_decode_streams: the inverse back end = NumRecords x blockReader.writeRecord (compress.go:944-1078);
+ *   an empty plusLines stream reproduces the v1 "+\n" rule (compress.go:995-999). */
+int fqz_encode_streams(fqz_ctx *ctx, const uint8_t *fastq, size_t n, int phred64, uint8_t *const out[6], const size_t cap[6],
+                       size_t len[6], uint64_t info[6]);
+int fqz_decode_streams(fqz_ctx *ctx, const uint8_t *const in[6], const size_t len[6], uint32_t num_records, int phred64, uint8_t *out,
+                       size_t out_cap, size_t *out_len);
+
+/* Entropy stage alone = zstd.Encoder.EncodeAll / zstd.Decoder.DecodeAll (compress.go:523-528,
+ * 785-814; klauspost/compress v1.19.1 is not in the reference tree).  Output of
+ * fqz_zstd_compress is a sequence of RFC 8878 frames with content checksums; empty input yields
+ * zero bytes.  fqz_zstd_decompress accepts any RFC 8878 frame sequence without dictionaries.
+ * policy: FQZ_ZPOLICY_* below. */
+#define FQZ_ZPOLICY_AUTO 0     /* LZ77 + Huffman literals + FSE sequences */
+#define FQZ_ZPOLICY_ENTROPY 1  /* literals-only blocks: Huffman / RLE / raw, no match search */
+int fqz_zstd_compress(fqz_ctx *ctx, const uint8_t *src, size_t n, int policy, uint8_t *dst, size_t cap, size_t *out_len);
+int fqz_zstd_decompress(fqz_ctx *ctx, const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
+
+/* ---- measurement support (bench.py): kernel launch counter and per-stage device timings taken
+ *      with CUDA events on the library's own stream. */
+#define FQZ_MAX_STAGES 32
+typedef struct {
+    uint64_t launches;                 /* kernels launched by this library since fqz_stats_reset */
+    uint32_t n_stages;
+    const char *stage_name[FQZ_MAX_STAGES];
+    double stage_ms[FQZ_MAX_STAGES];   /* accumulated device time, only while profiling is on */
+    uint64_t stage_launches[FQZ_MAX_STAGES];
+    uint64_t stage_bytes[FQZ_MAX_STAGES]; /* algorithmic bytes attributed to the stage */
+} fqz_stats;
+void fqz_stats_reset(fqz_ctx *ctx);
+void fqz_profile_enable(fqz_ctx *ctx, int on);
+int fqz_get_stats(fqz_ctx *ctx, fqz_stats *out);
+
+/* ---- synthetic FASTQ generator used by the tests and bench (counter-based RNG, identical bytes
+ *      on every device and in the CPU twin tests/synth.py).  kind: 0 = Illumina 150 bp Phred+33
+ *      (BASELINE config 2), 1 = variable length 50-300, Phred+64, 5 % N, plus payloads (config 4).
+ *      Writes records [first_record, first_record + num_records) to d_out. */
+int fqz_synth_device(fqz_ctx *ctx, int kind, uint64_t seed, uint64_t first_record, uint64_t num_records, void *d_out, size_t out_cap,
+                     size_t *out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQZGPU_H */

@@ -1,0 +1,55 @@
+"""Runs the CUDA front-end kernels through the CPU emulation (tests/emu) and compares the six
+pre-entropy streams with the oracle byte for byte.  Debug aid for the GPU kernels; the real
+parity tests are the -m gpu ones."""
+import pytest
+
+from tests.fastq_cases import BAD_CASES, GOOD_CASES, long_read
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.emu_lib import emu_context
+
+    return emu_context()
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_streams_match_oracle(emu, oracle, name):
+    text = GOOD_CASES[name]
+    want = oracle.encode_streams(text)
+    got = emu.encode_streams(text)
+    for k in ("nrec", "phred64", "orig_seq", "orig_qual", "consumed"):
+        assert got[k] == want[k], k
+    for nm, a, b in zip(oracle.STREAM_NAMES, got["streams"], want["streams"]):
+        assert a == b, nm
+
+
+@pytest.mark.parametrize("name", sorted(BAD_CASES))
+def test_errors_match_oracle(emu, oracle, name):
+    text, code, rec = BAD_CASES[name]
+    with pytest.raises(oracle.OracleError) as oe:
+        oracle.encode_streams(text)
+    assert oe.value.code == code
+    from fastqpacker_b200._binding import FqzError
+
+    with pytest.raises(FqzError) as ge:
+        emu.encode_streams(text)
+    assert ge.value.code == code and ge.value.record == rec
+
+
+def test_long_read_guard(emu, oracle):
+    from fastqpacker_b200._binding import FqzError
+
+    with pytest.raises(FqzError) as ge:
+        emu.encode_streams(long_read(66000))
+    assert ge.value.code == -4
+    ok = long_read(100)
+    want = oracle.encode_streams(ok)
+    got = emu.encode_streams(ok)
+    assert got["streams"] == want["streams"]
+
+
+def test_forced_phred(emu, oracle):
+    text = GOOD_CASES["three"]
+    for p in (0, 1):
+        assert emu.encode_streams(text, phred64=p)["streams"] == oracle.encode_streams(text, phred64=p)["streams"]
