@@ -1,0 +1,337 @@
+// fqz_api_zstd.cu — host orchestration of the zstd encode stage, container assembly
+// (block headers + payload order of internal/compress/compress.go:530-552,
+// internal/fqformat/container.go:83-113) and the compress entry points.
+#include <string.h>
+
+#include <algorithm>
+
+#include "fqz_host.h"
+#include "fqz_zstd.h"
+
+// ---------------------------------------------------------------------------------- assembly kernels
+// Copies every encoded frame from its slot to its final position.  final offset of frame f =
+// fixed[f] (headers in front of it) + scan[f] (compressed bytes of the frames before it).
+__global__ void __launch_bounds__(256) k_zassemble(const ZFrame *frames, u32 nframes, const u32 *scan, const u32 *fixed, const u8 *slots, u8 *out) {
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= nframes) return;
+    u32 size = scan[warp + 1] - scan[warp];
+    const u8 *src = slots + frames[warp].dst_off;  // 16-byte aligned slot
+    u8 *dst = out + (u64)fixed[warp] + scan[warp];
+    u32 head = (u32)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > size) head = size;
+    if (lane < head) dst[lane] = src[lane];
+    u32 nw = (size - head) >> 2;
+    for (u32 w = lane; w < nw; w += 32) *(u32 *)(dst + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
+    u32 t0 = head + 4u * nw;
+    if (lane < size - t0) dst[t0 + lane] = src[t0 + lane];
+}
+
+// 36-byte v2 block headers (container.go:97-109).  first[b*6+s] = index of the first frame of
+// stream s of block b (first[nblocks*6] = nframes).
+__global__ void k_write_block_headers(u32 nblocks, const u32 *first, const u32 *scan, const u32 *nrec, const u32 *orig, u32 base_off, u8 *out) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    u32 f0 = first[b * 6];
+    u8 *h = out + (u64)base_off + 36ull * b + scan[f0];
+    u32 v[9];
+    v[0] = nrec[b];
+    for (int s = 0; s < 6; s++) v[1 + s] = scan[first[b * 6 + s + 1]] - scan[first[b * 6 + s]];
+    v[7] = orig[b];  // OriginalSeqSize
+    v[8] = orig[b];  // OriginalQualSize (equal: every record has len(seq) == len(qual))
+    for (int i = 0; i < 9; i++) {
+        h[4 * i] = (u8)v[i];
+        h[4 * i + 1] = (u8)(v[i] >> 8);
+        h[4 * i + 2] = (u8)(v[i] >> 16);
+        h[4 * i + 3] = (u8)(v[i] >> 24);
+    }
+}
+
+// ---------------------------------------------------------------------------------- zstd batch
+struct ZBatch {
+    std::vector<ZFrame> frames;
+    std::vector<u32> idx_ent, idx_lz;
+    size_t slot_bytes = 0, ws_bytes = 0;
+    void add_stream(const u8 *d_src, size_t len, int policy) {
+        for (size_t o = 0; o < len; o += FQZ_ZFRAME) {
+            u32 l = (u32)std::min<size_t>(FQZ_ZFRAME, len - o);
+            ZFrame f;
+            f.src = (u64)(uintptr_t)(d_src + o);
+            f.dst_off = slot_bytes;
+            f.ws_off = 0;
+            f.src_len = l;
+            f.policy = (u32)policy;
+            slot_bytes += FQZ_ZSLOT(l);
+            if (policy == FQZ_ZPOLICY_AUTO) {
+                f.ws_off = ws_bytes;
+                ws_bytes += FQZ_ZWS(l);
+                idx_lz.push_back((u32)frames.size());
+            } else
+                idx_ent.push_back((u32)frames.size());
+            frames.push_back(f);
+        }
+    }
+};
+struct ZEncoded {
+    ZFrame *d_frames = nullptr;
+    u8 *d_slots = nullptr;
+    u32 *d_scan = nullptr;  // nframes+1, exclusive scan of frame sizes
+    u32 nframes = 0;
+};
+
+static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
+    cudaStream_t s = c->stream;
+    u32 nf = (u32)zb.frames.size();
+    ze.nframes = nf;
+    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size()) * sizeof(u32);
+    FQZ_TRY(fqz_pin_reserve(c, 8192 + up));
+    u8 *hp = c->h_pin + 4096;
+    memcpy(hp, zb.frames.data(), (size_t)nf * sizeof(ZFrame));
+    u32 *hidx = (u32 *)(hp + (size_t)nf * sizeof(ZFrame));
+    if (!zb.idx_ent.empty()) memcpy(hidx, zb.idx_ent.data(), zb.idx_ent.size() * sizeof(u32));
+    if (!zb.idx_lz.empty()) memcpy(hidx + zb.idx_ent.size(), zb.idx_lz.data(), zb.idx_lz.size() * sizeof(u32));
+    u8 *d_up = (u8 *)c->arena.alloc(up + 16);
+    ze.d_slots = (u8 *)c->arena.alloc(zb.slot_bytes + 16);
+    u8 *d_ws = (u8 *)c->arena.alloc(zb.ws_bytes + 16);
+    u32 *d_hash = (u32 *)c->arena.alloc((size_t)(nf + 1) * sizeof(u32));
+    ze.d_scan = (u32 *)c->arena.alloc((size_t)(nf + 2) * sizeof(u32));
+    if (!d_up || !ze.d_slots || !d_ws || !d_hash || !ze.d_scan) {
+        c->err = "arena: out of device memory (zstd stage)";
+        return FQZ_E_CUDA;
+    }
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_up, hp, up, cudaMemcpyHostToDevice, s));
+    ze.d_frames = (ZFrame *)d_up;
+    u32 *d_idx = (u32 *)(d_up + (size_t)nf * sizeof(ZFrame));
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(ze.d_scan + nf, 0, sizeof(u32), s));
+    u64 ent_bytes = 0, lz_bytes = 0;
+    for (u32 i : zb.idx_ent) ent_bytes += zb.frames[i].src_len;
+    for (u32 i : zb.idx_lz) lz_bytes += zb.frames[i].src_len;
+    {
+        StageScope sc(c, ST_XXH64, src_bytes);
+        fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
+    }
+    {
+        StageScope sc(c, ST_ZENC_LZ, lz_bytes);
+        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, s);
+    }
+    {
+        StageScope sc(c, ST_ZENC_ENTROPY, ent_bytes);
+        fqz_launch_zenc(ze.d_frames, d_idx, (u32)zb.idx_ent.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 0, s);
+    }
+    {
+        StageScope sc(c, ST_SCAN, 0);
+        FQZ_TRY(fqz_scan_excl_u32(c, ze.d_scan, (u64)nf + 1, (u64)nf + 1, 1));
+    }
+    return FQZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- fqz_zstd_compress (entropy stage alone)
+extern "C" int fqz_zstd_compress(fqz_ctx *c, const uint8_t *src, size_t n, int policy, uint8_t *dst, size_t cap, size_t *out_len) {
+    if (!c || !out_len || (!src && n)) return FQZ_E_INVALID_ARG;
+    if (n > FQZ_MAX_WINDOW) return FQZ_E_TOO_LARGE;
+    cudaSetDevice(c->device);
+    c->arena.reset();
+    c->err.clear();
+    *out_len = 0;
+    if (n == 0) return FQZ_OK;  // EncodeAll of an empty slice yields zero bytes
+    cudaStream_t s = c->stream;
+    u8 *d_src = (u8 *)c->arena.alloc(n + 64);
+    if (!d_src) return FQZ_E_CUDA;
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_src, src, n, cudaMemcpyHostToDevice, s));
+    ZBatch zb;
+    zb.add_stream(d_src, n, policy == FQZ_ZPOLICY_ENTROPY ? FQZ_ZPOLICY_ENTROPY : FQZ_ZPOLICY_AUTO);
+    ZEncoded ze;
+    FQZ_TRY(zbatch_encode(c, zb, ze, n));
+    u32 nf = ze.nframes;
+    u32 *h = (u32 *)c->h_pin;
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, ze.d_scan + nf, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    size_t total = h[0];
+    *out_len = total;
+    if (total > cap) return FQZ_E_NOSPACE;
+    u8 *d_out = (u8 *)c->arena.alloc(total + 16);
+    u32 *d_fixed = (u32 *)c->arena.alloc((size_t)nf * sizeof(u32));
+    if (!d_out || !d_fixed) return FQZ_E_CUDA;
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_fixed, 0, (size_t)nf * sizeof(u32), s));
+    {
+        StageScope sc(c, ST_ASSEMBLE, 2 * total);
+        FQZ_LAUNCH(k_zassemble, (nf * 32 + 255) / 256, 256, 0, s, ze.d_frames, nf, ze.d_scan, d_fixed, ze.d_slots, d_out);
+    }
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    FQZ_CUDA_TRY(c, cudaGetLastError());
+    return FQZ_OK;
+}
+
+// ---------------------------------------------------------------------------------- compress one window (device -> device)
+// Stream policies: packed bases and delta-coded qualities go through the literals-only path
+// (Huffman beats LZ+Huffman on them); the four structured streams get LZ77.
+static const int kStreamPolicy[6] = {FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_AUTO, FQZ_ZPOLICY_AUTO, FQZ_ZPOLICY_AUTO,
+                                     FQZ_ZPOLICY_AUTO};
+
+// Compresses the whole blocks of d_text[0..n) into d_out.  Emits the 10-byte file header first
+// when `with_file_header`.  Returns bytes written in *out_len, text consumed in *consumed.
+int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, bool with_file_header,
+                        u32 header_block_size, u8 *d_out, size_t out_cap, size_t *out_len, u64 *consumed, u64 *records, u32 *phred_out) {
+    cudaStream_t s = c->stream;
+    FrontOut fo;
+    FQZ_TRY(fqz_run_frontend(c, d_text, n, is_last, rec_base, phred_mode, 0, fo));
+    *consumed = fo.consumed;
+    *records = fo.R;
+    *phred_out = fo.phred64;
+    u32 nb = fo.nblocks;
+    ZBatch zb;
+    std::vector<u32> first((size_t)nb * 6 + 1), nrec(nb);
+    u64 stream_bytes = 0;
+    for (u32 b = 0; b < nb; b++) {
+        nrec[b] = (u32)std::min<u64>(FQZ_BLOCK_RECORDS, fo.R - (u64)b * FQZ_BLOCK_RECORDS);
+        for (int a = 0; a < 6; a++) {
+            first[(size_t)b * 6 + a] = (u32)zb.frames.size();
+            size_t o0 = fo.blk_off[a][b], o1 = fo.blk_off[a][b + 1];
+            zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a]);
+            stream_bytes += o1 - o0;
+        }
+    }
+    first[(size_t)nb * 6] = (u32)zb.frames.size();
+    u32 nf = (u32)zb.frames.size();
+    u32 hdr0 = with_file_header ? 10u : 0u;
+    if (nf == 0) {  // no records: header-only output (compress.go:203-213)
+        *out_len = hdr0;
+        if (hdr0 > out_cap) return FQZ_E_NOSPACE;
+    }
+    ZEncoded ze;
+    if (nf) FQZ_TRY(zbatch_encode(c, zb, ze, stream_bytes));
+    // fixed offsets (headers in front of each frame) + small tables, one upload
+    std::vector<u32> fixed(nf);
+    for (u32 b = 0; b < nb; b++)
+        for (u32 f = first[(size_t)b * 6]; f < first[(size_t)(b + 1) * 6]; f++) fixed[f] = hdr0 + 36u * (b + 1);
+    size_t up_words = (size_t)nf + first.size() + 2 * (size_t)nb;
+    // the frame upload in zbatch_encode reads the same pinned buffer: wait before reusing it
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    FQZ_TRY(fqz_pin_reserve(c, 8192 + up_words * 4));
+    u32 *hp = (u32 *)(c->h_pin + 4096);
+    if (nf) memcpy(hp, fixed.data(), (size_t)nf * 4);
+    memcpy(hp + nf, first.data(), first.size() * 4);
+    if (nb) memcpy(hp + nf + first.size(), nrec.data(), (size_t)nb * 4);
+    if (nb) memcpy(hp + nf + first.size() + nb, fo.orig.data(), (size_t)nb * 4);
+    u32 *d_tab = (u32 *)c->arena.alloc(up_words * 4 + 16);
+    if (!d_tab) return FQZ_E_CUDA;
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_tab, hp, up_words * 4, cudaMemcpyHostToDevice, s));
+    u32 *d_fixed = d_tab, *d_first = d_tab + nf, *d_nrec = d_first + first.size(), *d_orig = d_nrec + nb;
+    size_t total = hdr0;
+    if (nf) {
+        u32 *h = (u32 *)c->h_pin;
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, ze.d_scan + nf, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        total = (size_t)hdr0 + 36ull * nb + h[0];
+    }
+    *out_len = total;
+    if (total > out_cap) return FQZ_E_NOSPACE;
+    if (with_file_header) {  // container.go:35-45
+        u8 *fh = c->h_pin + 512;
+        fh[0] = 'F'; fh[1] = 'Q'; fh[2] = 'Z'; fh[3] = 0;
+        fh[4] = 2;
+        u32 bs = header_block_size ? header_block_size : FQZ_BLOCK_RECORDS;  // compress.go:129-131
+        fh[5] = (u8)bs; fh[6] = (u8)(bs >> 8); fh[7] = (u8)(bs >> 16); fh[8] = (u8)(bs >> 24);
+        fh[9] = fo.phred64 ? 2 : 0;  // FlagPhred64, compress.go:162-164
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_out, fh, 10, cudaMemcpyHostToDevice, s));
+    }
+    if (nf) {
+        StageScope sc(c, ST_ASSEMBLE, 2 * (total - hdr0));
+        FQZ_LAUNCH(k_write_block_headers, (nb + 63) / 64, 64, 0, s, nb, d_first, ze.d_scan, d_nrec, d_orig, hdr0, d_out);
+        FQZ_LAUNCH(k_zassemble, (nf * 32 + 255) / 256, 256, 0, s, ze.d_frames, nf, ze.d_scan, d_fixed, ze.d_slots, d_out);
+    }
+    return FQZ_OK;
+}
+
+extern "C" size_t fqz_compress_bound(size_t n) { return n + n / 32 + 65536; }
+
+extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, uint32_t header_block_size, void *d_out, size_t out_cap,
+                                   size_t *out_len) {
+    if (!c || !out_len || (!d_fastq && n) || !d_out) return FQZ_E_INVALID_ARG;
+    if (((uintptr_t)d_fastq & 15u) != 0) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    // a buffer larger than one device window is processed as a sequence of windows, each cut at a
+    // block boundary (the host only walks; all data stays in HBM)
+    const u64 WIN = (u64)1 << 30;
+    u64 pos = 0, rec_base = 0;
+    size_t written = 0;
+    bool first = true;
+    while (first || pos < n) {
+        c->arena.reset();
+        u64 left = n - pos;
+        u64 take = left;
+        bool last = true;
+        if (left > WIN + (WIN >> 2)) {
+            take = WIN;
+            last = false;
+        }
+        // windows must start 16-byte aligned for the vector loads: copy the unaligned remainder
+        const u8 *wptr = (const u8 *)d_fastq + pos;
+        if (((uintptr_t)wptr & 15u) != 0) {
+            u8 *tmp = (u8 *)c->arena.alloc(take + 64);
+            if (!tmp) return FQZ_E_CUDA;
+            StageScope sc(c, ST_COPY, 2 * take);
+            FQZ_CUDA_TRY(c, cudaMemcpyAsync(tmp, wptr, take, cudaMemcpyDeviceToDevice, c->stream));
+            wptr = tmp;
+        }
+        size_t wl = 0;
+        u64 used = 0, recs = 0;
+        u32 ph = 0;
+        int rc = fqz_compress_window(c, wptr, take, last, rec_base, first ? -1 : -2, first, header_block_size, (u8 *)d_out + written,
+                                     out_cap - written, &wl, &used, &recs, &ph);
+        if (rc == FQZ_E_NEED_MORE && !last) {  // no complete block in this window: widen it
+            return FQZ_E_TOO_LARGE;
+        }
+        if (rc != FQZ_OK) {
+            if (rc == FQZ_E_NOSPACE) *out_len = written + wl;
+            return rc;
+        }
+        written += wl;
+        pos += last ? left : used;
+        rec_base += recs;
+        first = false;
+        if (last) break;
+    }
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    FQZ_CUDA_TRY(c, cudaGetLastError());
+    *out_len = written;
+    return FQZ_OK;
+}
+
+extern "C" int fqz_compress(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap,
+                            size_t *out_len) {
+    if (!c || !out_len || (!fastq && n) || !out) return FQZ_E_INVALID_ARG;
+    if (n > FQZ_MAX_WINDOW) return FQZ_E_TOO_LARGE;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    c->arena.reset();
+    *out_len = 0;
+    cudaStream_t s = c->stream;
+    size_t ocap = fqz_compress_bound(n);
+    u8 *d_in = nullptr, *d_o = nullptr;
+    // input and output live outside the per-window arena
+    FQZ_CUDA_TRY(c, cudaMalloc((void **)&d_in, n + 256));
+    if (cudaMalloc((void **)&d_o, ocap + 256) != cudaSuccess) {
+        cudaFree(d_in);
+        c->err = "cudaMalloc(output)";
+        return FQZ_E_CUDA;
+    }
+    int rc = FQZ_OK;
+    size_t m = 0;
+    do {
+        if (cudaMemsetAsync(d_in + (n & ~(size_t)15), 0, 64, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+        if (n && cudaMemcpyAsync(d_in, fastq, n, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+        rc = fqz_compress_device(c, d_in, n, header_block_size, d_o, ocap, &m);
+        if (rc != FQZ_OK) break;
+        *out_len = m;
+        if (m > out_cap) { rc = FQZ_E_NOSPACE; break; }
+        if (cudaMemcpyAsync(out, d_o, m, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+        if (cudaStreamSynchronize(s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+    } while (0);
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
+    cudaFree(d_in);
+    cudaFree(d_o);
+    return rc;
+}

@@ -1,0 +1,27 @@
+// fqz_zstd.h — host-visible structures and launchers of the GPU zstd (RFC 8878) entropy stage.
+#pragma once
+#include "fqz_common.cuh"
+
+// Every stream is cut into frames of at most FQZ_ZFRAME bytes; each frame is an independent zstd
+// frame holding one block, so frames encode AND decode in parallel and each carries its own
+// XXH64 content checksum.  Decoders (klauspost DecodeAll, libzstd) decode
+// concatenated frames back to back.
+#define FQZ_ZFRAME 65536u
+#define FQZ_ZFRAME_LOG 16
+#define FQZ_ZSLOT(len) ((((size_t)(len) + 512) + 15) & ~(size_t)15)  // output slot of one frame: raw fallback + table scratch always fit
+#define FQZ_ZWS(len) (((size_t)(len)*3 + 255) & ~(size_t)63)  // LZ workspace: literals + sequence arrays
+
+struct ZFrame {
+    u64 src;      // device address of the frame's content
+    u64 dst_off;  // into the slot arena
+    u64 ws_off;   // into the LZ workspace arena (policy AUTO only)
+    u32 src_len;  // 1..FQZ_ZFRAME
+    u32 policy;   // FQZ_ZPOLICY_*
+};
+
+#define ZENC_WARPS 4
+
+void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
+// index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
+void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
+                     cudaStream_t s);

@@ -1,0 +1,935 @@
+// fqz_zstd_dec.cu — GPU zstd (RFC 8878) decoder: replaces zstd.Decoder.DecodeAll (reference call
+// sites internal/compress/compress.go:785-814; decoder options :120-122).  Must accept everything
+// the reference's encoder (klauspost/compress v1.19.1 SpeedFastest, go.mod:8, not in the tree) can
+// emit — multi-block frames, raw / RLE / compressed blocks, 1- and 4-stream Huffman literals,
+// treeless literals, predefined / RLE / FSE / repeat sequence tables, repeat offsets, matches that
+// reach into earlier blocks, content checksums — as well as the small independent frames written by
+// fqz_zstd_enc.cu.  No dictionaries (the reference uses none, compress.go:523-528).
+//
+// Pipeline over a batch of streams (each a chain of frames):
+//   k_zd_walk      1 thread / stream : frame + block headers -> frame / block tables
+//   k_zd_literals  1 warp  / block   : Huffman (4 lanes = 4 streams) / raw / RLE literals
+//   k_zd_sequences 1 warp  / block   : FSE tables + serial sequence decode
+//   k_zd_execute   1 warp  / frame   : repeat-offset resolution + LZ77 copies, block after block
+//   k_zd_checksum  4 lanes / frame   : XXH64 of the regenerated content
+#include "fqz_zstd.h"
+#include "fqz_zstd_dec.h"
+#include "fqz_zstd_tables.cuh"
+
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------- backward bit reader
+struct BitR {
+    const u8 *start;
+    const u8 *ptr;
+    u64 cont;
+    u32 consumed;  // bits consumed from the top of `cont`
+    bool bad;
+    __device__ static u64 load_le(const u8 *p, u32 n) {  // n <= 8 bytes
+        u64 v = 0;
+        for (u32 i = 0; i < n; i++) v |= (u64)p[i] << (8 * i);
+        return v;
+    }
+    __device__ void init(const u8 *s, u32 size) {
+        start = s;
+        bad = false;
+        if (size == 0) {
+            bad = true;
+            ptr = s;
+            cont = 0;
+            consumed = 64;
+            return;
+        }
+        u32 last = s[size - 1];
+        if (last == 0) bad = true;  // the end mark is missing
+        u32 hb = last ? hibit32(last) : 0;
+        if (size >= 8) {
+            ptr = s + size - 8;
+            cont = load_le(ptr, 8);
+            consumed = 8 - hb;
+        } else {
+            ptr = s;
+            cont = load_le(s, size);
+            consumed = 8 - hb + (8 - size) * 8;
+        }
+    }
+    __device__ __forceinline__ u32 look(u32 n) const {  // n in 1..32; bits past the start read as 0
+        return (u32)(((cont << (consumed & 63)) >> 1) >> (63 - n));
+    }
+    __device__ __forceinline__ void skip(u32 n) { consumed += n; }
+    __device__ __forceinline__ u32 read(u32 n) {
+        if (n == 0) return 0;
+        u32 v = look(n);
+        skip(n);
+        return v;
+    }
+    __device__ __forceinline__ void reload() {
+        if (consumed > 64) {
+            bad = true;  // read past the beginning of the stream
+            consumed = 64;
+            return;
+        }
+        if (ptr >= start + 8) {
+            ptr -= consumed >> 3;
+            consumed &= 7;
+            cont = load_le(ptr, 8);
+            return;
+        }
+        if (ptr == start) return;
+        u32 nb = consumed >> 3;
+        if (ptr - nb < start) nb = (u32)(ptr - start);
+        ptr -= nb;
+        consumed -= nb * 8;
+        cont = load_le(ptr, 8);
+    }
+    __device__ bool finished() const { return ptr == start && consumed == 64; }
+};
+
+// ---------------------------------------------------------------------------------- FSE decode tables
+struct FseDEnt {
+    u16 base;  // new state base
+    u8 sym;
+    u8 nb;
+};
+// Reads an FSE table description (RFC 8878 §4.1.1).  Returns bytes consumed, 0 on error.
+__device__ static u32 fse_read_ncount(const u8 *p, u32 avail, short *norm, u32 *maxSymIO, u32 *tlogOut, u32 maxLog) {
+    if (avail < 1) return 0;
+    u32 maxSym = *maxSymIO;
+    u64 bits = 0;
+    u32 have = 0, pos = 0;
+#define NC_FILL()                                   \
+    while (have <= 56 && pos < avail) {             \
+        bits |= (u64)p[pos++] << have;              \
+        have += 8;                                  \
+    }
+    NC_FILL();
+    u32 tlog = (u32)(bits & 15) + 5;
+    bits >>= 4;
+    have -= 4;
+    if (tlog > maxLog) return 0;
+    int remaining = (1 << tlog) + 1, threshold = 1 << tlog;
+    u32 nbBits = tlog + 1;
+    u32 sym = 0;
+    bool prev0 = false;
+    while (remaining > 1 && sym <= maxSym) {
+        NC_FILL();
+        if (prev0) {
+            u32 n0 = sym;
+            for (;;) {
+                NC_FILL();
+                u32 r = (u32)(bits & 3);
+                bits >>= 2;
+                if (have < 2) return 0;
+                have -= 2;
+                n0 += r;
+                if (r != 3) break;
+            }
+            if (n0 > maxSym + 1) return 0;
+            while (sym < n0) norm[sym++] = 0;
+            if (sym > maxSym) break;
+            NC_FILL();
+        }
+        int mx = (2 * threshold - 1) - remaining;
+        int count;
+        if (have < nbBits) return 0;
+        if ((int)(bits & (u32)(threshold - 1)) < mx) {
+            count = (int)(bits & (u32)(threshold - 1));
+            bits >>= (nbBits - 1);
+            have -= nbBits - 1;
+        } else {
+            count = (int)(bits & (u32)(2 * threshold - 1));
+            if (count >= threshold) count -= mx;
+            bits >>= nbBits;
+            have -= nbBits;
+        }
+        count--;
+        remaining -= count < 0 ? -count : count;
+        norm[sym++] = (short)count;
+        prev0 = (count == 0);
+        while (remaining < threshold) {
+            nbBits--;
+            threshold >>= 1;
+        }
+    }
+#undef NC_FILL
+    if (remaining != 1) return 0;
+    *maxSymIO = sym - 1;
+    *tlogOut = tlog;
+    // bytes consumed = everything pulled minus whole unused bytes
+    u32 used = pos - (have >> 3);
+    return used;
+}
+__device__ static void fse_build_dtable(const short *norm, u32 maxSym, u32 tlog, FseDEnt *dt, u16 *symNext /*>=maxSym+1*/) {
+    u32 tsize = 1u << tlog, mask = tsize - 1, step = (tsize >> 1) + (tsize >> 3) + 3;
+    u32 high = tsize - 1;
+    for (u32 s = 0; s <= maxSym; s++) {
+        if (norm[s] == -1) {
+            dt[high--].sym = (u8)s;
+            symNext[s] = 1;
+        } else
+            symNext[s] = (u16)norm[s];
+    }
+    u32 pos = 0;
+    for (u32 s = 0; s <= maxSym; s++)
+        for (int i = 0; i < norm[s]; i++) {
+            dt[pos].sym = (u8)s;
+            pos = (pos + step) & mask;
+            while (pos > high) pos = (pos + step) & mask;
+        }
+    for (u32 u = 0; u < tsize; u++) {
+        u32 s = dt[u].sym;
+        u32 nx = symNext[s]++;
+        u32 nb = tlog - hibit32(nx);
+        dt[u].nb = (u8)nb;
+        dt[u].base = (u16)((nx << nb) - tsize);
+    }
+}
+
+// ---------------------------------------------------------------------------------- header parsing helpers
+__device__ __forceinline__ u32 rd24(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16); }
+__device__ __forceinline__ u32 rd32(const u8 *p) { return rd24(p) | ((u32)p[3] << 24); }
+
+// Literals section header.  Returns header size (0 = corrupt).
+__device__ static u32 parse_lit_header(const u8 *p, u32 avail, u32 *type, u32 *regen, u32 *csize, u32 *nstreams) {
+    if (avail < 1) return 0;
+    u32 b0 = p[0];
+    u32 t = b0 & 3, fmt = (b0 >> 2) & 3;
+    *type = t;
+    *nstreams = 1;
+    if (t < 2) {  // raw / RLE
+        if (fmt == 0 || fmt == 2) {
+            *regen = b0 >> 3;
+            *csize = (t == 0) ? *regen : 1;
+            return 1;
+        }
+        if (fmt == 1) {
+            if (avail < 2) return 0;
+            *regen = (b0 >> 4) | ((u32)p[1] << 4);
+            *csize = (t == 0) ? *regen : 1;
+            return 2;
+        }
+        if (avail < 3) return 0;
+        *regen = (rd24(p) >> 4);
+        *csize = (t == 0) ? *regen : 1;
+        return 3;
+    }
+    if (fmt == 0 || fmt == 1) {
+        if (avail < 3) return 0;
+        u32 h = rd24(p);
+        *regen = (h >> 4) & 0x3FF;
+        *csize = (h >> 14) & 0x3FF;
+        *nstreams = fmt == 0 ? 1 : 4;
+        return 3;
+    }
+    if (fmt == 2) {
+        if (avail < 4) return 0;
+        u32 h = rd32(p);
+        *regen = (h >> 4) & 0x3FFF;
+        *csize = (h >> 18) & 0x3FFF;
+        *nstreams = 4;
+        return 4;
+    }
+    if (avail < 5) return 0;
+    u32 h = rd32(p);
+    *regen = (h >> 4) & 0x3FFFF;
+    *csize = ((h >> 22) & 0x3FF) | ((u32)p[4] << 10);
+    *nstreams = 4;
+    return 5;
+}
+
+// ---------------------------------------------------------------------------------- walk: frames and blocks of each stream
+// pass 0 (tables == nullptr): counts frames / blocks / output bytes per stream.
+// pass 1: fills the tables at the bases computed by the host.
+__global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill) {
+    u32 si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nstreams) return;
+    ZDStream st = streams[si];
+    const u8 *p = (const u8 *)(uintptr_t)st.src;
+    u64 n = st.csize, pos = 0;
+    ZDStreamInfo inf;
+    inf.nframes = 0;
+    inf.nblocks = 0;
+    inf.out_bytes = 0;
+    inf.status = 0;
+    inf.lit_bytes = 0;
+    inf.nseq = 0;
+    u32 fbase = 0, bbase = 0;
+    u64 obase = 0;
+    if (fill) {
+        fbase = info[si].frame_base;
+        bbase = info[si].block_base;
+        obase = info[si].out_base;
+    }
+    while (pos < n) {
+        if (n - pos < 4) { inf.status = 1; break; }
+        u32 magic = rd32(p + pos);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+            if (n - pos < 8) { inf.status = 1; break; }
+            u64 sz = rd32(p + pos + 4);
+            if (n - pos - 8 < sz) { inf.status = 1; break; }
+            pos += 8 + sz;
+            continue;
+        }
+        if (magic != ZSTD_MAGIC) { inf.status = 1; break; }
+        if (n - pos < 6) { inf.status = 1; break; }
+        u32 fhd = p[pos + 4];
+        u32 fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did = fhd & 3;
+        if (fhd & 8) { inf.status = 1; break; }  // reserved bit
+        if (did) { inf.status = 2; break; }      // dictionaries are not used by the reference
+        u64 h = pos + 5;
+        u64 window = 0;
+        if (!single) {
+            u32 wd = p[h++];
+            u32 e = wd >> 3, m = wd & 7;
+            window = ((u64)1 << (10 + e));
+            window += (window >> 3) * m;
+        }
+        u32 fcs_size = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+        if (n - h < fcs_size) { inf.status = 1; break; }
+        u64 fcs = ~0ull;
+        if (fcs_size == 1) fcs = p[h];
+        else if (fcs_size == 2) fcs = (u64)(p[h] | (p[h + 1] << 8)) + 256;
+        else if (fcs_size == 4) fcs = rd32(p + h);
+        else if (fcs_size == 8) fcs = (u64)rd32(p + h) | ((u64)rd32(p + h + 4) << 32);
+        h += fcs_size;
+        if (single) window = fcs;
+        u32 fidx = fbase + inf.nframes;
+        u32 first_block = bbase + inf.nblocks;
+        u32 nb = 0;
+        u64 bound = 0;
+        // per-frame entropy table provenance (treeless literals / repeat-mode FSE tables)
+        u32 huf_src = 0xFFFFFFFFu, fse_src[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        bool ok = true;
+        for (;;) {
+            if (n - h < 3) { ok = false; break; }
+            u32 bh = rd24(p + h);
+            u32 last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+            h += 3;
+            if (type == 3) { ok = false; break; }
+            u32 csz = (type == 1) ? 1 : bsz;
+            if (n - h < csz || bsz > ZSTD_BLOCK_MAX) { ok = false; break; }
+            if (type == 2 && bsz < 2) { ok = false; break; }
+            u32 bidx = first_block + nb;
+            u32 lit_regen = 0, nseq = 0;
+            ZDBlock B;
+            if (type == 2) {
+                const u8 *c = p + h;
+                u32 lt, lr, lc, ls;
+                u32 lh = parse_lit_header(c, csz, &lt, &lr, &lc, &ls);
+                if (!lh || lh + lc > csz) { ok = false; break; }
+                lit_regen = lr;
+                u32 so = lh + lc;  // sequences section
+                if (so >= csz) { ok = false; break; }
+                u32 b0 = c[so];
+                u32 sh = 1;
+                if (b0 == 0) nseq = 0;
+                else if (b0 < 128) nseq = b0;
+                else if (b0 < 255) {
+                    if (so + 2 > csz) { ok = false; break; }
+                    nseq = ((b0 - 128) << 8) + c[so + 1];
+                    sh = 2;
+                } else {
+                    if (so + 3 > csz) { ok = false; break; }
+                    nseq = c[so + 1] + ((u32)c[so + 2] << 8) + 0x7F00;
+                    sh = 3;
+                }
+                if (fill) {
+                    B.lit_type = (u8)lt;
+                    B.lit_streams = (u8)ls;
+                    B.lit_hdr = (u8)lh;
+                    B.lit_csize = lc;
+                    B.huf_block = (lt == 3) ? huf_src : bidx;
+                    B.seq_pos = so + sh;
+                    B.modes = 0;
+                    for (int t = 0; t < 3; t++) {
+                        B.fse_block[t] = bidx;
+                        B.tab_pos[t] = 0;
+                    }
+                    if (lt == 3 && huf_src == 0xFFFFFFFFu) { ok = false; break; }
+                }
+                if (lt == 2) huf_src = bidx;
+                if (nseq) {
+                    if (so + sh >= csz) { ok = false; break; }
+                    u32 modes = c[so + sh];
+                    if (modes & 3) { ok = false; break; }
+                    u32 tp = so + sh + 1;
+                    // locate the three table descriptions (LL, OF, ML order) and the bitstream
+                    const u32 maxLogs[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
+                    const u32 maxSyms[3] = {ZSTD_MAX_LL, ZSTD_MAX_OF, ZSTD_MAX_ML};
+                    for (int t = 0; t < 3 && ok; t++) {
+                        u32 m = (modes >> (6 - 2 * t)) & 3;
+                        if (fill) B.tab_pos[t] = tp;
+                        if (m == 1) {
+                            if (tp >= csz) ok = false;
+                            tp += 1;
+                            fse_src[t] = bidx;
+                        } else if (m == 2) {
+                            short nrm[64];
+                            u32 ms = maxSyms[t], tl = 0;
+                            u32 used = (tp < csz) ? fse_read_ncount(c + tp, csz - tp, nrm, &ms, &tl, maxLogs[t]) : 0;
+                            if (!used) ok = false;
+                            tp += used;
+                            fse_src[t] = bidx;
+                        } else if (m == 0) {
+                            fse_src[t] = bidx;
+                        } else {  // repeat
+                            if (fse_src[t] == 0xFFFFFFFFu) ok = false;
+                            if (fill) B.fse_block[t] = fse_src[t];
+                        }
+                    }
+                    if (!ok) break;
+                    if (tp > csz) { ok = false; break; }
+                    if (fill) {
+                        B.modes = (u8)modes;
+                        B.bits_pos = tp;
+                    }
+                } else if (fill)
+                    B.bits_pos = so + sh;
+            }
+            if (fill) {
+                B.src = (u64)(uintptr_t)(p + h);
+                B.csize = csz;
+                B.type = (u8)type;
+                B.frame = fidx;
+                B.rsize = (type == 2) ? 0u : bsz;
+                B.lit_regen = lit_regen;
+                B.nseq = nseq;
+                B.lit_off = 0;
+                B.seq_off = 0;
+                B.err = 0;
+                blocks[bidx] = B;
+            }
+            inf.lit_bytes += lit_regen;
+            inf.nseq += nseq;
+            bound += (type == 2) ? ZSTD_BLOCK_MAX : bsz;
+            h += csz;
+            nb++;
+            if (last) break;
+        }
+        if (!ok) { inf.status = 1; break; }
+        u32 ck = 0;
+        if (has_ck) {
+            if (n - h < 4) { inf.status = 1; break; }
+            ck = rd32(p + h);
+            h += 4;
+        }
+        u64 osz = (fcs != ~0ull) ? fcs : bound;
+        if (fcs != ~0ull && fcs > bound) { inf.status = 1; break; }
+        if (fill) {
+            ZDFrame F;
+            F.dst_off = obase + inf.out_bytes;
+            F.content_size = fcs;
+            F.first_block = first_block;
+            F.nblocks = nb;
+            F.has_ck = has_ck;
+            F.ck = ck;
+            F.stream = si;
+            F.out_cap = osz;
+            F.out_size = 0;
+            F.err = 0;
+            F.window = window;
+            frames[fidx] = F;
+        }
+        inf.out_bytes += osz;
+        inf.nframes++;
+        inf.nblocks += nb;
+        pos = h;
+    }
+    if (!fill) {
+        info[si].nframes = inf.nframes;
+        info[si].nblocks = inf.nblocks;
+        info[si].out_bytes = inf.out_bytes;
+        info[si].status = inf.status;
+        info[si].lit_bytes = inf.lit_bytes;
+        info[si].nseq = inf.nseq;
+    } else if (inf.status)
+        info[si].status = inf.status;
+}
+
+// ---------------------------------------------------------------------------------- literals
+#define ZD_WARPS 4
+struct LitScratch {
+    u16 dt[1 << HUF_MAXBITS];  // nbBits << 8 | symbol
+    u8 weights[256];
+    u32 rank[16];
+    FseDEnt wdt[64];
+    u16 wnext[16];
+    short wnorm[16];
+};
+// Builds the Huffman decode table of block `hb` (its literals section carries the tree).  Returns
+// tableLog (0 on error) and *tree_size = bytes of the tree description.
+__device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 *tree_size) {
+    u32 lane = lane_id();
+    const u8 *p = (const u8 *)(uintptr_t)hb.src + hb.lit_hdr;
+    u32 avail = hb.lit_csize;
+    u32 nsym = 0, tsz = 0, bad = 0;
+    for (u32 i = lane; i < 256; i += 32) S.weights[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        if (avail < 1) bad = 1;
+        else {
+            u32 hbyte = p[0];
+            if (hbyte >= 128) {
+                nsym = hbyte - 127;
+                tsz = 1 + (nsym + 1) / 2;
+                if (tsz > avail) bad = 1;
+                else
+                    for (u32 i = 0; i < nsym; i++) {
+                        u32 b = p[1 + i / 2];
+                        S.weights[i] = (u8)((i & 1) ? (b & 15) : (b >> 4));
+                    }
+            } else {
+                tsz = 1 + hbyte;
+                if (hbyte == 0 || tsz > avail) bad = 1;
+                else {
+                    u32 ms = 12, tl = 0;
+                    u32 used = fse_read_ncount(p + 1, hbyte, S.wnorm, &ms, &tl, 6);
+                    if (!used || used >= hbyte) bad = 1;
+                    else {
+                        fse_build_dtable(S.wnorm, ms, tl, S.wdt, S.wnext);
+                        BitR br;
+                        br.init(p + 1 + used, hbyte - used);
+                        u32 s1 = br.read(tl), s2 = br.read(tl);
+                        br.reload();
+                        // two interleaved states; the stream ends when the bits run out
+                        for (;;) {
+                            if (nsym >= 254) { bad = 1; break; }
+                            S.weights[nsym++] = S.wdt[s1].sym;
+                            {
+                                u32 nb = S.wdt[s1].nb;
+                                if (br.consumed + nb > 64 && br.ptr == br.start) { S.weights[nsym++] = S.wdt[s2].sym; break; }
+                                s1 = S.wdt[s1].base + br.read(nb);
+                                br.reload();
+                            }
+                            if (nsym >= 254) { bad = 1; break; }
+                            S.weights[nsym++] = S.wdt[s2].sym;
+                            {
+                                u32 nb = S.wdt[s2].nb;
+                                if (br.consumed + nb > 64 && br.ptr == br.start) { S.weights[nsym++] = S.wdt[s1].sym; break; }
+                                s2 = S.wdt[s2].base + br.read(nb);
+                                br.reload();
+                            }
+                        }
+                        if (br.bad) bad = 1;
+                    }
+                }
+            }
+        }
+        if (!bad) {  // implied last weight
+            u32 total = 0;
+            for (u32 i = 0; i < nsym; i++) {
+                u32 w = S.weights[i];
+                if (w > HUF_MAXBITS + 1) { bad = 1; break; }
+                if (w) total += 1u << (w - 1);
+            }
+            if (total == 0) bad = 1;
+            if (!bad) {
+                u32 tl = hibit32(total) + 1;
+                u32 rest = (1u << tl) - total;
+                if (tl > HUF_MAXBITS + 1 || (rest & (rest - 1)) != 0) bad = 1;
+                else {
+                    S.weights[nsym] = (u8)(hibit32(rest) + 1);
+                    nsym++;
+                    S.rank[15] = tl;
+                }
+            }
+        }
+        S.rank[14] = bad;
+        S.rank[13] = nsym;
+        S.rank[12] = tsz;
+    }
+    __syncwarp();
+    bad = S.rank[14];
+    u32 tl = S.rank[15];
+    nsym = S.rank[13];
+    *tree_size = S.rank[12];
+    __syncwarp();
+    if (bad || tl > HUF_MAXBITS) return 0;
+    // rank starts: weight 1 first
+    if (lane < 12) S.rank[lane] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < nsym; i += 32)
+        if (S.weights[i]) atomicAdd(&S.rank[S.weights[i]], 1u);
+    __syncwarp();
+    if (lane == 0) {
+        u32 start = 0;
+        for (u32 w = 1; w <= tl; w++) {
+            u32 c = S.rank[w];
+            S.rank[w] = start;
+            start += c << (w - 1);
+        }
+        S.rank[0] = start;  // must equal 1 << tl
+    }
+    __syncwarp();
+    if (S.rank[0] != (1u << tl)) return 0;
+    for (u32 s = lane; s < nsym; s += 32) {
+        u32 w = S.weights[s];
+        if (!w) continue;
+        u32 idx = 0;
+        for (u32 t = 0; t < s; t++) idx += (S.weights[t] == w) ? 1u : 0u;
+        u32 len = 1u << (w - 1);
+        u32 at = S.rank[w] + idx * len;
+        u16 e = (u16)(((tl + 1 - w) << 8) | s);
+        for (u32 k = 0; k < len; k++) S.dt[at + k] = e;
+    }
+    __syncwarp();
+    return tl;
+}
+
+// one Huffman stream, decoded by one lane
+__device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 n, const u16 *dt, u32 tl) {
+    BitR br;
+    br.init(src, csize);
+    if (br.bad) return false;
+    u32 i = 0;
+    while (i < n) {
+        // a reload guarantees >= 57 fresh bits (or the stream start): up to 5 symbols of <= 11 bits
+        br.reload();
+        u32 burst = min(n - i, 5u);
+        for (u32 k = 0; k < burst; k++) {
+            u32 e = dt[br.look(tl)];
+            br.skip(e >> 8);
+            dst[i++] = (u8)e;
+        }
+    }
+    br.reload();
+    return !br.bad && br.ptr == br.start && br.consumed == 64;
+}
+
+__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out) {
+    __shared__ LitScratch scratch[ZD_WARPS];
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 bi = blockIdx.x * ZD_WARPS + warp;
+    if (bi >= nblocks) return;
+    ZDBlock B = blocks[bi];
+    if (B.type != 2) return;
+    LitScratch &S = scratch[warp];
+    const u8 *c = (const u8 *)(uintptr_t)B.src;
+    // literals of a sequence-free first block are the block's content: decode them in place
+    const ZDFrame &F = frames[B.frame];
+    bool direct = (B.nseq == 0 && bi == F.first_block);
+    u8 *dst = direct ? out + F.dst_off : litbuf + B.lit_off;
+    u32 n = B.lit_regen;
+    if (direct && n > F.out_cap) {
+        if (lane == 0) blocks[bi].err = 1;
+        return;
+    }
+    u32 err = 0;
+    if (B.lit_type == 0) {
+        const u8 *s = c + B.lit_hdr;
+        for (u32 i = lane; i < n; i += 32) dst[i] = s[i];
+    } else if (B.lit_type == 1) {
+        u8 v = c[B.lit_hdr];
+        for (u32 i = lane; i < n; i += 32) dst[i] = v;
+    } else {
+        ZDBlock HB = (B.huf_block == bi) ? B : blocks[B.huf_block];
+        u32 tree = 0;
+        u32 tl = warp_huf_read_table(HB, S, &tree);
+        if (!tl) err = 1;
+        else {
+            if (B.lit_type == 3) tree = 0;  // treeless: the streams start right after the header
+            const u8 *sp = c + B.lit_hdr + tree;
+            u32 avail = B.lit_csize - tree;
+            if (tree > B.lit_csize) err = 1;
+            else if (B.lit_streams == 1) {
+                bool ok = true;
+                if (lane == 0) ok = huf_decode_stream(sp, avail, dst, n, S.dt, tl);
+                if (!__all_sync(FULL, ok)) err = 1;
+            } else {
+                bool ok = true;
+                if (avail < 10) ok = false;
+                else {
+                    u32 s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
+                    u32 seg = (n + 3) / 4;
+                    if (6 + s1 + s2 + s3 >= avail || 3 * seg > n) ok = false;
+                    else if (lane < 4) {
+                        u32 off = 6 + (lane > 0 ? s1 : 0) + (lane > 1 ? s2 : 0) + (lane > 2 ? s3 : 0);
+                        u32 cs = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : avail - 6 - s1 - s2 - s3;
+                        u32 cnt = lane < 3 ? seg : n - 3 * seg;
+                        ok = huf_decode_stream(sp + off, cs, dst + lane * seg, cnt, S.dt, tl);
+                    }
+                }
+                if (!__all_sync(FULL, ok)) err = 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (err) blocks[bi].err = 1;
+        if (direct && !err) blocks[bi].rsize = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------- sequences
+struct SeqScratch {
+    FseDEnt dt[3][512];
+    u16 next[64];
+    short norm[64];
+};
+// Builds the decode table of stream type t (0 LL, 1 OF, 2 ML) for block B.  Returns tableLog,
+// 0xFF on error; RLE tables have log 0 and a single entry.
+__device__ static u32 build_seq_table(const ZDBlock &B, const ZDBlock *blocks, int t, SeqScratch &S) {
+    const ZDBlock &SB = (B.fse_block[t] == 0xFFFFFFFFu) ? B : blocks[B.fse_block[t]];
+    u32 m = (SB.modes >> (6 - 2 * t)) & 3;
+    const u8 *c = (const u8 *)(uintptr_t)SB.src;
+    const u32 maxLogs[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
+    const u32 maxSyms[3] = {ZSTD_MAX_LL, ZSTD_MAX_OF, ZSTD_MAX_ML};
+    if (m == 0) {
+        const short *dn = (t == 0) ? kLLDefNorm : (t == 1 ? kOFDefNorm : kMLDefNorm);
+        u32 ms = (t == 0) ? 35 : (t == 1 ? 28 : 52);
+        u32 tl = (t == 1) ? ZSTD_OF_DEFLOG : ZSTD_LL_DEFLOG;
+        for (u32 s = 0; s <= ms; s++) S.norm[s] = dn[s];
+        fse_build_dtable(S.norm, ms, tl, S.dt[t], S.next);
+        return tl;
+    }
+    if (m == 1) {
+        u32 sym = c[SB.tab_pos[t]];
+        if (sym > maxSyms[t]) return 0xFF;
+        S.dt[t][0].sym = (u8)sym;
+        S.dt[t][0].nb = 0;
+        S.dt[t][0].base = 0;
+        return 0;
+    }
+    if (m == 2) {
+        u32 ms = maxSyms[t], tl = 0;
+        u32 used = fse_read_ncount(c + SB.tab_pos[t], SB.csize - SB.tab_pos[t], S.norm, &ms, &tl, maxLogs[t]);
+        if (!used) return 0xFF;
+        fse_build_dtable(S.norm, ms, tl, S.dt[t], S.next);
+        return tl;
+    }
+    return 0xFF;  // a repeat chain always ends at a block with its own table
+}
+
+__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf) {
+    __shared__ SeqScratch scratch[ZD_WARPS];
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 bi = blockIdx.x * ZD_WARPS + warp;
+    if (bi >= nblocks) return;
+    ZDBlock B = blocks[bi];
+    if (B.type != 2 || B.nseq == 0) return;
+    SeqScratch &S = scratch[warp];
+    if (lane == 0) {
+        u32 err = 0;
+        u32 tl[3];
+        for (int t = 0; t < 3; t++) {
+            tl[t] = build_seq_table(B, blocks, t, S);
+            if (tl[t] == 0xFF) err = 1;
+        }
+        u32 *sq = seqbuf + 3ull * B.seq_off;
+        u64 total = 0;
+        if (!err) {
+            const u8 *c = (const u8 *)(uintptr_t)B.src;
+            BitR br;
+            br.init(c + B.bits_pos, B.csize - B.bits_pos);
+            u32 sLL = br.read(tl[0]), sOF = br.read(tl[1]), sML = br.read(tl[2]);
+            br.reload();
+            for (u32 i = 0; i < B.nseq; i++) {
+                FseDEnt eLL = S.dt[0][sLL], eOF = S.dt[1][sOF], eML = S.dt[2][sML];
+                u32 ofc = eOF.sym, mlc = eML.sym, llc = eLL.sym;
+                if (ofc > 31 || mlc > 52 || llc > 35) { err = 1; break; }
+                u32 ofv = (1u << ofc) + br.read(ofc);
+                if (ofc + kMLBits[mlc] + kLLBits[llc] > 40) br.reload();
+                u32 ml = kMLBase[mlc] + br.read(kMLBits[mlc]);
+                u32 ll = kLLBase[llc] + br.read(kLLBits[llc]);
+                br.reload();
+                sq[3 * i] = ll;
+                sq[3 * i + 1] = ml;
+                sq[3 * i + 2] = ofv;
+                total += (u64)ll + ml;
+                if (i + 1 < B.nseq) {
+                    sLL = eLL.base + br.read(eLL.nb);
+                    sML = eML.base + br.read(eML.nb);
+                    sOF = eOF.base + br.read(eOF.nb);
+                    br.reload();
+                }
+                if (br.bad) { err = 1; break; }
+            }
+            if (!br.finished()) err = 1;
+        }
+        if (err || total > ZSTD_BLOCK_MAX) blocks[bi].err = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------- execution
+// One warp per frame: blocks in order, sequences in order; each copy is spread over the 32 lanes.
+__device__ __forceinline__ void warp_copy(u8 *dst, const u8 *src, u32 n, u32 lane) {
+    for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out) {
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 fi = blockIdx.x * ZD_WARPS + warp;
+    if (fi >= nframes) return;
+    ZDFrame F = frames[fi];
+    u8 *base = out + F.dst_off;
+    u64 o = 0;  // bytes regenerated so far in this frame
+    u32 rep0 = 1, rep1 = 4, rep2 = 8;
+    u32 err = 0;
+    for (u32 b = 0; b < F.nblocks && !err; b++) {
+        ZDBlock B = blocks[F.first_block + b];
+        if (B.err) { err = 1; break; }
+        const u8 *c = (const u8 *)(uintptr_t)B.src;
+        if (B.type == 0) {
+            if (o + B.rsize > F.out_cap) { err = 1; break; }
+            warp_copy(base + o, c, B.rsize, lane);
+            o += B.rsize;
+        } else if (B.type == 1) {
+            if (o + B.rsize > F.out_cap) { err = 1; break; }
+            u8 v = c[0];
+            for (u32 i = lane; i < B.rsize; i += 32) base[o + i] = v;
+            o += B.rsize;
+        } else if (B.nseq == 0) {
+            if (o + B.lit_regen > F.out_cap) { err = 1; break; }
+            if (!(b == 0)) warp_copy(base + o, litbuf + B.lit_off, B.lit_regen, lane);  // first block: decoded in place
+            o += B.lit_regen;
+        } else {
+            const u8 *lit = litbuf + B.lit_off;
+            const u32 *sq = seqbuf + 3ull * B.seq_off;
+            u32 lp = 0;
+            u64 o0 = o;
+            for (u32 i = 0; i < B.nseq; i++) {
+                u32 ll = sq[3 * i], ml = sq[3 * i + 1], ofv = sq[3 * i + 2];
+                // repeat offsets (RFC 8878 §3.1.1.5)
+                u32 off;
+                if (ofv > 3) {
+                    off = ofv - 3;
+                    rep2 = rep1; rep1 = rep0; rep0 = off;
+                } else {
+                    u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
+                    if (idx == 0) off = rep0;
+                    else {
+                        off = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
+                        if (idx != 1) rep2 = rep1;
+                        rep1 = rep0;
+                        rep0 = off;
+                    }
+                }
+                if (lp + ll > B.lit_regen || off == 0 || off > o + ll || o + ll + ml > F.out_cap) { err = 1; break; }
+                warp_copy(base + o, lit + lp, ll, lane);
+                lp += ll;
+                o += ll;
+                __syncwarp();
+                u8 *d = base + o;
+                const u8 *s = d - off;
+                if (off >= ml) {
+                    for (u32 k = lane; k < ml; k += 32) d[k] = s[k];
+                } else {  // overlapping match: the source is the last `off` bytes, repeated
+                    for (u32 k = lane; k < ml; k += 32) d[k] = s[k % off];
+                }
+                o += ml;
+                __syncwarp();
+            }
+            if (err) break;
+            u32 rest = B.lit_regen - lp;
+            if (o + rest > F.out_cap) { err = 1; break; }
+            warp_copy(base + o, lit + lp, rest, lane);
+            o += rest;
+            if (o - o0 > ZSTD_BLOCK_MAX) { err = 1; break; }
+        }
+        __syncwarp();
+    }
+    if (!err && F.content_size != ~0ull && o != F.content_size) err = 1;
+    if (lane == 0) {
+        frames[fi].out_size = o;
+        frames[fi].err = err;
+    }
+}
+
+// ---------------------------------------------------------------------------------- content checksum
+__device__ __forceinline__ u64 zrotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ u64 zxxh_round(u64 acc, u64 in) { return zrotl64(acc + in * XXP2, 31) * XXP1; }
+__device__ __forceinline__ u64 zxxh_merge(u64 h, u64 v) { return (h ^ zxxh_round(0, v)) * XXP1 + XXP4; }
+__device__ __forceinline__ u64 zld64(const u8 *p) { return (u64)ld_u32_unaligned(p) | ((u64)ld_u32_unaligned(p + 4) << 32); }
+__global__ void __launch_bounds__(128) k_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 fi = t >> 2, q = t & 3;
+    u32 gm = group_mask(4);
+    bool live = fi < nframes;
+    ZDFrame F = frames[live ? fi : nframes - 1];
+    const u8 *p = out + F.dst_off;
+    u64 len = (F.err || !F.has_ck) ? 0 : F.out_size;
+    u64 acc = (q == 0) ? XXP1 + XXP2 : (q == 1) ? XXP2 : (q == 2) ? 0ull : 0ull - XXP1;
+    u64 nstripes = len >> 5;
+    const u8 *s = p + 8u * q;
+    for (u64 i = 0; i < nstripes; i++) acc = zxxh_round(acc, zld64(s + 32ull * i));
+    u64 a0 = __shfl_sync(gm, acc, 0, 4), a1 = __shfl_sync(gm, acc, 1, 4), a2 = __shfl_sync(gm, acc, 2, 4), a3 = __shfl_sync(gm, acc, 3, 4);
+    u64 h;
+    if (len >= 32) {
+        h = zrotl64(a0, 1) + zrotl64(a1, 7) + zrotl64(a2, 12) + zrotl64(a3, 18);
+        h = zxxh_merge(h, a0);
+        h = zxxh_merge(h, a1);
+        h = zxxh_merge(h, a2);
+        h = zxxh_merge(h, a3);
+    } else
+        h = XXP5;
+    h += len;
+    const u8 *tp = p + 32ull * nstripes;
+    u32 rem = (u32)(len & 31);
+    while (rem >= 8) {
+        h ^= zxxh_round(0, zld64(tp));
+        h = zrotl64(h, 27) * XXP1 + XXP4;
+        tp += 8;
+        rem -= 8;
+    }
+    if (rem >= 4) {
+        h ^= (u64)ld_u32_unaligned(tp) * XXP1;
+        h = zrotl64(h, 23) * XXP2 + XXP3;
+        tp += 4;
+        rem -= 4;
+    }
+    while (rem) {
+        h ^= (u64)(*tp) * XXP5;
+        h = zrotl64(h, 11) * XXP1;
+        tp++;
+        rem--;
+    }
+    h ^= h >> 33;
+    h *= XXP2;
+    h ^= h >> 29;
+    h *= XXP3;
+    h ^= h >> 32;
+    if (live && q == 0 && F.has_ck && !F.err && (u32)h != F.ck) frames[fi].err = 2;
+}
+
+// stream-level verdict: first failing frame wins; also gathers the decoded size of each stream
+__global__ void k_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res) {
+    u32 si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nstreams) return;
+    ZDStreamInfo I = info[si];
+    u64 total = 0;
+    u32 err = I.status;
+    bool contiguous = true;
+    for (u32 f = 0; f < I.nframes; f++) {
+        const ZDFrame &F = frames[I.frame_base + f];
+        if (F.err && !err) err = 10 + F.err;
+        if (F.out_size != F.out_cap) contiguous = false;
+        total += F.out_size;
+    }
+    res[si].err = err;
+    res[si].size = total;
+    res[si].contiguous = contiguous ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------- host launchers
+void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s) {
+    if (!nstreams) return;
+    FQZ_LAUNCH(k_zd_walk, (nstreams + 31) / 32, 32, 0, s, streams, nstreams, info, frames, blocks, fill);
+}
+void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_zd_literals, (nblocks + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, frames, litbuf, out);
+}
+void fqz_launch_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_zd_sequences, (nblocks + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, seqbuf);
+}
+void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s) {
+    if (!nframes) return;
+    FQZ_LAUNCH(k_zd_execute, (nframes + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, frames, nframes, blocks, litbuf, seqbuf, out);
+}
+void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s) {
+    if (!nframes) return;
+    FQZ_LAUNCH(k_zd_checksum, (nframes * 4 + 127) / 128, 128, 0, s, frames, nframes, out);
+}
+void fqz_launch_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res, cudaStream_t s) {
+    if (!nstreams) return;
+    FQZ_LAUNCH(k_zd_finish, (nstreams + 63) / 64, 64, 0, s, frames, info, nstreams, res);
+}

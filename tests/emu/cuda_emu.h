@@ -27,7 +27,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
-#define __constant__ static const
+#define __constant__ const
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(x) alignas(x)

@@ -13,5 +13,6 @@ def emu_context():
         subprocess.check_call(["make", "-C", HERE, "-s", "-j8"])
         from fastqpacker_b200._binding import FqzLibrary
 
-        _ctx = FqzLibrary(os.path.join(HERE, "_build", "libfqzgpu_emu.so")).context(0)
+        # FQZ_EMU_LIB selects the ASan/UBSan variant (make SAN=... B=_build_asan), run under LD_PRELOAD=libasan
+        _ctx = FqzLibrary(os.environ.get("FQZ_EMU_LIB", os.path.join(HERE, "_build", "libfqzgpu_emu.so"))).context(0)
     return _ctx

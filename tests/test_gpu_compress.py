@@ -1,0 +1,126 @@
+"""GPU compress path through the C-ABI: GPU-written .fqz must decode to the original FASTQ under
+the oracle's reference-shaped decoder (libzstd standing in for klauspost's DecodeAll, i.e. the
+proxy for `fqpack -d`), container layout must follow internal/fqformat/container.go."""
+import random
+import struct
+
+import numpy as np
+import pytest
+
+from tests import synth
+from tests.fastq_cases import BAD_CASES, GOOD_CASES, long_read
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fastqpacker_b200 as fq
+
+    return fq.context(0)
+
+
+def _walk(fqz):
+    """(header fields, [(nrec, sizes[6], orig_seq, orig_qual)]) following container.go."""
+    assert fqz[:4] == b"FQZ\x00" and fqz[4] == 2
+    pos, blocks = 10, []
+    while pos < len(fqz):
+        v = struct.unpack("<9I", fqz[pos : pos + 36])
+        blocks.append(v)
+        pos += 36 + sum(v[1:7])
+    assert pos == len(fqz)
+    return (struct.unpack("<I", fqz[5:9])[0], fqz[9]), blocks
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize(
+    "name",
+    ["empty1", "tiny", "zeros", "text", "quality_like", "random", "big_mixed", "runs", "one_frame_exact", "frame_plus_one"],
+)
+def test_zstd_frames_decode_under_libzstd(ctx, oracle, name, policy):
+    rnd = random.Random(hash(name) & 0xFFFF)
+    data = {
+        "empty1": b"x",
+        "tiny": b"abc",
+        "zeros": bytes(100000),
+        "text": b"hello world, hello zstd " * 5000,
+        "quality_like": bytes(rnd.choice([0, 0, 0, 0, 0, 0, 1, 255, 2, 254, 3]) for _ in range(300000)),
+        "random": bytes(rnd.randrange(256) for _ in range(200000)),
+        "big_mixed": b"".join(bytes([rnd.randrange(4)]) * rnd.randrange(1, 40) + b"@ERR%d/1" % i for i in range(20000)),
+        "runs": b"".join(bytes([i & 255]) * (i % 700) for i in range(600)),
+        "one_frame_exact": bytes(rnd.randrange(7) for _ in range(65536)),
+        "frame_plus_one": bytes(rnd.randrange(7) for _ in range(65537)),
+    }[name]
+    z = ctx.zstd_compress(data, policy)
+    assert z[:4] == b"\x28\xb5\x2f\xfd"
+    assert oracle.zstd_decompress(z) == data
+    if len(data) > 1000 and name != "random":
+        assert len(z) < len(data)
+
+
+def test_zstd_empty(ctx):
+    assert ctx.zstd_compress(b"", 0) == b""  # EncodeAll(empty) -> zero bytes
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_compress_decodes_under_oracle(ctx, oracle, name):
+    text = GOOD_CASES[name]
+    want = oracle.decompress(oracle.compress(text))  # the reference's own (lossy-normalising) round trip
+    fqz = ctx.compress(text)
+    assert oracle.decompress(fqz) == want
+    (bs, flags), blocks = _walk(fqz)
+    ref_fqz = oracle.compress(text)
+    assert fqz[:10] == ref_fqz[:10]  # magic, version 2, BlockSize echo, Phred flag
+    assert len(blocks) == (1 if want else 0)
+
+
+def test_header_block_size_echo(ctx, oracle):
+    text = GOOD_CASES["three"]
+    fqz = ctx.compress(text, block_size=100)
+    assert struct.unpack("<I", fqz[5:9])[0] == 100  # informational only
+    assert oracle.decompress(fqz) == text
+
+
+@pytest.mark.parametrize("name", sorted(BAD_CASES))
+def test_compress_errors(ctx, name):
+    from fastqpacker_b200 import FqzError
+
+    text, code, rec = BAD_CASES[name]
+    with pytest.raises(FqzError) as e:
+        ctx.compress(text)
+    assert e.value.code == code
+
+
+def test_compress_long_read(ctx, oracle):
+    from fastqpacker_b200 import FqzError
+
+    with pytest.raises(FqzError) as e:
+        ctx.compress(long_read(66000))
+    assert e.value.code == -4 and "ambiguous bases beyond position" in str(e.value)
+    ok = long_read(100)
+    assert oracle.decompress(ctx.compress(ok)) == ok
+
+
+@pytest.mark.parametrize("kind,count", [(0, 250000), (1, 130000)])
+def test_compress_multi_block(ctx, oracle, kind, count):
+    """BASELINE configs 2 / 4 shapes: several 100 000-record blocks, ratio next to the CPU path's."""
+    import torch
+
+    cap = count * 800
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.synth_device(kind, 0x5EED0001 + kind * 3, 0, count, buf.data_ptr(), cap)
+    text = buf[:n].cpu().numpy()
+    fqz = ctx.compress(text)
+    (bs, flags), blocks = _walk(fqz)
+    assert flags == (2 if kind else 0)
+    assert [b[0] for b in blocks] == [100000] * (count // 100000) + ([count % 100000] if count % 100000 else [])
+    assert oracle.decompress(fqz) == text.tobytes()
+    ref = oracle.compress(text, threads=8)
+    ratio_gpu, ratio_ref = n / len(fqz), n / len(ref)
+    print(f"kind {kind}: ratio gpu {ratio_gpu:.3f} vs cpu-oracle(libzstd-1) {ratio_ref:.3f}")
+    assert ratio_gpu > 0.98 * ratio_ref  # BASELINE target: within 2 % of the CPU path
+    # pre-entropy streams inside the GPU-written container equal the oracle's, block by block
+    for b in range(len(blocks)):
+        got, nrec = oracle.block_streams(fqz, b)
+        want, nrec2 = oracle.block_streams(ref, b)
+        assert nrec == nrec2 and got == want
