@@ -70,6 +70,8 @@ class FqzLibrary:
         L.fqz_profile_enable.argtypes = [vp, i32]
         L.fqz_profile_enable.restype = None
         L.fqz_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.fqz_get_stream.argtypes = [vp]
+        L.fqz_get_stream.restype = vp
         self._opt(L, "fqz_decode_streams", [vp, vp, vp, u32, i32, vp, sz, szp])
         self._opt(L, "fqz_zstd_compress", [vp, vp, sz, i32, vp, sz, szp])
         self._opt(L, "fqz_zstd_decompress", [vp, vp, sz, vp, sz, szp])
@@ -245,6 +247,10 @@ class FqzContext:
         return _DStream(self)
 
     # ---- measurement --------------------------------------------------------------------------
+    def stream_handle(self) -> int:
+        """cudaStream_t of the context (for torch.cuda.ExternalStream / CUDA-event timing)."""
+        return int(self.lib.L.fqz_get_stream(self.h) or 0)
+
     def stats_reset(self):
         self.lib.L.fqz_stats_reset(self.h)
 

@@ -1,0 +1,411 @@
+// fqz_api_decompress.cu — host orchestration of the decompress path: container walk, zstd decode of
+// the six (v1: five) streams of every block, back end, and the decompress entry points.
+// Replaces compress.Decompress / decompressJobToPooledBuffer / blockReader.writeRecord
+// (internal/compress/compress.go:558-604, 780-837, 944-1078).
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "fqz_backend.h"
+#include "fqz_host.h"
+#include "fqz_zstd_dec.h"
+
+static const int kErrOfBk[8] = {0,
+                                FQZ_E_TRUNC_LEN,
+                                FQZ_E_TRUNC_NPOS,
+                                FQZ_E_TRUNC_HEADER,
+                                FQZ_E_TRUNC_SEQ,
+                                FQZ_E_NPOS_RANGE,
+                                FQZ_E_TRUNC_PLUS,
+                                FQZ_E_TRUNC_QUAL};
+// compress.go:787-813
+static const char *kStreamWhat[6] = {"sequences", "quality", "headers", "plus-line payload", "N positions", "lengths"};
+
+#define DEC_TABLE_CAP 1024u                  // fqz blocks per container-walk pass
+#define DEC_WINDOW_BYTES ((u64)256 << 20)    // compressed bytes per device window
+#define DEC_WINDOW_OUT ((u64)1280 << 20)     // decoded stream bytes per device window (keeps FASTQ offsets below 2^32)
+
+static int backend_error(fqz_ctx *c, const std::vector<BkBlock> &blks, u64 key, u64 block_base) {
+    u32 kind = (u32)(key & 0xFF);
+    u64 rec = key >> 8;
+    size_t b = 0;
+    while (b + 1 < blks.size() && blks[b + 1].rec_base <= rec) b++;
+    int code = kErrOfBk[kind < 8 ? kind : 0];
+    char msg[200];
+    snprintf(msg, sizeof msg, "decompressing block %llu: %s (record %llu of the block)", (unsigned long long)(block_base + b), fqz_strerror(code),
+             (unsigned long long)(rec - blks[b].rec_base));
+    c->err = msg;
+    return code;
+}
+
+// Back end over blocks whose six decoded streams are resident in HBM.  d_out == nullptr: the
+// output is allocated from the arena and returned in *d_res.
+static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *d_out, size_t out_cap, u8 **d_res, size_t *out_len,
+                       u64 block_base) {
+    cudaStream_t s = c->stream;
+    u32 nb = (u32)blks.size();
+    u64 R = 0;
+    u32 max_nrec = 0;
+    for (auto &B : blks) {
+        // a header claiming more records than the lengths stream holds fails at the first missing
+        // length ("truncated length data", compress.go:1047): one record past the end is enough
+        u64 have = (u64)B.size[5] / 4;
+        if (B.nrec > have) B.nrec = (u32)(have + 1);
+        B.rec_base = R;
+        R += B.nrec;
+        max_nrec = std::max(max_nrec, B.nrec);
+    }
+    *out_len = 0;
+    if (d_res) *d_res = nullptr;
+    if (R == 0) return FQZ_OK;
+    if (R >= 0xFFFF0000ull || nb > 65535u) return FQZ_E_TOO_LARGE;
+    size_t blk_b = (size_t)nb * sizeof(BkBlock), tot_b = (size_t)nb * sizeof(BkTotals);
+    FQZ_TRY(fqz_pin_reserve(c, 8192 + blk_b + tot_b));
+    u8 *hp = c->h_pin + 4096;
+    memcpy(hp, blks.data(), blk_b);
+    FqzDecStatus *hst = (FqzDecStatus *)c->h_pin;
+    hst->err_key = ~0ull;
+    u64 stride = ((R + 1 + 63) / 64) * 64;
+    BkBlock *d_blks = (BkBlock *)c->arena.alloc(blk_b);
+    BkTotals *d_tot = (BkTotals *)c->arena.alloc(tot_b);
+    FqzDecStatus *d_st = (FqzDecStatus *)c->arena.alloc(64);
+    u32 *d_offs = (u32 *)c->arena.alloc((size_t)(3 * (R + nb)) * sizeof(u32));
+    u32 *d_sz = (u32 *)c->arena.alloc((size_t)(3 * stride) * sizeof(u32));
+    if (!d_blks || !d_tot || !d_st || !d_offs || !d_sz) {
+        c->err = "arena: out of device memory (back end tables)";
+        return FQZ_E_CUDA;
+    }
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_blks, hp, blk_b, cudaMemcpyHostToDevice, s));
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_st, hst, sizeof(FqzDecStatus), cudaMemcpyHostToDevice, s));
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_tot, 0, tot_b, s));
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_sz, 0, (size_t)(3 * stride) * sizeof(u32), s));
+    u64 hdr_bytes = 0;
+    for (auto &B : blks) hdr_bytes += (u64)B.size[2] + B.size[3] + B.size[4];
+    {
+        StageScope sc(c, ST_WALK, hdr_bytes);
+        fqz_launch_walk_prefixes(d_blks, nb, d_offs, d_st, s);
+    }
+    {
+        StageScope sc(c, ST_OFFSETS, 0);
+        fqz_launch_record_sizes(d_blks, nb, max_nrec, d_offs, d_sz, stride, d_tot, d_st, s);
+    }
+    BkTotals *htot = (BkTotals *)(hp + blk_b);
+    FqzDecStatus *hst2 = (FqzDecStatus *)(c->h_pin + 64);
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot, d_tot, tot_b, cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (hst2->err_key != ~0ull) {
+        // a sequence / quality stream may run short at an earlier record than the failure seen so far
+        bool wrap = false;
+        for (u32 b = 0; b < nb; b++) wrap |= htot[b].packed >= (1ull << 32) || htot[b].bases >= (1ull << 32);
+        if (!wrap) {
+            FQZ_TRY(fqz_scan_excl_u32(c, d_sz, R + 1, stride, 3));
+            fqz_launch_check_seq_qual(d_blks, nb, max_nrec, d_sz, stride, d_st, s);
+            FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
+            FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
+        return backend_error(c, blks, hst2->err_key, block_base);
+    }
+    u64 total = 0, stream_bytes = 0;
+    for (u32 b = 0; b < nb; b++) {
+        if (htot[b].packed >= (1ull << 32) || htot[b].bases >= (1ull << 32))  // cannot fit any real stream
+            return backend_error(c, blks, (blks[b].rec_base << 8) | BK_E_TRUNC_SEQ, block_base);
+        total += htot[b].fastq;
+        for (int a = 0; a < 6; a++) stream_bytes += blks[b].size[a];
+    }
+    if (total >= 0xFFFFFF00ull) return FQZ_E_TOO_LARGE;
+    *out_len = (size_t)total;
+    if (d_out) {
+        if (total > out_cap) return FQZ_E_NOSPACE;
+    } else {
+        d_out = (u8 *)c->arena.alloc((size_t)total + 64);
+        if (!d_out) {
+            c->err = "arena: out of device memory (FASTQ output)";
+            return FQZ_E_CUDA;
+        }
+        *d_res = d_out;
+    }
+    {
+        StageScope sc(c, ST_SCAN, 0);
+        FQZ_TRY(fqz_scan_excl_u32(c, d_sz, R + 1, stride, 3));
+    }
+    {
+        StageScope sc(c, ST_EMIT, stream_bytes + total);
+        fqz_launch_emit(d_blks, nb, max_nrec, d_offs, d_sz, stride, phred64, d_out, d_st, s);
+    }
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    FQZ_CUDA_TRY(c, cudaGetLastError());
+    if (hst2->err_key != ~0ull) return backend_error(c, blks, hst2->err_key, block_base);
+    return FQZ_OK;
+}
+
+// Entropy stage + back end for `nb` blocks of a container resident at d_fqz.
+static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, u32 nb, u32 phred64, u8 *d_out, size_t out_cap, u8 **d_res,
+                         size_t *out_len, u64 block_base) {
+    std::vector<ZDStream> zs((size_t)nb * 6);
+    for (u32 b = 0; b < nb; b++) {
+        u64 off = ent[b].payload_off;
+        for (int a = 0; a < 6; a++) {
+            zs[(size_t)b * 6 + a].src = (u64)(uintptr_t)(d_fqz + off);
+            zs[(size_t)b * 6 + a].csize = ent[b].size[a];
+            off += ent[b].size[a];
+        }
+    }
+    ZDecodeOut zo;
+    int rc = fqz_zdecode_batch(c, zs, DEC_WINDOW_OUT, zo);
+    if (rc == FQZ_E_ZSTD && zo.err_stream >= 0) {
+        char msg[240];
+        snprintf(msg, sizeof msg, "decompressing block %llu: decompressing %s: %s", (unsigned long long)(block_base + zo.err_stream / 6),
+                 kStreamWhat[zo.err_stream % 6], c->err.c_str());
+        c->err = msg;
+    }
+    if (rc != FQZ_OK) return rc;
+    std::vector<BkBlock> blks(nb);
+    for (u32 b = 0; b < nb; b++) {
+        BkBlock &B = blks[b];
+        for (int a = 0; a < 6; a++) {
+            size_t i = (size_t)b * 6 + a;
+            if (zo.size[i] >= (1ull << 32)) return FQZ_E_TOO_LARGE;
+            B.stream[a] = (u64)(uintptr_t)(zo.d_base + zo.off[i]);
+            B.size[a] = (u32)zo.size[i];
+        }
+        B.nrec = ent[b].nrec;
+        B.pad = 0;
+        B.rec_base = 0;
+    }
+    return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base);
+}
+
+struct DecState {
+    bool have_header = false;
+    u32 version = 2, phred64 = 0;
+    u64 block_base = 0;  // blocks decoded so far (error texts)
+};
+
+// Parses the 10-byte file header at d_fqz (container.go:48-67; version check compress.go:571-573).
+static int read_file_header(fqz_ctx *c, const u8 *d_fqz, u64 n, DecState &st) {
+    u8 *h = c->h_pin + 128;
+    size_t take = (size_t)std::min<u64>(n, 10);
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_fqz, take, cudaMemcpyDeviceToHost, c->stream));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (n < 4) return FQZ_E_TRUNC_FILE;
+    if (!(h[0] == 'F' && h[1] == 'Q' && h[2] == 'Z' && h[3] == 0)) return FQZ_E_MAGIC;
+    if (n < 10) return FQZ_E_TRUNC_FILE;
+    st.version = h[4];
+    if (st.version != 1 && st.version != 2) {
+        char msg[64];
+        snprintf(msg, sizeof msg, "unsupported file version: %u", st.version);
+        c->err = msg;
+        return FQZ_E_VERSION;
+    }
+    st.phred64 = (h[9] & 2) ? 1u : 0u;  // FlagPhred64, compress.go:576-579
+    st.have_header = true;
+    return FQZ_OK;
+}
+
+// Decodes the complete blocks of d_fqz[pos0, n).  d_out != nullptr: FASTQ goes to that device
+// buffer; else each window is staged in the arena and copied to h_out.  *consumed = offset after
+// the last block decoded.  A partial trailing block is an error only when is_last.
+static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool is_last, bool partial_ok, DecState &st, u8 *d_out, u8 *h_out,
+                             size_t out_cap, size_t *out_len, u64 *consumed) {
+    cudaStream_t s = c->stream;
+    u64 pos = pos0;
+    size_t written = 0;
+    *out_len = 0;
+    *consumed = pos0;
+    std::vector<FqzBlockEntry> ent;
+    while (pos < n) {
+        c->arena.reset();
+        FqzBlockEntry *d_tab = (FqzBlockEntry *)c->arena.alloc(DEC_TABLE_CAP * sizeof(FqzBlockEntry));
+        FqzWalkResult *d_wr = (FqzWalkResult *)c->arena.alloc(sizeof(FqzWalkResult));
+        if (!d_tab || !d_wr) return FQZ_E_CUDA;
+        fqz_launch_walk_container(d_fqz, n, pos, st.version, d_tab, DEC_TABLE_CAP, DEC_WINDOW_BYTES, d_wr, s);
+        FQZ_TRY(fqz_pin_reserve(c, 8192 + DEC_TABLE_CAP * sizeof(FqzBlockEntry)));
+        FqzWalkResult *hwr = (FqzWalkResult *)(c->h_pin + 256);
+        FqzBlockEntry *htab = (FqzBlockEntry *)(c->h_pin + 4096);
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(hwr, d_wr, sizeof(FqzWalkResult), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        FqzWalkResult wr = *hwr;
+        if (wr.nblocks) {
+            FQZ_CUDA_TRY(c, cudaMemcpyAsync(htab, d_tab, (size_t)wr.nblocks * sizeof(FqzBlockEntry), cudaMemcpyDeviceToHost, s));
+            FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+            ent.assign(htab, htab + wr.nblocks);
+        } else
+            ent.clear();
+        u32 done = 0;
+        u32 take = wr.nblocks;
+        while (done < wr.nblocks) {
+            take = std::min(take, wr.nblocks - done);
+            c->arena.reset();  // the table lives on in `ent`
+            size_t wl = 0;
+            u8 *d_res = nullptr;
+            int rc = decode_blocks(c, d_fqz, ent.data() + done, take, st.phred64, d_out ? d_out + written : nullptr, out_cap - written,
+                                   &d_res, &wl, st.block_base);
+            if (rc == FQZ_E_TOO_LARGE && take > 1) {  // the window decodes to more than one device pass holds
+                take = (take + 1) / 2;
+                continue;
+            }
+            if (rc == FQZ_OK && !d_out && wl > out_cap - written) rc = FQZ_E_NOSPACE;
+            if (rc == FQZ_E_NOSPACE) {
+                if (written && partial_ok) {  // streaming callers keep the progress made so far
+                    *out_len = written;
+                    return FQZ_OK;
+                }
+                *out_len = written + wl;
+                return FQZ_E_NOSPACE;
+            }
+            if (rc != FQZ_OK) return rc;
+            if (!d_out && wl) {
+                StageScope sc(c, ST_COPY, wl);
+                FQZ_CUDA_TRY(c, cudaMemcpyAsync(h_out + written, d_res, wl, cudaMemcpyDeviceToHost, s));
+                FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+            }
+            written += wl;
+            done += take;
+            st.block_base += take;
+            const FqzBlockEntry &L = ent[done - 1];
+            u64 end = L.payload_off;
+            for (int a = 0; a < 6; a++) end += L.size[a];
+            pos = end;
+            *consumed = pos;
+            *out_len = written;
+        }
+        if (wr.status) {  // truncated block header / payload after the blocks just decoded
+            if (is_last) {
+                c->err = "reading block: unexpected EOF";
+                return FQZ_E_TRUNC_FILE;
+            }
+            break;  // streaming: the caller re-presents the tail with more data
+        }
+        if (wr.nblocks == 0) break;
+    }
+    *out_len = written;
+    return FQZ_OK;
+}
+
+extern "C" int fqz_decompress_device(fqz_ctx *c, const void *d_fqz, size_t n, void *d_out, size_t out_cap, size_t *out_len) {
+    if (!c || !out_len || (!d_fqz && n) || (!d_out && out_cap)) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    DecState st;
+    FQZ_TRY(read_file_header(c, (const u8 *)d_fqz, n, st));
+    u64 used = 0;
+    static u8 dummy;
+    int rc = decompress_blocks(c, (const u8 *)d_fqz, n, 10, true, false, st, d_out ? (u8 *)d_out : &dummy, nullptr, out_cap, out_len, &used);
+    return rc;
+}
+
+extern "C" int fqz_decompress(fqz_ctx *c, const uint8_t *fqz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!c || !out_len || (!fqz && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    u8 *d_in = nullptr;
+    FQZ_CUDA_TRY(c, cudaMalloc((void **)&d_in, n + 256));
+    int rc = FQZ_OK;
+    do {
+        if (cudaMemsetAsync(d_in + (n & ~(size_t)15), 0, 64, c->stream) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+        if (n && cudaMemcpyAsync(d_in, fqz, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
+        DecState st;
+        rc = read_file_header(c, d_in, n, st);
+        if (rc != FQZ_OK) break;
+        u64 used = 0;
+        static u8 dummy;
+        rc = decompress_blocks(c, d_in, n, 10, true, false, st, nullptr, out ? out : &dummy, out_cap, out_len, &used);
+    } while (0);
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
+    cudaFree(d_in);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- streaming (Seam B)
+struct fqz_dstream {
+    fqz_ctx *c;
+    DecState st;
+    u8 *d_in = nullptr;
+    size_t d_cap = 0;
+};
+extern "C" int fqz_decompress_begin(fqz_ctx *c, fqz_dstream **out) {
+    if (!c || !out) return FQZ_E_INVALID_ARG;
+    *out = new fqz_dstream();
+    (*out)->c = c;
+    return FQZ_OK;
+}
+extern "C" void fqz_decompress_end(fqz_dstream *s) {
+    if (!s) return;
+    cudaSetDevice(s->c->device);
+    if (s->d_in) cudaFree(s->d_in);
+    delete s;
+}
+extern "C" int fqz_decompress_feed(fqz_dstream *s, const uint8_t *fqz, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
+                                   size_t *consumed) {
+    if (!s || !out_len || !consumed || (!fqz && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
+    fqz_ctx *c = s->c;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    *consumed = 0;
+    if (n > FQZ_MAX_WINDOW) {  // take a window's worth; the caller re-presents the rest
+        n = FQZ_MAX_WINDOW;
+        is_last = 0;
+    }
+    u64 pos = 0;
+    if (!s->st.have_header && n < 10 && !is_last) return FQZ_E_NEED_MORE;
+    if (n + 256 > s->d_cap) {
+        if (s->d_in) cudaFree(s->d_in);
+        s->d_in = nullptr;
+        s->d_cap = 0;
+        size_t cap = n + n / 4 + 4096;
+        FQZ_CUDA_TRY(c, cudaMalloc((void **)&s->d_in, cap));
+        s->d_cap = cap;
+    }
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(s->d_in + (n & ~(size_t)15), 0, 64, c->stream));
+    if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(s->d_in, fqz, n, cudaMemcpyHostToDevice, c->stream));
+    if (!s->st.have_header) {
+        FQZ_TRY(read_file_header(c, s->d_in, n, s->st));
+        pos = 10;
+        *consumed = 10;
+    }
+    u64 used = pos;
+    static u8 dummy;
+    int rc = decompress_blocks(c, s->d_in, n, pos, is_last != 0, true, s->st, nullptr, out ? out : &dummy, out_cap, out_len, &used);
+    if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *consumed = (size_t)used;
+    if (rc == FQZ_OK && !is_last && used == pos && pos < n && *out_len == 0 && *consumed == 0) return FQZ_E_NEED_MORE;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- block level
+extern "C" int fqz_decode_streams(fqz_ctx *c, const uint8_t *const in[6], const size_t len[6], uint32_t num_records, int phred64, uint8_t *out,
+                                  size_t out_cap, size_t *out_len) {
+    if (!c || !in || !len || !out_len) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->arena.reset();
+    c->err.clear();
+    *out_len = 0;
+    cudaStream_t s = c->stream;
+    std::vector<BkBlock> blks(1);
+    BkBlock &B = blks[0];
+    for (int a = 0; a < 6; a++) {
+        if (len[a] >= (1ull << 31)) return FQZ_E_TOO_LARGE;
+        u8 *d = (u8 *)c->arena.alloc(len[a] + 64);
+        if (!d) return FQZ_E_CUDA;
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d + (len[a] & ~(size_t)15), 0, 64, s));
+        if (len[a]) FQZ_CUDA_TRY(c, cudaMemcpyAsync(d, in[a], len[a], cudaMemcpyHostToDevice, s));
+        B.stream[a] = (u64)(uintptr_t)d;
+        B.size[a] = (u32)len[a];
+    }
+    B.nrec = num_records;
+    B.pad = 0;
+    B.rec_base = 0;
+    u8 *d_res = nullptr;
+    size_t total = 0;
+    FQZ_TRY(backend_run(c, blks, phred64 ? 1u : 0u, nullptr, 0, &d_res, &total, 0));
+    *out_len = total;
+    if (total > out_cap) return FQZ_E_NOSPACE;
+    if (total) FQZ_CUDA_TRY(c, cudaMemcpyAsync(out, d_res, total, cudaMemcpyDeviceToHost, s));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    return FQZ_OK;
+}

@@ -245,54 +245,62 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
 
 extern "C" size_t fqz_compress_bound(size_t n) { return n + n / 32 + 65536; }
 
-extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, uint32_t header_block_size, void *d_out, size_t out_cap,
-                                   size_t *out_len) {
-    if (!c || !out_len || (!d_fastq && n) || !d_out) return FQZ_E_INVALID_ARG;
-    if (((uintptr_t)d_fastq & 15u) != 0) return FQZ_E_INVALID_ARG;
-    cudaSetDevice(c->device);
-    c->err.clear();
-    *out_len = 0;
-    // a buffer larger than one device window is processed as a sequence of windows, each cut at a
-    // block boundary (the host only walks; all data stays in HBM)
-    const u64 WIN = (u64)1 << 30;
-    u64 pos = 0, rec_base = 0;
-    size_t written = 0;
+// file-level state carried from window to window (Phred flag of the first block, record count)
+struct CompState {
     bool first = true;
-    while (first || pos < n) {
+    u64 rec_base = 0;
+    u32 phred64 = 0;
+};
+
+// Compresses d_fastq[0..n) window by window (each window cut at a block boundary; the host only
+// walks, all data stays in HBM).  !is_last: only whole 100 000-record blocks are taken and
+// *consumed tells the caller where the unconsumed tail starts.
+static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_last, CompState &st, u32 header_block_size, u8 *d_out,
+                                size_t out_cap, size_t *out_len, u64 *consumed) {
+    const u64 WIN = (u64)1 << 30;
+    u64 pos = 0;
+    size_t written = 0;
+    *out_len = 0;
+    *consumed = 0;
+    while (st.first || pos < n) {
         c->arena.reset();
         u64 left = n - pos;
         u64 take = left;
-        bool last = true;
+        bool last = is_last;
         if (left > WIN + (WIN >> 2)) {
             take = WIN;
             last = false;
         }
         // windows must start 16-byte aligned for the vector loads: copy the unaligned remainder
-        const u8 *wptr = (const u8 *)d_fastq + pos;
+        const u8 *wptr = d_fastq + pos;
         if (((uintptr_t)wptr & 15u) != 0) {
             u8 *tmp = (u8 *)c->arena.alloc(take + 64);
             if (!tmp) return FQZ_E_CUDA;
             StageScope sc(c, ST_COPY, 2 * take);
             FQZ_CUDA_TRY(c, cudaMemcpyAsync(tmp, wptr, take, cudaMemcpyDeviceToDevice, c->stream));
+            FQZ_CUDA_TRY(c, cudaMemsetAsync(tmp + take, 0, 64, c->stream));
             wptr = tmp;
         }
         size_t wl = 0;
         u64 used = 0, recs = 0;
         u32 ph = 0;
-        int rc = fqz_compress_window(c, wptr, take, last, rec_base, first ? -1 : -2, first, header_block_size, (u8 *)d_out + written,
-                                     out_cap - written, &wl, &used, &recs, &ph);
-        if (rc == FQZ_E_NEED_MORE && !last) {  // no complete block in this window: widen it
-            return FQZ_E_TOO_LARGE;
+        int rc = fqz_compress_window(c, wptr, take, last, st.rec_base, st.first ? -1 : (int)st.phred64, st.first, header_block_size,
+                                     d_out + written, out_cap - written, &wl, &used, &recs, &ph);
+        if (rc == FQZ_E_NEED_MORE) {
+            if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside a full device window
+            break;                                    // streaming: the tail waits for more data
         }
         if (rc != FQZ_OK) {
             if (rc == FQZ_E_NOSPACE) *out_len = written + wl;
             return rc;
         }
+        if (st.first) st.phred64 = ph;
         written += wl;
-        pos += last ? left : used;
-        rec_base += recs;
-        first = false;
-        if (last) break;
+        pos += (last && is_last) ? left : used;
+        st.rec_base += recs;
+        st.first = false;
+        *consumed = pos;
+        if (take == left) break;
     }
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     FQZ_CUDA_TRY(c, cudaGetLastError());
@@ -300,10 +308,84 @@ extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, ui
     return FQZ_OK;
 }
 
+extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, uint32_t header_block_size, void *d_out, size_t out_cap,
+                                   size_t *out_len) {
+    if (!c || !out_len || (!d_fastq && n) || !d_out) return FQZ_E_INVALID_ARG;
+    if (((uintptr_t)d_fastq & 15u) != 0) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    CompState st;
+    u64 used = 0;
+    return compress_device_impl(c, (const u8 *)d_fastq, n, true, st, header_block_size, (u8 *)d_out, out_cap, out_len, &used);
+}
+
+// ---------------------------------------------------------------------------------- streaming (Seam B)
+struct fqz_cstream {
+    fqz_ctx *c;
+    CompState st;
+    u32 header_block_size = 0;
+    u8 *d_in = nullptr, *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+};
+extern "C" int fqz_compress_begin(fqz_ctx *c, uint32_t header_block_size, fqz_cstream **out) {
+    if (!c || !out) return FQZ_E_INVALID_ARG;
+    *out = new fqz_cstream();
+    (*out)->c = c;
+    (*out)->header_block_size = header_block_size;
+    return FQZ_OK;
+}
+extern "C" void fqz_compress_end(fqz_cstream *s) {
+    if (!s) return;
+    cudaSetDevice(s->c->device);
+    if (s->d_in) cudaFree(s->d_in);
+    if (s->d_out) cudaFree(s->d_out);
+    delete s;
+}
+static int dev_reserve(fqz_ctx *c, u8 **p, size_t *cap, size_t need) {
+    if (need <= *cap) return FQZ_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 8 + 4096;
+    FQZ_CUDA_TRY(c, cudaMalloc((void **)p, want));
+    *cap = want;
+    return FQZ_OK;
+}
+extern "C" int fqz_compress_feed(fqz_cstream *s, const uint8_t *fastq, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
+                                 size_t *consumed) {
+    if (!s || !out_len || !consumed || (!fastq && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
+    fqz_ctx *c = s->c;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    *consumed = 0;
+    if (n > FQZ_MAX_WINDOW) {  // take a window's worth; the caller re-presents the rest
+        n = FQZ_MAX_WINDOW;
+        is_last = 0;
+    }
+    size_t ocap = fqz_compress_bound(n);
+    FQZ_TRY(dev_reserve(c, &s->d_in, &s->in_cap, n + 256));
+    FQZ_TRY(dev_reserve(c, &s->d_out, &s->out_cap, ocap + 256));
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(s->d_in + (n & ~(size_t)15), 0, 64, c->stream));
+    if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(s->d_in, fastq, n, cudaMemcpyHostToDevice, c->stream));
+    CompState trial = s->st;  // committed only when the output fits
+    size_t m = 0;
+    u64 used = 0;
+    int rc = compress_device_impl(c, s->d_in, n, is_last != 0, trial, s->header_block_size, s->d_out, ocap, &m, &used);
+    if (rc != FQZ_OK) return rc;
+    if (used == 0 && m == 0 && !is_last) return FQZ_E_NEED_MORE;
+    *out_len = m;
+    if (m > out_cap) return FQZ_E_NOSPACE;  // nothing consumed; retry with a larger buffer
+    if (m) FQZ_CUDA_TRY(c, cudaMemcpyAsync(out, s->d_out, m, cudaMemcpyDeviceToHost, c->stream));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    s->st = trial;
+    *consumed = (size_t)used;
+    return FQZ_OK;
+}
+
 extern "C" int fqz_compress(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap,
                             size_t *out_len) {
     if (!c || !out_len || (!fastq && n) || !out) return FQZ_E_INVALID_ARG;
-    if (n > FQZ_MAX_WINDOW) return FQZ_E_TOO_LARGE;
     cudaSetDevice(c->device);
     c->err.clear();
     c->arena.reset();

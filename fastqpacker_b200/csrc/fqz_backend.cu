@@ -1,0 +1,313 @@
+// fqz_backend.cu — decompress back end: six decoded streams per block -> FASTQ text, bit-exact
+// with blockReader.writeRecord (internal/compress/compress.go:944-1078) and
+// encoder.AppendUnpackBases / DeltaDecode / DenormalizeQuality (sequence.go:188-223,
+// quality.go:66-75,107-118).
+//
+//   k_walk_prefixes   the header / plus / N-position streams are chains of u16-length-prefixed
+//                     items with no index (compress.go:977-1015,1055-1078): one warp per
+//                     (block, stream) stages the stream through shared memory and one lane hops
+//                     from prefix to prefix, emitting one offset per record
+//   k_record_sizes    per record: L, packed size, FASTQ bytes; validation ("truncated ... data")
+//   k_emit_fastq      16 lanes per record: '@'+header, unpacked bases with N restored, '+'+payload,
+//                     prefix-summed qualities; all wide stores aligned to the destination
+#include "fqz_backend.h"
+
+#define WALK_CHUNK 8192u
+
+// kind: 0 headers, 1 plus, 2 npos.  offs has nrec+1 entries per (block, kind): item r starts at offs[r].
+__global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs_base, FqzDecStatus *st) {
+    __shared__ u32 sm_words[4][(WALK_CHUNK + 16) / 4];
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 wi = blockIdx.x * 4 + warp;
+    if (wi >= nblocks * 3) return;
+    u32 b = wi / 3, kind = wi % 3;
+    BkBlock B = blks[b];
+    int sidx = kind == 0 ? 2 : (kind == 1 ? 3 : 4);
+    const u8 *p = (const u8 *)(uintptr_t)B.stream[sidx];
+    u32 size = B.size[sidx], nrec = B.nrec;
+    u32 *offs = offs_base + (3ull * B.rec_base + (u64)kind * nrec) + 3ull * b + kind;  // (nrec+1) entries per kind
+    if (kind == 1 && size == 0) {  // v1 files / empty plus stream: every plus line is "+" (compress.go:995-999)
+        for (u32 r = lane; r <= nrec; r += 32) offs[r] = 0;
+        return;
+    }
+    u8 *buf = (u8 *)sm_words[warp];
+    u32 pos = 0, r = 0;
+    u32 err = 0;
+    while (r < nrec && !err) {
+        u32 cb = pos & ~3u;
+        u32 ce = min(size, cb + WALK_CHUNK);
+        if (pos + 2 > size) { err = 1; break; }  // no room for the length prefix of item r
+        // stage [cb, ce) (the stream base is 64-byte aligned)
+        for (u32 i = cb + 4 * lane; i < ce; i += 128) *(u32 *)(buf + (i - cb)) = *(const u32 *)(p + i);
+        __syncwarp();
+        if (lane == 0) {
+            while (r < nrec && pos + 2 <= ce) {
+                u32 len = (u32)buf[pos - cb] | ((u32)buf[pos - cb + 1] << 8);
+                u32 next = pos + 2 + (kind == 2 ? 2 * len : len);
+                if (next > size) { err = 1; break; }  // item r runs past the end of the stream
+                offs[r++] = pos;
+                pos = next;
+            }
+        }
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        err = __shfl_sync(0xffffffffu, err, 0);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        offs[nrec] = pos;
+        if (err) {
+            u32 code = kind == 0 ? BK_E_TRUNC_HEADER : (kind == 1 ? BK_E_TRUNC_PLUS : BK_E_TRUNC_NPOS);
+            atomicMin(&st->err_key, ((u64)(B.rec_base + r) << 8) | code);
+        }
+    }
+}
+
+// Per record: sizes for the scans.  sz[0*stride + R] = packed bytes, sz[1*stride + R] = FASTQ bytes,
+// sz[2*stride + R] = bases (R = window-global record index).  64-bit per-block totals let the host
+// rule out u32 wrap-around before the scans are trusted.
+__global__ void __launch_bounds__(256)
+k_record_sizes(const BkBlock *blks, u32 nblocks, const u32 *offs_base, u32 *sz, u64 stride, BkTotals *tot, FqzDecStatus *st) {
+    u32 b = blockIdx.y;
+    BkBlock B = blks[b];
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = r < B.nrec;
+    u64 R = B.rec_base + r;
+    u32 L = 0, fq = 0, pk = 0;
+    if (live) {
+        const u32 *oh = offs_base + 3ull * B.rec_base + 3ull * b;
+        const u32 *op = oh + (B.nrec + 1);
+        u32 code = 0;
+        if (4ull * r + 4 > B.size[5]) code = BK_E_TRUNC_LEN;  // compress.go:1047
+        else L = *(const u32 *)((const u8 *)(uintptr_t)B.stream[5] + 4ull * r);
+        u32 H = oh[r + 1] - oh[r] - 2;
+        u32 P = B.size[3] ? op[r + 1] - op[r] - 2 : 0u;
+        if (code) {
+            atomicMin(&st->err_key, (R << 8) | code);
+            L = 0;
+        }
+        pk = (u32)(((u64)L + 3u) >> 2);
+        fq = H + P + 6u;
+        sz[0 * stride + R] = pk;
+        sz[1 * stride + R] = fq + 2u * L;
+        sz[2 * stride + R] = L;
+    }
+    // warp totals -> one atomic per warp
+    u64 tp = pk, tf = (u64)fq + 2ull * L, tb = L;
+    for (int d = 16; d > 0; d >>= 1) {
+        tp += __shfl_xor_sync(0xffffffffu, tp, d);
+        tf += __shfl_xor_sync(0xffffffffu, tf, d);
+        tb += __shfl_xor_sync(0xffffffffu, tb, d);
+    }
+    if (lane_id() == 0 && tf) {
+        atomicAdd(&tot[b].packed, tp);
+        atomicAdd(&tot[b].fastq, tf);
+        atomicAdd(&tot[b].bases, tb);
+    }
+}
+
+// Error path only: the sequence / quality truncation checks of k_emit_fastq without the emit, so
+// that the first failure in the reference's record order is reported when several streams are short.
+__global__ void __launch_bounds__(256) k_check_seq_qual(const BkBlock *blks, u32 nblocks, const u32 *sc, u64 stride, FqzDecStatus *st) {
+    u32 b = blockIdx.y;
+    BkBlock B = blks[b];
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.nrec) return;
+    u64 R = B.rec_base + r;
+    u32 L = sc[2 * stride + R + 1] - sc[2 * stride + R];
+    u32 o_seq = sc[0 * stride + R] - sc[0 * stride + B.rec_base];
+    u32 o_qual = sc[2 * stride + R] - sc[2 * stride + B.rec_base];
+    if ((u64)o_seq + ((L + 3u) >> 2) > B.size[0]) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_SEQ);
+    else if ((u64)o_qual + L > B.size[1]) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_QUAL);
+}
+
+// ---------------------------------------------------------------------------------- emit
+template <int W>
+__device__ __forceinline__ void bk_group_copy(u8 *dst, const u8 *src, u32 n, u32 g) {
+    u32 head = (u32)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > n) head = n;
+    if (g < head) dst[g] = src[g];
+    u32 nw = (n - head) >> 2;
+    for (u32 w = g; w < nw; w += W) *(u32 *)(dst + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
+    u32 t0 = head + 4u * nw;
+    if (g < n - t0) dst[t0 + g] = src[t0 + g];
+}
+// four consecutive bases starting at base index i of a packed record -> 4 ASCII bytes
+__device__ __forceinline__ u32 unpack4(const u8 *packed, u32 i) {
+    u32 bit = 2u * i;
+    u32 x = ld_u32_unaligned(packed + (bit >> 3)) >> (bit & 7u);
+    u32 b = x & 0xFFu;
+    u32 sel = (b & 3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);
+    return __byte_perm(0x54474341u, 0u, sel);  // "ACGT"
+}
+// inclusive byte-wise prefix sum (mod 256) inside a word
+__device__ __forceinline__ u32 prefix4(u32 x) {
+    x = __vadd4(x, x << 8);
+    return __vadd4(x, x << 16);
+}
+
+__global__ void __launch_bounds__(256)
+k_emit_fastq(const BkBlock *blks, u32 nblocks, const u32 *offs_base, const u32 *sc, u64 stride, u32 phred64, u8 *out, FqzDecStatus *st) {
+    const int W = 16;
+    u32 b = blockIdx.y;
+    BkBlock B = blks[b];
+    u32 g = threadIdx.x & (W - 1);
+    u32 gm = group_mask(W);
+    u32 r = blockIdx.x * (blockDim.x / W) + threadIdx.x / W;
+    if (r >= B.nrec) return;
+    const u32 *oh = offs_base + 3ull * B.rec_base + 3ull * b;
+    const u32 *op = oh + (B.nrec + 1);
+    const u32 *on = op + (B.nrec + 1);
+    u64 R = B.rec_base + r;
+    u32 L = sc[2 * stride + R + 1] - sc[2 * stride + R];
+    u32 o_seq = sc[0 * stride + R] - sc[0 * stride + B.rec_base];
+    u32 o_qual = sc[2 * stride + R] - sc[2 * stride + B.rec_base];
+    u8 *d = out + sc[1 * stride + R];
+    // "truncated sequence data" / "truncated quality data" (compress.go:1019,1032): the record is skipped
+    if ((u64)o_seq + ((L + 3u) >> 2) > B.size[0]) {
+        if (g == 0) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_SEQ);
+        return;
+    }
+    if ((u64)o_qual + L > B.size[1]) {
+        if (g == 0) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_QUAL);
+        return;
+    }
+    const u8 *hs = (const u8 *)(uintptr_t)B.stream[2] + oh[r] + 2;
+    u32 H = oh[r + 1] - oh[r] - 2;
+    // '@' header '\n'
+    if (g == 0) d[0] = '@';
+    bk_group_copy<W>(d + 1, hs, H, g);
+    if (g == 0) d[1 + H] = '\n';
+    d += H + 2;
+    // sequence: dst-aligned words of 4 bases
+    {
+        const u8 *pk = (const u8 *)(uintptr_t)B.stream[0] + o_seq;
+        u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if (head > L) head = L;
+        if (g < head) d[g] = (u8)(unpack4(pk, g) & 0xFFu);
+        u32 nw = (L - head) >> 2;
+        for (u32 w = g; w < nw; w += W) *(u32 *)(d + head + 4u * w) = unpack4(pk, head + 4u * w);
+        u32 t0 = head + 4u * nw;
+        if (g < L - t0) d[t0 + g] = (u8)(unpack4(pk, t0 + g) & 0xFFu);
+        __syncwarp(gm);
+        // restore N (sequence.go:217-220)
+        const u8 *np = (const u8 *)(uintptr_t)B.stream[4] + on[r];
+        u32 nn = (on[r + 1] - on[r] - 2) >> 1;
+        for (u32 k = g; k < nn; k += W) {
+            u32 pos = (u32)np[2 + 2 * k] | ((u32)np[3 + 2 * k] << 8);
+            if (pos < L) d[pos] = 'N';
+            else atomicMin(&st->err_key, (R << 8) | BK_E_NPOS_RANGE);  // the reference panics here
+        }
+        if (g == 0) d[L] = '\n';
+        d += L + 1;
+    }
+    // '+' payload '\n'
+    {
+        u32 P = 0;
+        const u8 *ps = nullptr;
+        if (B.size[3]) {
+            P = op[r + 1] - op[r] - 2;
+            ps = (const u8 *)(uintptr_t)B.stream[3] + op[r] + 2;
+        }
+        if (g == 0) d[0] = '+';
+        if (P) bk_group_copy<W>(d + 1, ps, P, g);
+        if (g == 0) d[1 + P] = '\n';
+        d += P + 2;
+    }
+    // quality: running sum mod 256 from the record start, plus the Phred offset
+    {
+        const u8 *q = (const u8 *)(uintptr_t)B.stream[1] + o_qual;
+        u32 offw = (phred64 ? 64u : 33u) * 0x01010101u;
+        u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if (head == 0) head = 4;
+        if (head > L) head = L;
+        u32 nunits = L ? 1u + ((L - head + 3u) >> 2) : 0u;
+        u32 rounds = (nunits + W - 1) / W;
+        u32 carry = 0;
+        for (u32 j = 0; j < rounds; j++) {
+            u32 u = j * W + g;
+            u32 x = 0, i0 = 0, cnt = 0;
+            if (u < nunits) {
+                if (u == 0) { i0 = 0; cnt = head; }
+                else { i0 = head + 4u * (u - 1); cnt = min(4u, L - i0); }
+                x = ld_u32_unaligned(q + i0);
+                if (cnt < 4) x &= 0xFFFFFFFFu >> (8u * (4u - cnt));
+            }
+            u32 pre = prefix4(x);
+            u32 tot = (pre >> 24) & 0xFFu;            // sum of the unit's bytes (zero-padded)
+            u32 incl = group_incl_scan(tot, gm, W);
+            u32 before = (carry + incl - tot) & 0xFFu;
+            u32 v = __vadd4(__vadd4(pre, before * 0x01010101u), offw);
+            if (u < nunits) {
+                if (cnt == 4 && u > 0) *(u32 *)(d + i0) = v;
+                else
+                    for (u32 k = 0; k < cnt; k++) d[i0 + k] = (u8)(v >> (8 * k));
+            }
+            carry = (carry + __shfl_sync(gm, incl, W - 1, W)) & 0xFFu;
+        }
+        if (g == 0) d[L] = '\n';
+    }
+}
+
+// ---------------------------------------------------------------------------------- container walk
+// Serial hop over the block headers of a .fqz resident in HBM (the format has no index:
+// readNextDecompressJob, compress.go:721-758; header layouts container.go:116-152).  Stops after
+// `cap` blocks or once the entered blocks span more than max_bytes.
+__global__ void k_walk_container(const u8 *f, u64 n, u64 pos, u32 version, FqzBlockEntry *tab, u32 cap, u64 max_bytes, FqzWalkResult *res) {
+    if (threadIdx.x || blockIdx.x) return;
+    u32 hsz = version == 1 ? 32u : 36u;
+    u32 nb = 0, status = 0;
+    u64 start = pos;
+    while (pos < n && nb < cap) {
+        if (n - pos < hsz) { status = 1; break; }  // "reading block header: unexpected EOF"
+        u32 v[9];
+        for (u32 i = 0; i < hsz / 4; i++) {
+            const u8 *q = f + pos + 4 * i;
+            v[i] = (u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24);
+        }
+        FqzBlockEntry e;
+        e.nrec = v[0];
+        e.pad = 0;
+        if (version == 1) {  // seq, qual, headers, npos, lens (container.go:85-96)
+            e.size[0] = v[1]; e.size[1] = v[2]; e.size[2] = v[3]; e.size[3] = 0; e.size[4] = v[4]; e.size[5] = v[5];
+        } else {
+            for (int i = 0; i < 6; i++) e.size[i] = v[1 + i];
+        }
+        u64 payload = 0;
+        for (int i = 0; i < 6; i++) payload += e.size[i];
+        if (n - pos - hsz < payload) { status = 1; break; }  // "reading compressed data: unexpected EOF"
+        if (nb > 0 && pos + hsz + payload - start > max_bytes) break;
+        e.payload_off = pos + hsz;
+        tab[nb++] = e;
+        pos += hsz + payload;
+    }
+    res->next_pos = pos;
+    res->nblocks = nb;
+    res->status = status;
+    res->done = (pos >= n && !status) ? 1u : 0u;
+    res->pad = 0;
+}
+
+// ---------------------------------------------------------------------------------- host launchers
+void fqz_launch_walk_container(const u8 *fqz, u64 n, u64 pos, u32 version, FqzBlockEntry *table, u32 cap, u64 max_bytes,
+                               FqzWalkResult *res, cudaStream_t s) {
+    FQZ_LAUNCH(k_walk_container, 1, 32, 0, s, fqz, n, pos, version, table, cap, max_bytes, res);
+}
+void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs, FqzDecStatus *st, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_walk_prefixes, (nblocks * 3 + 3) / 4, 128, 0, s, blks, nblocks, offs, st);
+}
+void fqz_launch_record_sizes(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, u32 *sz, u64 stride, BkTotals *tot,
+                             FqzDecStatus *st, cudaStream_t s) {
+    if (!nblocks || !max_nrec) return;
+    FQZ_LAUNCH(k_record_sizes, dim3((max_nrec + 255) / 256, nblocks), 256, 0, s, blks, nblocks, offs, sz, stride, tot, st);
+}
+void fqz_launch_check_seq_qual(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *sc, u64 stride, FqzDecStatus *st, cudaStream_t s) {
+    if (!nblocks || !max_nrec) return;
+    FQZ_LAUNCH(k_check_seq_qual, dim3((max_nrec + 255) / 256, nblocks), 256, 0, s, blks, nblocks, sc, stride, st);
+}
+void fqz_launch_emit(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, const u32 *sc, u64 stride, u32 phred64, u8 *out,
+                     FqzDecStatus *st, cudaStream_t s) {
+    if (!nblocks || !max_nrec) return;
+    FQZ_LAUNCH(k_emit_fastq, dim3((max_nrec + 15) / 16, nblocks), 256, 0, s, blks, nblocks, offs, sc, stride, phred64, out, st);
+}

@@ -200,6 +200,7 @@ extern "C" void fqz_stats_reset(fqz_ctx *c) {
     c->prof.clear();
     c->launches_base = g_fqz_launches;
 }
+extern "C" void *fqz_get_stream(fqz_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" void fqz_profile_enable(fqz_ctx *c, int on) {
     if (c) c->prof.on = on != 0;
 }

@@ -101,6 +101,16 @@ int fqz_pin_reserve(fqz_ctx *c, size_t bytes);
 int fqz_io_reserve(fqz_ctx *c, size_t bytes);
 int fqz_scan_excl_u32(fqz_ctx *c, u32 *d, u64 n, u64 stride, u32 narr);
 
+// ---- zstd decode stage (fqz_api_dec.cu)
+struct ZDStream;
+struct ZDecodeOut {
+    u8 *d_base = nullptr;
+    std::vector<u64> off, size;  // per stream
+    int err_stream = -1;
+};
+// max_out: give up with FQZ_E_TOO_LARGE (before allocating) when the streams decode to more bytes; 0 = no limit
+int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_out, ZDecodeOut &out);
+
 // ---- compress front end (fqz_api_front.cu)
 struct FrontOut {
     u64 R = 0;          // records encoded from this window

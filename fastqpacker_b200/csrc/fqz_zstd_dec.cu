@@ -54,7 +54,8 @@ struct BitR {
         }
     }
     __device__ __forceinline__ u32 look(u32 n) const {  // n in 1..32; bits past the start read as 0
-        return (u32)(((cont << (consumed & 63)) >> 1) >> (63 - n));
+        if (consumed >= 64) return 0;
+        return (u32)(((cont << consumed) >> 1) >> (63 - n));
     }
     __device__ __forceinline__ void skip(u32 n) { consumed += n; }
     __device__ __forceinline__ u32 read(u32 n) {
@@ -254,11 +255,13 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
     inf.lit_bytes = 0;
     inf.nseq = 0;
     u32 fbase = 0, bbase = 0;
-    u64 obase = 0;
+    u64 obase = 0, lbase = 0, sbase = 0;
     if (fill) {
         fbase = info[si].frame_base;
         bbase = info[si].block_base;
         obase = info[si].out_base;
+        lbase = info[si].lit_base;
+        sbase = info[si].seq_base;
     }
     while (pos < n) {
         if (n - pos < 4) { inf.status = 1; break; }
@@ -394,8 +397,8 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
                 B.rsize = (type == 2) ? 0u : bsz;
                 B.lit_regen = lit_regen;
                 B.nseq = nseq;
-                B.lit_off = 0;
-                B.seq_off = 0;
+                B.lit_off = lbase + inf.lit_bytes;
+                B.seq_off = sbase + inf.nseq;
                 B.err = 0;
                 blocks[bidx] = B;
             }
@@ -908,7 +911,37 @@ __global__ void k_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32
     res[si].contiguous = contiguous ? 1u : 0u;
 }
 
+// Streams whose frames carried no content size were given upper-bound output regions: close the
+// gaps so that every stream is contiguous again (one warp per stream, frames moved left in order).
+__global__ void __launch_bounds__(128) k_zd_compact(ZDFrame *frames, const ZDStreamInfo *info, const ZDStreamResult *res, u32 nstreams, u8 *out) {
+    u32 si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (si >= nstreams) return;
+    if (res[si].contiguous || res[si].err) return;
+    ZDStreamInfo I = info[si];
+    u64 run = I.out_base;
+    for (u32 f = 0; f < I.nframes; f++) {
+        ZDFrame F = frames[I.frame_base + f];
+        if (F.dst_off != run) {
+            u8 *d = out + run;
+            const u8 *s = out + F.dst_off;
+            for (u64 i = 0; i < F.out_size; i += 32) {
+                u8 v = 0;
+                if (i + lane < F.out_size) v = s[i + lane];
+                __syncwarp();
+                if (i + lane < F.out_size) d[i + lane] = v;
+                __syncwarp();
+            }
+            if (lane == 0) frames[I.frame_base + f].dst_off = run;
+        }
+        run += F.out_size;
+    }
+}
+
 // ---------------------------------------------------------------------------------- host launchers
+void fqz_launch_zd_compact(ZDFrame *frames, const ZDStreamInfo *info, const ZDStreamResult *res, u32 nstreams, u8 *out, cudaStream_t s) {
+    if (!nstreams) return;
+    FQZ_LAUNCH(k_zd_compact, (nstreams * 32 + 127) / 128, 128, 0, s, frames, info, res, nstreams, out);
+}
 void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s) {
     if (!nstreams) return;
     FQZ_LAUNCH(k_zd_walk, (nstreams + 31) / 32, 32, 0, s, streams, nstreams, info, frames, blocks, fill);

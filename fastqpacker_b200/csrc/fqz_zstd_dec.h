@@ -1,0 +1,61 @@
+// fqz_zstd_dec.h — tables exchanged between the kernels of the GPU zstd decoder.
+#pragma once
+#include "fqz_common.cuh"
+
+struct ZDStream {  // compressed bytes of one stream: a chain of zstd frames (possibly none)
+    u64 src;       // device address
+    u64 csize;
+};
+struct ZDStreamInfo {
+    u32 nframes, nblocks;
+    u64 out_bytes;   // sum of frame content sizes (upper bound for frames without a content size)
+    u64 lit_bytes;   // sum of regenerated literal sizes
+    u64 nseq;        // sum of sequence counts
+    u32 status;      // 0 ok, 1 corrupt, 2 unsupported (dictionary)
+    u32 frame_base, block_base;  // filled by the host before the second walk
+    u64 out_base, lit_base, seq_base;
+};
+struct ZDFrame {
+    u64 dst_off;        // into the output arena
+    u64 content_size;   // ~0 when the frame header has none
+    u64 out_cap;        // bytes reserved at dst_off
+    u64 out_size;       // bytes regenerated (k_zd_execute)
+    u64 window;
+    u32 first_block, nblocks;
+    u32 has_ck, ck;
+    u32 stream;
+    u32 err;            // 1 corrupt, 2 checksum mismatch
+};
+struct ZDBlock {
+    u64 src;            // device address of the block content
+    u64 lit_off;        // into the literal arena
+    u64 seq_off;        // sequence index into the sequence arena (3 x u32 per sequence)
+    u32 csize;          // stored size (1 for RLE)
+    u32 rsize;          // regenerated size for raw / RLE blocks
+    u32 frame;
+    u32 lit_regen, lit_csize;
+    u32 nseq;
+    u32 seq_pos;        // offset of the symbol-compression-modes byte
+    u32 bits_pos;       // offset of the sequence bitstream
+    u32 tab_pos[3];     // offsets of the LL / OF / ML table descriptions
+    u32 huf_block;      // block whose literals section holds the Huffman tree (treeless literals)
+    u32 fse_block[3];   // block whose table description is reused (repeat mode)
+    u8 type;            // 0 raw, 1 RLE, 2 compressed
+    u8 lit_type, lit_streams, lit_hdr;
+    u8 modes;
+    u8 err;
+    u8 pad[2];
+};
+struct ZDStreamResult {
+    u64 size;
+    u32 err;
+    u32 contiguous;
+};
+
+void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s);
+void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s);
+void fqz_launch_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf, cudaStream_t s);
+void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s);
+void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s);
+void fqz_launch_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res, cudaStream_t s);
+void fqz_launch_zd_compact(ZDFrame *frames, const ZDStreamInfo *info, const ZDStreamResult *res, u32 nstreams, u8 *out, cudaStream_t s);

@@ -127,6 +127,9 @@ typedef struct {
     uint64_t stage_bytes[FQZ_MAX_STAGES]; /* algorithmic bytes attributed to the stage */
 } fqz_stats;
 void fqz_stats_reset(fqz_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a
+ * caller can bracket calls with its own CUDA events (bench.py times on this stream). */
+void *fqz_get_stream(fqz_ctx *ctx);
 void fqz_profile_enable(fqz_ctx *ctx, int on);
 int fqz_get_stats(fqz_ctx *ctx, fqz_stats *out);
 

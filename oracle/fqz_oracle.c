@@ -776,6 +776,117 @@ int orc_decompress(const uint8_t *f, size_t n, uint8_t *out, size_t cap, size_t 
     return rc;
 }
 
+/* Parallel whole-file decode: compress.go:630-719 (serial container walk = the single producer,
+ * W workers each decoding whole blocks, output concatenated in block order = the ordered collector).
+ * Used by bench.py as the multi-core CPU baseline; results equal orc_decompress. */
+typedef struct {
+    const uint8_t *f;
+    size_t nblocks;
+    size_t *off;      /* payload offset per block */
+    uint32_t *nrec;
+    uint32_t (*sz)[6];
+    int version, phred64;
+    buf_t *outs;
+    int *rcs;
+    size_t next;
+    pthread_mutex_t mu;
+} djob_t;
+
+static void *dworker(void *arg) {
+    djob_t *j = (djob_t *)arg;
+    for (;;) {
+        pthread_mutex_lock(&j->mu);
+        size_t b = j->next++;
+        pthread_mutex_unlock(&j->mu);
+        if (b >= j->nblocks) break;
+        buf_t s[6];
+        memset(s, 0, sizeof s);
+        size_t pos = j->off[b];
+        int rc = 0;
+        for (int i = 0; i < 6 && rc == 0; i++) {
+            if (j->version == 1 && i == 3) continue;
+            rc = zstd_decode_all(j->f + pos, j->sz[b][i], &s[i]);
+            pos += j->sz[b][i];
+        }
+        if (rc == 0) rc = decode_records(s, j->nrec[b], j->phred64, &j->outs[b]);
+        for (int i = 0; i < 6; i++) free(s[i].p);
+        j->rcs[b] = rc;
+    }
+    return NULL;
+}
+
+int orc_decompress_mt(const uint8_t *f, size_t n, int threads, uint8_t *out, size_t cap, size_t *out_len) {
+    if (libs()) return ORC_E_NOLIB;
+    if (n < 4) return ORC_E_TRUNC_FILE;
+    if (!(f[0] == 'F' && f[1] == 'Q' && f[2] == 'Z' && f[3] == 0)) return ORC_E_MAGIC;
+    if (n < 10) return ORC_E_TRUNC_FILE;
+    int version = f[4];
+    if (version != 1 && version != 2) return ORC_E_VERSION;
+    size_t hsz = version == 1 ? 32 : 36, pos = 10, nb = 0, capb = 64;
+    djob_t j;
+    memset(&j, 0, sizeof j);
+    j.off = (size_t *)malloc(sizeof(size_t) * capb);
+    j.nrec = (uint32_t *)malloc(sizeof(uint32_t) * capb);
+    j.sz = (uint32_t(*)[6])malloc(sizeof(uint32_t[6]) * capb);
+    int rc = 0;
+    while (pos < n) {
+        if (pos + hsz > n) { rc = ORC_E_TRUNC_FILE; break; }
+        if (nb == capb) {
+            capb *= 2;
+            j.off = (size_t *)realloc(j.off, sizeof(size_t) * capb);
+            j.nrec = (uint32_t *)realloc(j.nrec, sizeof(uint32_t) * capb);
+            j.sz = (uint32_t(*)[6])realloc(j.sz, sizeof(uint32_t[6]) * capb);
+        }
+        const uint8_t *h = f + pos;
+        j.nrec[nb] = rd_u32(h);
+        if (version == 1) {
+            j.sz[nb][0] = rd_u32(h + 4); j.sz[nb][1] = rd_u32(h + 8); j.sz[nb][2] = rd_u32(h + 12); j.sz[nb][3] = 0;
+            j.sz[nb][4] = rd_u32(h + 16); j.sz[nb][5] = rd_u32(h + 20);
+        } else
+            for (int i = 0; i < 6; i++) j.sz[nb][i] = rd_u32(h + 4 + 4 * i);
+        pos += hsz;
+        j.off[nb] = pos;
+        size_t pay = 0;
+        for (int i = 0; i < 6; i++) pay += j.sz[nb][i];
+        if (pos + pay > n) { rc = ORC_E_TRUNC_FILE; break; }
+        pos += pay;
+        nb++;
+    }
+    j.f = f;
+    j.nblocks = nb;
+    j.version = version;
+    j.phred64 = (f[9] & 2) ? 1 : 0;
+    j.outs = (buf_t *)calloc(nb ? nb : 1, sizeof(buf_t));
+    j.rcs = (int *)calloc(nb ? nb : 1, sizeof(int));
+    pthread_mutex_init(&j.mu, NULL);
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > nb) threads = (int)(nb ? nb : 1);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, dworker, &j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    size_t total = 0;
+    for (size_t b = 0; b < nb; b++) {
+        if (j.rcs[b] && !rc) rc = j.rcs[b];
+        total += j.outs[b].n;
+    }
+    if (rc == 0) {
+        *out_len = total;
+        if (total > cap) rc = ORC_E_NOSPACE;
+        else {
+            size_t o = 0;
+            for (size_t b = 0; b < nb; b++) {
+                if (j.outs[b].n) memcpy(out + o, j.outs[b].p, j.outs[b].n);
+                o += j.outs[b].n;
+            }
+        }
+    }
+    for (size_t b = 0; b < nb; b++) free(j.outs[b].p);
+    free(j.outs); free(j.rcs); free(j.off); free(j.nrec); free(j.sz);
+    pthread_mutex_destroy(&j.mu);
+    return rc;
+}
+
 /* Split one block of a .fqz into its six decoded streams (for checking GPU-written frames
  * with libzstd and for feeding reference-shaped streams to the GPU back end).
  * block_index counts from 0.  out[i] are malloc'd here; free with orc_free. */

@@ -42,8 +42,8 @@ class OracleError(Exception):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "fqz_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fqz_oracle.c", "fqz_synth_cpu.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libfqzoracle.so"])
     return _SO
 
@@ -89,6 +89,10 @@ def lib():
         L.orc_decode_streams.restype = C.c_int
         L.orc_block_streams.argtypes = [u8p, sz, sz, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.orc_block_streams.restype = C.c_int
+        L.orc_decompress_mt.argtypes = [u8p, sz, C.c_int, u8p, sz, szp]
+        L.orc_decompress_mt.restype = C.c_int
+        L.orc_synth.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, u8p, sz, szp]
+        L.orc_synth.restype = C.c_int
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_free.restype = None
         _lib = L
@@ -297,3 +301,44 @@ def block_streams(fqz, block_index: int = 0):
         if outs[i]:
             lib().orc_free(outs[i])
     return res, nrec.value
+
+
+def decompress_mt(fqz, threads: int, cap: int):
+    """Multi-threaded whole-file decode (block-parallel like compress.go:630-719) -> numpy uint8."""
+    import numpy as np
+
+    p, n, k = _in(fqz)
+    out = np.empty(cap, dtype=np.uint8)
+    m = C.c_size_t(0)
+    rc = lib().orc_decompress_mt(p, n, threads, C.c_void_p(out.ctypes.data), cap, C.byref(m))
+    if rc:
+        raise OracleError(rc)
+    return out[: m.value]
+
+
+def compress_np(text, threads: int = 1, level: int = 1):
+    """compress() returning a numpy view (no bytes copy) for the timed CPU baseline."""
+    import numpy as np
+
+    p, n, k = _in(text)
+    cap = n + n // 8 + (1 << 16)
+    out = np.empty(cap, dtype=np.uint8)
+    m = C.c_size_t(0)
+    info = (C.c_uint64 * 4)()
+    rc = lib().orc_compress(p, n, 0, level, threads, 2, C.c_void_p(out.ctypes.data), cap, C.byref(m), info)
+    if rc:
+        raise OracleError(rc, f"record {info[3]}")
+    return out[: m.value]
+
+
+def synth(kind: int, seed: int, first: int, count: int):
+    """CPU twin of the device FASTQ generator -> numpy uint8."""
+    import numpy as np
+
+    cap = count * (400 if kind == 0 else 760) + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    m = C.c_size_t(0)
+    rc = lib().orc_synth(kind, seed, first, count, C.c_void_p(out.ctypes.data), cap, C.byref(m))
+    if rc:
+        raise OracleError(rc)
+    return out[: m.value]

@@ -1,0 +1,248 @@
+"""Decompress-side parity checks shared by the CPU-emulation tests (tests/test_emu_decode.py) and
+the GPU tests (tests/test_gpu_decompress.py).  `ctx` is a fastqpacker_b200 FqzContext, `oracle`
+the CPU oracle module (libzstd stands in for klauspost/compress)."""
+import random
+import struct
+
+import pytest
+
+
+def _zstd_data(name, scale=1.0):
+    rnd = random.Random(sum(name.encode()) * 7919)
+    n = lambda k: max(1, int(k * scale))
+    if name == "tiny":
+        return b"abc"
+    if name == "one":
+        return b"x"
+    if name == "zeros":
+        return bytes(n(300000))
+    if name == "text":
+        return b"hello world, hello zstd " * n(9000)
+    if name == "quality_like":
+        return bytes(rnd.choice([0, 0, 0, 0, 0, 0, 1, 255, 2, 254, 3]) for _ in range(n(400000)))
+    if name == "random":
+        return bytes(rnd.randrange(256) for _ in range(n(200000)))
+    if name == "headers_like":
+        return b"".join(b"\x21\x00ERR532393.%d HWI-ST571:218:C2DACACXX:5:1101:%d:%d/1" % (i, 1000 + i * 7 % 20000, 2000 + i) for i in range(n(12000)))
+    if name == "runs":
+        return b"".join(bytes([i & 255]) * (i % 700) for i in range(n(900)))
+    if name == "mixed":
+        return b"".join(bytes([rnd.randrange(4)]) * rnd.randrange(1, 40) + b"@ERR%d/1" % i for i in range(n(20000)))
+    if name == "lengths_like":
+        return struct.pack("<I", 150) * n(100000)
+    if name == "small_alphabet":
+        return bytes(rnd.randrange(7) for _ in range(n(140000)))
+    raise KeyError(name)
+
+
+ZSTD_DATA = ["tiny", "one", "zeros", "text", "quality_like", "random", "headers_like", "runs", "mixed", "lengths_like", "small_alphabet"]
+
+
+def check_zstd_libzstd_frames(ctx, oracle, name, level, scale=1.0):
+    """Frames written by libzstd (multi-block, FSE/repeat tables, treeless literals, repeat offsets,
+    cross-block matches) must decode bit-exact on the device."""
+    data = _zstd_data(name, scale)
+    z = oracle.zstd_compress(data, level)
+    assert ctx.zstd_decompress(z) == data
+    # concatenated frames decode back to back (klauspost DecodeAll / libzstd behaviour)
+    z2 = z + oracle.zstd_compress(b"second frame " * 10, level)
+    assert ctx.zstd_decompress(z2) == data + b"second frame " * 10
+
+
+def check_zstd_round_trip(ctx, oracle, name, policy, scale=1.0):
+    data = _zstd_data(name, scale)
+    z = ctx.zstd_compress(data, policy)
+    assert oracle.zstd_decompress(z) == data
+    assert ctx.zstd_decompress(z) == data
+
+
+def check_back_end(ctx, oracle, text):
+    """six pre-entropy streams -> FASTQ == NumRecords x blockReader.writeRecord."""
+    enc = oracle.encode_streams(text)
+    want = oracle.decode_streams(enc["streams"], enc["nrec"], enc["phred64"])
+    got = ctx.decode_streams(enc["streams"], enc["nrec"], enc["phred64"])
+    assert got == want
+    if enc["nrec"]:
+        # v1 rule: an empty plus stream yields bare '+' lines (compress.go:995-999)
+        s = list(enc["streams"])
+        s[3] = b""
+        assert ctx.decode_streams(s, enc["nrec"], enc["phred64"]) == oracle.decode_streams(s, enc["nrec"], enc["phred64"])
+
+
+def check_decompress_reference_written(ctx, oracle, text):
+    """reference-shaped .fqz (oracle container + libzstd frames) decodes bit-exact on the device."""
+    for level in (1, 5):
+        fqz = oracle.compress(text, level=level)
+        assert ctx.decompress(fqz) == oracle.decompress(fqz)
+
+
+def check_round_trip(ctx, oracle, text):
+    fqz = ctx.compress(text)
+    want = oracle.decompress(oracle.compress(text))  # the reference's own (lossy-normalising) round trip
+    assert oracle.decompress(fqz) == want
+    assert ctx.decompress(fqz) == want
+
+
+def check_v1_file(ctx, oracle):
+    """v1 container: 32-byte block headers, five streams, plus lines rebuilt as '+'
+    (compress_test.go:502-592)."""
+    from tests.fastq_cases import GOOD_CASES
+
+    for name in ("three", "plus_payload", "rand_small"):
+        text = GOOD_CASES[name]
+        v1 = oracle.compress(text, version=1)
+        assert v1[4] == 1
+        want = oracle.decompress(v1)
+        assert ctx.decompress(v1) == want
+
+
+_TRUNC_CODES = {0: -11, 1: -12, 2: -9, 3: -10, 4: -14, 5: -13}
+
+
+def check_decode_errors(ctx, oracle):
+    """'truncated ... data' errors of blockReader (compress.go:979-1057): same error as the oracle,
+    whichever stream runs short first in the reference's per-record order."""
+    from fastqpacker_b200._binding import FqzError
+    from tests.fastq_cases import GOOD_CASES
+
+    text = GOOD_CASES["rand_plus"] + GOOD_CASES["nbases"].replace(b"IIII!!!!IIII", b"hhhhhhhhhhhh")
+    enc = oracle.encode_streams(text, phred64=1)
+    streams, nrec = enc["streams"], enc["nrec"]
+    assert ctx.decode_streams(streams, nrec, 1) == oracle.decode_streams(streams, nrec, 1)
+    rnd = random.Random(5)
+    for which in range(6):
+        for cut in (1, 2, 3, 7, len(streams[which]) // 2, len(streams[which]) - 1):
+            s = list(streams)
+            s[which] = s[which][: len(s[which]) - cut]
+            if which == 3 and not s[which]:
+                continue  # an empty plus stream is the v1 rule, not an error
+            with pytest.raises(oracle.OracleError) as oe:
+                oracle.decode_streams(s, nrec, 1)
+            with pytest.raises(FqzError) as ge:
+                ctx.decode_streams(s, nrec, 1)
+            assert ge.value.code == oe.value.code, (which, cut)
+    # two streams short at once: the reference's per-record order decides
+    for _ in range(12):
+        s = list(streams)
+        for which in rnd.sample(range(6), 2):
+            s[which] = s[which][: rnd.randrange(1, len(s[which]))]
+        if not s[3]:
+            continue
+        with pytest.raises(oracle.OracleError) as oe:
+            oracle.decode_streams(s, nrec, 1)
+        with pytest.raises(FqzError) as ge:
+            ctx.decode_streams(s, nrec, 1)
+        assert ge.value.code == oe.value.code
+    # more records claimed than present
+    with pytest.raises(FqzError) as ge:
+        ctx.decode_streams(streams, nrec + 5, 1)
+    assert ge.value.code == -13
+    # N position beyond the read (the reference panics; both sides report -17)
+    s = list(streams)
+    npos = bytearray(s[4])
+    k = len(npos) - 2  # last position of the last record
+    npos[k : k + 2] = struct.pack("<H", 5000)
+    s[4] = bytes(npos)
+    with pytest.raises(FqzError) as ge:
+        ctx.decode_streams(s, nrec, 1)
+    assert ge.value.code == -17
+
+
+def check_file_errors(ctx, oracle):
+    from fastqpacker_b200._binding import FqzError
+    from tests.fastq_cases import GOOD_CASES
+
+    fqz = oracle.compress(GOOD_CASES["rand_small"])
+    cases = {
+        "bad_magic": (b"FQX\x00" + fqz[4:], -5),
+        "short_magic": (fqz[:3], -7),
+        "short_header": (fqz[:8], -7),
+        "bad_version": (fqz[:4] + b"\x03" + fqz[5:], -6),
+        "cut_block_header": (fqz[:30], -7),
+        "cut_payload": (fqz[:-9], -7),
+    }
+    for name, (blob, code) in cases.items():
+        with pytest.raises(oracle.OracleError) as oe:
+            oracle.decompress(blob)
+        assert oe.value.code == code, name
+        with pytest.raises(FqzError) as ge:
+            ctx.decompress(blob)
+        assert ge.value.code == code, name
+    # corrupt frames: flip one byte inside each stream's payload in turn
+    sizes = struct.unpack("<9I", fqz[10:46])[1:7]
+    pos = 46
+    for i, sz in enumerate(sizes):
+        bad = bytearray(fqz)
+        bad[pos + sz // 2] ^= 0x5A
+        pos += sz
+        try:
+            want = oracle.decompress(bytes(bad))
+        except oracle.OracleError as e:
+            want = e.code
+        try:
+            got = ctx.decompress(bytes(bad))
+        except FqzError as e:
+            got = e.code
+        if isinstance(want, int):
+            assert isinstance(got, int) and got < 0, (i, want, got)  # both reject (the first check that trips may differ)
+        else:
+            assert got == want
+    assert ctx.decompress(fqz[:10]) == b""  # header-only file (compress_test.go:160-173)
+
+
+def check_streaming(ctx, oracle, nrec=300, chunk=None):
+    """Seam B feed() calls: windows cut at arbitrary byte positions give the same bytes as the
+    whole-buffer calls."""
+    import numpy as np
+
+    from tests import synth
+
+    text = synth.fastq(1, 11, 0, nrec)
+    want_fqz = ctx.compress(text)
+    out = np.empty(len(text) + (1 << 16), dtype=np.uint8)
+    cs = ctx.compress_stream()
+    got = b""
+    pos = 0
+    chunk = chunk or max(64, len(text) // 3)
+    window = b""
+    while True:
+        window += text[pos : pos + chunk]
+        pos += chunk
+        last = pos >= len(text)
+        try:
+            m, used = cs.feed(window, last, out)
+        except Exception as e:  # FQZ_E_NEED_MORE: no complete block yet
+            assert getattr(e, "code", 0) == -35 and not last
+            continue
+        got += out[:m].tobytes()
+        window = window[used:]
+        if last:
+            assert not window
+            break
+    cs.close()
+    assert got == want_fqz
+    # decompress side, fed in pieces that split headers and payloads
+    want = oracle.decompress(want_fqz)
+    ds = ctx.decompress_stream()
+    big = np.empty(len(want) + 4096, dtype=np.uint8)
+    res = b""
+    pos = 0
+    window = b""
+    step = max(7, len(want_fqz) // 5)
+    while True:
+        window += want_fqz[pos : pos + step]
+        pos += step
+        last = pos >= len(want_fqz)
+        try:
+            m, used = ds.feed(window, last, big)
+        except Exception as e:
+            assert getattr(e, "code", 0) == -35 and not last
+            continue
+        assert m >= 0
+        res += big[:m].tobytes()
+        window = window[used:]
+        if last:
+            assert not window
+            break
+    ds.close()
+    assert res == want

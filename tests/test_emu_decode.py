@@ -1,0 +1,68 @@
+"""Runs the CUDA decompress kernels (zstd decoder, prefix walk, FASTQ emit) through the CPU
+emulation (tests/emu) against the oracle.  Debug aid for the GPU kernels; the real parity tests are
+the -m gpu ones (tests/test_gpu_decompress.py), which reuse these cases."""
+import pytest
+
+from tests.decode_cases import (
+    ZSTD_DATA,
+    check_back_end,
+    check_decode_errors,
+    check_decompress_reference_written,
+    check_file_errors,
+    check_round_trip,
+    check_streaming,
+    check_v1_file,
+    check_zstd_libzstd_frames,
+    check_zstd_round_trip,
+)
+from tests.fastq_cases import GOOD_CASES
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.emu_lib import emu_context
+
+    return emu_context()
+
+
+@pytest.mark.parametrize("level", [1, 3, 9])
+@pytest.mark.parametrize("name", sorted(ZSTD_DATA))
+def test_zstd_decodes_libzstd_frames(emu, oracle, name, level):
+    check_zstd_libzstd_frames(emu, oracle, name, level, scale=0.25)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("name", sorted(ZSTD_DATA))
+def test_zstd_round_trip(emu, oracle, name, policy):
+    check_zstd_round_trip(emu, oracle, name, policy, scale=0.25)
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_back_end_matches_oracle(emu, oracle, name):
+    check_back_end(emu, oracle, GOOD_CASES[name])
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_decompress_reference_written(emu, oracle, name):
+    check_decompress_reference_written(emu, oracle, GOOD_CASES[name])
+
+
+@pytest.mark.parametrize("name", ["three", "rand_small", "rand_plus", "lossy", "empty"])
+def test_round_trip(emu, oracle, name):
+    check_round_trip(emu, oracle, GOOD_CASES[name])
+
+
+def test_v1_file(emu, oracle):
+    check_v1_file(emu, oracle)
+
+
+def test_decode_errors(emu, oracle):
+    check_decode_errors(emu, oracle)
+
+
+def test_file_errors(emu, oracle):
+    check_file_errors(emu, oracle)
+
+
+def test_streaming(emu, oracle):
+    check_streaming(emu, oracle, nrec=300)

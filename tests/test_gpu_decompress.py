@@ -1,0 +1,119 @@
+"""GPU decompress path through the C-ABI: reference-shaped .fqz (oracle container + libzstd frames,
+the stand-in for files written by fqpack) and GPU-written .fqz must decode bit-exact; error
+behaviour follows internal/compress/compress.go:558-604,780-837,944-1078."""
+import numpy as np
+import pytest
+
+from tests import synth
+from tests.decode_cases import (
+    ZSTD_DATA,
+    check_back_end,
+    check_decode_errors,
+    check_decompress_reference_written,
+    check_file_errors,
+    check_round_trip,
+    check_streaming,
+    check_v1_file,
+    check_zstd_libzstd_frames,
+    check_zstd_round_trip,
+)
+from tests.fastq_cases import GOOD_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fastqpacker_b200 as fq
+
+    return fq.context(0)
+
+
+@pytest.mark.parametrize("level", [1, 3, 9, 19])
+@pytest.mark.parametrize("name", sorted(ZSTD_DATA))
+def test_zstd_decodes_libzstd_frames(ctx, oracle, name, level):
+    check_zstd_libzstd_frames(ctx, oracle, name, level, scale=4.0 if level < 19 else 1.0)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("name", sorted(ZSTD_DATA))
+def test_zstd_round_trip(ctx, oracle, name, policy):
+    check_zstd_round_trip(ctx, oracle, name, policy, scale=4.0)
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_back_end_matches_oracle(ctx, oracle, name):
+    check_back_end(ctx, oracle, GOOD_CASES[name])
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_decompress_reference_written(ctx, oracle, name):
+    check_decompress_reference_written(ctx, oracle, GOOD_CASES[name])
+
+
+@pytest.mark.parametrize("name", sorted(GOOD_CASES))
+def test_round_trip(ctx, oracle, name):
+    check_round_trip(ctx, oracle, GOOD_CASES[name])
+
+
+def test_v1_file(ctx, oracle):
+    check_v1_file(ctx, oracle)
+
+
+def test_decode_errors(ctx, oracle):
+    check_decode_errors(ctx, oracle)
+
+
+def test_file_errors(ctx, oracle):
+    check_file_errors(ctx, oracle)
+
+
+def test_streaming_small(ctx, oracle):
+    check_streaming(ctx, oracle, nrec=300)
+
+
+def test_streaming_multi_block(ctx, oracle):
+    """250 000 records = 3 fqz blocks; feed windows that end inside blocks."""
+    check_streaming(ctx, oracle, nrec=250000, chunk=30_000_000)
+
+
+def _device_fastq(ctx, kind, seed, count):
+    import torch
+
+    cap = count * 800 + 4096
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.synth_device(kind, seed, 0, count, buf.data_ptr(), cap)
+    return buf, n
+
+
+@pytest.mark.parametrize("kind,count", [(0, 250000), (1, 130000)])
+def test_decompress_multi_block(ctx, oracle, kind, count):
+    """BASELINE config 3 shapes at test size: GPU-written and reference-written files, several blocks."""
+    buf, n = _device_fastq(ctx, kind, 0x5EED0001 + kind * 3, count)
+    text = buf[:n].cpu().numpy()
+    ref = oracle.compress(text, threads=8)
+    got = ctx.decompress(ref, cap=n + 4096)
+    assert got == text.tobytes()
+    fqz = ctx.compress(text)
+    assert ctx.decompress(fqz, cap=n + 4096) == text.tobytes()
+
+
+def test_device_round_trip_large(ctx):
+    """Size-independent property at a larger size: decompress(compress(x)) == x entirely on the device
+    (2 000 000 records, ~0.73 GB, 20 fqz blocks)."""
+    import torch
+
+    count = 2_000_000
+    buf, n = _device_fastq(ctx, 0, 0x5EED0001, count)
+    out = torch.empty(n // 2 + (1 << 20), dtype=torch.uint8, device="cuda")
+    m = ctx.compress_device(buf.data_ptr(), n, out.data_ptr(), out.numel())
+    back = torch.empty(n + 4096, dtype=torch.uint8, device="cuda")
+    k = ctx.decompress_device(out.data_ptr(), m, back.data_ptr(), back.numel())
+    assert k == n
+    assert torch.equal(back[:n], buf[:n])
+    # NOSPACE reports the size needed
+    from fastqpacker_b200 import FqzError
+
+    with pytest.raises(FqzError) as e:
+        ctx.decompress_device(out.data_ptr(), m, back.data_ptr(), 1000)
+    assert e.value.code == -15
