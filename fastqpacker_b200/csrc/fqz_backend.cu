@@ -12,54 +12,90 @@
 //                     prefix-summed qualities; all wide stores aligned to the destination
 #include "fqz_backend.h"
 
-#define WALK_CHUNK 8192u
+#define WALK_CH 4096u  // bytes per staged chunk (plus 16 bytes of overlap so a prefix never straddles)
 
 // kind: 0 headers, 1 plus, 2 npos.  offs has nrec+1 entries per (block, kind): item r starts at offs[r].
+// One lane per chain: the hop pos -> pos + 2 + len is a serial dependency, so the only lever is
+// latency.  The stream is staged chunk by chunk into shared memory by the TMA unit (1-D bulk
+// copies, double buffered: chunk c+1 lands while chunk c is walked), and the lane hops through
+// shared memory at ~40 cycles per item.
 __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs_base, FqzDecStatus *st) {
-    __shared__ u32 sm_words[4][(WALK_CHUNK + 16) / 4];
+    __shared__ uint4 sm_buf[4][2][(WALK_CH + 16) / 16];
+    __shared__ u64 sm_bar[4][2];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
     u32 wi = blockIdx.x * 4 + warp;
     if (wi >= nblocks * 3) return;
     u32 b = wi / 3, kind = wi % 3;
-    BkBlock B = blks[b];
+    const BkBlock *Bp = blks + b;
     int sidx = kind == 0 ? 2 : (kind == 1 ? 3 : 4);
-    const u8 *p = (const u8 *)(uintptr_t)B.stream[sidx];
-    u32 size = B.size[sidx], nrec = B.nrec;
-    u32 *offs = offs_base + (3ull * B.rec_base + (u64)kind * nrec) + 3ull * b + kind;  // (nrec+1) entries per kind
+    const u8 *p = (const u8 *)(uintptr_t)Bp->stream[sidx];
+    u32 size = Bp->size[sidx], nrec = Bp->nrec;
+    u64 rec_base = Bp->rec_base;
+    u32 *offs = offs_base + (3ull * rec_base + (u64)kind * nrec) + 3ull * b + kind;  // (nrec+1) entries per kind
     if (kind == 1 && size == 0) {  // v1 files / empty plus stream: every plus line is "+" (compress.go:995-999)
         for (u32 r = lane; r <= nrec; r += 32) offs[r] = 0;
         return;
     }
-    u8 *buf = (u8 *)sm_words[warp];
-    u32 pos = 0, r = 0;
-    u32 err = 0;
-    while (r < nrec && !err) {
-        u32 cb = pos & ~3u;
-        u32 ce = min(size, cb + WALK_CHUNK);
+    if (lane != 0) return;
+    u64 *bar = sm_bar[warp];
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    u32 nchunks = (size + WALK_CH - 1) / WALK_CH;
+    u32 ph[2] = {0, 0};
+    bool pending[2] = {false, false};
+    auto issue = [&](u32 c, u32 slot) {
+        if (c >= nchunks) return;
+        u32 off = c * WALK_CH;
+        u32 bytes = min(WALK_CH + 16u, (size - off + 15u) & ~15u);  // the stream carries FQZ_PAD readable bytes of slack
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_load_1d(sm_buf[warp][slot], p + off, bytes, &bar[slot]);
+#ifdef FQZ_EMU
+        bar[slot] += 1;
+#endif
+        pending[slot] = true;
+    };
+    auto wait = [&](u32 slot) {
+        if (!pending[slot]) return;
+        mbar_wait(&bar[slot], ph[slot]);
+        ph[slot] ^= 1u;
+        pending[slot] = false;
+    };
+    u32 pos = 0, r = 0, err = 0;
+    u32 c = 0, slot = 0;
+    issue(0, 0);
+    issue(1, 1);
+    while (r < nrec) {
         if (pos + 2 > size) { err = 1; break; }  // no room for the length prefix of item r
-        // stage [cb, ce) (the stream base is 64-byte aligned)
-        for (u32 i = cb + 4 * lane; i < ce; i += 128) *(u32 *)(buf + (i - cb)) = *(const u32 *)(p + i);
-        __syncwarp();
-        if (lane == 0) {
-            while (r < nrec && pos + 2 <= ce) {
-                u32 len = (u32)buf[pos - cb] | ((u32)buf[pos - cb + 1] << 8);
-                u32 next = pos + 2 + (kind == 2 ? 2 * len : len);
-                if (next > size) { err = 1; break; }  // item r runs past the end of the stream
-                offs[r++] = pos;
-                pos = next;
+        u32 nc = pos / WALK_CH;
+        if (nc != c) {
+            if (nc == c + 1) {  // the prefetched chunk; refill the slot just left
+                slot ^= 1u;
+                issue(nc + 1, slot ^ 1u);
+            } else {  // a long item jumped over the prefetched chunk
+                wait(slot ^ 1u);
+                issue(nc, slot);
+                issue(nc + 1, slot ^ 1u);
             }
+            c = nc;
         }
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        err = __shfl_sync(0xffffffffu, err, 0);
-        __syncwarp();
+        wait(slot);
+        const u8 *buf = (const u8 *)sm_buf[warp][slot];
+        u32 cbase = c * WALK_CH, cend = cbase + WALK_CH;
+        while (r < nrec && pos < cend && pos + 2 <= size) {
+            u32 len = (u32)buf[pos - cbase] | ((u32)buf[pos - cbase + 1] << 8);
+            u32 next = pos + 2 + (kind == 2 ? 2 * len : len);
+            if (next > size) { err = 1; break; }  // item r runs past the end of the stream
+            offs[r++] = pos;
+            pos = next;
+        }
+        if (err) break;
     }
-    if (lane == 0) {
-        offs[nrec] = pos;
-        if (err) {
-            u32 code = kind == 0 ? BK_E_TRUNC_HEADER : (kind == 1 ? BK_E_TRUNC_PLUS : BK_E_TRUNC_NPOS);
-            atomicMin(&st->err_key, ((u64)(B.rec_base + r) << 8) | code);
-        }
+    wait(0);  // no bulk copy may still be in flight when the CTA's shared memory is released
+    wait(1);
+    offs[nrec] = pos;
+    if (err) {
+        u32 code = kind == 0 ? BK_E_TRUNC_HEADER : (kind == 1 ? BK_E_TRUNC_PLUS : BK_E_TRUNC_NPOS);
+        atomicMin(&st->err_key, ((u64)(rec_base + r) << 8) | code);
     }
 }
 

@@ -852,7 +852,27 @@ __global__ void __launch_bounds__(128) k_zd_checksum(ZDFrame *frames, u32 nframe
     u64 acc = (q == 0) ? XXP1 + XXP2 : (q == 1) ? XXP2 : (q == 2) ? 0ull : 0ull - XXP1;
     u64 nstripes = len >> 5;
     const u8 *s = p + 8u * q;
-    for (u64 i = 0; i < nstripes; i++) acc = zxxh_round(acc, zld64(s + 32ull * i));
+    {
+        // serial multiply-rotate chain, independent loads: keep 8 stripes in flight
+        const u32 *w = (const u32 *)((uintptr_t)s & ~(uintptr_t)3);
+        const u32 sh = (u32)((uintptr_t)s & 3u) * 8u;
+        u64 i = 0;
+        for (; i + 8 <= nstripes; i += 8) {
+            u32 a[8], b[8], c[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a[k] = w[8 * (i + k)];
+                b[k] = w[8 * (i + k) + 1];
+                c[k] = w[8 * (i + k) + 2];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                u64 v = (u64)__funnelshift_r(a[k], b[k], sh) | ((u64)__funnelshift_r(b[k], c[k], sh) << 32);
+                acc = zxxh_round(acc, v);
+            }
+        }
+        for (; i < nstripes; i++) acc = zxxh_round(acc, zld64(s + 32ull * i));
+    }
     u64 a0 = __shfl_sync(gm, acc, 0, 4), a1 = __shfl_sync(gm, acc, 1, 4), a2 = __shfl_sync(gm, acc, 2, 4), a3 = __shfl_sync(gm, acc, 3, 4);
     u64 h;
     if (len >= 32) {

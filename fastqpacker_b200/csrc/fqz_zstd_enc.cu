@@ -980,7 +980,28 @@ __device__ static u64 xxh64_quad(const u8 *p, u32 len, u32 q /*0..3*/, u32 gmask
     u64 acc = (q == 0) ? XXP1 + XXP2 : (q == 1) ? XXP2 : (q == 2) ? 0ull : 0ull - XXP1;
     u32 nstripes = len >> 5;
     const u8 *s = p + 8u * q;
-    for (u32 i = 0; i < nstripes; i++) acc = xxh_round(acc, ld_u64_unaligned(s + 32ull * i));
+    {
+        // the rounds are a serial multiply-rotate chain, the loads are not: keep 8 stripes in flight
+        // (three aligned words cover any 8 unaligned bytes, merged with funnel shifts)
+        const u32 *w = (const u32 *)((uintptr_t)s & ~(uintptr_t)3);
+        const u32 sh = (u32)((uintptr_t)s & 3u) * 8u;
+        u32 i = 0;
+        for (; i + 8 <= nstripes; i += 8) {
+            u32 a[8], b[8], c[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a[k] = w[8 * (i + k)];
+                b[k] = w[8 * (i + k) + 1];
+                c[k] = w[8 * (i + k) + 2];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                u64 v = (u64)__funnelshift_r(a[k], b[k], sh) | ((u64)__funnelshift_r(b[k], c[k], sh) << 32);
+                acc = xxh_round(acc, v);
+            }
+        }
+        for (; i < nstripes; i++) acc = xxh_round(acc, ld_u64_unaligned(s + 32ull * i));
+    }
     u64 a0 = __shfl_sync(gmask, acc, 0, 4), a1 = __shfl_sync(gmask, acc, 1, 4), a2 = __shfl_sync(gmask, acc, 2, 4), a3 = __shfl_sync(gmask, acc, 3, 4);
     u64 h;
     if (len >= 32) {
