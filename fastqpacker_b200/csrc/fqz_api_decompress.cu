@@ -41,8 +41,9 @@ static int backend_error(fqz_ctx *c, const std::vector<BkBlock> &blks, u64 key, 
 
 // Back end over blocks whose six decoded streams are resident in HBM.  d_out == nullptr: the
 // output is allocated from the arena and returned in *d_res.
+// io_slot >= 0: the output goes to that staging slot of the copy pipeline instead of the arena.
 static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *d_out, size_t out_cap, u8 **d_res, size_t *out_len,
-                       u64 block_base) {
+                       u64 block_base, int io_slot = -1) {
     cudaStream_t s = c->stream;
     u32 nb = (u32)blks.size();
     u64 R = 0;
@@ -119,7 +120,8 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
     if (d_out) {
         if (total > out_cap) return FQZ_E_NOSPACE;
     } else {
-        d_out = (u8 *)c->arena.alloc((size_t)total + 64);
+        if (io_slot >= 0) FQZ_TRY(fqz_io_out_acquire(c, io_slot, (size_t)total + 64, &d_out));
+        else d_out = (u8 *)c->arena.alloc((size_t)total + 64);
         if (!d_out) {
             c->err = "arena: out of device memory (FASTQ output)";
             return FQZ_E_CUDA;
@@ -143,7 +145,7 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
 
 // Entropy stage + back end for `nb` blocks of a container resident at d_fqz.
 static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, u32 nb, u32 phred64, u8 *d_out, size_t out_cap, u8 **d_res,
-                         size_t *out_len, u64 block_base) {
+                         size_t *out_len, u64 block_base, int io_slot = -1) {
     std::vector<ZDStream> zs((size_t)nb * 6);
     for (u32 b = 0; b < nb; b++) {
         u64 off = ent[b].payload_off;
@@ -175,7 +177,7 @@ static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, 
         B.pad = 0;
         B.rec_base = 0;
     }
-    return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base);
+    return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base, io_slot);
 }
 
 struct DecState {
@@ -184,12 +186,16 @@ struct DecState {
     u64 block_base = 0;  // blocks decoded so far (error texts)
 };
 
-// Parses the 10-byte file header at d_fqz (container.go:48-67; version check compress.go:571-573).
+// Parses the 10-byte file header (container.go:48-67; version check compress.go:571-573).
+static int parse_file_header(fqz_ctx *c, const u8 *h, u64 n, DecState &st);
 static int read_file_header(fqz_ctx *c, const u8 *d_fqz, u64 n, DecState &st) {
     u8 *h = c->h_pin + 128;
     size_t take = (size_t)std::min<u64>(n, 10);
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_fqz, take, cudaMemcpyDeviceToHost, c->stream));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return parse_file_header(c, h, n, st);
+}
+static int parse_file_header(fqz_ctx *c, const u8 *h, u64 n, DecState &st) {
     if (n < 4) return FQZ_E_TRUNC_FILE;
     if (!(h[0] == 'F' && h[1] == 'Q' && h[2] == 'Z' && h[3] == 0)) return FQZ_E_MAGIC;
     if (n < 10) return FQZ_E_TRUNC_FILE;
@@ -208,16 +214,27 @@ static int read_file_header(fqz_ctx *c, const u8 *d_fqz, u64 n, DecState &st) {
 // Decodes the complete blocks of d_fqz[pos0, n).  d_out != nullptr: FASTQ goes to that device
 // buffer; else each window is staged in the arena and copied to h_out.  *consumed = offset after
 // the last block decoded.  A partial trailing block is an error only when is_last.
+// host_io: d_fqz is c->io.d_in still being uploaded; windows gate on the chunks they read and
+// every window's FASTQ is downloaded from an alternating staging slot while the next one is decoded.
 static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool is_last, bool partial_ok, DecState &st, u8 *d_out, u8 *h_out,
-                             size_t out_cap, size_t *out_len, u64 *consumed) {
+                             size_t out_cap, size_t *out_len, u64 *consumed, bool host_io = false) {
     cudaStream_t s = c->stream;
     u64 pos = pos0;
     size_t written = 0;
     *out_len = 0;
     *consumed = pos0;
     std::vector<FqzBlockEntry> ent;
-    while (pos < n) {
+    u64 n_all = n;
+    u64 want = 0;
+    int win = 0;
+    while (pos < n_all) {
         c->arena.reset();
+        if (host_io) {  // the walk must not look at bytes that have not arrived yet
+            size_t avail = 0;
+            want = std::max<u64>(want, pos + DEC_WINDOW_BYTES + ((u64)32 << 20));
+            FQZ_TRY(fqz_io_gate(c, (size_t)std::min<u64>(n_all, want), &avail));
+            n = avail;
+        }
         FqzBlockEntry *d_tab = (FqzBlockEntry *)c->arena.alloc(DEC_TABLE_CAP * sizeof(FqzBlockEntry));
         FqzWalkResult *d_wr = (FqzWalkResult *)c->arena.alloc(sizeof(FqzWalkResult));
         if (!d_tab || !d_wr) return FQZ_E_CUDA;
@@ -241,8 +258,9 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
             c->arena.reset();  // the table lives on in `ent`
             size_t wl = 0;
             u8 *d_res = nullptr;
+            int slot = host_io ? (win & 1) : -1;
             int rc = decode_blocks(c, d_fqz, ent.data() + done, take, st.phred64, d_out ? d_out + written : nullptr, out_cap - written,
-                                   &d_res, &wl, st.block_base);
+                                   &d_res, &wl, st.block_base, slot);
             if (rc == FQZ_E_TOO_LARGE && take > 1) {  // the window decodes to more than one device pass holds
                 take = (take + 1) / 2;
                 continue;
@@ -258,9 +276,14 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
             }
             if (rc != FQZ_OK) return rc;
             if (!d_out && wl) {
-                StageScope sc(c, ST_COPY, wl);
-                FQZ_CUDA_TRY(c, cudaMemcpyAsync(h_out + written, d_res, wl, cudaMemcpyDeviceToHost, s));
-                FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+                if (host_io) {
+                    FQZ_TRY(fqz_io_download(c, slot, h_out + written, d_res, wl));
+                    win++;
+                } else {
+                    StageScope sc(c, ST_COPY, wl);
+                    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h_out + written, d_res, wl, cudaMemcpyDeviceToHost, s));
+                    FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+                }
             }
             written += wl;
             done += take;
@@ -271,6 +294,10 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
             pos = end;
             *consumed = pos;
             *out_len = written;
+        }
+        if (wr.status && n < n_all) {  // ran into bytes still in flight, not a truncated file: widen the gate
+            if (wr.nblocks == 0) want = std::max<u64>(want, n + DEC_WINDOW_BYTES);
+            continue;
         }
         if (wr.status) {  // truncated block header / payload after the blocks just decoded
             if (is_last) {
@@ -303,21 +330,19 @@ extern "C" int fqz_decompress(fqz_ctx *c, const uint8_t *fqz, size_t n, uint8_t 
     cudaSetDevice(c->device);
     c->err.clear();
     *out_len = 0;
-    u8 *d_in = nullptr;
-    FQZ_CUDA_TRY(c, cudaMalloc((void **)&d_in, n + 256));
-    int rc = FQZ_OK;
-    do {
-        if (cudaMemsetAsync(d_in + (n & ~(size_t)15), 0, 64, c->stream) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-        if (n && cudaMemcpyAsync(d_in, fqz, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-        DecState st;
-        rc = read_file_header(c, d_in, n, st);
-        if (rc != FQZ_OK) break;
+    DecState st;
+    FQZ_TRY(parse_file_header(c, fqz, n, st));  // the header is read on the host; the payload streams to the device
+    int rc = fqz_io_upload(c, fqz, n);
+    size_t m = 0;
+    if (rc == FQZ_OK) {
         u64 used = 0;
         static u8 dummy;
-        rc = decompress_blocks(c, d_in, n, 10, true, false, st, nullptr, out ? out : &dummy, out_cap, out_len, &used);
-    } while (0);
+        rc = decompress_blocks(c, c->io.d_in, n, 10, true, false, st, nullptr, out ? out : &dummy, out_cap, &m, &used, true);
+    }
+    int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *out_len = m;
     if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
-    cudaFree(d_in);
     return rc;
 }
 

@@ -255,9 +255,12 @@ struct CompState {
 // Compresses d_fastq[0..n) window by window (each window cut at a block boundary; the host only
 // walks, all data stays in HBM).  !is_last: only whole 100 000-record blocks are taken and
 // *consumed tells the caller where the unconsumed tail starts.
+// h_out != nullptr: host pipeline mode — d_fastq is c->io.d_in still being uploaded (every window
+// first gates the compute stream on the chunks it reads) and each window's output is downloaded to
+// h_out on the copy stream while the next window is coded.
 static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_last, CompState &st, u32 header_block_size, u8 *d_out,
-                                size_t out_cap, size_t *out_len, u64 *consumed) {
-    const u64 WIN = (u64)1 << 30;
+                                size_t out_cap, size_t *out_len, u64 *consumed, u8 *h_out = nullptr, size_t h_cap = 0) {
+    const u64 WIN = (u64)1 << 30;  // the entropy kernels are latency-bound per frame: large windows keep every SM busy
     u64 pos = 0;
     size_t written = 0;
     *out_len = 0;
@@ -271,6 +274,7 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
             take = WIN;
             last = false;
         }
+        if (h_out) FQZ_TRY(fqz_io_gate(c, pos + take, nullptr));
         // windows must start 16-byte aligned for the vector loads: copy the unaligned remainder
         const u8 *wptr = d_fastq + pos;
         if (((uintptr_t)wptr & 15u) != 0) {
@@ -295,6 +299,13 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
             return rc;
         }
         if (st.first) st.phred64 = ph;
+        if (h_out) {
+            if (written + wl > h_cap) {
+                *out_len = written + wl;
+                return FQZ_E_NOSPACE;
+            }
+            FQZ_TRY(fqz_io_download(c, 0, h_out + written, d_out + written, wl));
+        }
         written += wl;
         pos += (last && is_last) ? left : used;
         st.rec_base += recs;
@@ -390,30 +401,19 @@ extern "C" int fqz_compress(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t
     c->err.clear();
     c->arena.reset();
     *out_len = 0;
-    cudaStream_t s = c->stream;
     size_t ocap = fqz_compress_bound(n);
-    u8 *d_in = nullptr, *d_o = nullptr;
-    // input and output live outside the per-window arena
-    FQZ_CUDA_TRY(c, cudaMalloc((void **)&d_in, n + 256));
-    if (cudaMalloc((void **)&d_o, ocap + 256) != cudaSuccess) {
-        cudaFree(d_in);
-        c->err = "cudaMalloc(output)";
-        return FQZ_E_CUDA;
-    }
-    int rc = FQZ_OK;
+    u8 *d_o = nullptr;
+    int rc = fqz_io_upload(c, fastq, n);
+    if (rc == FQZ_OK) rc = fqz_io_out_acquire(c, 0, ocap, &d_o);
     size_t m = 0;
-    do {
-        if (cudaMemsetAsync(d_in + (n & ~(size_t)15), 0, 64, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-        if (n && cudaMemcpyAsync(d_in, fastq, n, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-        rc = fqz_compress_device(c, d_in, n, header_block_size, d_o, ocap, &m);
-        if (rc != FQZ_OK) break;
-        *out_len = m;
-        if (m > out_cap) { rc = FQZ_E_NOSPACE; break; }
-        if (cudaMemcpyAsync(out, d_o, m, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-        if (cudaStreamSynchronize(s) != cudaSuccess) { rc = FQZ_E_CUDA; break; }
-    } while (0);
+    if (rc == FQZ_OK) {
+        CompState st;
+        u64 used = 0;
+        rc = compress_device_impl(c, c->io.d_in, n, true, st, header_block_size, d_o, ocap, &m, &used, out, out_cap);
+    }
+    int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *out_len = m;
     if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
-    cudaFree(d_in);
-    cudaFree(d_o);
     return rc;
 }

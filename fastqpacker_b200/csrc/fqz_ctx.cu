@@ -120,6 +120,116 @@ int fqz_io_reserve(fqz_ctx *c, size_t bytes) {
     return FQZ_OK;
 }
 
+// ---------------------------------------------------------------------------------- copy pipeline
+static int io_init(fqz_ctx *c) {
+    IoPipe &io = c->io;
+    if (io.s_h2d) return FQZ_OK;
+    FQZ_CUDA_TRY(c, cudaStreamCreateWithFlags(&io.s_h2d, cudaStreamNonBlocking));
+    FQZ_CUDA_TRY(c, cudaStreamCreateWithFlags(&io.s_d2h, cudaStreamNonBlocking));
+    FQZ_CUDA_TRY(c, cudaEventCreateWithFlags(&io.ev_done, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) FQZ_CUDA_TRY(c, cudaEventCreateWithFlags(&io.ev_out[k], cudaEventDisableTiming));
+    return FQZ_OK;
+}
+static int io_dev_reserve(fqz_ctx *c, u8 **p, size_t *cap, size_t need) {
+    if (need <= *cap) return FQZ_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 8 + 4096;
+    FQZ_CUDA_TRY(c, cudaMalloc((void **)p, want));
+    *cap = want;
+    return FQZ_OK;
+}
+int fqz_io_upload(fqz_ctx *c, const u8 *host, size_t n) {
+    FQZ_TRY(io_init(c));
+    IoPipe &io = c->io;
+    FQZ_TRY(io_dev_reserve(c, &io.d_in, &io.in_cap, n + 256));
+    size_t nchunks = (n + FQZ_IO_CHUNK - 1) / FQZ_IO_CHUNK;
+    while (io.ev_chunk.size() < nchunks) {
+        cudaEvent_t e = nullptr;
+        FQZ_CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        io.ev_chunk.push_back(e);
+    }
+    io.n = n;
+    io.gated = 0;
+    // the slack after the input must hold defined bytes (vector loads look a few bytes past the end)
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(io.d_in + (n & ~(size_t)15), 0, 64, io.s_h2d));
+    for (size_t k = 0; k < nchunks; k++) {
+        size_t off = k * FQZ_IO_CHUNK, len = n - off < FQZ_IO_CHUNK ? n - off : FQZ_IO_CHUNK;
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(io.d_in + off, host + off, len, cudaMemcpyHostToDevice, io.s_h2d));
+        FQZ_CUDA_TRY(c, cudaEventRecord(io.ev_chunk[k], io.s_h2d));
+    }
+    if (nchunks == 0) {  // empty input: still order the memset before the compute stream
+        if (io.ev_chunk.empty()) {
+            cudaEvent_t e = nullptr;
+            FQZ_CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            io.ev_chunk.push_back(e);
+        }
+        FQZ_CUDA_TRY(c, cudaEventRecord(io.ev_chunk[0], io.s_h2d));
+        FQZ_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, io.ev_chunk[0], 0));
+    }
+    return FQZ_OK;
+}
+int fqz_io_gate(fqz_ctx *c, size_t upto, size_t *avail) {
+    IoPipe &io = c->io;
+    if (upto > io.n) upto = io.n;
+    if (upto > io.gated) {
+        size_t k = (upto - 1) / FQZ_IO_CHUNK;  // chunks complete in order on one stream: waiting for the last one is enough
+        FQZ_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, io.ev_chunk[k], 0));
+        size_t end = (k + 1) * FQZ_IO_CHUNK;
+        io.gated = end < io.n ? end : io.n;
+    }
+    if (avail) *avail = io.gated;
+    return FQZ_OK;
+}
+int fqz_io_out_acquire(fqz_ctx *c, int slot, size_t bytes, u8 **p) {
+    FQZ_TRY(io_init(c));
+    IoPipe &io = c->io;
+    if (io.out_busy[slot]) {  // the previous download from this slot must have drained
+        FQZ_CUDA_TRY(c, cudaEventSynchronize(io.ev_out[slot]));
+        io.out_busy[slot] = false;
+    }
+    FQZ_TRY(io_dev_reserve(c, &io.d_out[slot], &io.out_cap[slot], bytes + 256));
+    *p = io.d_out[slot];
+    return FQZ_OK;
+}
+int fqz_io_download(fqz_ctx *c, int slot, u8 *host_dst, const u8 *dev_src, size_t bytes) {
+    IoPipe &io = c->io;
+    if (!bytes) return FQZ_OK;
+    FQZ_CUDA_TRY(c, cudaEventRecord(io.ev_done, c->stream));
+    FQZ_CUDA_TRY(c, cudaStreamWaitEvent(io.s_d2h, io.ev_done, 0));
+    FQZ_CUDA_TRY(c, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, io.s_d2h));
+    FQZ_CUDA_TRY(c, cudaEventRecord(io.ev_out[slot], io.s_d2h));
+    io.out_busy[slot] = true;
+    return FQZ_OK;
+}
+int fqz_io_finish(fqz_ctx *c) {
+    IoPipe &io = c->io;
+    if (!io.s_h2d) return FQZ_OK;
+    cudaError_t e1 = cudaStreamSynchronize(io.s_h2d), e2 = cudaStreamSynchronize(io.s_d2h), e3 = cudaStreamSynchronize(c->stream);
+    io.out_busy[0] = io.out_busy[1] = false;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        c->err = std::string("copy pipeline: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+        return FQZ_E_CUDA;
+    }
+    return FQZ_OK;
+}
+void fqz_io_release(fqz_ctx *c) {
+    IoPipe &io = c->io;
+    if (io.s_h2d) cudaStreamSynchronize(io.s_h2d);
+    if (io.s_d2h) cudaStreamSynchronize(io.s_d2h);
+    if (io.d_in) cudaFree(io.d_in);
+    for (int k = 0; k < 2; k++) {
+        if (io.d_out[k]) cudaFree(io.d_out[k]);
+        if (io.ev_out[k]) cudaEventDestroy(io.ev_out[k]);
+    }
+    if (io.ev_done) cudaEventDestroy(io.ev_done);
+    for (auto e : io.ev_chunk) cudaEventDestroy(e);
+    if (io.s_h2d) cudaStreamDestroy(io.s_h2d);
+    if (io.s_d2h) cudaStreamDestroy(io.s_d2h);
+    io = IoPipe();
+}
+
 extern "C" int fqz_abi_version(void) { return FQZ_ABI_VERSION; }
 
 extern "C" int fqz_init(int device, fqz_ctx **out) {
@@ -156,6 +266,7 @@ extern "C" void fqz_destroy(fqz_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->prof.collect();
     for (auto e : c->prof.pool) cudaEventDestroy(e);
+    fqz_io_release(c);
     c->arena.release();
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_phred) cudaFree(c->d_phred);

@@ -71,6 +71,23 @@ struct Profiler {
     void clear();
 };
 
+// Host-buffer entry points: copy engine pipeline.  Input is uploaded in chunks on its own stream
+// (an event per chunk gates the compute stream), results are downloaded on a third stream while the
+// next window is being coded.  Device staging buffers persist across calls (no cudaMalloc per call).
+#define FQZ_IO_CHUNK ((size_t)32 << 20)
+struct IoPipe {
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    u8 *d_in = nullptr;
+    size_t in_cap = 0;
+    u8 *d_out[2] = {nullptr, nullptr};
+    size_t out_cap[2] = {0, 0};
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};  // download of slot k finished
+    bool out_busy[2] = {false, false};
+    cudaEvent_t ev_done = nullptr;                // compute of a window finished
+    std::vector<cudaEvent_t> ev_chunk;
+    size_t n = 0, gated = 0;  // input bytes of the current call / bytes the compute stream already waits for
+};
+
 struct fqz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -85,6 +102,7 @@ struct fqz_ctx {
     size_t h_io_cap = 0;
     int sm_count = 148;
     u64 launches_base = 0;
+    IoPipe io;
 };
 
 // RAII stage marker: CUDA events around the launches of one pipeline stage when profiling is on
@@ -99,6 +117,13 @@ struct StageScope {
 
 int fqz_pin_reserve(fqz_ctx *c, size_t bytes);
 int fqz_io_reserve(fqz_ctx *c, size_t bytes);
+// ---- copy pipeline (fqz_ctx.cu)
+int fqz_io_upload(fqz_ctx *c, const u8 *host, size_t n);             // starts the chunked upload into c->io.d_in
+int fqz_io_gate(fqz_ctx *c, size_t upto, size_t *avail);             // compute stream waits until [0, upto) has arrived
+int fqz_io_out_acquire(fqz_ctx *c, int slot, size_t bytes, u8 **p);  // device staging for one window's output
+int fqz_io_download(fqz_ctx *c, int slot, u8 *host_dst, const u8 *dev_src, size_t bytes);  // after the compute queued so far
+int fqz_io_finish(fqz_ctx *c);
+void fqz_io_release(fqz_ctx *c);
 int fqz_scan_excl_u32(fqz_ctx *c, u32 *d, u64 n, u64 stride, u32 narr);
 
 // ---- zstd decode stage (fqz_api_dec.cu)
