@@ -118,6 +118,8 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
         return kErrOfKind[kind < 5 ? kind : 0];
     }
     out.phred64 = *hphred;
+    out.d_offs = d_sizes;
+    out.offs_stride = stride;
     out.consumed = R ? (u64)(*hcons) + 1 : (is_last ? n : 0);
     if (is_last && R == R_all) out.consumed = n;  // an unterminated / partial last record is dropped
     for (int a = 0; a < 5; a++) out.blk_off[a].assign(hb + a * (out.nblocks + 1), hb + (a + 1) * (out.nblocks + 1));

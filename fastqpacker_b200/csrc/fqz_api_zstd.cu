@@ -49,22 +49,27 @@ __global__ void k_write_block_headers(u32 nblocks, const u32 *first, const u32 *
 // ---------------------------------------------------------------------------------- zstd batch
 struct ZBatch {
     std::vector<ZFrame> frames;
-    std::vector<u32> idx_ent, idx_lz;
+    std::vector<u32> idx_ent, idx_lz, idx_items;
     size_t slot_bytes = 0, ws_bytes = 0;
-    void add_stream(const u8 *d_src, size_t len, int policy) {
-        for (size_t o = 0; o < len; o += FQZ_ZFRAME) {
-            u32 l = (u32)std::min<size_t>(FQZ_ZFRAME, len - o);
+    // items / item_base / item_count: see ZFrame (policy FQZ_ZPOLICY_ITEMS only)
+    void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0) {
+        const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : FQZ_ZFRAME;
+        for (size_t o = 0; o < len; o += fsz) {
+            u32 l = (u32)std::min<size_t>(fsz, len - o);
             ZFrame f;
             f.src = (u64)(uintptr_t)(d_src + o);
             f.dst_off = slot_bytes;
             f.ws_off = 0;
             f.src_len = l;
             f.policy = (u32)policy;
+            f.items = (u64)(uintptr_t)items;
+            f.item_base = item_base + (u32)o;
+            f.item_count = item_count;
             slot_bytes += FQZ_ZSLOT(l);
-            if (policy == FQZ_ZPOLICY_AUTO) {
+            if (policy == FQZ_ZPOLICY_AUTO || policy == FQZ_ZPOLICY_ITEMS) {
                 f.ws_off = ws_bytes;
                 ws_bytes += FQZ_ZWS(l);
-                idx_lz.push_back((u32)frames.size());
+                (policy == FQZ_ZPOLICY_ITEMS ? idx_items : idx_lz).push_back((u32)frames.size());
             } else
                 idx_ent.push_back((u32)frames.size());
             frames.push_back(f);
@@ -82,13 +87,14 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     cudaStream_t s = c->stream;
     u32 nf = (u32)zb.frames.size();
     ze.nframes = nf;
-    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size()) * sizeof(u32);
+    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size()) * sizeof(u32);
     FQZ_TRY(fqz_pin_reserve(c, 8192 + up));
     u8 *hp = c->h_pin + 4096;
     memcpy(hp, zb.frames.data(), (size_t)nf * sizeof(ZFrame));
     u32 *hidx = (u32 *)(hp + (size_t)nf * sizeof(ZFrame));
     if (!zb.idx_ent.empty()) memcpy(hidx, zb.idx_ent.data(), zb.idx_ent.size() * sizeof(u32));
     if (!zb.idx_lz.empty()) memcpy(hidx + zb.idx_ent.size(), zb.idx_lz.data(), zb.idx_lz.size() * sizeof(u32));
+    if (!zb.idx_items.empty()) memcpy(hidx + zb.idx_ent.size() + zb.idx_lz.size(), zb.idx_items.data(), zb.idx_items.size() * sizeof(u32));
     u8 *d_up = (u8 *)c->arena.alloc(up + 16);
     ze.d_slots = (u8 *)c->arena.alloc(zb.slot_bytes + 16);
     u8 *d_ws = (u8 *)c->arena.alloc(zb.ws_bytes + 16);
@@ -105,6 +111,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     u64 ent_bytes = 0, lz_bytes = 0;
     for (u32 i : zb.idx_ent) ent_bytes += zb.frames[i].src_len;
     for (u32 i : zb.idx_lz) lz_bytes += zb.frames[i].src_len;
+    for (u32 i : zb.idx_items) lz_bytes += zb.frames[i].src_len;
     {
         StageScope sc(c, ST_XXH64, src_bytes);
         fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
@@ -112,10 +119,12 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     {
         StageScope sc(c, ST_ZENC_LZ, lz_bytes);
         fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, s);
+        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size() + zb.idx_lz.size(), (u32)zb.idx_items.size(), d_hash, ze.d_slots, d_ws, ze.d_scan,
+                        2, s);
     }
     {
         StageScope sc(c, ST_ZENC_ENTROPY, ent_bytes);
-        fqz_launch_zenc(ze.d_frames, d_idx, (u32)zb.idx_ent.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 0, s);
+        fqz_launch_zenc_huf(ze.d_frames, d_idx, (u32)zb.idx_ent.size(), d_hash, ze.d_slots, ze.d_scan, s);
     }
     {
         StageScope sc(c, ST_SCAN, 0);
@@ -165,8 +174,8 @@ extern "C" int fqz_zstd_compress(fqz_ctx *c, const uint8_t *src, size_t n, int p
 // ---------------------------------------------------------------------------------- compress one window (device -> device)
 // Stream policies: packed bases and delta-coded qualities go through the literals-only path
 // (Huffman beats LZ+Huffman on them); the four structured streams get LZ77.
-static const int kStreamPolicy[6] = {FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_AUTO, FQZ_ZPOLICY_AUTO, FQZ_ZPOLICY_AUTO,
-                                     FQZ_ZPOLICY_AUTO};
+static const int kStreamPolicy[6] = {FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_ITEMS, FQZ_ZPOLICY_ITEMS, FQZ_ZPOLICY_ITEMS,
+                                     FQZ_ZPOLICY_ITEMS};
 
 // Compresses the whole blocks of d_text[0..n) into d_out.  Emits the 10-byte file header first
 // when `with_file_header`.  Returns bytes written in *out_len, text consumed in *consumed.
@@ -187,7 +196,12 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
         for (int a = 0; a < 6; a++) {
             first[(size_t)b * 6 + a] = (u32)zb.frames.size();
             size_t o0 = fo.blk_off[a][b], o1 = fo.blk_off[a][b + 1];
-            zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a]);
+            if (kStreamPolicy[a] == FQZ_ZPOLICY_ITEMS) {
+                // headers / plus lines / N positions: item starts = the scanned per-record offsets; lengths: 4-byte items
+                if (a < 5) zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride, (u32)o0, (u32)fo.R + 1);
+                else zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], nullptr, 0, 4);
+            } else
+                zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a]);
             stream_bytes += o1 - o0;
         }
     }

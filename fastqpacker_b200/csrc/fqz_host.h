@@ -145,6 +145,8 @@ struct FrontOut {
     u8 *d_streams[6] = {0};
     std::vector<u32> blk_off[6];  // nblocks+1 boundaries of each stream (bytes)
     std::vector<u32> orig;        // per block: sum of sequence lengths (== quality lengths)
+    const u32 *d_offs = nullptr;  // device: 5 arrays (seq, qual, hdr, plus, npos) of R+1 scanned stream offsets
+    u64 offs_stride = 0;
 };
 // phred_mode: -1 detect on the first block of the file (rec_base must be 0), -2 use c->d_phred as
 // already decided, 0/1 force.  max_records: cap on records taken (0 = all whole blocks / all).

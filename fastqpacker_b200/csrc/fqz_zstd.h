@@ -8,20 +8,28 @@
 // concatenated frames back to back.
 #define FQZ_ZFRAME 65536u
 #define FQZ_ZFRAME_LOG 16
+// literals-only policy: frames of up to eight 16 KiB blocks sharing one Huffman tree (k_zenc_huf)
+#define FQZ_ZFRAME_ENT 131072u
+#define FQZ_ZBLOCK_ENT 16384u
 #define FQZ_ZSLOT(len) ((((size_t)(len) + 512) + 15) & ~(size_t)15)  // output slot of one frame: raw fallback + table scratch always fit
-#define FQZ_ZWS(len) (((size_t)(len)*3 + 255) & ~(size_t)63)  // LZ workspace: literals + sequence arrays
+#define FQZ_ZWS(len) (((size_t)(len)*6 + 1023) & ~(size_t)63)  // LZ workspace: literals + match / sequence arrays (<= len/2 + 2 entries, 10 B each)
 
 struct ZFrame {
     u64 src;      // device address of the frame's content
     u64 dst_off;  // into the slot arena
     u64 ws_off;   // into the LZ workspace arena (policy AUTO only)
-    u32 src_len;  // 1..FQZ_ZFRAME
-    u32 policy;   // FQZ_ZPOLICY_*
+    u32 src_len;  // 1..FQZ_ZFRAME (policy AUTO) / 1..FQZ_ZFRAME_ENT (policy ENTROPY)
+    u32 policy;   // FQZ_ZPOLICY_* or FQZ_ZPOLICY_ITEMS
+    u64 items;      // item matcher: device address of the u32 item-start offsets of the stream (0 = fixed stride)
+    u32 item_base;  // offset of this frame's first byte in the coordinates of items[]
+    u32 item_count; // entries of items[] including the end sentinel; fixed stride: the stride in bytes
 };
+#define FQZ_ZPOLICY_ITEMS 2  // internal: LZ by item matcher (needs the item boundaries of the stream)
 
 #define ZENC_WARPS 4
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s);
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
                      cudaStream_t s);

@@ -49,6 +49,17 @@ struct WarpScratchLZ {
     u8 tmpsym[512];  // FSE symbol spreading
     short norm[64];
 };
+#define ZI_MAXM 8  // matches kept per item and lane (the rest of a pathological item stays literal)
+struct WarpScratchItems {
+    u32 hist[256];
+    u16 hlut[256];
+    union {
+        u32 mbuf[32 * ZI_MAXM * 2];  // per lane: (pos | len << 16, offset)
+        EntropyScratch e;
+    } u;
+    u8 tmpsym[512];
+    short norm[64];
+};
 struct WarpScratchEnt {
     u32 hist[256];
     u16 hlut[256];
@@ -663,7 +674,8 @@ __device__ static u32 warp_write_literals(const u8 *lit, u32 n, u8 *out, WS &S) 
 // ---------------------------------------------------------------------------------- sequences section
 // seq arrays: ll[] (u16), ml[] (u16, matchLength-3), of[] (u32: raw offset on entry, offBase after).
 // Returns section size; sets *ovf when the slot would overflow.
-__device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nseq, u8 *out, u32 cap, WarpScratchLZ &S, bool *ovf) {
+template <class WS>
+__device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nseq, u8 *out, u32 cap, WS &S, bool *ovf) {
     u32 lane = lane_id();
     *ovf = false;
     if (nseq == 0) {
@@ -877,6 +889,251 @@ __device__ static u32 warp_lz_parse(const u8 *src, u32 len, u16 *htab, u8 *lit, 
     return nseq;
 }
 
+// ---------------------------------------------------------------------------------- item matcher (warp)
+// The four structured streams are chains of items (u16 length + bytes per header / plus line,
+// u16 count + positions per read, u32 per length) and consecutive items resemble each other.
+// Instead of a hash-table search, every lane takes one item and tries two candidate offsets:
+//   d1 = length of the previous item  (item r aligned with item r-1 at their starts)
+//   d2 = length of this item          (aligned at their ends: what follows a variable-width field)
+// A match may run up to ZI_AHEAD bytes past its item, so that equal neighbours fuse into one long
+// match in the serial clean-up pass.  All 32 lanes work on 32 consecutive items at a time.
+#define ZI_AHEAD 32u
+#define ZI_MINMATCH 3u
+
+// number of leading positions q in [p, lim) with S[q] == S[q - d]
+__device__ __forceinline__ u32 zi_match_len(const u8 *S, u32 p, u32 d, u32 lim) {
+    u32 l = 0;
+    while (p + l < lim) {
+        u32 x = ld_u32_unaligned(S + p + l) ^ ld_u32_unaligned(S + p + l - d);
+        u32 rem = lim - (p + l);
+        if (x == 0) {
+            if (rem <= 4) return l + rem;
+            l += 4;
+        } else {
+            u32 k = ((u32)__ffs((int)x) - 1u) >> 3;
+            return l + min(k, rem);
+        }
+    }
+    return l;
+}
+
+// Parse of src[0..len) with item boundaries.  items != nullptr: items[i] - item_base is the frame
+// position of item i (monotonic, nitems entries, the last one an end sentinel); items == nullptr:
+// fixed stride `nitems` bytes.  Emits sequences into sll/sml/sof (raw offsets) and literals into lit.
+__device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, u32 item_base, u32 nitems, u32 *mbuf, u8 *lit, u16 *sll,
+                                      u16 *sml, u32 *sof, u16 *slo, u32 *nlit_out) {
+    u32 lane = lane_id();
+    // first item that overlaps the frame
+    long long i0 = 0, iend = 0;  // items [i0, iend) overlap [0, len)
+    if (items) {
+        // largest i with items[i] <= item_base (binary search, uniform)
+        u32 lo = 0, hi = nitems - 1;  // invariant: items[lo] <= item_base (items[0] is the stream start)
+        while (lo < hi) {
+            u32 mid = (lo + hi + 1) >> 1;
+            if (items[mid] <= item_base) lo = mid; else hi = mid - 1;
+        }
+        i0 = lo;
+        iend = (long long)nitems - 1;  // the sentinel is not an item
+    } else {
+        i0 = 0;  // frames of fixed-stride streams start on an item boundary
+        iend = ((long long)len + nitems - 1) / nitems;
+    }
+    u32 nm = 0;  // matches found so far (uncompacted list in sll = pos, sml = len, sof = offset)
+    bool have_tail = false;  // last entry of the list, kept in registers so that the next round can extend it
+    u32 tail_pos = 0, tail_end = 0, tail_off = 0, tail_idx = 0;
+    for (long long ib = i0; ib < iend; ib += 32) {
+        long long i = ib + lane;
+        long long s = 0, e = 0;
+        u32 d1 = 0, d2 = 0;
+        bool live = i < iend;
+        if (live) {
+            if (items) {
+                s = (long long)items[i] - item_base;
+                e = (long long)items[i + 1] - item_base;
+                d2 = (u32)(e - s);
+                d1 = (i > 0) ? (u32)(items[i] - items[i - 1]) : 0u;
+            } else {
+                s = i * nitems;
+                e = s + nitems;
+                d1 = d2 = nitems;
+            }
+            if (s >= (long long)len) live = false;
+        }
+        // uniform exit: item starts are monotonic, so once lane 0 is past the frame all lanes are
+        if (__all_sync(FULL, !live)) break;
+        u32 cnt = 0;
+        if (live) {
+            u32 p = (u32)max(s, 0ll), stop = (u32)min(e, (long long)len);
+            u32 lim = (u32)min((long long)len, e + (long long)ZI_AHEAD);
+            if (d1 > 65535u) d1 = 0;
+            if (d2 > 65535u || d2 == d1) d2 = 0;
+            while (p < stop && cnt < ZI_MAXM) {
+                u32 la = (d1 && p >= d1) ? zi_match_len(src, p, d1, lim) : 0u;
+                u32 lb = (d2 && p >= d2) ? zi_match_len(src, p, d2, lim) : 0u;
+                u32 best = max(la, lb);
+                if (best >= ZI_MINMATCH) {
+                    mbuf[(lane * ZI_MAXM + cnt) * 2] = p | (best << 16);
+                    mbuf[(lane * ZI_MAXM + cnt) * 2 + 1] = (la >= lb) ? d1 : d2;
+                    cnt++;
+                    p += best;
+                } else
+                    p += max(best, 1u);
+            }
+        }
+        // ---- fuse chains inside the round: the first match of an item is absorbed by the last match
+        //      of the item before it (or by the tail of the previous round) when both use the same
+        //      offset and touch; runs of fully matched items (the all-zero plus / N streams, equal
+        //      lengths) collapse into one entry instead of one per item
+        u32 fpos = 0, fend = 0, foff = 0, lpos = 0, lend = 0, loff = 0;
+        if (cnt) {
+            u32 v = mbuf[(lane * ZI_MAXM) * 2];
+            fpos = v & 0xFFFFu;
+            fend = fpos + (v >> 16);
+            foff = mbuf[(lane * ZI_MAXM) * 2 + 1];
+            u32 w = mbuf[(lane * ZI_MAXM + cnt - 1) * 2];
+            lpos = w & 0xFFFFu;
+            lend = lpos + (w >> 16);
+            loff = mbuf[(lane * ZI_MAXM + cnt - 1) * 2 + 1];
+        }
+        u32 pend_ = __shfl_up_sync(FULL, lend, 1), poff = __shfl_up_sync(FULL, loff, 1), pcnt = __shfl_up_sync(FULL, cnt, 1);
+        if (lane == 0) {
+            pend_ = tail_end;
+            poff = tail_off;
+            pcnt = have_tail ? 1u : 0u;
+        }
+        bool absorbed = cnt > 0 && pcnt > 0 && foff == poff && fpos <= pend_;
+        u32 A = __ballot_sync(FULL, absorbed), S1 = __ballot_sync(FULL, cnt == 1);
+        // chain that starts at lane h (h = -1: the tail): absorbed lanes h+1 .. h+t
+        auto chain_len = [&](int h) -> u32 {
+            if (h >= 31) return 0u;
+            u32 a = A >> (h + 1), s1 = S1 >> (h + 1);
+            u32 run = (u32)__ffs((int)~a) - 1u;   // consecutive absorbed lanes (ffs(0) = 0 -> 0xFFFFFFFF only if a == ~0)
+            if (~a == 0u) run = 32u;
+            u32 c1 = (~s1 == 0u) ? 32u : (u32)__ffs((int)~s1) - 1u;  // of which single-match items
+            u32 t = (run <= c1) ? run : c1 + 1u;
+            return min(t, 31u - (u32)h);
+        };
+        bool head = cnt > 0 && !(absorbed && cnt == 1);
+        u32 t_me = head ? chain_len((int)lane) : 0u;
+        u32 src_lane = min(lane + t_me, 31u);
+        u32 ext_end = __shfl_sync(FULL, fend, (int)src_lane);
+        if (t_me) lend = max(lend, ext_end);
+        // the tail of the previous round may grow (lane 0 speaks for it)
+        u32 t_tail = have_tail ? chain_len(-1) : 0u;
+        u32 tail_new_end = __shfl_sync(FULL, fend, (int)(t_tail ? t_tail - 1u : 0u));
+        if (t_tail) {
+            tail_end = max(tail_end, tail_new_end);
+            if (lane == 0) sml[tail_idx] = (u16)(tail_end - tail_pos);
+        }
+        u32 nwr = cnt - (absorbed ? 1u : 0u);
+        u32 incl = group_incl_scan(nwr, FULL, 32);
+        u32 tot = __shfl_sync(FULL, incl, 31);
+        u32 at = nm + incl - nwr;
+        for (u32 k = (absorbed ? 1u : 0u), o = 0; k < cnt; k++, o++) {
+            u32 v = mbuf[(lane * ZI_MAXM + k) * 2];
+            u32 pp = v & 0xFFFFu, ln = v >> 16;
+            if (k == cnt - 1) ln = lend - lpos;  // possibly extended over the absorbed neighbours
+            sll[at + o] = (u16)pp;
+            sml[at + o] = (u16)ln;  // < 65536: a match cannot start at 0
+            sof[at + o] = mbuf[(lane * ZI_MAXM + k) * 2 + 1];
+        }
+        // new tail = last entry written in this round
+        u32 W = __ballot_sync(FULL, nwr > 0);
+        if (W) {
+            int lw = 31 - __clz((int)W);
+            tail_pos = __shfl_sync(FULL, lpos, lw);
+            tail_end = __shfl_sync(FULL, lend, lw);
+            tail_off = __shfl_sync(FULL, loff, lw);
+            tail_idx = __shfl_sync(FULL, at + nwr - 1u, lw);
+            have_tail = true;
+        }
+        nm += tot;
+        __syncwarp();
+    }
+    __syncwarp();
+    // serial clean-up (lane 0): fuse / trim overlapping matches, turn positions into literal lengths
+    u32 nseq = 0, nlit = 0;
+    if (lane == 0) {
+        u32 pend = 0;      // end of the last kept match
+        u32 kpos = 0, klen = 0, koff = 0;
+        bool have = false;
+        for (u32 i = 0; i <= nm; i++) {
+            u32 p = 0, l = 0, o = 0;
+            bool last = (i == nm);
+            if (!last) {
+                p = sll[i];
+                l = sml[i];
+                o = sof[i];
+                if (have && o == koff && p <= kpos + klen) {  // same offset, touching or overlapping: one match
+                    u32 e2 = max(kpos + klen, p + l);
+                    klen = e2 - kpos;
+                    continue;
+                }
+                if (have && p < kpos + klen) {  // overlap with a different offset: keep what is left
+                    u32 cut = kpos + klen - p;
+                    if (l < cut + ZI_MINMATCH) continue;
+                    p += cut;
+                    l -= cut;
+                }
+            }
+            if (have) {  // flush the pending match
+                u32 ll = kpos - pend;
+                sll[nseq] = (u16)ll;
+                sml[nseq] = (u16)(klen - 3u);
+                sof[nseq] = koff;
+                slo[nseq] = (u16)nlit;
+                nlit += ll;
+                pend = kpos + klen;
+                nseq++;
+            }
+            if (!last) {
+                kpos = p;
+                klen = l;
+                koff = o;
+                have = true;
+            }
+        }
+        mbuf[0] = nseq;
+        mbuf[1] = nlit;
+        mbuf[2] = pend;
+    }
+    __syncwarp();
+    nseq = mbuf[0];
+    nlit = mbuf[1];
+    u32 pend = mbuf[2];
+#ifdef FQZ_EMU
+    if (lane == 0 && getenv("FQZ_DEBUG")) fprintf(stderr, "item_parse len %u nm %u nseq %u nlit(before tail) %u pend %u items %p stride/count %u\n", len, nm, nseq, nlit, pend, (const void *)items, nitems);
+#endif
+    __syncwarp();
+    // literals: the bytes in front of every match, then the tail
+    {
+        u32 mstart = 0;  // running sum of ll + ml is not needed: the source of sequence i ends where its match starts
+        (void)mstart;
+        // position of match i = (sum of ll and ml of sequences < i) + ll_i; recomputed with a warp scan per 32 sequences
+        u32 base = 0;
+        for (u32 i0s = 0; i0s < nseq; i0s += 32) {
+            u32 i = i0s + lane;
+            u32 ll = 0, ml = 0;
+            if (i < nseq) {
+                ll = sll[i];
+                ml = (u32)sml[i] + 3u;
+            }
+            u32 inc = group_incl_scan(ll + ml, FULL, 32);
+            u32 startpos = base + inc - (ll + ml);  // where this sequence's literals begin
+            if (i < nseq) {
+                u32 dsto = slo[i];
+                for (u32 k = 0; k < ll; k++) lit[dsto + k] = src[startpos + k];
+            }
+            base += __shfl_sync(FULL, inc, 31);
+        }
+    }
+    for (u32 i = pend + lane; i < len; i += 32) lit[nlit + (i - pend)] = src[i];
+    nlit += len - pend;
+    __syncwarp();
+    *nlit_out = nlit;
+    return nseq;
+}
+
 // ---------------------------------------------------------------------------------- frame writer
 __device__ __forceinline__ void write_frame_header(u8 *o, u32 len) {
     o[0] = 0x28; o[1] = 0xB5; o[2] = 0x2F; o[3] = 0xFD;
@@ -889,10 +1146,12 @@ __device__ __forceinline__ void write_block_header(u8 *o, u32 type, u32 size) {
     o[0] = (u8)h; o[1] = (u8)(h >> 8); o[2] = (u8)(h >> 16);
 }
 
-template <bool LZ>
+// MODE 0: literals-only (legacy, superseded by k_zenc_huf), 1: hash-table LZ77, 2: item matcher
+template <int MODE>
 __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
                                                           u8 *ws, u32 *out_sizes) {
-    typedef typename std::conditional<LZ, WarpScratchLZ, WarpScratchEnt>::type WS;
+    constexpr bool LZ = MODE != 0;
+    typedef typename std::conditional<MODE == 1, WarpScratchLZ, typename std::conditional<MODE == 2, WarpScratchItems, WarpScratchEnt>::type>::type WS;
     __shared__ WS scratch[ZENC_WARPS];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
     u32 wi = blockIdx.x * ZENC_WARPS + warp;
@@ -925,15 +1184,22 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
     if (!done) {
         u32 total = 0;
         bool ovf = false;
-        if (LZ && fr.policy == 0 && len >= 64) {
+        if (LZ && fr.policy != 1u /* FQZ_ZPOLICY_ENTROPY */ && len >= 64) {
             if constexpr (LZ) {
                 u8 *lit = ws + fr.ws_off;
-                u32 maxseq = len / 4 + 1;
+                // item matcher: the uncompacted match list holds at most one entry per two bytes (items are >= 2 bytes)
+                u32 maxseq = ((MODE == 2 ? len / 2 : len / 3) + 2u) & ~1u;  // even: keeps sof 4-byte aligned
                 u16 *sll = (u16 *)(lit + ((len + 15u) & ~15u));
                 u16 *sml = sll + maxseq;
-                u32 *sof = (u32 *)(sml + maxseq);  // 4*maxseq bytes after sll: 4-byte aligned
+                u32 *sof = (u32 *)(sml + maxseq);
                 u32 nlit = 0;
-                u32 nseq = warp_lz_parse(src, len, S.u.htab, lit, sll, sml, sof, &nlit);
+                u32 nseq;
+                if constexpr (MODE == 2) {
+                    u16 *slo = (u16 *)(sof + maxseq);
+                    nseq = warp_item_parse(src, len, (const u32 *)(uintptr_t)fr.items, fr.item_base, fr.item_count, S.u.mbuf, lit, sll, sml,
+                                           sof, slo, &nlit);
+                } else
+                    nseq = warp_lz_parse(src, len, S.u.htab, lit, sll, sml, sof, &nlit);
                 __syncwarp();
                 u32 lsz = warp_write_literals(nseq ? (const u8 *)lit : src, nlit, body, S);
                 __syncwarp();
@@ -965,6 +1231,392 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
         u32 hsh = hashes[fi];
         ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
         out_sizes[fi] = 13 + payload + 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------- literals-only frames: one CTA per frame
+// Frames of the ENTROPY policy (packed bases, delta-coded qualities) hold up to eight 16 KiB blocks
+// that share ONE Huffman tree: block 0 carries the tree description, blocks 1.. are "treeless"
+// (RFC 8878 literals type 3).  One CTA (8 warps) codes one frame:
+//   1. per-stream histograms (8 blocks x 4 streams, two u16 counters per word, coalesced 128-byte reads)
+//   2. frame histogram -> length-limited Huffman code (CTA-parallel rank sort, serial merge)
+//   3. exact size of every stream = <stream histogram, code lengths>  -> final layout, headers
+//   4. every warp encodes the four streams of its block straight into their final position: 128
+//      symbols per step, warp scan of the code lengths, bits OR-ed into a shared-memory stage that is
+//      flushed with aligned 32-bit stores
+// Decoders see ordinary multi-block frames; the GPU decoder decodes the 32 streams of a frame in parallel.
+#define ZH_THREADS 256
+#define ZH_WARPS 8
+#define ZH_STAGE_WORDS 192
+#define ZH_FLUSH_BITS 4096u
+#define ZH_MIN_HUF 1024u  // blocks / frames below this are stored raw
+
+struct ZhShared {
+    u32 shist[32][128];  // per-stream histograms: symbol s in bits 16*(s&1).. of word s>>1 (<= 4096 symbols per stream)
+    u32 hist[256];
+    u32 keys[256];
+    u16 hlut[256];  // code << 4 | nbBits
+    HufTmp huf;
+    u8 tmpsym[512];
+    short norm[64];
+    u8 tree[384];
+    u32 sbits[32], sdst[32], ssize[32];
+    u32 misc[8];  // 0 mode, 1 treeSize, 2 total bytes, 3 distinct, 4 maxSym, 5 maxBits
+    u32 stage[ZH_WARPS][ZH_STAGE_WORDS];
+};
+
+// histogram of src[a, b) (one Huffman stream) by one warp
+__device__ static void warp_stream_hist(const u8 *src, u32 a, u32 b, u32 *h2) {
+    u32 lane = lane_id();
+    u32 zeros = 0;
+#pragma unroll 4
+    for (u32 p = a + 4u * lane; p < b; p += 128u) {
+        u32 x = ld_u32_unaligned(src + p);
+        u32 nv = min(4u, b - p);
+#pragma unroll
+        for (u32 k = 0; k < 4; k++) {
+            u32 sy = (x >> (8u * k)) & 0xFFu;
+            if (k < nv) {
+                if (sy == 0) zeros++;
+                else atomicAdd(&h2[sy >> 1], 1u << (16u * (sy & 1u)));
+            }
+        }
+    }
+    zeros = __reduce_add_sync(FULL, zeros);
+    if (lane == 0 && zeros) atomicAdd(&h2[0], zeros);
+}
+
+// CTA-wide (256 threads) version of warp_huf_build: hist[256] -> H.len / hlut.  Returns maxBits
+// (0 when fewer than two distinct symbols); misc[3] = distinct symbols, misc[4] = last present symbol.
+__device__ static u32 cta_huf_build(const u32 *hist, u32 total, u16 *hlut, HufTmp &H, u32 *keys, u32 *misc) {
+    u32 tid = threadIdx.x;
+    u32 c = hist[tid];
+    u32 m = (u32)__syncthreads_count(c != 0);
+    if (tid == 0) misc[4] = 0;
+    __syncthreads();
+    if (c) atomicMax(&misc[4], tid);
+    if (tid == 0) misc[3] = m;
+    __syncthreads();
+    if (m < 2) return 0;
+    u32 maxBits = 0;
+    for (int iter = 0;; iter++) {
+        u32 flo = 0;
+        bool ones = false;
+        if (iter > 0) {
+            if (iter <= 7) flo = max(1u, total >> (11 - iter));
+            else ones = true;
+        }
+        u32 cs = c ? (ones ? 1u : max(c, flo)) : 0u;
+        keys[tid] = cs;
+        __syncthreads();
+        if (c) {  // rank among the present symbols by (count', symbol)
+            u32 rank = 0;
+            for (u32 t = 0; t < 256; t++) {
+                u32 kt = keys[t];
+                rank += (kt != 0 && (kt < cs || (kt == cs && t < tid))) ? 1u : 0u;
+            }
+            H.ssym[rank] = (u8)tid;
+            H.node_w[rank] = cs;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u32 li = 0, ni = m, ne = m;
+            for (u32 k = 0; k + 1 < m; k++) {
+                u32 a, b;
+                if (li < m && (ni >= ne || H.node_w[li] <= H.node_w[ni])) a = li++; else a = ni++;
+                if (li < m && (ni >= ne || H.node_w[li] <= H.node_w[ni])) b = li++; else b = ni++;
+                H.node_w[ne] = H.node_w[a] + H.node_w[b];
+                H.node_par[a] = (u16)ne;
+                H.node_par[b] = (u16)ne;
+                ne++;
+            }
+            u32 root = ne - 1;
+            H.node_dep[root] = 0;
+            u32 md = 0;
+            for (int i = (int)root - 1; i >= 0; i--) {
+                u32 d = H.node_dep[H.node_par[i]] + 1u;
+                H.node_dep[i] = (u8)min(d, 255u);
+                if ((u32)i < m && d > md) md = d;
+            }
+            misc[5] = md;
+        }
+        __syncthreads();
+        maxBits = misc[5];
+        __syncthreads();
+        if (maxBits <= HUF_MAXBITS) break;
+    }
+    H.len[tid] = 0;
+    __syncthreads();
+    if (tid < m) H.len[H.ssym[tid]] = H.node_dep[tid];
+    u32 *cnt_len = H.node_w;  // reuse: [l] symbols of length l, [16 + l] first code value of length l
+    __syncthreads();
+    if (tid < 32) cnt_len[tid] = 0;
+    __syncthreads();
+    u32 l = H.len[tid];
+    if (l) atomicAdd(&cnt_len[l], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        u32 cells = 0;
+        for (u32 w = 1; w <= maxBits; w++) {  // weight w <-> length maxBits+1-w
+            u32 ll = maxBits + 1 - w;
+            u32 cc = cnt_len[ll];
+            cnt_len[16 + ll] = cells >> (w - 1);
+            cells += cc << (w - 1);
+        }
+    }
+    __syncthreads();
+    u32 e = 0;
+    if (l) {
+        u32 idx = 0;
+        for (u32 t = 0; t < tid; t++) idx += (H.len[t] == l) ? 1u : 0u;
+        e = ((cnt_len[16 + l] + idx) << 4) | l;
+    }
+    hlut[tid] = (u16)e;
+    __syncthreads();
+    return maxBits;
+}
+
+// One warp encodes the Huffman stream of src[a, b) to dst (exactly ((bits + 1) + 7) / 8 bytes).
+// The LAST symbol goes to the lowest bits (the decoder reads the stream backwards).
+__device__ static void warp_stream_encode(const u8 *src, u32 a, u32 b, const u16 *hlut, u8 *dst, u32 *stage) {
+    u32 lane = lane_id();
+    const u32 al = (u32)((uintptr_t)dst & 3u);  // stage byte i <-> global byte gbase[i]
+    u8 *gbase = dst - al;
+    for (u32 i = lane; i < ZH_STAGE_WORDS; i += 32) stage[i] = 0;
+    __syncwarp();
+    u32 P = 8u * al;
+    bool first = true;
+    u32 m = b - a, T = (m + 127u) >> 7;
+    for (u32 t = 0; t < T; t++) {
+        int idx0 = (int)(b - 128u * t) - 4 * (int)(lane + 1u);  // lane 0 owns the highest indices = lowest bits
+        u64 v = 0;
+        u32 L = 0;
+        if (idx0 >= (int)a) {
+            u32 x = ld_u32_unaligned(src + idx0);
+#pragma unroll
+            for (int k = 3; k >= 0; k--) {
+                u32 e = hlut[(x >> (8 * k)) & 0xFFu];
+                v |= (u64)(e >> 4) << L;
+                L += e & 15u;
+            }
+        } else {
+            for (int k = 3; k >= 0; k--) {
+                int idx = idx0 + k;
+                if (idx >= (int)a) {
+                    u32 e = hlut[src[idx]];
+                    v |= (u64)(e >> 4) << L;
+                    L += e & 15u;
+                }
+            }
+        }
+        u32 incl = group_incl_scan(L, FULL, 32);
+        u32 tot = __shfl_sync(FULL, incl, 31);
+        u32 bit = P + incl - L;
+        if (L) {
+            u32 w = bit >> 5, sh = bit & 31u;
+            u32 v0 = (u32)v, v1 = (u32)(v >> 32);
+            atomicOr(&stage[w], v0 << sh);
+            u32 mid = __funnelshift_l(v0, v1, sh);
+            if (mid) atomicOr(&stage[w + 1], mid);
+            u32 hi = sh ? (v1 >> (32u - sh)) : 0u;
+            if (hi) atomicOr(&stage[w + 2], hi);
+        }
+        __syncwarp();
+        P += tot;
+        if (P >= ZH_FLUSH_BITS) {  // flush the complete words, keep the partial one
+            u32 nw = P >> 5;
+            for (u32 i = lane; i < nw; i += 32) {
+                u32 wv = stage[i];
+                u8 *g = gbase + 4u * i;
+                if (i == 0 && first && al) {
+                    for (u32 k = al; k < 4; k++) g[k] = (u8)(wv >> (8u * k));
+                } else
+                    *(u32 *)g = wv;
+            }
+            __syncwarp();
+            u32 carry = stage[nw];
+            __syncwarp();
+            for (u32 i = lane; i < nw + 4u; i += 32) stage[i] = 0;
+            __syncwarp();
+            if (lane == 0) stage[0] = carry;
+            __syncwarp();
+            gbase += 4u * nw;
+            P &= 31u;
+            first = false;
+        }
+    }
+    if (lane == 0) stage[P >> 5] |= 1u << (P & 31u);  // end mark
+    P += 1;
+    __syncwarp();
+    u32 nbytes = (P + 7u) >> 3;  // stage bytes in use (the first `al` of the first word are not ours)
+    u32 nw = nbytes >> 2;
+    for (u32 i = lane; i < nw; i += 32) {
+        u32 wv = stage[i];
+        u8 *g = gbase + 4u * i;
+        if (i == 0 && first && al) {
+            for (u32 k = al; k < 4; k++) g[k] = (u8)(wv >> (8u * k));
+        } else
+            *(u32 *)g = wv;
+    }
+    u32 t0 = 4u * nw;
+    if (lane < nbytes - t0) {
+        u32 i = t0 + lane;
+        if (!(first && i < al)) gbase[i] = (u8)(stage[i >> 2] >> (8u * (i & 3u)));
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
+                                                         u32 *out_sizes) {
+    __shared__ ZhShared S;
+    u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    u32 fi = index ? index[blockIdx.x] : blockIdx.x;
+    ZFrame fr = frames[fi];
+    const u8 *src = (const u8 *)(uintptr_t)fr.src;
+    u8 *out = slots + fr.dst_off;
+    const u32 n = fr.src_len;
+    const u32 nblk = (n + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT;  // <= 8
+    // ---- 1. per-stream histograms
+    for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) (&S.shist[0][0])[i] = 0;
+    __syncthreads();
+    if (warp < nblk) {
+        u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
+        for (u32 k = 0; k < 4; k++) {
+            u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
+            warp_stream_hist(src, a, b, S.shist[warp * 4 + k]);
+        }
+    }
+    __syncthreads();
+    {
+        u32 c = 0;
+        for (u32 st = 0; st < 32; st++) c += (S.shist[st][tid >> 1] >> (16u * (tid & 1u))) & 0xFFFFu;
+        S.hist[tid] = c;
+    }
+    __syncthreads();
+    // ---- 2. code
+    u32 mode = 0;  // 0 raw block, 1 RLE block, 2 Huffman blocks
+    u32 maxBits = 0;
+    if (n >= ZH_MIN_HUF) maxBits = cta_huf_build(S.hist, n, S.hlut, S.huf, S.keys, S.misc);
+    else {
+        u32 distinct = (u32)__syncthreads_count(S.hist[tid] != 0);
+        if (tid == 0) S.misc[3] = distinct;
+        __syncthreads();
+    }
+    const u32 distinct = S.misc[3];
+    if (distinct == 1 && n > 1) mode = 1;
+    else if (maxBits) {
+        if (tid == 0) S.misc[1] = huf_write_tree(S.tree, S.huf, maxBits, S.misc[4], S.norm, S.tmpsym);
+        // ---- 3. exact stream sizes
+        {
+            u32 st = tid >> 3, j = tid & 7u, bits = 0;
+            for (u32 sy = 32u * j; sy < 32u * j + 32u; sy++) bits += ((S.shist[st][sy >> 1] >> (16u * (sy & 1u))) & 0xFFFFu) * S.huf.len[sy];
+            bits = group_sum(bits, group_mask(8), 8);
+            if (j == 0) {
+                S.sbits[st] = bits;
+                S.ssize[st] = (bits + 8u) >> 3;  // + end mark, rounded up
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u32 treeSize = S.misc[1];
+            u32 off = 10;
+            for (u32 k = 0; k < nblk; k++) {
+                u32 bn = min(FQZ_ZBLOCK_ENT, n - k * FQZ_ZBLOCK_ENT);
+                if (bn < ZH_MIN_HUF) {  // short tail: raw block
+                    S.sdst[4 * k] = off + 3;
+                    off += 3 + bn;
+                } else {
+                    u32 pos = off + 3 + 5 + (k == 0 ? treeSize : 0u) + 6;
+                    for (u32 q = 0; q < 4; q++) {
+                        S.sdst[4 * k + q] = pos;
+                        pos += S.ssize[4 * k + q];
+                    }
+                    off = pos + 1;
+                }
+            }
+            S.misc[2] = off + 4;
+            S.misc[0] = (treeSize != 0 && off + 4 < n + 17u) ? 2u : 0u;
+        }
+        __syncthreads();
+        mode = S.misc[0];
+    }
+    const u32 hsh = hashes[fi];
+    if (mode == 2) {
+        if (tid == 0) {  // frame header, block headers, literals headers, tree, jump tables
+            u32 treeSize = S.misc[1];
+            out[0] = 0x28; out[1] = 0xB5; out[2] = 0x2F; out[3] = 0xFD;
+            out[4] = 0x84;  // FCS 4 bytes, window descriptor present, content checksum, no dictionary
+            out[5] = (u8)((17 - 10) << 3);  // window = 128 KiB
+            out[6] = (u8)n; out[7] = (u8)(n >> 8); out[8] = (u8)(n >> 16); out[9] = (u8)(n >> 24);
+            for (u32 k = 0; k < nblk; k++) {
+                u32 bn = min(FQZ_ZBLOCK_ENT, n - k * FQZ_ZBLOCK_ENT);
+                u32 lastf = (k + 1 == nblk) ? 1u : 0u;
+                if (bn < ZH_MIN_HUF) {
+                    u8 *bh = out + S.sdst[4 * k] - 3;
+                    u32 h = lastf | (0u << 1) | (bn << 3);
+                    bh[0] = (u8)h; bh[1] = (u8)(h >> 8); bh[2] = (u8)(h >> 16);
+                    continue;
+                }
+                u32 tsz = (k == 0) ? treeSize : 0u;
+                u8 *bh = out + S.sdst[4 * k] - 6 - tsz - 5 - 3;
+                u32 csize = tsz + 6 + S.ssize[4 * k] + S.ssize[4 * k + 1] + S.ssize[4 * k + 2] + S.ssize[4 * k + 3];
+                u32 content = 5 + csize + 1;
+                u32 h = lastf | (2u << 1) | (content << 3);
+                bh[0] = (u8)h; bh[1] = (u8)(h >> 8); bh[2] = (u8)(h >> 16);
+                u8 *lh = bh + 3;
+                u32 lw = (k == 0 ? 2u : 3u) | (3u << 2) | (bn << 4) | (csize << 22);  // 4 streams, 18-bit sizes
+                lh[0] = (u8)lw; lh[1] = (u8)(lw >> 8); lh[2] = (u8)(lw >> 16); lh[3] = (u8)(lw >> 24);
+                lh[4] = (u8)(csize >> 10);
+                u8 *tp = lh + 5;
+                for (u32 i = 0; i < tsz; i++) tp[i] = S.tree[i];
+                u8 *jt = tp + tsz;
+                st_u16_unaligned(jt, S.ssize[4 * k]);
+                st_u16_unaligned(jt + 2, S.ssize[4 * k + 1]);
+                st_u16_unaligned(jt + 4, S.ssize[4 * k + 2]);
+                out[S.sdst[4 * k + 3] + S.ssize[4 * k + 3]] = 0;  // sequences section: none
+            }
+            u8 *ck = out + S.misc[2] - 4;
+            ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
+            out_sizes[fi] = S.misc[2];
+        }
+        // ---- 4. encode
+        if (warp < nblk) {
+            u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
+            if (bn < ZH_MIN_HUF) {
+                u8 *d = out + S.sdst[4 * warp];
+                for (u32 i = lane; i < bn; i += 32) d[i] = src[b0 + i];
+            } else {
+                for (u32 k = 0; k < 4; k++) {
+                    u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
+                    warp_stream_encode(src, a, b, S.hlut, out + S.sdst[4 * warp + k], S.stage[warp]);
+                }
+            }
+        }
+        return;
+    }
+    // ---- raw / RLE: a single block
+    if (tid == 0) {
+        out[0] = 0x28; out[1] = 0xB5; out[2] = 0x2F; out[3] = 0xFD;
+        out[4] = 0x84;
+        out[5] = (u8)((17 - 10) << 3);
+        out[6] = (u8)n; out[7] = (u8)(n >> 8); out[8] = (u8)(n >> 16); out[9] = (u8)(n >> 24);
+        u32 h = 1u | (mode << 1) | (n << 3);
+        out[10] = (u8)h; out[11] = (u8)(h >> 8); out[12] = (u8)(h >> 16);
+        u32 payload = (mode == 1) ? 1u : n;
+        if (mode == 1) out[13] = src[0];
+        u8 *ck = out + 13 + payload;
+        ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
+        out_sizes[fi] = 13 + payload + 4;
+    }
+    if (mode == 0) {  // dst-aligned word copy
+        u8 *d = out + 13;
+        u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if (head > n) head = n;
+        if (tid < head) d[tid] = src[tid];
+        u32 nw = (n - head) >> 2;
+        for (u32 w = tid; w < nw; w += ZH_THREADS) *(u32 *)(d + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
+        u32 t0 = head + 4u * nw;
+        if (tid < n - t0) d[t0 + tid] = src[t0 + tid];
     }
 }
 
@@ -1056,10 +1708,15 @@ void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream
     u32 threads = 128, grid = (nframes * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_frames, grid, threads, 0, s, frames, nframes, hashes);
 }
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+    if (!nidx) return;
+    FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes);
+}
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
                      cudaStream_t s) {
     if (!nidx) return;
     u32 grid = (nidx + ZENC_WARPS - 1) / ZENC_WARPS;
-    if (lz) FQZ_LAUNCH(k_zenc<true>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes);
-    else FQZ_LAUNCH(k_zenc<false>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes);
+    if (lz == 2) FQZ_LAUNCH(k_zenc<2>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes);
+    else if (lz) FQZ_LAUNCH(k_zenc<1>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes);
+    else FQZ_LAUNCH(k_zenc<0>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes);
 }

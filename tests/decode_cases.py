@@ -56,6 +56,26 @@ def check_zstd_round_trip(ctx, oracle, name, policy, scale=1.0):
     assert ctx.zstd_decompress(z) == data
 
 
+ENT_SIZES = [1, 2, 31, 1023, 1024, 1025, 4099, 16383, 16384, 16385, 2 * 16384 + 500, 2 * 16384 + 1024, 131071, 131072, 131073, 131072 + 1023,
+             131072 + 1024, 3 * 131072 + 77]
+
+
+def check_zstd_ent_sizes(ctx, oracle, n):
+    """literals-only policy at block / frame boundaries (16 KiB blocks, 128 KiB frames, raw tails),
+    for compressible, incompressible and single-symbol content."""
+    rnd = random.Random(n)
+    skew = bytes(rnd.choice(b"\x00\x00\x00\x00\x00\x01\xff\x02\xfe\x07") for _ in range(n))
+    flat = bytes(rnd.randrange(256) for _ in range(n))
+    wide = bytes(min(255, int(rnd.expovariate(0.05))) for _ in range(n))  # many symbols, long codes
+    for data in (skew, flat, wide, b"\x07" * n):
+        z = ctx.zstd_compress(data, 1)
+        assert oracle.zstd_decompress(z) == data
+        assert ctx.zstd_decompress(z) == data
+    if n >= 4096:
+        assert len(ctx.zstd_compress(skew, 1)) < 0.45 * n
+        assert len(ctx.zstd_compress(flat, 1)) <= n + 17 * ((n + 131071) // 131072)
+
+
 def check_back_end(ctx, oracle, text):
     """six pre-entropy streams -> FASTQ == NumRecords x blockReader.writeRecord."""
     enc = oracle.encode_streams(text)

@@ -144,7 +144,8 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int m, in
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
     unsigned long long a[32]; emu::collective(mask, pred ? 1 : 0, a);
-    unsigned r = 0; for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r |= (unsigned)(a[i] & 1) << i; return r;
+    unsigned r = 0; for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r |= (unsigned)(a[i] & 1) << i;
+    return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
@@ -154,19 +155,23 @@ template <class T> static inline unsigned __match_any_sync(unsigned mask, T v) {
 }
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     unsigned long long a[32]; emu::collective(mask, v, a); unsigned r = 0;
-    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r += (unsigned)a[i]; return r;
+    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r += (unsigned)a[i];
+    return r;
 }
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
     unsigned long long a[32]; emu::collective(mask, v, a); unsigned r = 0xffffffffu;
-    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r = std::min(r, (unsigned)a[i]); return r;
+    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r = std::min(r, (unsigned)a[i]);
+    return r;
 }
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
     unsigned long long a[32]; emu::collective(mask, v, a); unsigned r = 0;
-    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r = std::max(r, (unsigned)a[i]); return r;
+    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r = std::max(r, (unsigned)a[i]);
+    return r;
 }
 static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
     unsigned long long a[32]; emu::collective(mask, v, a); unsigned r = 0;
-    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r |= (unsigned)a[i]; return r;
+    for (int i = 0; i < 32; i++) if ((mask >> i) & 1) r |= (unsigned)a[i];
+    return r;
 }
 
 // ------------------------------------------------------------------ atomics (single host thread)

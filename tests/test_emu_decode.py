@@ -4,6 +4,7 @@ the -m gpu ones (tests/test_gpu_decompress.py), which reuse these cases."""
 import pytest
 
 from tests.decode_cases import (
+    ENT_SIZES,
     ZSTD_DATA,
     check_back_end,
     check_decode_errors,
@@ -12,6 +13,7 @@ from tests.decode_cases import (
     check_round_trip,
     check_streaming,
     check_v1_file,
+    check_zstd_ent_sizes,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
 )
@@ -35,6 +37,11 @@ def test_zstd_decodes_libzstd_frames(emu, oracle, name, level):
 @pytest.mark.parametrize("name", sorted(ZSTD_DATA))
 def test_zstd_round_trip(emu, oracle, name, policy):
     check_zstd_round_trip(emu, oracle, name, policy, scale=0.25)
+
+
+@pytest.mark.parametrize("n", ENT_SIZES)
+def test_zstd_entropy_policy_sizes(emu, oracle, n):
+    check_zstd_ent_sizes(emu, oracle, n)
 
 
 @pytest.mark.parametrize("name", sorted(GOOD_CASES))

@@ -6,6 +6,7 @@ import pytest
 
 from tests import synth
 from tests.decode_cases import (
+    ENT_SIZES,
     ZSTD_DATA,
     check_back_end,
     check_decode_errors,
@@ -14,6 +15,7 @@ from tests.decode_cases import (
     check_round_trip,
     check_streaming,
     check_v1_file,
+    check_zstd_ent_sizes,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
 )
@@ -39,6 +41,11 @@ def test_zstd_decodes_libzstd_frames(ctx, oracle, name, level):
 @pytest.mark.parametrize("name", sorted(ZSTD_DATA))
 def test_zstd_round_trip(ctx, oracle, name, policy):
     check_zstd_round_trip(ctx, oracle, name, policy, scale=4.0)
+
+
+@pytest.mark.parametrize("n", ENT_SIZES + [5 * 131072 + 12345])
+def test_zstd_entropy_policy_sizes(ctx, oracle, n):
+    check_zstd_ent_sizes(ctx, oracle, n)
 
 
 @pytest.mark.parametrize("name", sorted(GOOD_CASES))
