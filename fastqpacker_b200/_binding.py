@@ -77,6 +77,7 @@ class FqzLibrary:
         self._opt(L, "fqz_zstd_decompress", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress", [vp, vp, sz, vp, sz, szp])
+        self._opt(L, "fqz_compress_shard", [vp, vp, sz, u32, i32, i32, vp, sz, szp, C.POINTER(C.c_int)])
         self._opt(L, "fqz_compress_device", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress_device", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress_bound", [sz], restype=sz)
@@ -199,6 +200,17 @@ class FqzContext:
         m = C.c_size_t(0)
         self._check(self.lib.L.fqz_compress(self.h, _ptr(a), a.size, block_size, _ptr(out), cap, C.byref(m)))
         return out[: m.value].tobytes()
+
+    def compress_shard(self, fastq, phred64: int = -1, file_header: bool = True, block_size: int = 0):
+        """One shard of a block-sharded file -> (bytes, phred64 flag in force); see fqz_compress_shard."""
+        a = _as_u8(fastq)
+        cap = int(self.lib.L.fqz_compress_bound(a.size))
+        out = np.empty(cap, dtype=np.uint8)
+        m, used = C.c_size_t(0), C.c_int(0)
+        self._check(
+            self.lib.L.fqz_compress_shard(self.h, _ptr(a), a.size, block_size, phred64, 1 if file_header else 0, _ptr(out), cap, C.byref(m), C.byref(used))
+        )
+        return out[: m.value].tobytes(), used.value
 
     def compress_into(self, fastq: np.ndarray, out: np.ndarray, block_size: int = 0) -> int:
         m = C.c_size_t(0)

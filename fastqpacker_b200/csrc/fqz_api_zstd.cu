@@ -264,6 +264,8 @@ struct CompState {
     bool first = true;
     u64 rec_base = 0;
     u32 phred64 = 0;
+    int forced_phred = -1;    // >= 0: the flag was decided elsewhere (block 0 lives on another GPU)
+    bool emit_header = true;  // false: a shard that is not the head of the file
 };
 
 // Compresses d_fastq[0..n) window by window (each window cut at a block boundary; the host only
@@ -302,7 +304,8 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
         size_t wl = 0;
         u64 used = 0, recs = 0;
         u32 ph = 0;
-        int rc = fqz_compress_window(c, wptr, take, last, st.rec_base, st.first ? -1 : (int)st.phred64, st.first, header_block_size,
+        int pmode = st.first ? (st.forced_phred >= 0 ? st.forced_phred : -1) : (int)st.phred64;
+        int rc = fqz_compress_window(c, wptr, take, last, st.rec_base, pmode, st.first && st.emit_header, header_block_size,
                                      d_out + written, out_cap - written, &wl, &used, &recs, &ph);
         if (rc == FQZ_E_NEED_MORE) {
             if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside a full device window
@@ -410,6 +413,11 @@ extern "C" int fqz_compress_feed(fqz_cstream *s, const uint8_t *fastq, size_t n,
 
 extern "C" int fqz_compress(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap,
                             size_t *out_len) {
+    return fqz_compress_shard(c, fastq, n, header_block_size, -1, 1, out, out_cap, out_len, nullptr);
+}
+
+extern "C" int fqz_compress_shard(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t header_block_size, int phred64, int emit_file_header,
+                                  uint8_t *out, size_t out_cap, size_t *out_len, int *phred64_used) {
     if (!c || !out_len || (!fastq && n) || !out) return FQZ_E_INVALID_ARG;
     cudaSetDevice(c->device);
     c->err.clear();
@@ -422,8 +430,11 @@ extern "C" int fqz_compress(fqz_ctx *c, const uint8_t *fastq, size_t n, uint32_t
     size_t m = 0;
     if (rc == FQZ_OK) {
         CompState st;
+        st.forced_phred = phred64 < 0 ? -1 : (phred64 ? 1 : 0);
+        st.emit_header = emit_file_header != 0;
         u64 used = 0;
         rc = compress_device_impl(c, c->io.d_in, n, true, st, header_block_size, d_o, ocap, &m, &used, out, out_cap);
+        if (phred64_used) *phred64_used = (int)st.phred64;
     }
     int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
     if (rc == FQZ_OK) rc = rc2;

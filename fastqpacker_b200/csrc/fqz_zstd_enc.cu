@@ -674,8 +674,26 @@ __device__ static u32 warp_write_literals(const u8 *lit, u32 n, u8 *out, WS &S) 
 // ---------------------------------------------------------------------------------- sequences section
 // seq arrays: ll[] (u16), ml[] (u16, matchLength-3), of[] (u32: raw offset on entry, offBase after).
 // Returns section size; sets *ovf when the slot would overflow.
+// offBase of one sequence given the repeat-offset history (RFC 8878 §3.1.1.5)
+__device__ __forceinline__ u32 zstd_off_base(u32 off, bool ll0, u32 &rep0, u32 &rep1, u32 &rep2) {
+    u32 ob;
+    if (!ll0) {
+        if (off == rep0) ob = 1;
+        else if (off == rep1) { ob = 2; rep1 = rep0; rep0 = off; }
+        else if (off == rep2) { ob = 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+        else { ob = off + 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+    } else {
+        if (off == rep1) { ob = 1; rep1 = rep0; rep0 = off; }
+        else if (off == rep2) { ob = 2; rep2 = rep1; rep1 = rep0; rep0 = off; }
+        else if (rep0 > 1 && off == rep0 - 1) { ob = 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+        else { ob = off + 3; rep2 = rep1; rep1 = rep0; rep0 = off; }
+    }
+    return ob;
+}
+
+// resolved: sof already holds offBase values (the item matcher resolves them in its clean-up pass)
 template <class WS>
-__device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nseq, u8 *out, u32 cap, WS &S, bool *ovf) {
+__device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nseq, u8 *out, u32 cap, WS &S, bool *ovf, bool resolved = false) {
     u32 lane = lane_id();
     *ovf = false;
     if (nseq == 0) {
@@ -683,7 +701,7 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
         return 1;
     }
     // 1. repeat-offset resolution (serial, RFC 8878 §3.1.1.5): offset -> offBase
-    if (lane == 0) {
+    if (lane == 0 && !resolved) {
         u32 rep0 = 1, rep1 = 4, rep2 = 8;
         for (u32 i = 0; i < nseq; i++) {
             u32 off = sof[i];
@@ -727,7 +745,6 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
         const u32 maxLog[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
         const u32 defLog[3] = {ZSTD_LL_DEFLOG, ZSTD_OF_DEFLOG, ZSTD_ML_DEFLOG};
         const u32 defMax[3] = {35, 28, 52};
-        u32 rleSym[3] = {0, 0, 0};
         for (int t = 0; t < 3; t++) {
             u32 maxSym = 0, most = 0, mostSym = 0;
             for (u32 s = 0; s < 64; s++)
@@ -746,7 +763,6 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
             FseCT &ct = S.u.e.fse[t];
             if (m == 1) {
                 out[o++] = (u8)mostSym;
-                rleSym[t] = mostSym;
                 tlog[t] = 0;
             } else if (m == 0) {
                 const short *dn = (t == 0) ? kLLDefNorm : (t == 1 ? kOFDefNorm : kMLDefNorm);
@@ -762,38 +778,64 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
             }
         }
         out[modes_at] = (u8)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));
-        // 3. interleaved FSE bitstream, written backwards (last sequence first)
+        S.hist[192] = o;
+        S.hist[193] = over ? 1u : 0u;
+        S.hist[194] = tlog[0];
+        S.hist[195] = tlog[1];
+        S.hist[196] = tlog[2];
+    }
+    __syncwarp();
+    // 3. interleaved FSE bitstream, written backwards (last sequence first).  The state chain is
+    //    serial (lane 0), but its operands are not: the warp stages 32 sequences at a time in shared
+    //    memory so that the chain never waits for global memory.
+    {
+        u32 o = S.hist[192];
+        over = S.hist[193] != 0;
+        u32 tl0 = S.hist[194], tl1 = S.hist[195], tl2 = S.hist[196];
+        u32 *stg = (u32 *)S.tmpsym;  // 32 x (ll | ml << 16), 32 x offBase: the table builders are done with it
+        BitW bw;
+        FseState sLL, sOF, sML;
+        if (lane == 0) bw.init(out + o, cap > o ? cap - o : 0);
+        bool started = false;
         if (!over) {
-            BitW bw;
-            bw.init(out + o, cap > o ? cap - o : 0);
-            FseState sLL, sOF, sML;
-            u32 i = nseq - 1;
-            u32 llc = zstd_ll_code(sll[i]), ofc = hibit32(sof[i]), mlc = zstd_ml_code(sml[i]);
-            sML.init(S.u.e.fse[2].tab, S.u.e.fse[2].dnb, S.u.e.fse[2].dfs, tlog[2], mlc);
-            sOF.init(S.u.e.fse[1].tab, S.u.e.fse[1].dnb, S.u.e.fse[1].dfs, tlog[1], ofc);
-            sLL.init(S.u.e.fse[0].tab, S.u.e.fse[0].dnb, S.u.e.fse[0].dfs, tlog[0], llc);
-            bw.add(sll[i] & ((1u << kLLBits[llc]) - 1u), kLLBits[llc]);
-            bw.add(sml[i] & ((1u << kMLBits[mlc]) - 1u), kMLBits[mlc]);
-            bw.add(sof[i] & ((1u << ofc) - 1u), ofc);
-            while (i-- > 0) {
-                llc = zstd_ll_code(sll[i]);
-                ofc = hibit32(sof[i]);
-                mlc = zstd_ml_code(sml[i]);
-                sOF.encode(bw, ofc);
-                sML.encode(bw, mlc);
-                sLL.encode(bw, llc);
-                bw.add(sll[i] & ((1u << kLLBits[llc]) - 1u), kLLBits[llc]);
-                bw.add(sml[i] & ((1u << kMLBits[mlc]) - 1u), kMLBits[mlc]);
-                bw.add(sof[i] & ((1u << ofc) - 1u), ofc);
+            for (u32 cend = nseq; cend > 0;) {
+                u32 cs = cend >= 32 ? cend - 32 : 0, cn = cend - cs;
+                __syncwarp();
+                if (lane < cn) {
+                    stg[lane] = (u32)sll[cs + lane] | ((u32)sml[cs + lane] << 16);
+                    stg[32 + lane] = sof[cs + lane];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    for (int k = (int)cn - 1; k >= 0; k--) {
+                        u32 vll = stg[k] & 0xFFFFu, vml = stg[k] >> 16, vof = stg[32 + k];
+                        u32 llc = zstd_ll_code(vll), ofc = hibit32(vof), mlc = zstd_ml_code(vml);
+                        if (!started) {
+                            sML.init(S.u.e.fse[2].tab, S.u.e.fse[2].dnb, S.u.e.fse[2].dfs, tl2, mlc);
+                            sOF.init(S.u.e.fse[1].tab, S.u.e.fse[1].dnb, S.u.e.fse[1].dfs, tl1, ofc);
+                            sLL.init(S.u.e.fse[0].tab, S.u.e.fse[0].dnb, S.u.e.fse[0].dfs, tl0, llc);
+                            started = true;
+                        } else {
+                            sOF.encode(bw, ofc);
+                            sML.encode(bw, mlc);
+                            sLL.encode(bw, llc);
+                        }
+                        bw.add(vll & ((1u << kLLBits[llc]) - 1u), kLLBits[llc]);
+                        bw.add(vml & ((1u << kMLBits[mlc]) - 1u), kMLBits[mlc]);
+                        bw.add(vof & ((1u << ofc) - 1u), ofc);
+                    }
+                }
+                cend = cs;
             }
-            sML.flush(bw);
-            sOF.flush(bw);
-            sLL.flush(bw);
-            u32 bs = bw.close();
-            over = bw.ovf;
-            total = o + bs;
+            if (lane == 0) {
+                sML.flush(bw);
+                sOF.flush(bw);
+                sLL.flush(bw);
+                u32 bs = bw.close();
+                over = bw.ovf;
+                total = o + bs;
+            }
         }
-        (void)rleSym;
     }
     total = __shfl_sync(FULL, total, 0);
     *ovf = __shfl_sync(FULL, over ? 1 : 0, 0) != 0;
@@ -1051,51 +1093,85 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
         __syncwarp();
     }
     __syncwarp();
-    // serial clean-up (lane 0): fuse / trim overlapping matches, turn positions into literal lengths
+    // serial clean-up (lane 0): fuse / trim what the rounds left overlapping, turn positions into
+    // literal lengths, resolve repeat offsets.  The list is read and written through shared-memory
+    // chunks of 32 entries so that the serial chain never waits for global memory.
     u32 nseq = 0, nlit = 0;
-    if (lane == 0) {
-        u32 pend = 0;      // end of the last kept match
+    {
+        u32 *inb = mbuf;             // 32 x (pos | len << 16), 32 x offset
+        u32 *outb = mbuf + 64;       // 64 x (ll | (ml-3) << 16), 64 x offBase, 64 x literal offset
+        u32 pend = 0;                // end of the last flushed match
         u32 kpos = 0, klen = 0, koff = 0;
         bool have = false;
-        for (u32 i = 0; i <= nm; i++) {
-            u32 p = 0, l = 0, o = 0;
-            bool last = (i == nm);
-            if (!last) {
-                p = sll[i];
-                l = sml[i];
-                o = sof[i];
-                if (have && o == koff && p <= kpos + klen) {  // same offset, touching or overlapping: one match
-                    u32 e2 = max(kpos + klen, p + l);
-                    klen = e2 - kpos;
-                    continue;
+        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        for (u32 base = 0; base <= nm; base += 32) {  // one extra iteration flushes the pending match
+            u32 cn = min(32u, nm - min(nm, base));
+            __syncwarp();
+            if (lane < cn) {
+                inb[lane] = (u32)sll[base + lane] | ((u32)sml[base + lane] << 16);
+                inb[32 + lane] = sof[base + lane];
+            }
+            __syncwarp();
+            u32 produced = 0;
+            if (lane == 0) {
+                bool final_round = base + 32 > nm;
+                for (u32 k = 0; k < cn + (final_round ? 1u : 0u); k++) {
+                    bool last = (k == cn);
+                    u32 p = 0, l = 0, o = 0;
+                    if (!last) {
+                        p = inb[k] & 0xFFFFu;
+                        l = inb[k] >> 16;
+                        o = inb[32 + k];
+                        if (have && o == koff && p <= kpos + klen) {  // same offset, touching or overlapping: one match
+                            klen = max(kpos + klen, p + l) - kpos;
+                            continue;
+                        }
+                        if (have && p < kpos + klen) {  // overlap with a different offset: keep what is left
+                            u32 cut = kpos + klen - p;
+                            if (l < cut + ZI_MINMATCH) continue;
+                            p += cut;
+                            l -= cut;
+                        }
+                    }
+                    if (have) {  // flush the pending match
+                        u32 ll = kpos - pend;
+                        u32 ob = zstd_off_base(koff, ll == 0, rep0, rep1, rep2);
+                        outb[produced] = ll | ((klen - 3u) << 16);
+                        outb[64 + produced] = ob;
+                        outb[128 + produced] = nlit;
+                        produced++;
+                        nlit += ll;
+                        pend = kpos + klen;
+                    }
+                    if (!last) {
+                        kpos = p;
+                        klen = l;
+                        koff = o;
+                        have = true;
+                    } else
+                        have = false;
                 }
-                if (have && p < kpos + klen) {  // overlap with a different offset: keep what is left
-                    u32 cut = kpos + klen - p;
-                    if (l < cut + ZI_MINMATCH) continue;
-                    p += cut;
-                    l -= cut;
-                }
+                outb[192] = produced;
+                outb[193] = nlit;
+                outb[194] = pend;
             }
-            if (have) {  // flush the pending match
-                u32 ll = kpos - pend;
-                sll[nseq] = (u16)ll;
-                sml[nseq] = (u16)(klen - 3u);
-                sof[nseq] = koff;
-                slo[nseq] = (u16)nlit;
-                nlit += ll;
-                pend = kpos + klen;
-                nseq++;
+            __syncwarp();
+            produced = outb[192];
+            // outputs never overtake inputs: entry nseq + j was read in this or an earlier chunk
+            for (u32 q = lane; q < produced; q += 32) {
+                sll[nseq + q] = (u16)outb[q];
+                sml[nseq + q] = (u16)(outb[q] >> 16);
+                sof[nseq + q] = outb[64 + q];
+                slo[nseq + q] = (u16)outb[128 + q];
             }
-            if (!last) {
-                kpos = p;
-                klen = l;
-                koff = o;
-                have = true;
-            }
+            nseq += produced;
         }
-        mbuf[0] = nseq;
-        mbuf[1] = nlit;
-        mbuf[2] = pend;
+        __syncwarp();
+        if (lane == 0) {
+            mbuf[0] = nseq;
+            mbuf[1] = outb[193];
+            mbuf[2] = outb[194];
+        }
     }
     __syncwarp();
     nseq = mbuf[0];
@@ -1204,7 +1280,7 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
                 u32 lsz = warp_write_literals(nseq ? (const u8 *)lit : src, nlit, body, S);
                 __syncwarp();
                 u32 ssz = 0;
-                if (lsz + 16 < body_cap) ssz = warp_write_sequences(sll, sml, sof, nseq, body + lsz, body_cap - lsz, S, &ovf);
+                if (lsz + 16 < body_cap) ssz = warp_write_sequences(sll, sml, sof, nseq, body + lsz, body_cap - lsz, S, &ovf, MODE == 2);
                 else ovf = true;
                 total = lsz + ssz;
             }

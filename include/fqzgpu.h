@@ -66,6 +66,14 @@ int fqz_abi_version(void);
 size_t fqz_compress_bound(size_t fastq_bytes);
 int fqz_compress(fqz_ctx *ctx, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap, size_t *out_len);
 int fqz_decompress(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
+/* One shard of a file that is split across GPUs on block boundaries (blocks are independent,
+ * compress.go:523-528).  phred64: -1 = detect on this shard's first block (the shard
+ * holding block 0 of the file, compress.go:146-164), 0 / 1 = the file-global decision made there.
+ * emit_file_header: 1 for the shard that starts the file, 0 for the others (blocks only), so that the
+ * host gather is a plain concatenation in shard order (collectAndWriteResults, compress.go:365-403).
+ * *phred64_used (optional) returns the flag in force. */
+int fqz_compress_shard(fqz_ctx *ctx, const uint8_t *fastq, size_t n, uint32_t header_block_size, int phred64, int emit_file_header,
+                       uint8_t *out, size_t out_cap, size_t *out_len, int *phred64_used);
 
 /* ---- streaming, HOST memory (Seam B): the Go producer feeds raw windows read from io.Reader and
  *      writes what comes back to io.Writer in order (replaces produceCompressJobs / workers /

@@ -124,3 +124,34 @@ def test_compress_multi_block(ctx, oracle, kind, count):
         got, nrec = oracle.block_streams(fqz, b)
         want, nrec2 = oracle.block_streams(ref, b)
         assert nrec == nrec2 and got == want
+
+
+def test_sharded_compress(ctx, oracle):
+    """SURVEY §8e flow on one GPU standing in for two ranks: block-aligned byte ranges, rank 0 decides
+    the Phred flag, the others are forced to it and emit blocks only; the ordered gather is a plain
+    concatenation and decodes to the original under the oracle."""
+    import torch
+
+    from fastqpacker_b200 import sharding
+
+    count = 230000
+    for kind in (0, 1):
+        cap = count * 800
+        buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        n = ctx.synth_device(kind, 0x5EED0001 + kind * 3, 0, count, buf.data_ptr(), cap)
+        text = buf[:n].cpu().numpy()
+        world = 2
+        allc = []
+        before = 0
+        for a, b in sharding.slice_bounds(n, world):
+            local = (np.flatnonzero(text[a:b] == 10) + a).tolist()
+            allc.append(sharding.block_cut_candidates(local, before))
+            before += len(local)
+        plan = sharding.plan_compress(allc, n, world)
+        head, flag = ctx.compress_shard(text[plan[0][0] : plan[0][1]], phred64=-1, file_header=True)
+        assert flag == kind
+        tail, flag2 = ctx.compress_shard(text[plan[1][0] : plan[1][1]], phred64=flag, file_header=False)
+        assert flag2 == flag and tail[:4] != b"FQZ\x00"
+        merged = head + tail
+        assert oracle.decompress(merged) == text.tobytes()
+        assert merged == ctx.compress(text)  # sharding does not change a single byte of the file

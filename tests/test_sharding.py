@@ -1,0 +1,87 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo.  Every rank plans from its own
+byte slice plus one tiny gather; the codec work itself is stood in for by the oracle here (the GPU
+version of the same flow is tests/test_gpu_compress.py::test_sharded_compress)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from fastqpacker_b200 import sharding  # noqa: E402
+
+RECORDS = 230_000  # three fqz blocks: 100 000 + 100 000 + 30 000
+
+
+def _text():
+    from oracle import fqz_oracle as oracle
+
+    return oracle.synth(0, 0x5EED0001, 0, RECORDS)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import fqz_oracle as oracle
+
+    text = _text()
+    n = text.size
+    a, b = sharding.slice_bounds(n, world)[rank]
+    # 1. local newline positions (on the GPU this is k_newline_count / k_newline_index)
+    local = (np.flatnonzero(text[a:b] == 10) + a).tolist()
+    counts = [None] * world
+    dist.all_gather_object(counts, len(local))  # the one tiny exchange
+    before = sum(counts[:rank])
+    cand = sharding.block_cut_candidates(local, before)
+    allc = [None] * world
+    dist.all_gather_object(allc, cand)
+    plan = sharding.plan_compress(allc, n, world)
+    lo, hi = plan[rank]
+    # 2. every rank codes its own whole blocks; rank 0 owns block 0 and therefore the Phred decision
+    part = oracle.compress(text[lo:hi].tobytes(), threads=2) if hi > lo else b"FQZ\x00\x02\xa0\x86\x01\x00\x00"
+    parts = [None] * world
+    dist.all_gather_object(parts, part)  # ordered host gather
+    if rank == 0:
+        merged = sharding.merge_compressed(parts)
+        whole = oracle.compress(text.tobytes(), threads=2)
+        assert plan[0][0] == 0 and plan[-1][1] == n
+        for r in range(world - 1):
+            assert plan[r][1] == plan[r + 1][0]
+            cut = plan[r][1]
+            assert cut == 0 or (text[cut - 1] == 10 and int((text[:cut] == 10).sum()) % sharding.LINES_PER_BLOCK == 0)
+        assert merged == whole  # same blocks, same order, same bytes
+        # 3. decompress side: contiguous block runs per rank, outputs concatenate to the original
+        shards = sharding.shard_container(merged, world)
+        back = b"".join(oracle.decompress(s) for s in shards)
+        assert back == text.tobytes()
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_plan_and_gather(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_plan_decompress_balances_and_covers():
+    from oracle import fqz_oracle as oracle
+
+    fqz = oracle.compress(_text().tobytes(), threads=4)
+    version, flags, blocks = sharding.walk_container(fqz)
+    assert version == 2 and [b.records for b in blocks] == [100000, 100000, 30000]
+    for world in (1, 2, 3, 4, 8):
+        plan = sharding.plan_decompress(blocks, world)
+        assert plan[0][0] == 0 and plan[-1][1] == len(blocks)
+        assert all(plan[i][1] == plan[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        sharding.walk_container(b"FQX\x00" + fqz[4:])
+    with pytest.raises(ValueError):
+        sharding.walk_container(fqz[:-5])
