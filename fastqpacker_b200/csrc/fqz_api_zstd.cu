@@ -53,7 +53,7 @@ struct ZBatch {
     size_t slot_bytes = 0, ws_bytes = 0;
     // items / item_base / item_count: see ZFrame (policy FQZ_ZPOLICY_ITEMS only)
     void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0) {
-        const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : FQZ_ZFRAME;
+        const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : (policy == FQZ_ZPOLICY_ITEMS ? FQZ_ZFRAME_ITEMS : FQZ_ZFRAME);
         for (size_t o = 0; o < len; o += fsz) {
             u32 l = (u32)std::min<size_t>(fsz, len - o);
             ZFrame f;

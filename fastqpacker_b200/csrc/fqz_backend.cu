@@ -12,16 +12,17 @@
 //                     prefix-summed qualities; all wide stores aligned to the destination
 #include "fqz_backend.h"
 
+#define ZW_MAXC 8u     // candidate item starts kept per lane (128 bytes)
 #define WALK_CH 4096u  // bytes per staged chunk (plus 16 bytes of overlap so a prefix never straddles)
 
 // kind: 0 headers, 1 plus, 2 npos.  offs has nrec+1 entries per (block, kind): item r starts at offs[r].
-// One lane per chain: the hop pos -> pos + 2 + len is a serial dependency, so the only lever is
-// latency.  The stream is staged chunk by chunk into shared memory by the TMA unit (1-D bulk
-// copies, double buffered: chunk c+1 lands while chunk c is walked), and the lane hops through
-// shared memory at ~40 cycles per item.
+// One warp per chain.  The stream is staged chunk by chunk into shared memory by the TMA unit (1-D
+// bulk copies, double buffered: chunk c+1 lands while chunk c is walked); the warp then advances by
+// verified runs of equal-length items (see below) instead of one serial hop per item.
 __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs_base, FqzDecStatus *st) {
     __shared__ uint4 sm_buf[4][2][(WALK_CH + 16) / 16];
     __shared__ u64 sm_bar[4][2];
+    __shared__ u16 sm_cand[4][ZW_MAXC][32];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
     u32 wi = blockIdx.x * 4 + warp;
     if (wi >= nblocks * 3) return;
@@ -36,26 +37,31 @@ __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 
         for (u32 r = lane; r <= nrec; r += 32) offs[r] = 0;
         return;
     }
-    if (lane != 0) return;
     u64 *bar = sm_bar[warp];
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    __syncwarp();
     u32 nchunks = (size + WALK_CH - 1) / WALK_CH;
     u32 ph[2] = {0, 0};
-    bool pending[2] = {false, false};
+    bool pending[2] = {false, false};  // uniform across the warp; lane 0 talks to the TMA unit, every lane waits on the barrier
     auto issue = [&](u32 c, u32 slot) {
         if (c >= nchunks) return;
-        u32 off = c * WALK_CH;
-        u32 bytes = min(WALK_CH + 16u, (size - off + 15u) & ~15u);  // the stream carries FQZ_PAD readable bytes of slack
-        mbar_expect_tx(&bar[slot], bytes);
-        tma_load_1d(sm_buf[warp][slot], p + off, bytes, &bar[slot]);
+        if (lane == 0) {
+            u32 off = c * WALK_CH;
+            u32 bytes = min(WALK_CH + 16u, (size - off + 15u) & ~15u);  // the stream carries FQZ_PAD readable bytes of slack
+            mbar_expect_tx(&bar[slot], bytes);
+            tma_load_1d(sm_buf[warp][slot], p + off, bytes, &bar[slot]);
 #ifdef FQZ_EMU
-        bar[slot] += 1;
+            bar[slot] += 1;
 #endif
+        }
         pending[slot] = true;
     };
     auto wait = [&](u32 slot) {
         if (!pending[slot]) return;
+        __syncwarp();
         mbar_wait(&bar[slot], ph[slot]);
         ph[slot] ^= 1u;
         pending[slot] = false;
@@ -80,22 +86,134 @@ __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 
         }
         wait(slot);
         const u8 *buf = (const u8 *)sm_buf[warp][slot];
-        u32 cbase = c * WALK_CH, cend = cbase + WALK_CH;
-        while (r < nrec && pos < cend && pos + 2 <= size) {
-            u32 len = (u32)buf[pos - cbase] | ((u32)buf[pos - cbase + 1] << 8);
-            u32 next = pos + 2 + (kind == 2 ? 2 * len : len);
-            if (next > size) { err = 1; break; }  // item r runs past the end of the stream
-            offs[r++] = pos;
-            pos = next;
+        u32 cbase = c * WALK_CH;
+        u32 lim = min(size, cbase + WALK_CH + 16u);  // bytes staged in this slot
+        if (kind == 0) {
+            // Headers: printable text behind a u16 length < 256, so the only zero bytes of the stream
+            // are the high bytes of the length prefixes.  Every lane scans 128 staged bytes for them
+            // (candidate item starts), the warp then PROVES the guess: the first candidate must be
+            // pos and every candidate must end exactly where the next one starts.  A chunk that
+            // fails the proof (binary headers, lengths >= 256, > ZW_MAXC items per 128 bytes) is
+            // walked serially instead, so the result never depends on the guess.
+            u32 rend = min(size, cbase + WALK_CH);
+            u16 *cl = &sm_cand[warp][0][lane];  // candidate j of this lane at cl[32 * j]: conflict-free
+            u32 k = 0;
+            {
+                // this lane owns the zero bytes at [q0, q0 + 128); it visits its 32 words in an order
+                // rotated by the lane index so that the 32 lanes always hit 32 different banks
+                u32 q0 = cbase + 128u * lane;
+                const u32 *wbuf = (const u32 *)buf + 32u * lane;
+                u64 zlo = 0, zhi = 0;  // one bit per byte of the 128
+                if (q0 < lim) {
+#pragma unroll 8
+                    for (u32 w = 0; w < 32; w++) {
+                        u32 idx = (w + lane) & 31u;
+                        u32 x = wbuf[idx];
+                        u32 nib = ((__vcmpeq4(x, 0u) & 0x01010101u) * 0x01020408u) >> 24;  // 4 flags -> 4 bits
+                        u64 sh = (u64)(nib & 0xFu) << (4u * (idx & 15u));
+                        if (idx < 16) zlo |= sh; else zhi |= sh;
+                    }
+                }
+                for (int half = 0; half < 3; half++) {
+                    // third round: the zero byte at offset WALK_CH (in the 16 staged overlap bytes) belongs to lane 31
+                    u64 m = half == 0 ? zlo : (half == 1 ? zhi : ((lane == 31 && buf[WALK_CH] == 0) ? 1ull : 0ull));
+                    while (m) {
+                        u32 b = (u32)__ffsll((long long)m) - 1u;
+                        m &= m - 1ull;
+                        u32 zpos = q0 + 64u * half + b;  // position of the zero byte = candidate start + 1
+                        if (zpos >= pos + 1u && zpos - 1u < rend && zpos + 1u <= size && zpos < lim) {
+                            if (k < ZW_MAXC) cl[32u * k] = (u16)(zpos - 1u - cbase);
+                            k++;
+                        }
+                    }
+                }
+            }
+            u32 over = __ballot_sync(0xffffffffu, k > ZW_MAXC);
+            u32 havem = __ballot_sync(0xffffffffu, k > 0);
+            u32 incl = group_incl_scan(k, 0xffffffffu, 32);
+            u32 total = __shfl_sync(0xffffffffu, incl, 31);
+            u32 ex = incl - k;
+            bool good = (over == 0) && total > 0;
+            // first candidate of the next lane that has one
+            u32 above = (lane == 31) ? 0u : (havem >> (lane + 1u));
+            int nl = above ? (int)lane + __ffs((int)above) : -1;
+            u32 c0 = k ? (u32)cl[0] : 0u;
+            u32 succ_other = __shfl_sync(0xffffffffu, c0, nl < 0 ? 0 : nl);
+            bool ok = true;
+            u32 last_next = 0;
+            if (good && k) {
+                for (u32 j = 0; j < k; j++) {
+                    u32 a = cl[32u * j];
+                    u32 nx = a + 2u + (u32)buf[a];  // relative to cbase
+                    if (j + 1 < k) ok = ok && (nx == (u32)cl[32u * (j + 1)]);
+                    else if (nl >= 0) ok = ok && (nx == succ_other);
+                    else {
+                        ok = ok && (cbase + nx <= size);
+                        last_next = cbase + nx;
+                    }
+                }
+                if (ex == 0) ok = ok && (cbase + (u32)cl[0] == pos);
+            }
+            good = good && __all_sync(0xffffffffu, ok);
+#ifdef FQZ_EMU
+            if (lane == 0 && getenv("FQZ_DEBUG")) fprintf(stderr, "walk hdr chunk %u pos %u total %u good %d\n", c, pos, total, (int)good);
+#endif
+            if (good) {
+                u32 acc = min(total, nrec - r);
+                for (u32 j = 0; j < k; j++)
+                    if (ex + j < acc) offs[r + ex + j] = cbase + (u32)cl[32u * j];
+                int lastl = 31 - __clz((int)havem);
+                pos = __shfl_sync(0xffffffffu, last_next, lastl);
+                r += acc;
+                continue;  // (when acc < total the loop ends: r == nrec)
+            }
+            // proof failed: lane 0 hops through the rest of this chunk
+            if (lane == 0) {
+                u32 cend = cbase + WALK_CH;
+                while (r < nrec && pos < cend && pos + 2 <= size) {
+                    u32 len = (u32)buf[pos - cbase] | ((u32)buf[pos - cbase + 1] << 8);
+                    u32 next = pos + 2 + len;
+                    if (next > size) { err = 1; break; }
+                    offs[r++] = pos;
+                    pos = next;
+                }
+            }
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            err = __shfl_sync(0xffffffffu, err, 0);
+            if (err) break;
+            continue;
         }
-        if (err) break;
+        // The hop pos -> pos + 2 + len is serial, but consecutive items very often have the same
+        // length (bare "+" lines, reads without N, headers of equal width): speculate that the next
+        // 32 items are as long as this one, let every lane check one of them, accept the verified run.
+        u32 len0 = (u32)buf[pos - cbase] | ((u32)buf[pos - cbase + 1] << 8);
+        u32 isz = 2u + (kind == 2 ? 2u * len0 : len0);
+        u32 cand = pos + lane * isz;
+        bool ok = false;
+        if (cand + 2u <= lim && cand < cbase + WALK_CH) {
+            u32 l = (u32)buf[cand - cbase] | ((u32)buf[cand - cbase + 1] << 8);
+            ok = (l == len0) && (cand + isz <= size);
+        }
+        u32 okm = __ballot_sync(0xffffffffu, ok);
+        u32 run = (~okm == 0u) ? 32u : (u32)__ffs((int)~okm) - 1u;
+        if (run == 0) {  // lane 0 failed: the item at pos runs past the end of the stream
+            err = 1;
+            break;
+        }
+        run = min(run, nrec - r);
+        if (lane < run) offs[r + lane] = cand;
+        r += run;
+        pos += run * isz;
     }
     wait(0);  // no bulk copy may still be in flight when the CTA's shared memory is released
     wait(1);
-    offs[nrec] = pos;
-    if (err) {
-        u32 code = kind == 0 ? BK_E_TRUNC_HEADER : (kind == 1 ? BK_E_TRUNC_PLUS : BK_E_TRUNC_NPOS);
-        atomicMin(&st->err_key, ((u64)(rec_base + r) << 8) | code);
+    if (lane == 0) {
+        offs[nrec] = pos;
+        if (err) {
+            u32 code = kind == 0 ? BK_E_TRUNC_HEADER : (kind == 1 ? BK_E_TRUNC_PLUS : BK_E_TRUNC_NPOS);
+            atomicMin(&st->err_key, ((u64)(rec_base + r) << 8) | code);
+        }
     }
 }
 

@@ -26,6 +26,7 @@ struct BitR {
     u32 consumed;  // bits consumed from the top of `cont`
     bool bad;
     __device__ static u64 load_le(const u8 *p, u32 n) {  // n <= 8 bytes
+        if (n == 8) return (u64)ld_u32_unaligned(p) | ((u64)ld_u32_unaligned(p + 4) << 32);  // aligned words + funnel shift
         u64 v = 0;
         for (u32 i = 0; i < n; i++) v |= (u64)p[i] << (8 * i);
         return v;
@@ -303,6 +304,7 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
         // per-frame entropy table provenance (treeless literals / repeat-mode FSE tables)
         u32 huf_src = 0xFFFFFFFFu, fse_src[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         bool ok = true;
+        u64 known_off = 0;  // output offset of the next block while it is still computable from headers (~0: not any more)
         for (;;) {
             if (n - h < 3) { ok = false; break; }
             u32 bh = rd24(p + h);
@@ -400,7 +402,13 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
                 B.lit_off = lbase + inf.lit_bytes;
                 B.seq_off = sbase + inf.nseq;
                 B.err = 0;
+                B.out_off = (known_off < 0xFFFFFFFFull) ? (u32)known_off : 0xFFFFFFFFu;
                 blocks[bidx] = B;
+            }
+            if (known_off != ~0ull) {
+                if (type != 2) known_off += bsz;
+                else if (nseq == 0) known_off += lit_regen;
+                else known_off = ~0ull;
             }
             inf.lit_bytes += lit_regen;
             inf.nseq += nseq;
@@ -579,86 +587,133 @@ __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 
     return tl;
 }
 
-// one Huffman stream, decoded by one lane
+// one Huffman stream, decoded by one lane; output assembled into aligned 32-bit stores
 __device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 n, const u16 *dt, u32 tl) {
     BitR br;
     br.init(src, csize);
     if (br.bad) return false;
     u32 i = 0;
-    while (i < n) {
-        // a reload guarantees >= 57 fresh bits (or the stream start): up to 5 symbols of <= 11 bits
+    while (i < n && ((uintptr_t)(dst + i) & 3u)) {
         br.reload();
-        u32 burst = min(n - i, 5u);
-        for (u32 k = 0; k < burst; k++) {
+        u32 e = dt[br.look(tl)];
+        br.skip(e >> 8);
+        dst[i++] = (u8)e;
+    }
+    while (i + 4 <= n) {  // a reload guarantees >= 57 fresh bits (or the stream start): four symbols of <= 11 bits
+        br.reload();
+        u32 w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
             u32 e = dt[br.look(tl)];
             br.skip(e >> 8);
-            dst[i++] = (u8)e;
+            w |= (e & 0xFFu) << (8 * k);
         }
+        *(u32 *)(dst + i) = w;
+        i += 4;
+    }
+    while (i < n) {
+        br.reload();
+        u32 e = dt[br.look(tl)];
+        br.skip(e >> 8);
+        dst[i++] = (u8)e;
     }
     br.reload();
     return !br.bad && br.ptr == br.start && br.consumed == 64;
 }
 
+// One warp takes eight consecutive blocks; lane = (block, Huffman stream).  Blocks that share a
+// Huffman table (the treeless blocks of the frames written by k_zenc_huf: 8 blocks x 4 streams = all
+// 32 lanes busy, one table build) are decoded together; blocks with their own trees (frames written
+// by the reference's encoder) take one pass per table.  Sequence-free blocks whose position in the
+// frame is known from the headers are decoded straight into the output.
+#define ZD_GROUP 8
 __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out) {
     __shared__ LitScratch scratch[ZD_WARPS];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
-    u32 bi = blockIdx.x * ZD_WARPS + warp;
-    if (bi >= nblocks) return;
-    ZDBlock B = blocks[bi];
-    if (B.type != 2) return;
+    u32 g = blockIdx.x * ZD_WARPS + warp;
+    u32 b0 = g * ZD_GROUP;
+    if (b0 >= nblocks) return;
     LitScratch &S = scratch[warp];
-    const u8 *c = (const u8 *)(uintptr_t)B.src;
-    // literals of a sequence-free first block are the block's content: decode them in place
-    const ZDFrame &F = frames[B.frame];
-    bool direct = (B.nseq == 0 && bi == F.first_block);
-    u8 *dst = direct ? out + F.dst_off : litbuf + B.lit_off;
-    u32 n = B.lit_regen;
-    if (direct && n > F.out_cap) {
-        if (lane == 0) blocks[bi].err = 1;
-        return;
+    u32 bl = lane >> 2, q = lane & 3u;
+    u32 bi = b0 + bl;
+    bool valid = bi < nblocks;
+    ZDBlock B;
+    if (valid) B = blocks[bi];
+    else {
+        B.type = 0;
+        B.lit_type = 0;
+        B.huf_block = 0xFFFFFFFFu;
     }
+    bool comp = valid && B.type == 2;
+    u8 *dst = nullptr;
+    u32 n = 0;
     u32 err = 0;
-    if (B.lit_type == 0) {
-        const u8 *s = c + B.lit_hdr;
-        for (u32 i = lane; i < n; i += 32) dst[i] = s[i];
-    } else if (B.lit_type == 1) {
-        u8 v = c[B.lit_hdr];
-        for (u32 i = lane; i < n; i += 32) dst[i] = v;
-    } else {
-        ZDBlock HB = (B.huf_block == bi) ? B : blocks[B.huf_block];
-        u32 tree = 0;
-        u32 tl = warp_huf_read_table(HB, S, &tree);
-        if (!tl) err = 1;
+    bool direct = false;
+    if (comp) {
+        const ZDFrame &F = frames[B.frame];
+        direct = (B.nseq == 0 && B.out_off != 0xFFFFFFFFu);
+        n = B.lit_regen;
+        if (direct && (u64)B.out_off + n > F.out_cap) {
+            err = 1;
+            comp = false;
+        } else
+            dst = direct ? out + F.dst_off + B.out_off : litbuf + B.lit_off;
+    }
+    // raw / RLE literals: the block's four lanes copy / fill
+    if (comp && B.lit_type < 2) {
+        const u8 *c = (const u8 *)(uintptr_t)B.src + B.lit_hdr;
+        if (B.lit_type == 0) for (u32 i = q; i < n; i += 4) dst[i] = c[i];
         else {
-            if (B.lit_type == 3) tree = 0;  // treeless: the streams start right after the header
-            const u8 *sp = c + B.lit_hdr + tree;
-            u32 avail = B.lit_csize - tree;
-            if (tree > B.lit_csize) err = 1;
-            else if (B.lit_streams == 1) {
-                bool ok = true;
-                if (lane == 0) ok = huf_decode_stream(sp, avail, dst, n, S.dt, tl);
-                if (!__all_sync(FULL, ok)) err = 1;
-            } else {
-                bool ok = true;
-                if (avail < 10) ok = false;
-                else {
-                    u32 s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
-                    u32 seg = (n + 3) / 4;
-                    if (6 + s1 + s2 + s3 >= avail || 3 * seg > n) ok = false;
-                    else if (lane < 4) {
-                        u32 off = 6 + (lane > 0 ? s1 : 0) + (lane > 1 ? s2 : 0) + (lane > 2 ? s3 : 0);
-                        u32 cs = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : avail - 6 - s1 - s2 - s3;
-                        u32 cnt = lane < 3 ? seg : n - 3 * seg;
-                        ok = huf_decode_stream(sp + off, cs, dst + lane * seg, cnt, S.dt, tl);
-                    }
-                }
-                if (!__all_sync(FULL, ok)) err = 1;
-            }
+            u8 v = c[0];
+            for (u32 i = q; i < n; i += 4) dst[i] = v;
         }
     }
-    if (lane == 0) {
-        if (err) blocks[bi].err = 1;
-        if (direct && !err) blocks[bi].rsize = n;
+    bool pending = comp && B.lit_type >= 2;
+    for (;;) {
+        u32 pm = __ballot_sync(FULL, pending);
+        if (!pm) break;
+        int fl = __ffs((int)pm) - 1;
+        u32 tsrc = __shfl_sync(FULL, B.huf_block, fl);
+        ZDBlock HB = blocks[tsrc];
+        u32 tree = 0;
+        u32 tl = warp_huf_read_table(HB, S, &tree);
+        bool mine = pending && B.huf_block == tsrc;
+        if (mine) {
+            if (!tl) err = 1;
+            else {
+                const u8 *c = (const u8 *)(uintptr_t)B.src;
+                u32 tsz = (B.lit_type == 3) ? 0u : tree;  // treeless: the streams start right after the header
+                const u8 *sp = c + B.lit_hdr + tsz;
+                if (tsz > B.lit_csize) err = 1;
+                else {
+                    u32 avail = B.lit_csize - tsz;
+                    if (B.lit_streams == 1) {
+                        if (q == 0 && !huf_decode_stream(sp, avail, dst, n, S.dt, tl)) err = 1;
+                    } else if (avail < 10) err = 1;
+                    else {
+                        u32 s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
+                        u32 seg = (n + 3) / 4;
+                        if (6 + s1 + s2 + s3 >= avail || 3 * seg > n) err = 1;
+                        else {
+                            u32 off = 6 + (q > 0 ? s1 : 0) + (q > 1 ? s2 : 0) + (q > 2 ? s3 : 0);
+                            u32 cs = q == 0 ? s1 : q == 1 ? s2 : q == 2 ? s3 : avail - 6 - s1 - s2 - s3;
+                            u32 cnt = q < 3 ? seg : n - 3 * seg;
+                            if (!huf_decode_stream(sp + off, cs, dst + q * seg, cnt, S.dt, tl)) err = 1;
+                        }
+                    }
+                }
+            }
+            pending = false;
+        }
+        __syncwarp();
+    }
+    // per block verdict
+    u32 e4 = err;
+    e4 |= __shfl_xor_sync(FULL, e4, 1);
+    e4 |= __shfl_xor_sync(FULL, e4, 2);
+    if (valid && q == 0) {
+        if (e4) blocks[bi].err = 1;
+        else if (comp && direct) blocks[bi].rsize = n;
     }
 }
 
@@ -781,7 +836,8 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
             o += B.rsize;
         } else if (B.nseq == 0) {
             if (o + B.lit_regen > F.out_cap) { err = 1; break; }
-            if (!(b == 0)) warp_copy(base + o, litbuf + B.lit_off, B.lit_regen, lane);  // first block: decoded in place
+            if (B.out_off == 0xFFFFFFFFu) warp_copy(base + o, litbuf + B.lit_off, B.lit_regen, lane);  // else: decoded in place
+            else if ((u64)B.out_off != o) { err = 1; break; }
             o += B.lit_regen;
         } else {
             const u8 *lit = litbuf + B.lit_off;
@@ -968,7 +1024,8 @@ void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *inf
 }
 void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s) {
     if (!nblocks) return;
-    FQZ_LAUNCH(k_zd_literals, (nblocks + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, frames, litbuf, out);
+    u32 groups = (nblocks + ZD_GROUP - 1) / ZD_GROUP;
+    FQZ_LAUNCH(k_zd_literals, (groups + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, frames, litbuf, out);
 }
 void fqz_launch_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf, cudaStream_t s) {
     if (!nblocks) return;

@@ -40,6 +40,8 @@ struct ZDBlock {
     u32 tab_pos[3];     // offsets of the LL / OF / ML table descriptions
     u32 huf_block;      // block whose literals section holds the Huffman tree (treeless literals)
     u32 fse_block[3];   // block whose table description is reused (repeat mode)
+    u32 out_off;        // offset of this block's output inside its frame when every block before it has a size
+                        // known from the headers alone (raw, RLE, sequence-free); ~0 otherwise
     u8 type;            // 0 raw, 1 RLE, 2 compressed
     u8 lit_type, lit_streams, lit_hdr;
     u8 modes;
