@@ -31,12 +31,12 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
     for (auto &st : streams) cbytes += st.csize;
     {
         StageScope sc(c, ST_ZDEC_SCAN, 0);
-        fqz_launch_zd_walk(d_streams, ns, d_info, nullptr, nullptr, 0, s);
+        fqz_launch_zd_hop(d_streams, ns, d_info, nullptr, nullptr, 0, s);
     }
     ZDStreamInfo *hinfo = (ZDStreamInfo *)(hp + in_b);
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(hinfo, d_info, info_b, cudaMemcpyDeviceToHost, s));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
-    u64 nframes = 0, nblocks = 0, obytes = 0, lbytes = 0, nseq = 0;
+    u64 nframes = 0, nblocks = 0, obytes = 0;
     for (u32 i = 0; i < ns; i++) {
         if (hinfo[i].status) {
             out.err_stream = (int)i;
@@ -46,30 +46,46 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
         hinfo[i].frame_base = (u32)nframes;
         hinfo[i].block_base = (u32)nblocks;
         hinfo[i].out_base = obytes;
-        hinfo[i].lit_base = lbytes;
-        hinfo[i].seq_base = nseq;
+        hinfo[i].lit_base = 0;
+        hinfo[i].seq_base = 0;
         out.off[i] = obytes;
         nframes += hinfo[i].nframes;
         nblocks += hinfo[i].nblocks;
         obytes += (hinfo[i].out_bytes + 63) & ~(u64)63;  // each stream starts 64-byte aligned
-        lbytes += hinfo[i].lit_bytes;
-        nseq += hinfo[i].nseq;
     }
-    if (nframes >= (1ull << 31) || nblocks >= (1ull << 31) || (max_out && obytes > max_out)) return FQZ_E_TOO_LARGE;
+    if (nframes >= (1ull << 31) || nblocks >= (1ull << 31) || obytes >= (1ull << 32) || (max_out && obytes > max_out)) return FQZ_E_TOO_LARGE;
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_info, hinfo, info_b, cudaMemcpyHostToDevice, s));
     ZDFrame *d_frames = (ZDFrame *)c->arena.alloc((size_t)(nframes + 1) * sizeof(ZDFrame));
     ZDBlock *d_blocks = (ZDBlock *)c->arena.alloc((size_t)(nblocks + 1) * sizeof(ZDBlock));
+    const u32 cstride = (u32)nblocks + 1;
+    u32 *d_cnt = (u32 *)c->arena.alloc((size_t)cstride * 2 * sizeof(u32));  // literals, sequences per block (+ totals after the scan)
     u8 *d_out = (u8 *)c->arena.alloc(obytes + 64);
-    u8 *d_lit = (u8 *)c->arena.alloc(lbytes + 64);
-    u32 *d_seq = (u32 *)c->arena.alloc((size_t)nseq * 12 + 64);
-    if (!d_frames || !d_blocks || !d_out || !d_lit || !d_seq) {
+    if (!d_frames || !d_blocks || !d_cnt || !d_out) {
         c->err = "arena: out of device memory (zstd decode tables)";
         return FQZ_E_CUDA;
     }
     out.d_base = d_out;
+    u64 lbytes = 0, nseq = 0;
     {
         StageScope sc(c, ST_ZDEC_SCAN, cbytes);
-        fqz_launch_zd_walk(d_streams, ns, d_info, d_frames, d_blocks, 1, s);
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, (size_t)cstride * 2 * sizeof(u32), s));
+        fqz_launch_zd_hop(d_streams, ns, d_info, d_frames, d_blocks, 1, s);
+        fqz_launch_zd_parse(d_blocks, (u32)nblocks, d_cnt, cstride, s);
+        fqz_launch_zd_link(d_frames, (u32)nframes, d_blocks, d_cnt, cstride, s);
+        FQZ_TRY(fqz_scan_excl_u32(c, d_cnt, cstride, cstride, 2));
+        fqz_launch_zd_offsets(d_blocks, (u32)nblocks, d_cnt, cstride, s);
+        u32 *htot = (u32 *)c->h_pin;
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot, d_cnt + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 1, d_cnt + cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        lbytes = htot[0];  // <= obytes < 2^32 (k_zd_link rejects frames that claim more than their output)
+        nseq = htot[1];
+    }
+    u8 *d_lit = (u8 *)c->arena.alloc(lbytes + 64);
+    u32 *d_seq = (u32 *)c->arena.alloc((size_t)nseq * 12 + 64);
+    if (!d_lit || !d_seq) {
+        c->err = "arena: out of device memory (zstd decode arenas)";
+        return FQZ_E_CUDA;
     }
     {
         StageScope sc(c, ST_ZDEC_LITERALS, lbytes);

@@ -17,12 +17,21 @@ __global__ void __launch_bounds__(256) k_zassemble(const ZFrame *frames, u32 nfr
     u32 size = scan[warp + 1] - scan[warp];
     const u8 *src = slots + frames[warp].dst_off;  // 16-byte aligned slot
     u8 *dst = out + (u64)fixed[warp] + scan[warp];
-    u32 head = (u32)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    // 16-byte stores to the (arbitrarily aligned) destination; the slot is 16-byte aligned, so the
+    // source of every vector is five aligned words merged with funnel shifts
+    u32 head = (u32)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > size) head = size;
     if (lane < head) dst[lane] = src[lane];
-    u32 nw = (size - head) >> 2;
-    for (u32 w = lane; w < nw; w += 32) *(u32 *)(dst + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
-    u32 t0 = head + 4u * nw;
+    u32 nv = (size - head) >> 4;
+    const u32 *sw = (const u32 *)src + (head >> 2);
+    const u32 bs = (head & 3u) * 8u;
+    uint4 *d16 = (uint4 *)(dst + head);
+    for (u32 v = lane; v < nv; v += 32) {
+        const u32 *sp = sw + 4u * v;
+        u32 w0 = sp[0], w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];  // w4 may lie in the slot's slack
+        d16[v] = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+    }
+    u32 t0 = head + 16u * nv;
     if (lane < size - t0) dst[t0 + lane] = src[t0 + lane];
 }
 

@@ -162,6 +162,9 @@ __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
 __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
     u32 done;
     do {
@@ -185,6 +188,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, u3
 // emulation: the barrier word holds the number of completed phases; copies are synchronous
 __device__ __forceinline__ void mbar_init(u64 *bar, u32) { *bar = 0; }
 __device__ __forceinline__ void mbar_expect_tx(u64 *, u32) {}
+__device__ __forceinline__ void mbar_arrive(u64 *) {}
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
     while ((*bar & 1u) == parity) emu::yield();
 }

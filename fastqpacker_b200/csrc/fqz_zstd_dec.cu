@@ -15,6 +15,7 @@
 #include "fqz_zstd.h"
 #include "fqz_zstd_dec.h"
 #include "fqz_zstd_tables.cuh"
+#include "fqz_xxh64.cuh"
 
 #define FULL 0xffffffffu
 
@@ -240,46 +241,45 @@ __device__ static u32 parse_lit_header(const u8 *p, u32 avail, u32 *type, u32 *r
 }
 
 // ---------------------------------------------------------------------------------- walk: frames and blocks of each stream
-// pass 0 (tables == nullptr): counts frames / blocks / output bytes per stream.
-// pass 1: fills the tables at the bases computed by the host.
-__global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill) {
+// The container gives one compressed size per stream, zstd gives no index inside it: frames and
+// blocks have to be hopped over serially.  The serial part is kept to the bare chain (one header
+// load per hop, k_zd_hop, one thread per stream); everything that can be read once a block's
+// position is known — literals header, sequence count, FSE table descriptions — is parsed by one
+// thread per BLOCK (k_zd_parse), and the per-frame bookkeeping (treeless / repeat table provenance,
+// output offsets known from headers alone) by one thread per frame (k_zd_link).
+// k_zd_hop pass 0 (fill == 0): counts frames / blocks / output bytes per stream.
+// pass 1: fills the frame table and the position part of the block table at the bases computed by the host.
+__global__ void k_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill) {
     u32 si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= nstreams) return;
     ZDStream st = streams[si];
     const u8 *p = (const u8 *)(uintptr_t)st.src;
     u64 n = st.csize, pos = 0;
-    ZDStreamInfo inf;
-    inf.nframes = 0;
-    inf.nblocks = 0;
-    inf.out_bytes = 0;
-    inf.status = 0;
-    inf.lit_bytes = 0;
-    inf.nseq = 0;
+    u32 nframes = 0, nblocks = 0, status = 0;
+    u64 out_bytes = 0;
     u32 fbase = 0, bbase = 0;
-    u64 obase = 0, lbase = 0, sbase = 0;
+    u64 obase = 0;
     if (fill) {
         fbase = info[si].frame_base;
         bbase = info[si].block_base;
         obase = info[si].out_base;
-        lbase = info[si].lit_base;
-        sbase = info[si].seq_base;
     }
     while (pos < n) {
-        if (n - pos < 4) { inf.status = 1; break; }
+        if (n - pos < 4) { status = 1; break; }
         u32 magic = rd32(p + pos);
         if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
-            if (n - pos < 8) { inf.status = 1; break; }
+            if (n - pos < 8) { status = 1; break; }
             u64 sz = rd32(p + pos + 4);
-            if (n - pos - 8 < sz) { inf.status = 1; break; }
+            if (n - pos - 8 < sz) { status = 1; break; }
             pos += 8 + sz;
             continue;
         }
-        if (magic != ZSTD_MAGIC) { inf.status = 1; break; }
-        if (n - pos < 6) { inf.status = 1; break; }
+        if (magic != ZSTD_MAGIC) { status = 1; break; }
+        if (n - pos < 6) { status = 1; break; }
         u32 fhd = p[pos + 4];
         u32 fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did = fhd & 3;
-        if (fhd & 8) { inf.status = 1; break; }  // reserved bit
-        if (did) { inf.status = 2; break; }      // dictionaries are not used by the reference
+        if (fhd & 8) { status = 1; break; }  // reserved bit
+        if (did) { status = 2; break; }      // dictionaries are not used by the reference
         u64 h = pos + 5;
         u64 window = 0;
         if (!single) {
@@ -289,7 +289,7 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
             window += (window >> 3) * m;
         }
         u32 fcs_size = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
-        if (n - h < fcs_size) { inf.status = 1; break; }
+        if (n - h < fcs_size) { status = 1; break; }
         u64 fcs = ~0ull;
         if (fcs_size == 1) fcs = p[h];
         else if (fcs_size == 2) fcs = (u64)(p[h] | (p[h + 1] << 8)) + 256;
@@ -297,14 +297,11 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
         else if (fcs_size == 8) fcs = (u64)rd32(p + h) | ((u64)rd32(p + h + 4) << 32);
         h += fcs_size;
         if (single) window = fcs;
-        u32 fidx = fbase + inf.nframes;
-        u32 first_block = bbase + inf.nblocks;
+        u32 fidx = fbase + nframes;
+        u32 first_block = bbase + nblocks;
         u32 nb = 0;
         u64 bound = 0;
-        // per-frame entropy table provenance (treeless literals / repeat-mode FSE tables)
-        u32 huf_src = 0xFFFFFFFFu, fse_src[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         bool ok = true;
-        u64 known_off = 0;  // output offset of the next block while it is still computable from headers (~0: not any more)
         for (;;) {
             if (n - h < 3) { ok = false; break; }
             u32 bh = rd24(p + h);
@@ -314,121 +311,51 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
             u32 csz = (type == 1) ? 1 : bsz;
             if (n - h < csz || bsz > ZSTD_BLOCK_MAX) { ok = false; break; }
             if (type == 2 && bsz < 2) { ok = false; break; }
-            u32 bidx = first_block + nb;
-            u32 lit_regen = 0, nseq = 0;
-            ZDBlock B;
-            if (type == 2) {
-                const u8 *c = p + h;
-                u32 lt, lr, lc, ls;
-                u32 lh = parse_lit_header(c, csz, &lt, &lr, &lc, &ls);
-                if (!lh || lh + lc > csz) { ok = false; break; }
-                lit_regen = lr;
-                u32 so = lh + lc;  // sequences section
-                if (so >= csz) { ok = false; break; }
-                u32 b0 = c[so];
-                u32 sh = 1;
-                if (b0 == 0) nseq = 0;
-                else if (b0 < 128) nseq = b0;
-                else if (b0 < 255) {
-                    if (so + 2 > csz) { ok = false; break; }
-                    nseq = ((b0 - 128) << 8) + c[so + 1];
-                    sh = 2;
-                } else {
-                    if (so + 3 > csz) { ok = false; break; }
-                    nseq = c[so + 1] + ((u32)c[so + 2] << 8) + 0x7F00;
-                    sh = 3;
-                }
-                if (fill) {
-                    B.lit_type = (u8)lt;
-                    B.lit_streams = (u8)ls;
-                    B.lit_hdr = (u8)lh;
-                    B.lit_csize = lc;
-                    B.huf_block = (lt == 3) ? huf_src : bidx;
-                    B.seq_pos = so + sh;
-                    B.modes = 0;
-                    for (int t = 0; t < 3; t++) {
-                        B.fse_block[t] = bidx;
-                        B.tab_pos[t] = 0;
-                    }
-                    if (lt == 3 && huf_src == 0xFFFFFFFFu) { ok = false; break; }
-                }
-                if (lt == 2) huf_src = bidx;
-                if (nseq) {
-                    if (so + sh >= csz) { ok = false; break; }
-                    u32 modes = c[so + sh];
-                    if (modes & 3) { ok = false; break; }
-                    u32 tp = so + sh + 1;
-                    // locate the three table descriptions (LL, OF, ML order) and the bitstream
-                    const u32 maxLogs[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
-                    const u32 maxSyms[3] = {ZSTD_MAX_LL, ZSTD_MAX_OF, ZSTD_MAX_ML};
-                    for (int t = 0; t < 3 && ok; t++) {
-                        u32 m = (modes >> (6 - 2 * t)) & 3;
-                        if (fill) B.tab_pos[t] = tp;
-                        if (m == 1) {
-                            if (tp >= csz) ok = false;
-                            tp += 1;
-                            fse_src[t] = bidx;
-                        } else if (m == 2) {
-                            short nrm[64];
-                            u32 ms = maxSyms[t], tl = 0;
-                            u32 used = (tp < csz) ? fse_read_ncount(c + tp, csz - tp, nrm, &ms, &tl, maxLogs[t]) : 0;
-                            if (!used) ok = false;
-                            tp += used;
-                            fse_src[t] = bidx;
-                        } else if (m == 0) {
-                            fse_src[t] = bidx;
-                        } else {  // repeat
-                            if (fse_src[t] == 0xFFFFFFFFu) ok = false;
-                            if (fill) B.fse_block[t] = fse_src[t];
-                        }
-                    }
-                    if (!ok) break;
-                    if (tp > csz) { ok = false; break; }
-                    if (fill) {
-                        B.modes = (u8)modes;
-                        B.bits_pos = tp;
-                    }
-                } else if (fill)
-                    B.bits_pos = so + sh;
-            }
             if (fill) {
+                ZDBlock B;
                 B.src = (u64)(uintptr_t)(p + h);
+                B.lit_off = 0;
+                B.seq_off = 0;
                 B.csize = csz;
-                B.type = (u8)type;
-                B.frame = fidx;
                 B.rsize = (type == 2) ? 0u : bsz;
-                B.lit_regen = lit_regen;
-                B.nseq = nseq;
-                B.lit_off = lbase + inf.lit_bytes;
-                B.seq_off = sbase + inf.nseq;
+                B.frame = fidx;
+                B.lit_regen = 0;
+                B.lit_csize = 0;
+                B.nseq = 0;
+                B.seq_pos = 0;
+                B.bits_pos = 0;
+                B.huf_block = 0xFFFFFFFFu;
+                for (int t = 0; t < 3; t++) {
+                    B.tab_pos[t] = 0;
+                    B.fse_block[t] = 0xFFFFFFFFu;
+                }
+                B.out_off = 0xFFFFFFFFu;
+                B.type = (u8)type;
+                B.lit_type = 0;
+                B.lit_streams = 0;
+                B.lit_hdr = 0;
+                B.modes = 0;
                 B.err = 0;
-                B.out_off = (known_off < 0xFFFFFFFFull) ? (u32)known_off : 0xFFFFFFFFu;
-                blocks[bidx] = B;
+                B.pad[0] = B.pad[1] = 0;
+                blocks[first_block + nb] = B;
             }
-            if (known_off != ~0ull) {
-                if (type != 2) known_off += bsz;
-                else if (nseq == 0) known_off += lit_regen;
-                else known_off = ~0ull;
-            }
-            inf.lit_bytes += lit_regen;
-            inf.nseq += nseq;
             bound += (type == 2) ? ZSTD_BLOCK_MAX : bsz;
             h += csz;
             nb++;
             if (last) break;
         }
-        if (!ok) { inf.status = 1; break; }
+        if (!ok) { status = 1; break; }
         u32 ck = 0;
         if (has_ck) {
-            if (n - h < 4) { inf.status = 1; break; }
+            if (n - h < 4) { status = 1; break; }
             ck = rd32(p + h);
             h += 4;
         }
         u64 osz = (fcs != ~0ull) ? fcs : bound;
-        if (fcs != ~0ull && fcs > bound) { inf.status = 1; break; }
+        if (fcs != ~0ull && fcs > bound) { status = 1; break; }
         if (fill) {
             ZDFrame F;
-            F.dst_off = obase + inf.out_bytes;
+            F.dst_off = obase + out_bytes;
             F.content_size = fcs;
             F.first_block = first_block;
             F.nblocks = nb;
@@ -441,20 +368,169 @@ __global__ void k_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *i
             F.window = window;
             frames[fidx] = F;
         }
-        inf.out_bytes += osz;
-        inf.nframes++;
-        inf.nblocks += nb;
+        out_bytes += osz;
+        nframes++;
+        nblocks += nb;
         pos = h;
     }
     if (!fill) {
-        info[si].nframes = inf.nframes;
-        info[si].nblocks = inf.nblocks;
-        info[si].out_bytes = inf.out_bytes;
-        info[si].status = inf.status;
-        info[si].lit_bytes = inf.lit_bytes;
-        info[si].nseq = inf.nseq;
-    } else if (inf.status)
-        info[si].status = inf.status;
+        info[si].nframes = nframes;
+        info[si].nblocks = nblocks;
+        info[si].out_bytes = out_bytes;
+        info[si].status = status;
+        info[si].lit_bytes = 0;
+        info[si].nseq = 0;
+    } else if (status)
+        info[si].status = status;
+}
+
+// One thread per block: literals header, sequence count, positions of the table descriptions.
+// cnt[0][b] = regenerated literals, cnt[1][b] = sequences of block b (scanned into arena offsets later).
+__global__ void __launch_bounds__(128) k_zd_parse(ZDBlock *blocks, u32 nblocks, u32 *cnt, u32 cnt_stride) {
+    u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nblocks) return;
+    u32 lit_regen = 0, nseq = 0;
+    const u32 type = blocks[bi].type;
+    if (type == 2) {
+        const u8 *c = (const u8 *)(uintptr_t)blocks[bi].src;
+        const u32 csz = blocks[bi].csize;
+        bool ok = true;
+        u32 lt = 0, lr = 0, lc = 0, ls = 0, so = 0, sh = 1, modes = 0, bits_pos = 0;
+        u32 tab_pos[3] = {0, 0, 0};
+        u32 lh = parse_lit_header(c, csz, &lt, &lr, &lc, &ls);
+        if (!lh || lh + lc > csz || lr > ZSTD_BLOCK_MAX) ok = false;
+        if (ok) {
+            so = lh + lc;  // sequences section
+            if (so >= csz) ok = false;
+        }
+        if (ok) {
+            u32 b0 = c[so];
+            if (b0 == 0) nseq = 0;
+            else if (b0 < 128) nseq = b0;
+            else if (b0 < 255) {
+                if (so + 2 > csz) ok = false;
+                else nseq = ((b0 - 128) << 8) + c[so + 1];
+                sh = 2;
+            } else {
+                if (so + 3 > csz) ok = false;
+                else nseq = c[so + 1] + ((u32)c[so + 2] << 8) + 0x7F00;
+                sh = 3;
+            }
+        }
+        if (ok && nseq) {
+            if (so + sh >= csz) ok = false;
+            else {
+                modes = c[so + sh];
+                if (modes & 3) ok = false;
+                u32 tp = so + sh + 1;
+                // locate the three table descriptions (LL, OF, ML order) and the bitstream
+                const u32 maxLogs[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
+                const u32 maxSyms[3] = {ZSTD_MAX_LL, ZSTD_MAX_OF, ZSTD_MAX_ML};
+                for (int t = 0; t < 3 && ok; t++) {
+                    u32 m = (modes >> (6 - 2 * t)) & 3;
+                    tab_pos[t] = tp;
+                    if (m == 1) {
+                        if (tp >= csz) ok = false;
+                        tp += 1;
+                    } else if (m == 2) {
+                        short nrm[64];
+                        u32 ms = maxSyms[t], tl = 0;
+                        u32 used = (tp < csz) ? fse_read_ncount(c + tp, csz - tp, nrm, &ms, &tl, maxLogs[t]) : 0;
+                        if (!used) ok = false;
+                        tp += used;
+                    }
+                }
+                if (ok && tp > csz) ok = false;
+                bits_pos = tp;
+            }
+        } else if (ok)
+            bits_pos = so + sh;
+        if (ok) {
+            lit_regen = lr;
+            ZDBlock &B = blocks[bi];
+            B.lit_type = (u8)lt;
+            B.lit_streams = (u8)ls;
+            B.lit_hdr = (u8)lh;
+            B.lit_csize = lc;
+            B.lit_regen = lr;
+            B.nseq = nseq;
+            B.seq_pos = so + sh;
+            B.bits_pos = bits_pos;
+            B.modes = (u8)modes;
+            for (int t = 0; t < 3; t++) B.tab_pos[t] = tab_pos[t];
+        } else {
+            nseq = 0;
+            blocks[bi].err = 1;
+        }
+    }
+    cnt[bi] = lit_regen;
+    cnt[cnt_stride + bi] = nseq;
+}
+
+// One thread per frame, blocks in order: which block holds the Huffman tree of a treeless block and
+// the FSE table of a repeat-mode block, where each block's output starts while that is computable
+// from the headers alone, and sanity limits that keep the literal / sequence arenas within the
+// output size (a frame that claims more is corrupt).
+__global__ void __launch_bounds__(128) k_zd_link(ZDFrame *frames, u32 nframes, ZDBlock *blocks, u32 *cnt, u32 cnt_stride) {
+    u32 fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= nframes) return;
+    const u32 b0 = frames[fi].first_block, nb = frames[fi].nblocks;
+    const u64 cap = frames[fi].out_cap;
+    u32 huf_src = 0xFFFFFFFFu, fse_src[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    u64 known_off = 0;  // ~0: not computable any more
+    u64 lit_sum = 0, seq_sum = 0;
+    bool bad = false;
+    for (u32 k = 0; k < nb; k++) {
+        ZDBlock &B = blocks[b0 + k];
+        u32 bidx = b0 + k;
+        if (B.err) { bad = true; break; }
+        B.out_off = (known_off < 0xFFFFFFFFull) ? (u32)known_off : 0xFFFFFFFFu;
+        if (B.type == 2) {
+            if (B.lit_type == 3) {
+                if (huf_src == 0xFFFFFFFFu) { bad = true; break; }
+                B.huf_block = huf_src;
+            } else {
+                B.huf_block = bidx;
+                if (B.lit_type == 2) huf_src = bidx;
+            }
+            if (B.nseq) {
+                for (int t = 0; t < 3; t++) {
+                    u32 m = (B.modes >> (6 - 2 * t)) & 3;
+                    if (m == 3) {
+                        if (fse_src[t] == 0xFFFFFFFFu) bad = true;
+                        B.fse_block[t] = fse_src[t];
+                    } else {
+                        B.fse_block[t] = bidx;
+                        fse_src[t] = bidx;
+                    }
+                }
+                if (bad) break;
+            }
+            lit_sum += B.lit_regen;
+            seq_sum += B.nseq;
+        }
+        if (known_off != ~0ull) {
+            if (B.type != 2) known_off += B.rsize;
+            else if (B.nseq == 0) known_off += B.lit_regen;
+            else known_off = ~0ull;
+        }
+    }
+    if (!bad && (lit_sum > cap || 3 * seq_sum > cap)) bad = true;
+    if (bad) {  // the whole frame is rejected: its blocks take no arena space and are skipped by the decode kernels
+        for (u32 k = 0; k < nb; k++) {
+            blocks[b0 + k].err = 1;
+            cnt[b0 + k] = 0;
+            cnt[cnt_stride + b0 + k] = 0;
+        }
+    }
+}
+
+// arena offsets of every block = the scanned literal / sequence counts
+__global__ void __launch_bounds__(128) k_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride) {
+    u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nblocks) return;
+    blocks[bi].lit_off = cnt[bi];
+    blocks[bi].seq_off = cnt[cnt_stride + bi];
 }
 
 // ---------------------------------------------------------------------------------- literals
@@ -644,7 +720,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, 
         B.lit_type = 0;
         B.huf_block = 0xFFFFFFFFu;
     }
-    bool comp = valid && B.type == 2;
+    bool comp = valid && B.type == 2 && !B.err;
     u8 *dst = nullptr;
     u32 n = 0;
     u32 err = 0;
@@ -763,7 +839,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_sequences(ZDBlock *blocks,
     u32 bi = blockIdx.x * ZD_WARPS + warp;
     if (bi >= nblocks) return;
     ZDBlock B = blocks[bi];
-    if (B.type != 2 || B.nseq == 0) return;
+    if (B.type != 2 || B.nseq == 0 || B.err) return;
     SeqScratch &S = scratch[warp];
     if (lane == 0) {
         u32 err = 0;
@@ -893,78 +969,19 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
 }
 
 // ---------------------------------------------------------------------------------- content checksum
-__device__ __forceinline__ u64 zrotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ u64 zxxh_round(u64 acc, u64 in) { return zrotl64(acc + in * XXP2, 31) * XXP1; }
-__device__ __forceinline__ u64 zxxh_merge(u64 h, u64 v) { return (h ^ zxxh_round(0, v)) * XXP1 + XXP4; }
-__device__ __forceinline__ u64 zld64(const u8 *p) { return (u64)ld_u32_unaligned(p) | ((u64)ld_u32_unaligned(p + 4) << 32); }
-__global__ void __launch_bounds__(128) k_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out) {
+// see fqz_xxh64.cuh: 4 threads per frame, 8 frames per warp, frames streamed through shared memory by TMA
+__global__ void __launch_bounds__(XX_WARPS * 32) k_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out) {
+    FQZ_DYN_SMEM(u8, smem);
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 fi = t >> 2, q = t & 3;
     u32 gm = group_mask(4);
     bool live = fi < nframes;
     ZDFrame F = frames[live ? fi : nframes - 1];
-    const u8 *p = out + F.dst_off;
-    u64 len = (F.err || !F.has_ck) ? 0 : F.out_size;
-    u64 acc = (q == 0) ? XXP1 + XXP2 : (q == 1) ? XXP2 : (q == 2) ? 0ull : 0ull - XXP1;
-    u64 nstripes = len >> 5;
-    const u8 *s = p + 8u * q;
-    {
-        // serial multiply-rotate chain, independent loads: keep 8 stripes in flight
-        const u32 *w = (const u32 *)((uintptr_t)s & ~(uintptr_t)3);
-        const u32 sh = (u32)((uintptr_t)s & 3u) * 8u;
-        u64 i = 0;
-        for (; i + 8 <= nstripes; i += 8) {
-            u32 a[8], b[8], c[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                a[k] = w[8 * (i + k)];
-                b[k] = w[8 * (i + k) + 1];
-                c[k] = w[8 * (i + k) + 2];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                u64 v = (u64)__funnelshift_r(a[k], b[k], sh) | ((u64)__funnelshift_r(b[k], c[k], sh) << 32);
-                acc = zxxh_round(acc, v);
-            }
-        }
-        for (; i < nstripes; i++) acc = zxxh_round(acc, zld64(s + 32ull * i));
-    }
-    u64 a0 = __shfl_sync(gm, acc, 0, 4), a1 = __shfl_sync(gm, acc, 1, 4), a2 = __shfl_sync(gm, acc, 2, 4), a3 = __shfl_sync(gm, acc, 3, 4);
-    u64 h;
-    if (len >= 32) {
-        h = zrotl64(a0, 1) + zrotl64(a1, 7) + zrotl64(a2, 12) + zrotl64(a3, 18);
-        h = zxxh_merge(h, a0);
-        h = zxxh_merge(h, a1);
-        h = zxxh_merge(h, a2);
-        h = zxxh_merge(h, a3);
-    } else
-        h = XXP5;
-    h += len;
-    const u8 *tp = p + 32ull * nstripes;
-    u32 rem = (u32)(len & 31);
-    while (rem >= 8) {
-        h ^= zxxh_round(0, zld64(tp));
-        h = zrotl64(h, 27) * XXP1 + XXP4;
-        tp += 8;
-        rem -= 8;
-    }
-    if (rem >= 4) {
-        h ^= (u64)ld_u32_unaligned(tp) * XXP1;
-        h = zrotl64(h, 23) * XXP2 + XXP3;
-        tp += 4;
-        rem -= 4;
-    }
-    while (rem) {
-        h ^= (u64)(*tp) * XXP5;
-        h = zrotl64(h, 11) * XXP1;
-        tp++;
-        rem--;
-    }
-    h ^= h >> 33;
-    h *= XXP2;
-    h ^= h >> 29;
-    h *= XXP3;
-    h ^= h >> 32;
+    u64 len = (!live || F.err || !F.has_ck) ? 0 : F.out_size;
+    u8 *rows;
+    u64 *bars;
+    xx_quad_smem(smem, &rows, &bars);
+    u64 h = xxh64_quad_staged(out + F.dst_off, len, q, gm, rows, bars);
     if (live && q == 0 && F.has_ck && !F.err && (u32)h != F.ck) frames[fi].err = 2;
 }
 
@@ -1018,9 +1035,21 @@ void fqz_launch_zd_compact(ZDFrame *frames, const ZDStreamInfo *info, const ZDSt
     if (!nstreams) return;
     FQZ_LAUNCH(k_zd_compact, (nstreams * 32 + 127) / 128, 128, 0, s, frames, info, res, nstreams, out);
 }
-void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s) {
+void fqz_launch_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s) {
     if (!nstreams) return;
-    FQZ_LAUNCH(k_zd_walk, (nstreams + 31) / 32, 32, 0, s, streams, nstreams, info, frames, blocks, fill);
+    FQZ_LAUNCH(k_zd_hop, (nstreams + 31) / 32, 32, 0, s, streams, nstreams, info, frames, blocks, fill);
+}
+void fqz_launch_zd_parse(ZDBlock *blocks, u32 nblocks, u32 *cnt, u32 cnt_stride, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_zd_parse, (nblocks + 127) / 128, 128, 0, s, blocks, nblocks, cnt, cnt_stride);
+}
+void fqz_launch_zd_link(ZDFrame *frames, u32 nframes, ZDBlock *blocks, u32 *cnt, u32 cnt_stride, cudaStream_t s) {
+    if (!nframes) return;
+    FQZ_LAUNCH(k_zd_link, (nframes + 127) / 128, 128, 0, s, frames, nframes, blocks, cnt, cnt_stride);
+}
+void fqz_launch_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_zd_offsets, (nblocks + 127) / 128, 128, 0, s, blocks, nblocks, cnt, cnt_stride);
 }
 void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s) {
     if (!nblocks) return;
@@ -1037,7 +1066,13 @@ void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const 
 }
 void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s) {
     if (!nframes) return;
-    FQZ_LAUNCH(k_zd_checksum, (nframes * 4 + 127) / 128, 128, 0, s, frames, nframes, out);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_zd_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+        attr_done = true;
+    }
+    u32 threads = XX_WARPS * 32;
+    FQZ_LAUNCH(k_zd_checksum, (nframes * 4 + threads - 1) / threads, threads, XX_SMEM, s, frames, nframes, out);
 }
 void fqz_launch_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res, cudaStream_t s) {
     if (!nstreams) return;

@@ -54,7 +54,10 @@ struct ZDStreamResult {
     u32 contiguous;
 };
 
-void fqz_launch_zd_walk(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s);
+void fqz_launch_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s);
+void fqz_launch_zd_parse(ZDBlock *blocks, u32 nblocks, u32 *cnt, u32 cnt_stride, cudaStream_t s);
+void fqz_launch_zd_link(ZDFrame *frames, u32 nframes, ZDBlock *blocks, u32 *cnt, u32 cnt_stride, cudaStream_t s);
+void fqz_launch_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, cudaStream_t s);
 void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s);
 void fqz_launch_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf, cudaStream_t s);
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s);

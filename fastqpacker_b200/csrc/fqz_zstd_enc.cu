@@ -14,6 +14,7 @@
 
 #include "fqz_zstd.h"
 #include "fqz_zstd_tables.cuh"
+#include "fqz_xxh64.cuh"
 
 #define FULL 0xffffffffu
 #define HLOG 12
@@ -1697,92 +1698,31 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
 }
 
 // ---------------------------------------------------------------------------------- XXH64 (frame content checksum)
-// XXH64 is four serial multiply-rotate lanes per frame and cannot be split inside a frame, so it is
-// parallelised ACROSS frames: 4 threads per frame, 8 frames per warp.
-__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
-__device__ __forceinline__ u64 xxh_round(u64 acc, u64 in) { return rotl64(acc + in * XXP2, 31) * XXP1; }
-__device__ __forceinline__ u64 xxh_merge(u64 h, u64 v) { return (h ^ xxh_round(0, v)) * XXP1 + XXP4; }
-__device__ __forceinline__ u64 ld_u64_unaligned(const u8 *p) { return (u64)ld_u32_unaligned(p) | ((u64)ld_u32_unaligned(p + 4) << 32); }
-
-__device__ static u64 xxh64_quad(const u8 *p, u32 len, u32 q /*0..3*/, u32 gmask) {
-    u64 acc = (q == 0) ? XXP1 + XXP2 : (q == 1) ? XXP2 : (q == 2) ? 0ull : 0ull - XXP1;
-    u32 nstripes = len >> 5;
-    const u8 *s = p + 8u * q;
-    {
-        // the rounds are a serial multiply-rotate chain, the loads are not: keep 8 stripes in flight
-        // (three aligned words cover any 8 unaligned bytes, merged with funnel shifts)
-        const u32 *w = (const u32 *)((uintptr_t)s & ~(uintptr_t)3);
-        const u32 sh = (u32)((uintptr_t)s & 3u) * 8u;
-        u32 i = 0;
-        for (; i + 8 <= nstripes; i += 8) {
-            u32 a[8], b[8], c[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                a[k] = w[8 * (i + k)];
-                b[k] = w[8 * (i + k) + 1];
-                c[k] = w[8 * (i + k) + 2];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                u64 v = (u64)__funnelshift_r(a[k], b[k], sh) | ((u64)__funnelshift_r(b[k], c[k], sh) << 32);
-                acc = xxh_round(acc, v);
-            }
-        }
-        for (; i < nstripes; i++) acc = xxh_round(acc, ld_u64_unaligned(s + 32ull * i));
-    }
-    u64 a0 = __shfl_sync(gmask, acc, 0, 4), a1 = __shfl_sync(gmask, acc, 1, 4), a2 = __shfl_sync(gmask, acc, 2, 4), a3 = __shfl_sync(gmask, acc, 3, 4);
-    u64 h;
-    if (len >= 32) {
-        h = rotl64(a0, 1) + rotl64(a1, 7) + rotl64(a2, 12) + rotl64(a3, 18);
-        h = xxh_merge(h, a0);
-        h = xxh_merge(h, a1);
-        h = xxh_merge(h, a2);
-        h = xxh_merge(h, a3);
-    } else
-        h = XXP5;
-    h += (u64)len;
-    const u8 *t = p + 32ull * nstripes;
-    u32 rem = len & 31;
-    while (rem >= 8) {
-        h ^= xxh_round(0, ld_u64_unaligned(t));
-        h = rotl64(h, 27) * XXP1 + XXP4;
-        t += 8;
-        rem -= 8;
-    }
-    if (rem >= 4) {
-        h ^= (u64)ld_u32_unaligned(t) * XXP1;
-        h = rotl64(h, 23) * XXP2 + XXP3;
-        t += 4;
-        rem -= 4;
-    }
-    while (rem) {
-        h ^= (u64)(*t) * XXP5;
-        h = rotl64(h, 11) * XXP1;
-        t++;
-        rem--;
-    }
-    h ^= h >> 33;
-    h *= XXP2;
-    h ^= h >> 29;
-    h *= XXP3;
-    h ^= h >> 32;
-    return h;
-}
-__global__ void __launch_bounds__(128) k_xxh64_frames(const ZFrame *frames, u32 nframes, u32 *hashes) {
+// see fqz_xxh64.cuh: 4 threads per frame, 8 frames per warp, frames streamed through shared memory by TMA
+__global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *frames, u32 nframes, u32 *hashes) {
+    FQZ_DYN_SMEM(u8, smem);
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 fi = t >> 2, q = t & 3;
     u32 gmask = group_mask(4);
     bool live = fi < nframes;
     u32 fj = live ? fi : nframes - 1;  // keep whole quads alive for the shuffles
     ZFrame fr = frames[fj];
-    u64 h = xxh64_quad((const u8 *)(uintptr_t)fr.src, fr.src_len, q, gmask);
+    u8 *rows;
+    u64 *bars;
+    xx_quad_smem(smem, &rows, &bars);
+    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)fr.src, live ? fr.src_len : 0u, q, gmask, rows, bars);
     if (live && q == 0) hashes[fi] = (u32)h;
 }
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
-    u32 threads = 128, grid = (nframes * 4 + threads - 1) / threads;
-    FQZ_LAUNCH(k_xxh64_frames, grid, threads, 0, s, frames, nframes, hashes);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+        attr_done = true;
+    }
+    u32 threads = XX_WARPS * 32, grid = (nframes * 4 + threads - 1) / threads;
+    FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes);
 }
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s) {
     if (!nidx) return;
