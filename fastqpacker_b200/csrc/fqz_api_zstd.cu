@@ -58,11 +58,26 @@ __global__ void k_write_block_headers(u32 nblocks, const u32 *first, const u32 *
 // ---------------------------------------------------------------------------------- zstd batch
 struct ZBatch {
     std::vector<ZFrame> frames;
-    std::vector<u32> idx_ent, idx_lz, idx_items;
+    std::vector<u32> idx_ent, idx_lz, idx_items, idx_index;
     size_t slot_bytes = 0, ws_bytes = 0;
     // items / item_base / item_count: see ZFrame (policy FQZ_ZPOLICY_ITEMS only)
     void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0) {
         const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : (policy == FQZ_ZPOLICY_ITEMS ? FQZ_ZFRAME_ITEMS : FQZ_ZFRAME);
+        const size_t nfr = (len + fsz - 1) / fsz;
+        if (nfr >= FQZ_ZINDEX_MIN) {  // frame index in front of the stream (FQZ_ZPOLICY_INDEX)
+            ZFrame f;
+            f.src = 0;
+            f.dst_off = slot_bytes;
+            f.ws_off = 0;
+            f.src_len = (u32)nfr;
+            f.policy = FQZ_ZPOLICY_INDEX;
+            f.items = 0;
+            f.item_base = 0;
+            f.item_count = 0;
+            slot_bytes += (FQZ_ZINDEX_BYTES(nfr) + 15u) & ~(size_t)15;
+            idx_index.push_back((u32)frames.size());
+            frames.push_back(f);
+        }
         for (size_t o = 0; o < len; o += fsz) {
             u32 l = (u32)std::min<size_t>(fsz, len - o);
             ZFrame f;
@@ -96,7 +111,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     cudaStream_t s = c->stream;
     u32 nf = (u32)zb.frames.size();
     ze.nframes = nf;
-    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size()) * sizeof(u32);
+    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size() + zb.idx_index.size()) * sizeof(u32);
     FQZ_TRY(fqz_pin_reserve(c, 8192 + up));
     u8 *hp = c->h_pin + 4096;
     memcpy(hp, zb.frames.data(), (size_t)nf * sizeof(ZFrame));
@@ -104,6 +119,8 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     if (!zb.idx_ent.empty()) memcpy(hidx, zb.idx_ent.data(), zb.idx_ent.size() * sizeof(u32));
     if (!zb.idx_lz.empty()) memcpy(hidx + zb.idx_ent.size(), zb.idx_lz.data(), zb.idx_lz.size() * sizeof(u32));
     if (!zb.idx_items.empty()) memcpy(hidx + zb.idx_ent.size() + zb.idx_lz.size(), zb.idx_items.data(), zb.idx_items.size() * sizeof(u32));
+    const size_t index_at = zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size();
+    if (!zb.idx_index.empty()) memcpy(hidx + index_at, zb.idx_index.data(), zb.idx_index.size() * sizeof(u32));
     u8 *d_up = (u8 *)c->arena.alloc(up + 16);
     ze.d_slots = (u8 *)c->arena.alloc(zb.slot_bytes + 16);
     u8 *d_ws = (u8 *)c->arena.alloc(zb.ws_bytes + 16);
@@ -137,6 +154,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     }
     {
         StageScope sc(c, ST_SCAN, 0);
+        fqz_launch_zindex(ze.d_frames, d_idx + index_at, (u32)zb.idx_index.size(), ze.d_slots, ze.d_scan, s);
         FQZ_TRY(fqz_scan_excl_u32(c, ze.d_scan, (u64)nf + 1, (u64)nf + 1, 1));
     }
     return FQZ_OK;

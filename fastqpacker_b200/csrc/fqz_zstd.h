@@ -27,10 +27,22 @@ struct ZFrame {
     u32 item_count; // entries of items[] including the end sentinel; fixed stride: the stride in bytes
 };
 #define FQZ_ZPOLICY_ITEMS 2  // internal: LZ by item matcher (needs the item boundaries of the stream)
+// internal: not a zstd frame but a SKIPPABLE frame (RFC 8878 §3.1.2) in front of a stream that was cut
+// into many frames: it lists the compressed size of each of the src_len frames that follow, so that
+// the GPU decoder can find them all at once instead of hopping header by header.  Every decoder,
+// the reference's included, skips it.  Layout: magic 0x184D2A5E, u32 payload size, then the payload
+// 'FQZI', u32 nframes, nframes x u32 compressed frame size.
+#define FQZ_ZPOLICY_INDEX 3
+#define FQZ_ZINDEX_MAGIC 0x184D2A5Eu
+#define FQZ_ZINDEX_SIG 0x495A5146u  // "FQZI" little-endian
+#define FQZ_ZINDEX_MIN 4u           // streams of fewer frames carry no index
+#define FQZ_ZINDEX_BYTES(n) (16u + 4u * (u32)(n))
 
 #define ZENC_WARPS 4
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
+// fills the index frames listed in index[0..nidx) from the sizes of the frames behind them
+void fqz_launch_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s);
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,

@@ -249,14 +249,129 @@ __device__ static u32 parse_lit_header(const u8 *p, u32 avail, u32 *type, u32 *r
 // output offsets known from headers alone) by one thread per frame (k_zd_link).
 // k_zd_hop pass 0 (fill == 0): counts frames / blocks / output bytes per stream.
 // pass 1: fills the frame table and the position part of the block table at the bases computed by the host.
-__global__ void k_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill) {
-    u32 si = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per stream.  Streams written by this library start with a skippable index frame
+// (FQZ_ZPOLICY_INDEX: the compressed size of every frame behind it): the lanes then hop 32 frames at
+// a time, and the index is only trusted as far as it is proven — every frame must start with the
+// zstd magic and its block chain must end exactly where the index says; any mismatch sends the
+// stream down the serial path (lane 0), which is also what streams of any other writer take.
+
+// Hops over ONE zstd frame at p[pos..n).  Returns 0 ok / 1 corrupt / 2 dictionary.  fill: writes
+// frames[fidx] and blocks[first_block ...].
+__device__ static u32 zd_hop_frame(const u8 *p, u64 n, u64 pos, bool fill, u32 fidx, u32 first_block, u64 dst_off, u32 si, ZDFrame *frames,
+                                   ZDBlock *blocks, u32 *nb_out, u64 *osz_out, u64 *end_out) {
+    if (n - pos < 6) return 1;
+    if (rd32(p + pos) != ZSTD_MAGIC) return 1;
+    u32 fhd = p[pos + 4];
+    u32 fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did = fhd & 3;
+    if (fhd & 8) return 1;  // reserved bit
+    if (did) return 2;      // dictionaries are not used by the reference
+    u64 h = pos + 5;
+    u64 window = 0;
+    if (!single) {
+        u32 wd = p[h++];
+        u32 e = wd >> 3, m = wd & 7;
+        window = ((u64)1 << (10 + e));
+        window += (window >> 3) * m;
+    }
+    u32 fcs_size = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
+    if (n - h < fcs_size) return 1;
+    u64 fcs = ~0ull;
+    if (fcs_size == 1) fcs = p[h];
+    else if (fcs_size == 2) fcs = (u64)(p[h] | (p[h + 1] << 8)) + 256;
+    else if (fcs_size == 4) fcs = rd32(p + h);
+    else if (fcs_size == 8) fcs = (u64)rd32(p + h) | ((u64)rd32(p + h + 4) << 32);
+    h += fcs_size;
+    if (single) window = fcs;
+    u32 nb = 0;
+    u64 bound = 0;
+    for (;;) {
+        if (n - h < 3) return 1;
+        u32 bh = rd24(p + h);
+        u32 last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
+        h += 3;
+        if (type == 3) return 1;
+        u32 csz = (type == 1) ? 1 : bsz;
+        if (n - h < csz || bsz > ZSTD_BLOCK_MAX) return 1;
+        if (type == 2 && bsz < 2) return 1;
+        if (fill) {
+            ZDBlock B;
+            B.src = (u64)(uintptr_t)(p + h);
+            B.lit_off = 0;
+            B.seq_off = 0;
+            B.csize = csz;
+            B.rsize = (type == 2) ? 0u : bsz;
+            B.frame = fidx;
+            B.lit_regen = 0;
+            B.lit_csize = 0;
+            B.nseq = 0;
+            B.seq_pos = 0;
+            B.bits_pos = 0;
+            B.huf_block = 0xFFFFFFFFu;
+            for (int t = 0; t < 3; t++) {
+                B.tab_pos[t] = 0;
+                B.fse_block[t] = 0xFFFFFFFFu;
+            }
+            B.out_off = 0xFFFFFFFFu;
+            B.type = (u8)type;
+            B.lit_type = 0;
+            B.lit_streams = 0;
+            B.lit_hdr = 0;
+            B.modes = 0;
+            B.err = 0;
+            B.pad[0] = B.pad[1] = 0;
+            blocks[first_block + nb] = B;
+        }
+        bound += (type == 2) ? ZSTD_BLOCK_MAX : bsz;
+        h += csz;
+        nb++;
+        if (last) break;
+    }
+    u32 ck = 0;
+    if (has_ck) {
+        if (n - h < 4) return 1;
+        ck = rd32(p + h);
+        h += 4;
+    }
+    u64 osz = (fcs != ~0ull) ? fcs : bound;
+    if (fcs != ~0ull && fcs > bound) return 1;
+    if (fill) {
+        ZDFrame F;
+        F.dst_off = dst_off;
+        F.content_size = fcs;
+        F.first_block = first_block;
+        F.nblocks = nb;
+        F.has_ck = has_ck;
+        F.ck = ck;
+        F.stream = si;
+        F.out_cap = osz;
+        F.out_size = 0;
+        F.err = 0;
+        F.window = window;
+        frames[fidx] = F;
+    }
+    *nb_out = nb;
+    *osz_out = osz;
+    *end_out = h;
+    return 0;
+}
+
+__device__ __forceinline__ u64 warp_incl_scan_u64(u64 v) {
+    u32 l = lane_id();
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, v, (unsigned)d);
+        if (l >= (u32)d) v += t;
+    }
+    return v;
+}
+
+#define ZD_HOP_WARPS 4
+__global__ void __launch_bounds__(ZD_HOP_WARPS * 32) k_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks,
+                                                            int fill) {
+    u32 si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (si >= nstreams) return;
     ZDStream st = streams[si];
     const u8 *p = (const u8 *)(uintptr_t)st.src;
-    u64 n = st.csize, pos = 0;
-    u32 nframes = 0, nblocks = 0, status = 0;
-    u64 out_bytes = 0;
+    const u64 n = st.csize;
     u32 fbase = 0, bbase = 0;
     u64 obase = 0;
     if (fill) {
@@ -264,124 +379,90 @@ __global__ void k_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *in
         bbase = info[si].block_base;
         obase = info[si].out_base;
     }
-    while (pos < n) {
-        if (n - pos < 4) { status = 1; break; }
-        u32 magic = rd32(p + pos);
-        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
-            if (n - pos < 8) { status = 1; break; }
-            u64 sz = rd32(p + pos + 4);
-            if (n - pos - 8 < sz) { status = 1; break; }
-            pos += 8 + sz;
-            continue;
+    u32 nframes = 0, nblocks = 0, status = 0;
+    u64 out_bytes = 0;
+    // ---- indexed path
+    bool indexed = false;
+    if (n >= 20 && rd32(p) == FQZ_ZINDEX_MAGIC && rd32(p + 8) == FQZ_ZINDEX_SIG) {
+        u32 nf = rd32(p + 12);
+        u64 isz = 16ull + 4ull * nf;
+        if (nf >= 1 && rd32(p + 4) == 8ull + 4ull * nf && isz < n) {
+            u64 sum = 0;
+            for (u32 k = lane; k < nf; k += 32) sum += rd32(p + 16 + 4ull * k);
+            for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            indexed = (sum == n - isz);
         }
-        if (magic != ZSTD_MAGIC) { status = 1; break; }
-        if (n - pos < 6) { status = 1; break; }
-        u32 fhd = p[pos + 4];
-        u32 fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, has_ck = (fhd >> 2) & 1, did = fhd & 3;
-        if (fhd & 8) { status = 1; break; }  // reserved bit
-        if (did) { status = 2; break; }      // dictionaries are not used by the reference
-        u64 h = pos + 5;
-        u64 window = 0;
-        if (!single) {
-            u32 wd = p[h++];
-            u32 e = wd >> 3, m = wd & 7;
-            window = ((u64)1 << (10 + e));
-            window += (window >> 3) * m;
-        }
-        u32 fcs_size = fcs_flag == 0 ? (single ? 1 : 0) : (fcs_flag == 1 ? 2 : (fcs_flag == 2 ? 4 : 8));
-        if (n - h < fcs_size) { status = 1; break; }
-        u64 fcs = ~0ull;
-        if (fcs_size == 1) fcs = p[h];
-        else if (fcs_size == 2) fcs = (u64)(p[h] | (p[h + 1] << 8)) + 256;
-        else if (fcs_size == 4) fcs = rd32(p + h);
-        else if (fcs_size == 8) fcs = (u64)rd32(p + h) | ((u64)rd32(p + h + 4) << 32);
-        h += fcs_size;
-        if (single) window = fcs;
-        u32 fidx = fbase + nframes;
-        u32 first_block = bbase + nblocks;
-        u32 nb = 0;
-        u64 bound = 0;
-        bool ok = true;
-        for (;;) {
-            if (n - h < 3) { ok = false; break; }
-            u32 bh = rd24(p + h);
-            u32 last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
-            h += 3;
-            if (type == 3) { ok = false; break; }
-            u32 csz = (type == 1) ? 1 : bsz;
-            if (n - h < csz || bsz > ZSTD_BLOCK_MAX) { ok = false; break; }
-            if (type == 2 && bsz < 2) { ok = false; break; }
-            if (fill) {
-                ZDBlock B;
-                B.src = (u64)(uintptr_t)(p + h);
-                B.lit_off = 0;
-                B.seq_off = 0;
-                B.csize = csz;
-                B.rsize = (type == 2) ? 0u : bsz;
-                B.frame = fidx;
-                B.lit_regen = 0;
-                B.lit_csize = 0;
-                B.nseq = 0;
-                B.seq_pos = 0;
-                B.bits_pos = 0;
-                B.huf_block = 0xFFFFFFFFu;
-                for (int t = 0; t < 3; t++) {
-                    B.tab_pos[t] = 0;
-                    B.fse_block[t] = 0xFFFFFFFFu;
+        if (indexed) {
+            u64 pos = isz;  // start of the first frame of the current chunk of 32
+            for (u32 f0 = 0; f0 < nf; f0 += 32) {
+                u32 k = f0 + lane;
+                bool live = k < nf;
+                u64 sz = live ? rd32(p + 16 + 4ull * k) : 0;
+                u64 incl = warp_incl_scan_u64(sz);
+                u64 start = pos + incl - sz;
+                u32 nb = 0, rc = 0;
+                u64 osz = 0, end = 0;
+                if (live) {
+                    // the frame is hopped inside its own bounds: a chain that leaves them is a mismatch
+                    rc = zd_hop_frame(p, start + sz, start, false, 0, 0, 0, si, frames, blocks, &nb, &osz, &end);
+                    if (rc == 0 && end != start + sz) rc = 1;
+                    if (rc) nb = 0, osz = 0;
                 }
-                B.out_off = 0xFFFFFFFFu;
-                B.type = (u8)type;
-                B.lit_type = 0;
-                B.lit_streams = 0;
-                B.lit_hdr = 0;
-                B.modes = 0;
-                B.err = 0;
-                B.pad[0] = B.pad[1] = 0;
-                blocks[first_block + nb] = B;
+                if (__any_sync(0xffffffffu, rc != 0)) {
+                    indexed = false;
+                    break;
+                }
+                u32 nbi = group_incl_scan(nb, 0xffffffffu, 32);
+                u64 oi = warp_incl_scan_u64(osz);
+                if (fill && live)
+                    zd_hop_frame(p, start + sz, start, true, fbase + nframes + lane, bbase + nblocks + nbi - nb, obase + out_bytes + oi - osz, si, frames,
+                                 blocks, &nb, &osz, &end);
+                nframes += min(32u, nf - f0);
+                nblocks += __shfl_sync(0xffffffffu, nbi, 31);
+                out_bytes += __shfl_sync(0xffffffffu, oi, 31);
+                pos += __shfl_sync(0xffffffffu, incl, 31);
             }
-            bound += (type == 2) ? ZSTD_BLOCK_MAX : bsz;
-            h += csz;
-            nb++;
-            if (last) break;
         }
-        if (!ok) { status = 1; break; }
-        u32 ck = 0;
-        if (has_ck) {
-            if (n - h < 4) { status = 1; break; }
-            ck = rd32(p + h);
-            h += 4;
-        }
-        u64 osz = (fcs != ~0ull) ? fcs : bound;
-        if (fcs != ~0ull && fcs > bound) { status = 1; break; }
-        if (fill) {
-            ZDFrame F;
-            F.dst_off = obase + out_bytes;
-            F.content_size = fcs;
-            F.first_block = first_block;
-            F.nblocks = nb;
-            F.has_ck = has_ck;
-            F.ck = ck;
-            F.stream = si;
-            F.out_cap = osz;
-            F.out_size = 0;
-            F.err = 0;
-            F.window = window;
-            frames[fidx] = F;
-        }
-        out_bytes += osz;
-        nframes++;
-        nblocks += nb;
-        pos = h;
     }
-    if (!fill) {
-        info[si].nframes = nframes;
-        info[si].nblocks = nblocks;
-        info[si].out_bytes = out_bytes;
-        info[si].status = status;
-        info[si].lit_bytes = 0;
-        info[si].nseq = 0;
-    } else if (status)
-        info[si].status = status;
+    // ---- serial path (lane 0): any frame sequence
+    if (!indexed) {
+        nframes = 0;
+        nblocks = 0;
+        out_bytes = 0;
+        if (lane == 0) {
+            u64 pos = 0;
+            while (pos < n) {
+                if (n - pos < 4) { status = 1; break; }
+                u32 magic = rd32(p + pos);
+                if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {  // skippable frame
+                    if (n - pos < 8) { status = 1; break; }
+                    u64 sz = rd32(p + pos + 4);
+                    if (n - pos - 8 < sz) { status = 1; break; }
+                    pos += 8 + sz;
+                    continue;
+                }
+                u32 nb = 0;
+                u64 osz = 0, end = 0;
+                u32 rc = zd_hop_frame(p, n, pos, fill != 0, fbase + nframes, bbase + nblocks, obase + out_bytes, si, frames, blocks, &nb, &osz, &end);
+                if (rc) { status = rc; break; }
+                out_bytes += osz;
+                nframes++;
+                nblocks += nb;
+                pos = end;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (!fill) {
+            info[si].nframes = nframes;
+            info[si].nblocks = nblocks;
+            info[si].out_bytes = out_bytes;
+            info[si].status = status;
+            info[si].lit_bytes = 0;
+            info[si].nseq = 0;
+        } else if (status)
+            info[si].status = status;
+    }
 }
 
 // One thread per block: literals header, sequence count, positions of the table descriptions.
@@ -1037,7 +1118,7 @@ void fqz_launch_zd_compact(ZDFrame *frames, const ZDStreamInfo *info, const ZDSt
 }
 void fqz_launch_zd_hop(const ZDStream *streams, u32 nstreams, ZDStreamInfo *info, ZDFrame *frames, ZDBlock *blocks, int fill, cudaStream_t s) {
     if (!nstreams) return;
-    FQZ_LAUNCH(k_zd_hop, (nstreams + 31) / 32, 32, 0, s, streams, nstreams, info, frames, blocks, fill);
+    FQZ_LAUNCH(k_zd_hop, (nstreams + ZD_HOP_WARPS - 1) / ZD_HOP_WARPS, ZD_HOP_WARPS * 32, 0, s, streams, nstreams, info, frames, blocks, fill);
 }
 void fqz_launch_zd_parse(ZDBlock *blocks, u32 nblocks, u32 *cnt, u32 cnt_stride, cudaStream_t s) {
     if (!nblocks) return;

@@ -315,21 +315,40 @@ __device__ static u32 warp_huf_build(const u32 *hist, u32 total, u16 *hlut, HufT
             if (iter <= 7) flo = max(1u, total >> (11 - iter));
             else ones = true;
         }
-        // rank sort of present symbols by (count', symbol)
-        for (u32 i = 0; i < 8; i++) {
-            u32 s = lane * 8 + i;
-            u32 c = hist[s];
-            if (!c) continue;
-            u32 cs = ones ? 1u : max(c, flo);
-            u32 rank = 0;
-            for (u32 t = 0; t < 256; t++) {
-                u32 ct = hist[t];
-                if (!ct) continue;
-                u32 cts = ones ? 1u : max(ct, flo);
-                rank += (cts < cs || (cts == cs && t < s)) ? 1u : 0u;
+        // rank sort of the present symbols by (count', symbol): the m keys count' << 8 | symbol are
+        // compacted first (they are distinct), so ranking costs m compares per symbol instead of 256
+        {
+            u32 *keys = (u32 *)H.node_par;  // 256 words; node_par is only written by the merge below
+            u32 at = group_incl_scan(present, FULL, 32) - present;
+            for (u32 i = 0; i < 8; i++) {
+                u32 s = lane * 8 + i;
+                u32 c = hist[s];
+                if (c) keys[at++] = ((ones ? 1u : max(c, flo)) << 8) | s;
             }
-            H.ssym[rank] = (u8)s;
-            H.node_w[rank] = cs;
+            __syncwarp();
+            u32 myk[8], myr[8];
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) {
+                u32 r = lane + 32u * j;
+                myk[j] = (r < m) ? keys[r] : 0xFFFFFFFFu;
+                myr[j] = 0;
+            }
+            const u32 nj = (m + 31u) >> 5;
+            for (u32 t = 0; t < m; t++) {
+                u32 kt = keys[t];
+#pragma unroll
+                for (u32 j = 0; j < 8; j++)
+                    if (j < nj) myr[j] += (kt < myk[j]) ? 1u : 0u;
+            }
+            __syncwarp();  // every lane has read the keys: node_w / ssym may alias nothing, but keep the phases apart
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) {
+                u32 r = lane + 32u * j;
+                if (r < m) {
+                    H.ssym[myr[j]] = (u8)myk[j];
+                    H.node_w[myr[j]] = myk[j] >> 8;
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -383,16 +402,21 @@ __device__ static u32 warp_huf_build(const u32 *hist, u32 total, u16 *hlut, HufT
         }
     }
     __syncwarp();
-    for (u32 i = 0; i < 8; i++) {
-        u32 s = lane * 8 + i;
-        u32 l = H.len[s];
-        u32 e = 0;
-        if (l) {
-            u32 idx = 0;
-            for (u32 t = 0; t < s; t++) idx += (H.len[t] == l) ? 1u : 0u;
-            e = ((cnt_len[16 + l] + idx) << 4) | l;
+    {
+        // index of a symbol among the symbols of its length, in symbol order: ranked over the compacted
+        // (symbol-ordered) list of present symbols; the rank-sorted list in ssym is no longer needed
+        u32 at = group_incl_scan(present, FULL, 32) - present;
+        for (u32 i = 0; i < 8; i++) {
+            u32 s = lane * 8 + i;
+            hlut[s] = 0;
+            if (hist[s]) H.ssym[at++] = (u8)s;
         }
-        hlut[s] = (u16)e;
+        __syncwarp();
+        for (u32 r = lane; r < m; r += 32) {
+            u32 s = H.ssym[r], l = H.len[s], idx = 0;
+            for (u32 t = 0; t < r; t++) idx += (H.len[H.ssym[t]] == l) ? 1u : 0u;
+            hlut[s] = (u16)(((cnt_len[16 + l] + idx) << 4) | l);
+        }
     }
     __syncwarp();
     return maxBits;
@@ -786,61 +810,151 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
         S.hist[196] = tlog[2];
     }
     __syncwarp();
-    // 3. interleaved FSE bitstream, written backwards (last sequence first).  The state chain is
-    //    serial (lane 0), but its operands are not: the warp stages 32 sequences at a time in shared
-    //    memory so that the chain never waits for global memory.
+    // 3. interleaved FSE bitstream, written backwards (last sequence first), 32 sequences per round:
+    //    A. the three state chains are the only serial part: lanes 0 / 1 / 2 walk the LL / OF / ML
+    //       chain of the round in lockstep and leave (value, nbBits) of every state flush in shared
+    //       memory — no bit writer on the chain;
+    //    B. every lane then assembles the whole bit packet of ONE sequence (three state flushes,
+    //       three extra-bit fields, <= 90 bits), a warp scan of the packet lengths gives its place,
+    //       and the packets are OR-ed into a shared-memory stage that is flushed to the (aligned)
+    //       output words with coalesced stores.
     {
         u32 o = S.hist[192];
         over = S.hist[193] != 0;
-        u32 tl0 = S.hist[194], tl1 = S.hist[195], tl2 = S.hist[196];
-        u32 *stg = (u32 *)S.tmpsym;  // 32 x (ll | ml << 16), 32 x offBase: the table builders are done with it
-        BitW bw;
-        FseState sLL, sOF, sML;
-        if (lane == 0) bw.init(out + o, cap > o ? cap - o : 0);
+        const u32 tl0 = S.hist[194], tl1 = S.hist[195], tl2 = S.hist[196];
+        u32 *codes = (u32 *)S.tmpsym;       // 32 x (llc | ofc << 8 | mlc << 16): the table builders are done with tmpsym
+        u16 *sb = (u16 *)(codes + 32);      // [3][32] state flushes: value | nbBits << 12
+        u32 *bst = (u32 *)S.hlut;           // 128-word bit stage (the literals are written: the Huffman LUT is free)
+        u8 *gout = out + o;
+        const u32 pre = (u32)((uintptr_t)gout & 3u) * 8u;  // bits of the aligned word in front of the bitstream
+        u32 *gw = (u32 *)((uintptr_t)gout & ~(uintptr_t)3);
+        const u32 capb = cap > o ? cap - o : 0u;
+        for (u32 i = lane; i < 128; i += 32) bst[i] = 0;
+        __syncwarp();
+        if (lane == 0 && pre) bst[0] = gw[0] & ((1u << pre) - 1u);  // table descriptions written above by this warp
+        __syncwarp();
+        u32 carry = pre, wpos = 0;
+        // chain state of lane t < 3 (0 LL, 1 OF, 2 ML)
+        const u32 ct = min(lane, 2u);
+        const u16 *ctab = S.u.e.fse[ct].tab;
+        const u32 *cdnb = S.u.e.fse[ct].dnb;
+        const int *cdfs = S.u.e.fse[ct].dfs;
+        const u32 ctl = (ct == 0) ? tl0 : (ct == 1 ? tl1 : tl2);
+        u32 st = 0;
         bool started = false;
         if (!over) {
             for (u32 cend = nseq; cend > 0;) {
-                u32 cs = cend >= 32 ? cend - 32 : 0, cn = cend - cs;
-                __syncwarp();
-                if (lane < cn) {
-                    stg[lane] = (u32)sll[cs + lane] | ((u32)sml[cs + lane] << 16);
-                    stg[32 + lane] = sof[cs + lane];
+                const u32 cs = cend >= 32 ? cend - 32 : 0, cn = cend - cs;
+                const bool live = lane < cn;  // lane j codes sequence cend-1-j: lane order = emission order
+                u32 vll = 0, vml = 0, vof = 1, llc = 0, ofc = 0, mlc = 0;
+                if (live) {
+                    u32 k = cend - 1u - lane;
+                    vll = sll[k];
+                    vml = sml[k];
+                    vof = sof[k];
+                    llc = zstd_ll_code(vll);
+                    ofc = hibit32(vof);
+                    mlc = zstd_ml_code(vml);
+                    codes[lane] = llc | (ofc << 8) | (mlc << 16);
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    for (int k = (int)cn - 1; k >= 0; k--) {
-                        u32 vll = stg[k] & 0xFFFFu, vml = stg[k] >> 16, vof = stg[32 + k];
-                        u32 llc = zstd_ll_code(vll), ofc = hibit32(vof), mlc = zstd_ml_code(vml);
-                        if (!started) {
-                            sML.init(S.u.e.fse[2].tab, S.u.e.fse[2].dnb, S.u.e.fse[2].dfs, tl2, mlc);
-                            sOF.init(S.u.e.fse[1].tab, S.u.e.fse[1].dnb, S.u.e.fse[1].dfs, tl1, ofc);
-                            sLL.init(S.u.e.fse[0].tab, S.u.e.fse[0].dnb, S.u.e.fse[0].dfs, tl0, llc);
-                            started = true;
-                        } else {
-                            sOF.encode(bw, ofc);
-                            sML.encode(bw, mlc);
-                            sLL.encode(bw, llc);
+                if (lane < 3) {
+                    if (ctl) {
+                        u32 j = 0;
+                        if (!started) {  // the last sequence only initialises the states
+                            u32 sym = (codes[0] >> (8u * lane)) & 0xFFu;
+                            u32 nbo = (cdnb[sym] + (1u << 15)) >> 16;
+                            u32 v = (nbo << 16) - cdnb[sym];
+                            st = ctab[(int)(v >> nbo) + cdfs[sym]];
+                            sb[lane * 32] = 0;
+                            j = 1;
                         }
-                        bw.add(vll & ((1u << kLLBits[llc]) - 1u), kLLBits[llc]);
-                        bw.add(vml & ((1u << kMLBits[mlc]) - 1u), kMLBits[mlc]);
-                        bw.add(vof & ((1u << ofc) - 1u), ofc);
-                    }
+                        for (; j < cn; j++) {
+                            u32 sym = (codes[j] >> (8u * lane)) & 0xFFu;
+                            u32 nbo = (st + cdnb[sym]) >> 16;
+                            sb[lane * 32 + j] = (u16)((st & ((1u << nbo) - 1u)) | (nbo << 12));
+                            st = ctab[(int)(st >> nbo) + cdfs[sym]];
+                        }
+                    } else
+                        for (u32 j = 0; j < cn; j++) sb[lane * 32 + j] = 0;  // RLE table: the state never emits bits
                 }
+                started = true;
+                __syncwarp();
+                u64 lo = 0;
+                u32 hi = 0, nb = 0;
+                if (live) {
+                    u32 fLL = sb[lane], fOF = sb[32 + lane], fML = sb[64 + lane];
+                    lo = fOF & 0xFFFu;
+                    nb = fOF >> 12;
+                    lo |= (u64)(fML & 0xFFFu) << nb;
+                    nb += fML >> 12;
+                    lo |= (u64)(fLL & 0xFFFu) << nb;
+                    nb += fLL >> 12;
+                    u32 lb = kLLBits[llc], mb = kMLBits[mlc];
+                    lo |= (u64)(vll & ((1u << lb) - 1u)) << nb;
+                    nb += lb;
+                    lo |= (u64)(vml & ((1u << mb) - 1u)) << nb;
+                    nb += mb;  // <= 59
+                    u32 ofx = vof & ((1u << ofc) - 1u);
+                    lo |= (u64)ofx << nb;
+                    if (nb + ofc > 64) hi = ofx >> (64u - nb);
+                    nb += ofc;
+                }
+                u32 incl = group_incl_scan(nb, FULL, 32);
+                u32 cbits = __shfl_sync(FULL, incl, 31);
+                if ((u64)wpos * 4u + ((carry + cbits + 7u) >> 3) + 16u > (u64)capb + (pre >> 3)) {
+                    over = true;
+                    break;
+                }
+                if (nb) {
+                    u32 off = carry + incl - nb, w = off >> 5, sh = off & 31u;
+                    u32 l0 = (u32)lo, l1 = (u32)(lo >> 32);
+                    u32 x0 = l0 << sh, x1 = __funnelshift_l(l0, l1, sh), x2 = __funnelshift_l(l1, hi, sh), x3 = __funnelshift_l(hi, 0u, sh);
+                    if (x0) atomicOr(&bst[w], x0);
+                    if (x1) atomicOr(&bst[w + 1], x1);
+                    if (x2) atomicOr(&bst[w + 2], x2);
+                    if (x3) atomicOr(&bst[w + 3], x3);
+                }
+                __syncwarp();
+                u32 T = carry + cbits, nw = T >> 5;
+                for (u32 i = lane; i < nw; i += 32) gw[wpos + i] = bst[i];
+                u32 lastw = bst[nw];
+                __syncwarp();
+                for (u32 i = lane; i <= nw + 3u; i += 32) bst[i] = 0;
+                __syncwarp();
+                if (lane == 0) bst[0] = lastw;
+                __syncwarp();
+                wpos += nw;
+                carry = T & 31u;
                 cend = cs;
             }
-            if (lane == 0) {
-                sML.flush(bw);
-                sOF.flush(bw);
-                sLL.flush(bw);
-                u32 bs = bw.close();
-                over = bw.ovf;
+            if (!over) {
+                // final state flush (ML, OF, LL) and the end mark
+                u32 sLLv = __shfl_sync(FULL, st, 0), sOFv = __shfl_sync(FULL, st, 1), sMLv = __shfl_sync(FULL, st, 2);
+                u32 pk = 0, nb = 0;
+                if (tl2) { pk |= (sMLv & ((1u << tl2) - 1u)) << nb; nb += tl2; }
+                if (tl1) { pk |= (sOFv & ((1u << tl1) - 1u)) << nb; nb += tl1; }
+                if (tl0) { pk |= (sLLv & ((1u << tl0) - 1u)) << nb; nb += tl0; }
+                pk |= 1u << nb;
+                nb += 1;  // <= 27
+                if (lane == 0) {
+                    bst[0] |= pk << carry;
+                    if (carry + nb > 32) bst[1] = pk >> (32u - carry);
+                }
+                __syncwarp();
+                u32 T = carry + nb, nby = (T + 7u) >> 3;
+                u8 *tail = (u8 *)(gw + wpos);
+                for (u32 i = lane; i < nby; i += 32) tail[i] = (u8)(bst[i >> 2] >> (8u * (i & 3u)));
+                u32 bs = wpos * 4u + nby - (pre >> 3);
+                if (bs > capb) over = true;
                 total = o + bs;
             }
         }
+        __syncwarp();
     }
-    total = __shfl_sync(FULL, total, 0);
-    *ovf = __shfl_sync(FULL, over ? 1 : 0, 0) != 0;
-    return total;
+    over = __any_sync(FULL, over);
+    *ovf = over;
+    return __shfl_sync(FULL, total, 0);
 }
 
 // ---------------------------------------------------------------------------------- LZ77 parse (warp)
@@ -1710,10 +1824,30 @@ __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *fr
     u8 *rows;
     u64 *bars;
     xx_quad_smem(smem, &rows, &bars);
-    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)fr.src, live ? fr.src_len : 0u, q, gmask, rows, bars);
+    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)fr.src, (live && fr.policy != FQZ_ZPOLICY_INDEX) ? fr.src_len : 0u, q, gmask, rows, bars);
     if (live && q == 0) hashes[fi] = (u32)h;
 }
 
+// One warp per index frame (see FQZ_ZPOLICY_INDEX): frame fi indexes the src_len frames fi+1 ...
+__global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes) {
+    u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (wi >= nidx) return;
+    u32 fi = index[wi];
+    u32 n = frames[fi].src_len;
+    u32 *o = (u32 *)(slots + frames[fi].dst_off);  // slots are 16-byte aligned
+    if (lane == 0) {
+        o[0] = FQZ_ZINDEX_MAGIC;
+        o[1] = 8u + 4u * n;
+        o[2] = FQZ_ZINDEX_SIG;
+        o[3] = n;
+        out_sizes[fi] = FQZ_ZINDEX_BYTES(n);
+    }
+    for (u32 k = lane; k < n; k += 32) o[4 + k] = out_sizes[fi + 1 + k];
+}
+void fqz_launch_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+    if (!nidx) return;
+    FQZ_LAUNCH(k_zindex, (nidx * 32 + 127) / 128, 128, 0, s, frames, index, nidx, slots, out_sizes);
+}
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
     static bool attr_done = false;

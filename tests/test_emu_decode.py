@@ -14,6 +14,7 @@ from tests.decode_cases import (
     check_streaming,
     check_v1_file,
     check_zstd_ent_sizes,
+    check_zstd_index,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
 )
@@ -42,6 +43,10 @@ def test_zstd_round_trip(emu, oracle, name, policy):
 @pytest.mark.parametrize("n", ENT_SIZES)
 def test_zstd_entropy_policy_sizes(emu, oracle, n):
     check_zstd_ent_sizes(emu, oracle, n)
+
+
+def test_zstd_index_frame(emu, oracle):
+    check_zstd_index(emu, oracle, policies=(1,), n=3 * 131072 + 333)
 
 
 @pytest.mark.parametrize("name", sorted(GOOD_CASES))
