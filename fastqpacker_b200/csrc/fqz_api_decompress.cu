@@ -9,6 +9,7 @@
 
 #include "fqz_backend.h"
 #include "fqz_host.h"
+#include "fqz_zstd.h"
 #include "fqz_zstd_dec.h"
 
 static const int kErrOfBk[8] = {0,
@@ -72,20 +73,26 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
     BkTotals *d_tot = (BkTotals *)c->arena.alloc(tot_b);
     FqzDecStatus *d_st = (FqzDecStatus *)c->arena.alloc(64);
     u32 *d_offs = (u32 *)c->arena.alloc((size_t)(3 * (R + nb)) * sizeof(u32));
+    u32 *d_ok = (u32 *)c->arena.alloc((size_t)nb * 3 * sizeof(u32));
+    u32 max_segments = 0;  // frames of the longest hinted chain (the writer cuts item streams every FQZ_ZFRAME_ITEMS bytes)
+    for (auto &B : blks)
+        for (int k = 0; k < 3; k++)
+            if (B.hint[k] && B.hint_size[k] >= 28) max_segments = std::max(max_segments, (B.size[2 + k] + FQZ_ZFRAME_ITEMS - 1) / FQZ_ZFRAME_ITEMS);
     u32 *d_sz = (u32 *)c->arena.alloc((size_t)(3 * stride) * sizeof(u32));
-    if (!d_blks || !d_tot || !d_st || !d_offs || !d_sz) {
+    if (!d_blks || !d_tot || !d_st || !d_offs || !d_sz || !d_ok) {
         c->err = "arena: out of device memory (back end tables)";
         return FQZ_E_CUDA;
     }
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_blks, hp, blk_b, cudaMemcpyHostToDevice, s));
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_st, hst, sizeof(FqzDecStatus), cudaMemcpyHostToDevice, s));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_tot, 0, tot_b, s));
+    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_ok, 0, (size_t)nb * 3 * sizeof(u32), s));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_sz, 0, (size_t)(3 * stride) * sizeof(u32), s));
     u64 hdr_bytes = 0;
     for (auto &B : blks) hdr_bytes += (u64)B.size[2] + B.size[3] + B.size[4];
     {
         StageScope sc(c, ST_WALK, hdr_bytes);
-        fqz_launch_walk_prefixes(d_blks, nb, d_offs, d_st, s);
+        fqz_launch_walk_prefixes(d_blks, nb, max_segments, d_offs, d_ok, d_st, s);
     }
     {
         StageScope sc(c, ST_OFFSETS, 0);
@@ -176,6 +183,11 @@ static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, 
         B.nrec = ent[b].nrec;
         B.pad = 0;
         B.rec_base = 0;
+        for (int k = 0; k < 3; k++) {  // compressed headers / plus / N-position streams: their index frames carry item hints
+            B.hint[k] = zs[(size_t)b * 6 + 2 + k].src;
+            B.hint_size[k] = (u32)zs[(size_t)b * 6 + 2 + k].csize;
+        }
+        B.pad2 = 0;
     }
     return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base, io_slot);
 }
@@ -425,6 +437,8 @@ extern "C" int fqz_decode_streams(fqz_ctx *c, const uint8_t *const in[6], const 
     B.nrec = num_records;
     B.pad = 0;
     B.rec_base = 0;
+    for (int k = 0; k < 3; k++) B.hint[k] = 0, B.hint_size[k] = 0;
+    B.pad2 = 0;
     u8 *d_res = nullptr;
     size_t total = 0;
     FQZ_TRY(backend_run(c, blks, phred64 ? 1u : 0u, nullptr, 0, &d_res, &total, 0));

@@ -11,6 +11,7 @@
 //   k_emit_fastq      16 lanes per record: '@'+header, unpacked bases with N restored, '+'+payload,
 //                     prefix-summed qualities; all wide stores aligned to the destination
 #include "fqz_backend.h"
+#include "fqz_zstd.h"
 
 #define ZW_MAXC 8u     // candidate item starts kept per lane (128 bytes)
 #define WALK_CH 4096u  // bytes per staged chunk (plus 16 bytes of overlap so a prefix never straddles)
@@ -19,25 +20,20 @@
 // One warp per chain.  The stream is staged chunk by chunk into shared memory by the TMA unit (1-D
 // bulk copies, double buffered: chunk c+1 lands while chunk c is walked); the warp then advances by
 // verified runs of equal-length items (see below) instead of one serial hop per item.
-__global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs_base, FqzDecStatus *st) {
-    __shared__ uint4 sm_buf[4][2][(WALK_CH + 16) / 16];
-    __shared__ u64 sm_bar[4][2];
-    __shared__ u16 sm_cand[4][ZW_MAXC][32];
+struct WalkSmem {
+    uint4 buf[4][2][(WALK_CH + 16) / 16];
+    u64 bar[4][2];
+    u16 cand[4][ZW_MAXC][32];
+};
+// Walks items r .. rend-1 of the chain p[0..size) starting at byte `pos`; writes offs[r'] for each and
+// returns the position behind the last item walked in *pos_out, the items walked in *r_out, and a
+// truncation flag in *err_out.  One warp; every lane returns the same values.
+__device__ static void walk_chain(const u8 *p, u32 size, u32 kind, u32 pos, u32 r, const u32 nrec, u32 *offs, WalkSmem &SM, u32 *pos_out,
+                                  u32 *r_out, u32 *err_out) {
     u32 warp = threadIdx.x >> 5, lane = lane_id();
-    u32 wi = blockIdx.x * 4 + warp;
-    if (wi >= nblocks * 3) return;
-    u32 b = wi / 3, kind = wi % 3;
-    const BkBlock *Bp = blks + b;
-    int sidx = kind == 0 ? 2 : (kind == 1 ? 3 : 4);
-    const u8 *p = (const u8 *)(uintptr_t)Bp->stream[sidx];
-    u32 size = Bp->size[sidx], nrec = Bp->nrec;
-    u64 rec_base = Bp->rec_base;
-    u32 *offs = offs_base + (3ull * rec_base + (u64)kind * nrec) + 3ull * b + kind;  // (nrec+1) entries per kind
-    if (kind == 1 && size == 0) {  // v1 files / empty plus stream: every plus line is "+" (compress.go:995-999)
-        for (u32 r = lane; r <= nrec; r += 32) offs[r] = 0;
-        return;
-    }
-    u64 *bar = sm_bar[warp];
+    uint4(*sm_buf)[2][(WALK_CH + 16) / 16] = SM.buf;
+    u16(*sm_cand)[ZW_MAXC][32] = SM.cand;
+    u64 *bar = SM.bar[warp];
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -63,13 +59,14 @@ __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 
         if (!pending[slot]) return;
         __syncwarp();
         mbar_wait(&bar[slot], ph[slot]);
+        __syncwarp();  // every lane has seen this phase complete before lane 0 may re-arm the barrier
         ph[slot] ^= 1u;
         pending[slot] = false;
     };
-    u32 pos = 0, r = 0, err = 0;
-    u32 c = 0, slot = 0;
-    issue(0, 0);
-    issue(1, 1);
+    u32 err = 0;
+    u32 c = pos / WALK_CH, slot = 0;
+    issue(c, 0);
+    issue(c + 1, 1);
     while (r < nrec) {
         if (pos + 2 > size) { err = 1; break; }  // no room for the length prefix of item r
         u32 nc = pos / WALK_CH;
@@ -208,6 +205,114 @@ __global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 
     }
     wait(0);  // no bulk copy may still be in flight when the CTA's shared memory is released
     wait(1);
+    __syncwarp();
+    *pos_out = pos;
+    *r_out = r;
+    *err_out = err;
+}
+
+// index frame of a compressed item stream (FQZ_ZPOLICY_INDEX, fqz_zstd.h): usable for the segmented
+// walk when it covers the decoded stream exactly.  Returns the frame count (0 = no usable hints).
+__device__ __forceinline__ u32 bk_rd32(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+__device__ static u32 walk_hint_frames(const u8 *h, u32 hsize, u32 size, u32 *fsz_out) {
+    if (!h || hsize < FQZ_ZINDEX_HDR + 8u || size == 0) return 0;
+    if (bk_rd32(h) != FQZ_ZINDEX_MAGIC || bk_rd32(h + 8) != FQZ_ZINDEX_SIG) return 0;
+    u32 nf = bk_rd32(h + 12), fsz = bk_rd32(h + 16);
+    if (nf == 0 || fsz == 0 || (u64)FQZ_ZINDEX_HDR + 8ull * nf > hsize || bk_rd32(h + 4) != FQZ_ZINDEX_HDR - 8u + 8u * nf) return 0;
+    if ((u64)fsz * (nf - 1) >= size || (u64)fsz * nf < size) return 0;
+    *fsz_out = fsz;
+    return nf;
+}
+
+// Segmented walk: one warp per (block, chain, frame of the compressed stream).  The index frame says
+// where the first item of every frame starts and how many items start in it; each warp walks its own
+// items and PROVES its part: it must arrive exactly at the start the index gives for the next frame
+// that has items (the end of the stream for the last one), and the counts must add up to nrec.  Every
+// proven segment bumps ok[block * 3 + kind]; k_walk_prefixes redoes any chain whose proof is incomplete.
+__global__ void __launch_bounds__(128) k_walk_segments(const BkBlock *blks, u32 nblocks, u32 *offs_base, u32 *ok) {
+    __shared__ WalkSmem SM;
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 seg = blockIdx.x * 4 + warp;
+    u32 b = blockIdx.y / 3, kind = blockIdx.y % 3;
+    const BkBlock *Bp = blks + b;
+    int sidx = kind == 0 ? 2 : (kind == 1 ? 3 : 4);
+    const u8 *p = (const u8 *)(uintptr_t)Bp->stream[sidx];
+    const u8 *h = (const u8 *)(uintptr_t)Bp->hint[kind];
+    u32 size = Bp->size[sidx], nrec = Bp->nrec;
+    u32 fsz = 0;
+    u32 nf = walk_hint_frames(h, Bp->hint_size[kind], size, &fsz);
+    if (seg >= nf) return;
+    const u8 *ent = h + FQZ_ZINDEX_HDR;
+    // records before this segment; first frame after it that has items
+    u32 before = 0;
+    for (u32 k = lane; k < seg; k += 32) before += bk_rd32(ent + 8ull * k + 4) >> 16;
+    before = group_sum(before, 0xffffffffu, 32);
+    u32 me = bk_rd32(ent + 8ull * seg + 4);
+    u32 first = me & 0xFFFFu, cnt = me >> 16;
+    bool good = !(first == 0xFFFFu && cnt == 0xFFFFu) && (cnt == 0 || first < fsz) && (u64)before + cnt <= nrec;
+    u32 expect = size;  // where the walk must end
+    bool last_items = true;
+    if (good) {
+        u32 nxt = 0xFFFFFFFFu;
+        for (u32 k0 = seg + 1; k0 < nf && nxt == 0xFFFFFFFFu; k0 += 32) {
+            u32 k = k0 + lane;
+            u32 e = (k < nf) ? bk_rd32(ent + 8ull * k + 4) : 0u;
+            u32 m = __ballot_sync(0xffffffffu, (e >> 16) != 0);
+            if (m) {
+                int l = __ffs((int)m) - 1;
+                u32 el = __shfl_sync(0xffffffffu, e, l);
+                nxt = (k0 + (u32)l) * fsz + (el & 0xFFFFu);
+            }
+        }
+        if (nxt != 0xFFFFFFFFu) {
+            expect = nxt;
+            last_items = false;
+        }
+    }
+    u32 *offs = offs_base + (3ull * Bp->rec_base + (u64)kind * nrec) + 3ull * b + kind;
+    if (good && cnt) {
+        u32 start = seg * fsz + first;
+        if (before == 0 && start != 0) good = false;  // the chain starts at byte 0
+        if (good) {
+            u32 pos = 0, r = 0, err = 0;
+#ifdef FQZ_EMU
+            if (getenv("FQZ_DEBUG")) fprintf(stderr, "seg b %u kind %u seg %u lane %u start %u before %u cnt %u expect %u\n", b, kind, seg, lane, start, before, cnt, expect);
+#endif
+            walk_chain(p, size, kind, start, before, before + cnt, offs, SM, &pos, &r, &err);
+            good = !err && r == before + cnt && pos == expect;
+            if (good && last_items) {
+                good = (r == nrec);
+                if (good && lane == 0) offs[nrec] = pos;
+            }
+        }
+    } else if (good && last_items && before != nrec)
+        good = false;  // nothing starts here or later, yet records are missing
+    if (good && lane == 0) atomicAdd(&ok[b * 3 + kind], 1u);
+}
+
+__global__ void __launch_bounds__(128) k_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs_base, const u32 *ok, FqzDecStatus *st) {
+    __shared__ WalkSmem SM;
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 wi = blockIdx.x * 4 + warp;
+    if (wi >= nblocks * 3) return;
+    u32 b = wi / 3, kind = wi % 3;
+    const BkBlock *Bp = blks + b;
+    int sidx = kind == 0 ? 2 : (kind == 1 ? 3 : 4);
+    const u8 *p = (const u8 *)(uintptr_t)Bp->stream[sidx];
+    u32 size = Bp->size[sidx], nrec = Bp->nrec;
+    u64 rec_base = Bp->rec_base;
+    u32 *offs = offs_base + (3ull * rec_base + (u64)kind * nrec) + 3ull * b + kind;  // (nrec+1) entries per kind
+    if (kind == 1 && size == 0) {  // v1 files / empty plus stream: every plus line is "+" (compress.go:995-999)
+        for (u32 r = lane; r <= nrec; r += 32) offs[r] = 0;
+        return;
+    }
+    if (ok) {  // every segment of this chain proved its part (k_walk_segments): nothing to redo
+        u32 fsz = 0;
+        u32 nf = walk_hint_frames((const u8 *)(uintptr_t)Bp->hint[kind], Bp->hint_size[kind], size, &fsz);
+        if (nf && ok[b * 3 + kind] == nf) return;
+    }
+    u32 pos = 0, r = 0, err = 0;
+    walk_chain(p, size, kind, 0, 0, nrec, offs, SM, &pos, &r, &err);
     if (lane == 0) {
         offs[nrec] = pos;
         if (err) {
@@ -447,9 +552,10 @@ void fqz_launch_walk_container(const u8 *fqz, u64 n, u64 pos, u32 version, FqzBl
                                FqzWalkResult *res, cudaStream_t s) {
     FQZ_LAUNCH(k_walk_container, 1, 32, 0, s, fqz, n, pos, version, table, cap, max_bytes, res);
 }
-void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs, FqzDecStatus *st, cudaStream_t s) {
+void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 max_segments, u32 *offs, u32 *ok, FqzDecStatus *st, cudaStream_t s) {
     if (!nblocks) return;
-    FQZ_LAUNCH(k_walk_prefixes, (nblocks * 3 + 3) / 4, 128, 0, s, blks, nblocks, offs, st);
+    if (max_segments && ok) FQZ_LAUNCH(k_walk_segments, dim3((max_segments + 3) / 4, nblocks * 3), 128, 0, s, blks, nblocks, offs, ok);
+    FQZ_LAUNCH(k_walk_prefixes, (nblocks * 3 + 3) / 4, 128, 0, s, blks, nblocks, offs, max_segments ? ok : nullptr, st);
 }
 void fqz_launch_record_sizes(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, u32 *sz, u64 stride, BkTotals *tot,
                              FqzDecStatus *st, cudaStream_t s) {

@@ -24,6 +24,12 @@ struct BkBlock {
     u32 nrec;
     u32 pad;
     u64 rec_base;   // window-global index of the block's first record
+    // compressed form of the header / plus / N-position streams (device address, bytes) when it is at
+    // hand: its index frame (FQZ_ZPOLICY_INDEX) lets the item chains be walked frame by frame in
+    // parallel.  0 = none (block-level entry points that start from decoded streams).
+    u64 hint[3];
+    u32 hint_size[3];
+    u32 pad2;
 };
 // per block, written by k_record_sizes: 64-bit totals so that the host can rule out u32 wrap
 struct BkTotals {
@@ -50,7 +56,8 @@ struct FqzWalkResult {
 
 void fqz_launch_walk_container(const u8 *fqz, u64 n, u64 pos, u32 version, FqzBlockEntry *table, u32 cap, u64 max_bytes,
                                FqzWalkResult *res, cudaStream_t s);
-void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 *offs, FqzDecStatus *st, cudaStream_t s);
+// max_segments: upper bound on the frames of any one chain (0 = no hints: serial walk only); ok: nblocks * 3 zeroed counters
+void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 max_segments, u32 *offs, u32 *ok, FqzDecStatus *st, cudaStream_t s);
 void fqz_launch_record_sizes(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, u32 *sz, u64 stride, BkTotals *tot,
                              FqzDecStatus *st, cudaStream_t s);
 void fqz_launch_check_seq_qual(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *sc, u64 stride, FqzDecStatus *st, cudaStream_t s);

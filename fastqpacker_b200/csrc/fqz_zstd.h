@@ -28,15 +28,20 @@ struct ZFrame {
 };
 #define FQZ_ZPOLICY_ITEMS 2  // internal: LZ by item matcher (needs the item boundaries of the stream)
 // internal: not a zstd frame but a SKIPPABLE frame (RFC 8878 §3.1.2) in front of a stream that was cut
-// into many frames: it lists the compressed size of each of the src_len frames that follow, so that
-// the GPU decoder can find them all at once instead of hopping header by header.  Every decoder,
-// the reference's included, skips it.  Layout: magic 0x184D2A5E, u32 payload size, then the payload
-// 'FQZI', u32 nframes, nframes x u32 compressed frame size.
+// into many frames.  It lists, for each of the src_len frames that follow, the compressed size and —
+// for the length-prefixed item streams — where the first item that starts inside the frame's content
+// lies and how many items start there, so that the GPU decoder can find all frames at once instead
+// of hopping header by header, and can walk the item chains of all frames in parallel.  Every
+// decoder, the reference's included, skips it; ours trusts it only as far as it proves true.
+// Layout: magic 0x184D2A5E, u32 payload size, then the payload: 'FQZI', u32 nframes, u32 content
+// bytes per frame (the last one may be shorter), nframes x {u32 compressed size, u16 offset of the
+// first item start, u16 item starts}.
 #define FQZ_ZPOLICY_INDEX 3
 #define FQZ_ZINDEX_MAGIC 0x184D2A5Eu
 #define FQZ_ZINDEX_SIG 0x495A5146u  // "FQZI" little-endian
 #define FQZ_ZINDEX_MIN 4u           // streams of fewer frames carry no index
-#define FQZ_ZINDEX_BYTES(n) (16u + 4u * (u32)(n))
+#define FQZ_ZINDEX_HDR 20u
+#define FQZ_ZINDEX_BYTES(n) (FQZ_ZINDEX_HDR + 8u * (u32)(n))
 
 #define ZENC_WARPS 4
 

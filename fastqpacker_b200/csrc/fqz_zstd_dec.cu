@@ -383,12 +383,12 @@ __global__ void __launch_bounds__(ZD_HOP_WARPS * 32) k_zd_hop(const ZDStream *st
     u64 out_bytes = 0;
     // ---- indexed path
     bool indexed = false;
-    if (n >= 20 && rd32(p) == FQZ_ZINDEX_MAGIC && rd32(p + 8) == FQZ_ZINDEX_SIG) {
+    if (n >= FQZ_ZINDEX_HDR + 8u && rd32(p) == FQZ_ZINDEX_MAGIC && rd32(p + 8) == FQZ_ZINDEX_SIG) {
         u32 nf = rd32(p + 12);
-        u64 isz = 16ull + 4ull * nf;
-        if (nf >= 1 && rd32(p + 4) == 8ull + 4ull * nf && isz < n) {
+        u64 isz = (u64)FQZ_ZINDEX_HDR + 8ull * nf;
+        if (nf >= 1 && rd32(p + 4) == isz - 8ull && isz < n) {
             u64 sum = 0;
-            for (u32 k = lane; k < nf; k += 32) sum += rd32(p + 16 + 4ull * k);
+            for (u32 k = lane; k < nf; k += 32) sum += rd32(p + FQZ_ZINDEX_HDR + 8ull * k);
             for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
             indexed = (sum == n - isz);
         }
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(ZD_HOP_WARPS * 32) k_zd_hop(const ZDStream *st
             for (u32 f0 = 0; f0 < nf; f0 += 32) {
                 u32 k = f0 + lane;
                 bool live = k < nf;
-                u64 sz = live ? rd32(p + 16 + 4ull * k) : 0;
+                u64 sz = live ? rd32(p + FQZ_ZINDEX_HDR + 8ull * k) : 0;
                 u64 incl = warp_incl_scan_u64(sz);
                 u64 start = pos + incl - sz;
                 u32 nb = 0, rc = 0;
@@ -744,38 +744,111 @@ __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 
     return tl;
 }
 
-// one Huffman stream, decoded by one lane; output assembled into aligned 32-bit stores
+// one Huffman stream, decoded by one lane; output assembled into aligned 32-bit stores.
+// The stream is read backwards in ALIGNED 32-bit words that are loaded three refills ahead of
+// their use, so the symbol chain (shift -> table lookup -> shift) never waits for global memory;
+// the bit window lives left-aligned in a 64-bit register.  Instead of guarding every read against
+// the start of the stream, the bits consumed are counted: a valid stream is consumed exactly
+// (RFC 8878 §4.2.2), anything else is corrupt.  Word loads are clamped to the aligned word that
+// holds src[0], so a corrupt stream never reads outside the block either.
+struct HufBits {
+    u64 bits;       // unread bits, left-aligned
+    u32 nb;         // valid bits in `bits`
+    const u32 *wp;  // next word to prefetch
+    const u32 *lo;  // aligned word that holds the first byte of the stream
+    u32 w0, w1, w2; // prefetched words, nearest first
+    __device__ __forceinline__ u32 fetch() {
+        u32 v = *wp;
+        wp = (wp > lo) ? wp - 1 : lo;
+        return v;
+    }
+    // src[csize - 1] != 0 (it holds the end mark).  Returns the payload bits of the stream.
+    __device__ __forceinline__ u32 init(const u8 *src, u32 csize) {
+        u32 hb = hibit32(src[csize - 1]);
+        const u8 *endp = src + csize;
+        lo = (const u32 *)((uintptr_t)src & ~(uintptr_t)3);
+        const u32 *wa = (const u32 *)((uintptr_t)(endp - 1) & ~(uintptr_t)3);
+        u32 k = (u32)((uintptr_t)(endp - 1) & 3u) + 1u;  // stream bytes in the top word
+        u32 v = *wa;
+        wp = (wa > lo) ? wa - 1 : lo;
+        bits = (u64)v << (64u - 8u * k);
+        bits <<= (8u - hb);  // padding and end mark
+        nb = 8u * k - (8u - hb);
+        w0 = fetch();
+        w1 = fetch();
+        w2 = fetch();
+        return (csize - 1u) * 8u + hb;
+    }
+    __device__ __forceinline__ void refill() {  // afterwards nb >= 33 (bits past the stream start are whatever memory holds)
+        if (nb <= 32) {
+            bits |= (u64)w0 << (32u - nb);
+            nb += 32;
+            w0 = w1;
+            w1 = w2;
+            w2 = fetch();
+        }
+    }
+    __device__ __forceinline__ u32 peek(u32 n) const { return (u32)(bits >> 32) >> (32u - n); }  // 1 <= n <= 32
+    __device__ __forceinline__ u32 take(u32 n) {  // 0 <= n <= 32, n <= nb
+        if (n == 0) return 0;
+        u32 v = peek(n);
+        drop(n);
+        return v;
+    }
+    __device__ __forceinline__ void drop(u32 n) {
+        bits <<= n;
+        nb -= n;
+    }
+};
+
 __device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 n, const u16 *dt, u32 tl) {
-    BitR br;
-    br.init(src, csize);
-    if (br.bad) return false;
+    if (csize == 0 || src[csize - 1] == 0) return false;  // empty, or the end mark is missing
+    HufBits hb;
+    const u32 total = hb.init(src, csize);
+    u32 used = 0;
     u32 i = 0;
     while (i < n && ((uintptr_t)(dst + i) & 3u)) {
-        br.reload();
-        u32 e = dt[br.look(tl)];
-        br.skip(e >> 8);
+        hb.refill();
+        u32 e = dt[hb.peek(tl)];
+        hb.drop(e >> 8);
+        used += e >> 8;
         dst[i++] = (u8)e;
     }
-    while (i + 4 <= n) {  // a reload guarantees >= 57 fresh bits (or the stream start): four symbols of <= 11 bits
-        br.reload();
+    while (i + 4 <= n) {  // a refill leaves >= 33 bits: two symbols of <= 11 bits each, twice
         u32 w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            u32 e = dt[br.look(tl)];
-            br.skip(e >> 8);
-            w |= (e & 0xFFu) << (8 * k);
+        hb.refill();
+        {
+            u32 e = dt[hb.peek(tl)];
+            hb.drop(e >> 8);
+            used += e >> 8;
+            w = e & 0xFFu;
+            e = dt[hb.peek(tl)];
+            hb.drop(e >> 8);
+            used += e >> 8;
+            w |= (e & 0xFFu) << 8;
+        }
+        hb.refill();
+        {
+            u32 e = dt[hb.peek(tl)];
+            hb.drop(e >> 8);
+            used += e >> 8;
+            w |= (e & 0xFFu) << 16;
+            e = dt[hb.peek(tl)];
+            hb.drop(e >> 8);
+            used += e >> 8;
+            w |= (e & 0xFFu) << 24;
         }
         *(u32 *)(dst + i) = w;
         i += 4;
     }
     while (i < n) {
-        br.reload();
-        u32 e = dt[br.look(tl)];
-        br.skip(e >> 8);
+        hb.refill();
+        u32 e = dt[hb.peek(tl)];
+        hb.drop(e >> 8);
+        used += e >> 8;
         dst[i++] = (u8)e;
     }
-    br.reload();
-    return !br.bad && br.ptr == br.start && br.consumed == 64;
+    return used == total;
 }
 
 // One warp takes eight consecutive blocks; lane = (block, Huffman stream).  Blocks that share a
@@ -933,32 +1006,44 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_sequences(ZDBlock *blocks,
         u64 total = 0;
         if (!err) {
             const u8 *c = (const u8 *)(uintptr_t)B.src;
-            BitR br;
-            br.init(c + B.bits_pos, B.csize - B.bits_pos);
-            u32 sLL = br.read(tl[0]), sOF = br.read(tl[1]), sML = br.read(tl[2]);
-            br.reload();
-            for (u32 i = 0; i < B.nseq; i++) {
-                FseDEnt eLL = S.dt[0][sLL], eOF = S.dt[1][sOF], eML = S.dt[2][sML];
-                u32 ofc = eOF.sym, mlc = eML.sym, llc = eLL.sym;
-                if (ofc > 31 || mlc > 52 || llc > 35) { err = 1; break; }
-                u32 ofv = (1u << ofc) + br.read(ofc);
-                if (ofc + kMLBits[mlc] + kLLBits[llc] > 40) br.reload();
-                u32 ml = kMLBase[mlc] + br.read(kMLBits[mlc]);
-                u32 ll = kLLBase[llc] + br.read(kLLBits[llc]);
-                br.reload();
-                sq[3 * i] = ll;
-                sq[3 * i + 1] = ml;
-                sq[3 * i + 2] = ofv;
-                total += (u64)ll + ml;
-                if (i + 1 < B.nseq) {
-                    sLL = eLL.base + br.read(eLL.nb);
-                    sML = eML.base + br.read(eML.nb);
-                    sOF = eOF.base + br.read(eOF.nb);
-                    br.reload();
+            const u32 bsz = B.csize - B.bits_pos;
+            if (bsz == 0 || c[B.csize - 1] == 0) err = 1;  // no bitstream, or its end mark is missing
+            else {
+                // same reader as the Huffman streams: aligned words prefetched ahead of the state chain,
+                // consumed bits counted and checked against the stream size at the end.  Every group of
+                // reads between two refills takes at most 32 bits (offset extra bits <= 31; match + literal
+                // length extra bits <= 16 + 16; three state updates <= 9 + 9 + 8).
+                HufBits br;
+                const u32 avail = br.init(c + B.bits_pos, bsz);
+                u32 used = tl[0] + tl[1] + tl[2];
+                br.refill();
+                u32 sLL = br.take(tl[0]), sOF = br.take(tl[1]), sML = br.take(tl[2]);
+                for (u32 i = 0; i < B.nseq; i++) {
+                    FseDEnt eLL = S.dt[0][sLL], eOF = S.dt[1][sOF], eML = S.dt[2][sML];
+                    u32 ofc = eOF.sym, mlc = eML.sym, llc = eLL.sym;
+                    if (ofc > 31 || mlc > 52 || llc > 35) { err = 1; break; }
+                    br.refill();
+                    u32 ofv = (1u << ofc) + br.take(ofc);
+                    br.refill();
+                    u32 mlb = kMLBits[mlc], llb = kLLBits[llc];
+                    u32 ml = kMLBase[mlc] + br.take(mlb);
+                    u32 ll = kLLBase[llc] + br.take(llb);
+                    used += ofc + mlb + llb;
+                    sq[3 * i] = ll;
+                    sq[3 * i + 1] = ml;
+                    sq[3 * i + 2] = ofv;
+                    total += (u64)ll + ml;
+                    if (i + 1 < B.nseq) {
+                        br.refill();
+                        sLL = eLL.base + br.take(eLL.nb);
+                        sML = eML.base + br.take(eML.nb);
+                        sOF = eOF.base + br.take(eOF.nb);
+                        used += (u32)eLL.nb + eML.nb + eOF.nb;
+                    }
+                    if (used > avail) { err = 1; break; }
                 }
-                if (br.bad) { err = 1; break; }
+                if (used != avail) err = 1;
             }
-            if (!br.finished()) err = 1;
         }
         if (err || total > ZSTD_BLOCK_MAX) blocks[bi].err = 1;
     }

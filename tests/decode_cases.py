@@ -74,7 +74,7 @@ def check_zstd_ent_sizes(ctx, oracle, n):
     if n >= 4096:
         assert len(ctx.zstd_compress(skew, 1)) < 0.45 * n
         nfr = (n + 131071) // 131072
-        index = 16 + 4 * nfr if nfr >= 4 else 0  # skippable frame index in front of streams of >= 4 frames
+        index = 20 + 8 * nfr if nfr >= 4 else 0  # skippable frame index in front of streams of >= 4 frames
         assert len(ctx.zstd_compress(flat, 1)) <= n + 17 * nfr + index
 
 
@@ -88,21 +88,27 @@ def check_zstd_index(ctx, oracle, policies=(0, 1), n=5 * 131072 + 333):
     data = bytes(rnd.choice(b"ACGTTTGA\x00\x01") for _ in range(n))
     for policy in policies:
         z = ctx.zstd_compress(data, policy)
-        magic, psize, sig, nfr = struct.unpack_from("<IIII", z, 0)
-        assert magic == 0x184D2A5E and sig == 0x495A5146 and psize == 8 + 4 * nfr and nfr >= 4
-        sizes = list(struct.unpack_from("<%dI" % nfr, z, 16))
-        assert sum(sizes) == len(z) - 16 - 4 * nfr
+        magic, psize, sig, nfr, fsz = struct.unpack_from("<IIIII", z, 0)
+        assert magic == 0x184D2A5E and sig == 0x495A5146 and psize == 12 + 8 * nfr and nfr >= 4
+        assert fsz == (131072 if policy == 1 else 65536)
+        ent = list(struct.unpack_from("<%dI" % (2 * nfr), z, 20))
+        sizes, hints = ent[0::2], ent[1::2]
+        body = 20 + 8 * nfr
+        assert sum(sizes) == len(z) - body and not any(hints)
         assert oracle.zstd_decompress(z) == data
         assert ctx.zstd_decompress(z) == data
+
+        def rebuild(sz):
+            return z[:20] + struct.pack("<%dI" % (2 * nfr), *[v for pair in zip(sz, hints) for v in pair]) + z[body:]
+
         # entries swapped (the sum still matches), entries wrong, foreign payload behind the same magic
         sw = sizes[:]
         sw[0], sw[1] = sw[1] + 1, sw[0] - 1
-        for bad in (sw, [s + 1 for s in sizes]):
-            t = z[:16] + struct.pack("<%dI" % nfr, *bad) + z[16 + 4 * nfr:]
-            assert ctx.zstd_decompress(t) == data
-        foreign = struct.pack("<II", 0x184D2A5E, 12) + b"hello world!" + z[16 + 4 * nfr:]
+        for bad in (sw, [v + 1 for v in sizes]):
+            assert ctx.zstd_decompress(rebuild(bad)) == data
+        foreign = struct.pack("<II", 0x184D2A5E, 12) + b"hello world!" + z[body:]
         assert ctx.zstd_decompress(foreign) == data
-        assert ctx.zstd_decompress(z[16 + 4 * nfr:]) == data  # and no index at all
+        assert ctx.zstd_decompress(z[body:]) == data  # and no index at all
 
 
 def check_back_end(ctx, oracle, text):
@@ -237,6 +243,50 @@ def check_file_errors(ctx, oracle):
         else:
             assert got == want
     assert ctx.decompress(fqz[:10]) == b""  # header-only file (compress_test.go:160-173)
+
+
+def check_item_hints(ctx, oracle, nrec=3000):
+    """The index frames of the header / plus / N-position streams carry, per 16 KiB frame, where the
+    first item starts and how many items start there; the device walks the frames in parallel and
+    proves every hand-over.  The hints of a GPU-written file must describe the decoded streams
+    exactly, and wrong hints must only cost the parallel walk, never the result."""
+    import struct
+
+    from tests import synth
+
+    for kind in (0, 1):
+        text = synth.fastq(kind, 21, 0, nrec)
+        fqz = ctx.compress(text)
+        assert oracle.decompress(fqz) == text
+        assert ctx.decompress(fqz) == text
+        hdr = struct.unpack_from("<9I", fqz, 10)
+        streams = oracle.encode_streams(text)["streams"]
+        pos = 10 + 36 + hdr[1] + hdr[2]
+        tampered = 0
+        for a in (2, 3, 4):  # headers, plus, npos
+            z = fqz[pos : pos + hdr[1 + a]]
+            raw = streams[a]
+            if z[:4] == b"\x5e\x2a\x4d\x18":
+                magic, psize, sig, nfr, fsz = struct.unpack_from("<IIIII", z, 0)
+                assert sig == 0x495A5146 and fsz == 16384 and nfr == (len(raw) + fsz - 1) // fsz
+                # item starts of the decoded stream
+                starts, q = [], 0
+                while q < len(raw):
+                    starts.append(q)
+                    n = raw[q] | (raw[q + 1] << 8)
+                    q += 2 + (2 * n if a == 4 else n)
+                for k in range(nfr):
+                    first, cnt = struct.unpack_from("<HH", z, 20 + 8 * k + 4)
+                    mine = [v for v in starts if k * fsz <= v < (k + 1) * fsz]
+                    assert cnt == len(mine) and (not mine or first == mine[0] - k * fsz)
+                for k, delta in ((0, (0, 1)), (1, (2, 0)), (nfr - 1, (0, -1))):
+                    at = pos + 20 + 8 * k + 4
+                    first, cnt = struct.unpack_from("<HH", fqz, at)
+                    bad = fqz[:at] + struct.pack("<HH", (first + delta[0]) & 0xFFFF, (cnt + delta[1]) & 0xFFFF) + fqz[at + 4 :]
+                    assert ctx.decompress(bad) == text
+                    tampered += 1
+            pos += hdr[1 + a]
+        assert tampered >= 3  # the header stream of 3000 records spans >= 4 frames
 
 
 def check_streaming(ctx, oracle, nrec=300, chunk=None):

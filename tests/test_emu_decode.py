@@ -15,6 +15,7 @@ from tests.decode_cases import (
     check_v1_file,
     check_zstd_ent_sizes,
     check_zstd_index,
+    check_item_hints,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
 )
@@ -43,6 +44,10 @@ def test_zstd_round_trip(emu, oracle, name, policy):
 @pytest.mark.parametrize("n", ENT_SIZES)
 def test_zstd_entropy_policy_sizes(emu, oracle, n):
     check_zstd_ent_sizes(emu, oracle, n)
+
+
+def test_item_hints(emu, oracle):
+    check_item_hints(emu, oracle)
 
 
 def test_zstd_index_frame(emu, oracle):

@@ -17,6 +17,7 @@ from tests.decode_cases import (
     check_v1_file,
     check_zstd_ent_sizes,
     check_zstd_index,
+    check_item_hints,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
 )
@@ -47,6 +48,10 @@ def test_zstd_round_trip(ctx, oracle, name, policy):
 @pytest.mark.parametrize("n", ENT_SIZES + [5 * 131072 + 12345])
 def test_zstd_entropy_policy_sizes(ctx, oracle, n):
     check_zstd_ent_sizes(ctx, oracle, n)
+
+
+def test_item_hints(ctx, oracle):
+    check_item_hints(ctx, oracle)
 
 
 def test_zstd_index_frame(ctx, oracle):
