@@ -58,42 +58,51 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
     ZDFrame *d_frames = (ZDFrame *)c->arena.alloc((size_t)(nframes + 1) * sizeof(ZDFrame));
     ZDBlock *d_blocks = (ZDBlock *)c->arena.alloc((size_t)(nblocks + 1) * sizeof(ZDBlock));
     const u32 cstride = (u32)nblocks + 1;
-    u32 *d_cnt = (u32 *)c->arena.alloc((size_t)cstride * 2 * sizeof(u32));  // literals, sequences per block (+ totals after the scan)
+    u32 *d_cnt = (u32 *)c->arena.alloc((size_t)cstride * 4 * sizeof(u32));  // literals, sequences, has-sequences, leads-a-literal-group per block (+ totals after the scan)
+    u32 *d_seqblk = (u32 *)c->arena.alloc((size_t)cstride * sizeof(u32));
+    u32 *d_litgrp = (u32 *)c->arena.alloc((size_t)cstride * sizeof(u32));
     u8 *d_out = (u8 *)c->arena.alloc(obytes + 64);
-    if (!d_frames || !d_blocks || !d_cnt || !d_out) {
+    if (!d_frames || !d_blocks || !d_cnt || !d_seqblk || !d_litgrp || !d_out) {
         c->err = "arena: out of device memory (zstd decode tables)";
         return FQZ_E_CUDA;
     }
     out.d_base = d_out;
     u64 lbytes = 0, nseq = 0;
+    u32 nsb = 0;   // blocks with sequences
+    u32 ngrp = 0;  // literal decode groups
     {
         StageScope sc(c, ST_ZDEC_SCAN, cbytes);
-        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, (size_t)cstride * 2 * sizeof(u32), s));
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_cnt, 0, (size_t)cstride * 4 * sizeof(u32), s));
         fqz_launch_zd_hop(d_streams, ns, d_info, d_frames, d_blocks, 1, s);
         fqz_launch_zd_parse(d_blocks, (u32)nblocks, d_cnt, cstride, s);
         fqz_launch_zd_link(d_frames, (u32)nframes, d_blocks, d_cnt, cstride, s);
-        FQZ_TRY(fqz_scan_excl_u32(c, d_cnt, cstride, cstride, 2));
-        fqz_launch_zd_offsets(d_blocks, (u32)nblocks, d_cnt, cstride, s);
+        FQZ_TRY(fqz_scan_excl_u32(c, d_cnt, cstride, cstride, 4));
+        fqz_launch_zd_offsets(d_blocks, (u32)nblocks, d_cnt, cstride, d_seqblk, d_litgrp, s);
         u32 *htot = (u32 *)c->h_pin;
         FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot, d_cnt + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
         FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 1, d_cnt + cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 2, d_cnt + 2 * (size_t)cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 3, d_cnt + 3 * (size_t)cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
         FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
         lbytes = htot[0];  // <= obytes < 2^32 (k_zd_link rejects frames that claim more than their output)
         nseq = htot[1];
+        nsb = htot[2];
+        ngrp = htot[3];
     }
     u8 *d_lit = (u8 *)c->arena.alloc(lbytes + 64);
     u32 *d_seq = (u32 *)c->arena.alloc((size_t)nseq * 12 + 64);
-    if (!d_lit || !d_seq) {
+    u32 *d_tabs = (u32 *)c->arena.alloc((size_t)nsb * FQZ_ZD_TAB_BYTES + 64);
+    if (!d_lit || !d_seq || !d_tabs) {
         c->err = "arena: out of device memory (zstd decode arenas)";
         return FQZ_E_CUDA;
     }
     {
         StageScope sc(c, ST_ZDEC_LITERALS, lbytes);
-        fqz_launch_zd_literals(d_blocks, (u32)nblocks, d_frames, d_lit, d_out, s);
+        fqz_launch_zd_literals(d_blocks, (u32)nblocks, d_litgrp, ngrp, d_frames, d_lit, d_out, s);
     }
     {
         StageScope sc(c, ST_ZDEC_SEQUENCES, nseq * 12);
-        fqz_launch_zd_sequences(d_blocks, (u32)nblocks, d_seq, s);
+        fqz_launch_zd_sequences(d_blocks, d_seqblk, nsb, d_cnt + 2 * (size_t)cstride, d_tabs, d_seq, s);
     }
     {
         StageScope sc(c, ST_ZDEC_EXECUTE, obytes);

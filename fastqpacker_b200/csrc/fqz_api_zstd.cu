@@ -74,10 +74,13 @@ struct ZBatch {
             f.items = 0;
             f.item_base = 0;
             f.item_count = 0;
+            f.index_of = 0;
+            f.pad = 0;
             slot_bytes += (FQZ_ZINDEX_BYTES(nfr) + 15u) & ~(size_t)15;
             idx_index.push_back((u32)frames.size());
             frames.push_back(f);
         }
+        const u32 index_of = (nfr >= FQZ_ZINDEX_MIN) ? (u32)frames.size() : 0u;  // 1 + number of the index frame just added
         for (size_t o = 0; o < len; o += fsz) {
             u32 l = (u32)std::min<size_t>(fsz, len - o);
             ZFrame f;
@@ -89,6 +92,8 @@ struct ZBatch {
             f.items = (u64)(uintptr_t)items;
             f.item_base = item_base + (u32)o;
             f.item_count = item_count;
+            f.index_of = index_of;
+            f.pad = 0;
             slot_bytes += FQZ_ZSLOT(l);
             if (policy == FQZ_ZPOLICY_AUTO || policy == FQZ_ZPOLICY_ITEMS) {
                 f.ws_off = ws_bytes;
@@ -154,7 +159,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     }
     {
         StageScope sc(c, ST_SCAN, 0);
-        fqz_launch_zindex(ze.d_frames, d_idx + index_at, (u32)zb.idx_index.size(), ze.d_slots, ze.d_scan, s);
+        if (!zb.idx_index.empty()) fqz_launch_zindex(ze.d_frames, nf, ze.d_slots, ze.d_scan, s);
         FQZ_TRY(fqz_scan_excl_u32(c, ze.d_scan, (u64)nf + 1, (u64)nf + 1, 1));
     }
     return FQZ_OK;

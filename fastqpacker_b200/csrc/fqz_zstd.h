@@ -25,6 +25,8 @@ struct ZFrame {
     u64 items;      // item matcher: device address of the u32 item-start offsets of the stream (0 = fixed stride)
     u32 item_base;  // offset of this frame's first byte in the coordinates of items[]
     u32 item_count; // entries of items[] including the end sentinel; fixed stride: the stride in bytes
+    u32 index_of;   // 1 + number of the FQZ_ZPOLICY_INDEX frame that lists this frame (0 = none)
+    u32 pad;
 };
 #define FQZ_ZPOLICY_ITEMS 2  // internal: LZ by item matcher (needs the item boundaries of the stream)
 // internal: not a zstd frame but a SKIPPABLE frame (RFC 8878 §3.1.2) in front of a stream that was cut
@@ -46,8 +48,8 @@ struct ZFrame {
 #define ZENC_WARPS 4
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
-// fills the index frames listed in index[0..nidx) from the sizes of the frames behind them
-void fqz_launch_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes, cudaStream_t s);
+// fills the index frames (FQZ_ZPOLICY_INDEX) from the sizes of the frames behind them
+void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s);
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,

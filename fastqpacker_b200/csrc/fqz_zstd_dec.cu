@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(ZD_HOP_WARPS * 32) k_zd_hop(const ZDStream *st
 }
 
 // One thread per block: literals header, sequence count, positions of the table descriptions.
-// cnt[0][b] = regenerated literals, cnt[1][b] = sequences of block b (scanned into arena offsets later).
+// cnt[0][b] = regenerated literals, cnt[1][b] = sequences of block b, cnt[2][b] = 1 when it has
+// sequences (all three scanned into arena offsets / table slots later).
 __global__ void __launch_bounds__(128) k_zd_parse(ZDBlock *blocks, u32 nblocks, u32 *cnt, u32 cnt_stride) {
     u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
     if (bi >= nblocks) return;
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(128) k_zd_parse(ZDBlock *blocks, u32 nblocks, 
     }
     cnt[bi] = lit_regen;
     cnt[cnt_stride + bi] = nseq;
+    cnt[2 * cnt_stride + bi] = nseq ? 1u : 0u;  // takes a slot of sequence decode tables
 }
 
 // One thread per frame, blocks in order: which block holds the Huffman tree of a treeless block and
@@ -597,21 +599,29 @@ __global__ void __launch_bounds__(128) k_zd_link(ZDFrame *frames, u32 nframes, Z
         }
     }
     if (!bad && (lit_sum > cap || 3 * seq_sum > cap)) bad = true;
+    // literal decode groups: up to ZD_GROUP consecutive blocks of ONE frame (they usually share a Huffman tree)
+    if (!bad)
+        for (u32 k = 0; k < nb; k += 8) cnt[3 * cnt_stride + b0 + k] = 1;
     if (bad) {  // the whole frame is rejected: its blocks take no arena space and are skipped by the decode kernels
         for (u32 k = 0; k < nb; k++) {
             blocks[b0 + k].err = 1;
             cnt[b0 + k] = 0;
             cnt[cnt_stride + b0 + k] = 0;
+            cnt[2 * cnt_stride + b0 + k] = 0;
         }
     }
 }
 
 // arena offsets of every block = the scanned literal / sequence counts
-__global__ void __launch_bounds__(128) k_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride) {
+__global__ void __launch_bounds__(128) k_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, u32 *seqblk, u32 *litgrp) {
     u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
     if (bi >= nblocks) return;
     blocks[bi].lit_off = cnt[bi];
     blocks[bi].seq_off = cnt[cnt_stride + bi];
+    u32 slot = cnt[2 * cnt_stride + bi];
+    if (cnt[2 * cnt_stride + bi + 1] != slot) seqblk[slot] = bi;  // the scanned array has nblocks + 1 entries
+    u32 g = cnt[3 * cnt_stride + bi];
+    if (cnt[3 * cnt_stride + bi + 1] != g) litgrp[g] = bi;
 }
 
 // ---------------------------------------------------------------------------------- literals
@@ -754,14 +764,9 @@ __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 
 struct HufBits {
     u64 bits;       // unread bits, left-aligned
     u32 nb;         // valid bits in `bits`
-    const u32 *wp;  // next word to prefetch
     const u32 *lo;  // aligned word that holds the first byte of the stream
+    u32 wi;         // index (from lo) of the next word to prefetch; sticks at 0
     u32 w0, w1, w2; // prefetched words, nearest first
-    __device__ __forceinline__ u32 fetch() {
-        u32 v = *wp;
-        wp = (wp > lo) ? wp - 1 : lo;
-        return v;
-    }
     // src[csize - 1] != 0 (it holds the end mark).  Returns the payload bits of the stream.
     __device__ __forceinline__ u32 init(const u8 *src, u32 csize) {
         u32 hb = hibit32(src[csize - 1]);
@@ -770,34 +775,43 @@ struct HufBits {
         const u32 *wa = (const u32 *)((uintptr_t)(endp - 1) & ~(uintptr_t)3);
         u32 k = (u32)((uintptr_t)(endp - 1) & 3u) + 1u;  // stream bytes in the top word
         u32 v = *wa;
-        wp = (wa > lo) ? wa - 1 : lo;
+        wi = (u32)(wa - lo);
         bits = (u64)v << (64u - 8u * k);
         bits <<= (8u - hb);  // padding and end mark
         nb = 8u * k - (8u - hb);
-        w0 = fetch();
-        w1 = fetch();
-        w2 = fetch();
+        wi = wi ? wi - 1u : 0u;
+        w0 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
+        w1 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
+        w2 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
         return (csize - 1u) * 8u + hb;
     }
-    __device__ __forceinline__ void refill() {  // afterwards nb >= 33 (bits past the stream start are whatever memory holds)
-        if (nb <= 32) {
-            bits |= (u64)w0 << (32u - nb);
-            nb += 32;
-            w0 = w1;
-            w1 = w2;
-            w2 = fetch();
-        }
+    // Afterwards nb >= 32 (bits past the stream start are whatever memory holds).  Branch-free on
+    // purpose: the 32 lanes of a warp run 32 different streams and would otherwise take this path at
+    // different times, every one of them paying for all the others.
+    __device__ __forceinline__ void refill() {
+        const bool need = nb <= 32u;
+        const u32 v = lo[wi];  // always a valid address; only used when `need`
+        const u64 add = (u64)w0 << ((32u - nb) & 63u);
+        bits |= need ? add : 0ull;
+        nb += need ? 32u : 0u;
+        w0 = need ? w1 : w0;
+        w1 = need ? w2 : w1;
+        w2 = need ? v : w2;
+        wi = (need && wi) ? wi - 1u : wi;
     }
     __device__ __forceinline__ u32 peek(u32 n) const { return (u32)(bits >> 32) >> (32u - n); }  // 1 <= n <= 32
+    __device__ __forceinline__ void drop(u32 n) {
+        bits <<= n;
+        nb -= n;
+    }
     __device__ __forceinline__ u32 take(u32 n) {  // 0 <= n <= 32, n <= nb
         if (n == 0) return 0;
         u32 v = peek(n);
         drop(n);
         return v;
-    }
-    __device__ __forceinline__ void drop(u32 n) {
-        bits <<= n;
-        nb -= n;
     }
 };
 
@@ -857,16 +871,17 @@ __device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 
 // by the reference's encoder) take one pass per table.  Sequence-free blocks whose position in the
 // frame is known from the headers are decoded straight into the output.
 #define ZD_GROUP 8
-__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out) {
+__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, u32 nblocks, const u32 *litgrp, u32 ngroups, const ZDFrame *frames,
+                                                               u8 *litbuf, u8 *out) {
     __shared__ LitScratch scratch[ZD_WARPS];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
     u32 g = blockIdx.x * ZD_WARPS + warp;
-    u32 b0 = g * ZD_GROUP;
-    if (b0 >= nblocks) return;
+    if (g >= ngroups) return;
+    const u32 b0 = litgrp[g];  // first block of the group; the group never leaves its frame
     LitScratch &S = scratch[warp];
     u32 bl = lane >> 2, q = lane & 3u;
     u32 bi = b0 + bl;
-    bool valid = bi < nblocks;
+    bool valid = bi < nblocks && blocks[bi].frame == blocks[b0].frame;
     ZDBlock B;
     if (valid) B = blocks[bi];
     else {
@@ -948,15 +963,20 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, 
 }
 
 // ---------------------------------------------------------------------------------- sequences
+// Decoding the sequences of one block is a serial chain (three FSE states fed by one backward
+// bitstream), so the parallelism is ACROSS blocks: k_zd_seq_tables builds the decode tables of every
+// block that has sequences into global memory (one warp per block, lanes 0/1/2 one table each), and
+// k_zd_seq_decode runs ONE THREAD per block with its tables in L2 — all 32 lanes of a warp busy on
+// 32 different blocks, where one warp per block kept a single lane busy.
 struct SeqScratch {
     FseDEnt dt[3][512];
-    u16 next[64];
-    short norm[64];
+    u16 next[3][64];
+    short norm[3][64];
+    u32 tl[3];
 };
-// Builds the decode table of stream type t (0 LL, 1 OF, 2 ML) for block B.  Returns tableLog,
-// 0xFF on error; RLE tables have log 0 and a single entry.
-__device__ static u32 build_seq_table(const ZDBlock &B, const ZDBlock *blocks, int t, SeqScratch &S) {
-    const ZDBlock &SB = (B.fse_block[t] == 0xFFFFFFFFu) ? B : blocks[B.fse_block[t]];
+// Builds the decode table of stream type t (0 LL, 1 OF, 2 ML) of block SB (which carries its own
+// description: modes 0 / 1 / 2).  Returns tableLog, 0xFF on error; RLE tables have log 0 and one entry.
+__device__ static u32 build_seq_table(const ZDBlock &SB, int t, SeqScratch &S) {
     u32 m = (SB.modes >> (6 - 2 * t)) & 3;
     const u8 *c = (const u8 *)(uintptr_t)SB.src;
     const u32 maxLogs[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
@@ -965,8 +985,8 @@ __device__ static u32 build_seq_table(const ZDBlock &B, const ZDBlock *blocks, i
         const short *dn = (t == 0) ? kLLDefNorm : (t == 1 ? kOFDefNorm : kMLDefNorm);
         u32 ms = (t == 0) ? 35 : (t == 1 ? 28 : 52);
         u32 tl = (t == 1) ? ZSTD_OF_DEFLOG : ZSTD_LL_DEFLOG;
-        for (u32 s = 0; s <= ms; s++) S.norm[s] = dn[s];
-        fse_build_dtable(S.norm, ms, tl, S.dt[t], S.next);
+        for (u32 s = 0; s <= ms; s++) S.norm[t][s] = dn[s];
+        fse_build_dtable(S.norm[t], ms, tl, S.dt[t], S.next[t]);
         return tl;
     }
     if (m == 1) {
@@ -979,74 +999,103 @@ __device__ static u32 build_seq_table(const ZDBlock &B, const ZDBlock *blocks, i
     }
     if (m == 2) {
         u32 ms = maxSyms[t], tl = 0;
-        u32 used = fse_read_ncount(c + SB.tab_pos[t], SB.csize - SB.tab_pos[t], S.norm, &ms, &tl, maxLogs[t]);
+        u32 used = fse_read_ncount(c + SB.tab_pos[t], SB.csize - SB.tab_pos[t], S.norm[t], &ms, &tl, maxLogs[t]);
         if (!used) return 0xFF;
-        fse_build_dtable(S.norm, ms, tl, S.dt[t], S.next);
+        fse_build_dtable(S.norm[t], ms, tl, S.dt[t], S.next[t]);
         return tl;
     }
-    return 0xFF;  // a repeat chain always ends at a block with its own table
+    return 0xFF;  // repeat mode: the table lives with another block
 }
 
-__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf) {
+// seqblk[slot] = block number of the slot-th block with sequences; tabs: ZD_TAB_WORDS u32 per slot:
+// three tables of 512 entries, then the three table logs (0xFF = bad / not this block's own table).
+#define ZD_TAB_WORDS (3u * 512u + 4u)
+__global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_seq_tables(const ZDBlock *blocks, const u32 *seqblk, u32 nsb, u32 *tabs) {
     __shared__ SeqScratch scratch[ZD_WARPS];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
-    u32 bi = blockIdx.x * ZD_WARPS + warp;
-    if (bi >= nblocks) return;
-    ZDBlock B = blocks[bi];
-    if (B.type != 2 || B.nseq == 0 || B.err) return;
+    u32 slot = blockIdx.x * ZD_WARPS + warp;
+    if (slot >= nsb) return;
+    const ZDBlock &B = blocks[seqblk[slot]];
     SeqScratch &S = scratch[warp];
-    if (lane == 0) {
-        u32 err = 0;
-        u32 tl[3];
-        for (int t = 0; t < 3; t++) {
-            tl[t] = build_seq_table(B, blocks, t, S);
-            if (tl[t] == 0xFF) err = 1;
-        }
-        u32 *sq = seqbuf + 3ull * B.seq_off;
-        u64 total = 0;
-        if (!err) {
-            const u8 *c = (const u8 *)(uintptr_t)B.src;
-            const u32 bsz = B.csize - B.bits_pos;
-            if (bsz == 0 || c[B.csize - 1] == 0) err = 1;  // no bitstream, or its end mark is missing
-            else {
-                // same reader as the Huffman streams: aligned words prefetched ahead of the state chain,
-                // consumed bits counted and checked against the stream size at the end.  Every group of
-                // reads between two refills takes at most 32 bits (offset extra bits <= 31; match + literal
-                // length extra bits <= 16 + 16; three state updates <= 9 + 9 + 8).
-                HufBits br;
-                const u32 avail = br.init(c + B.bits_pos, bsz);
-                u32 used = tl[0] + tl[1] + tl[2];
-                br.refill();
-                u32 sLL = br.take(tl[0]), sOF = br.take(tl[1]), sML = br.take(tl[2]);
-                for (u32 i = 0; i < B.nseq; i++) {
-                    FseDEnt eLL = S.dt[0][sLL], eOF = S.dt[1][sOF], eML = S.dt[2][sML];
-                    u32 ofc = eOF.sym, mlc = eML.sym, llc = eLL.sym;
-                    if (ofc > 31 || mlc > 52 || llc > 35) { err = 1; break; }
-                    br.refill();
-                    u32 ofv = (1u << ofc) + br.take(ofc);
-                    br.refill();
-                    u32 mlb = kMLBits[mlc], llb = kLLBits[llc];
-                    u32 ml = kMLBase[mlc] + br.take(mlb);
-                    u32 ll = kLLBase[llc] + br.take(llb);
-                    used += ofc + mlb + llb;
-                    sq[3 * i] = ll;
-                    sq[3 * i + 1] = ml;
-                    sq[3 * i + 2] = ofv;
-                    total += (u64)ll + ml;
-                    if (i + 1 < B.nseq) {
-                        br.refill();
-                        sLL = eLL.base + br.take(eLL.nb);
-                        sML = eML.base + br.take(eML.nb);
-                        sOF = eOF.base + br.take(eOF.nb);
-                        used += (u32)eLL.nb + eML.nb + eOF.nb;
-                    }
-                    if (used > avail) { err = 1; break; }
-                }
-                if (used != avail) err = 1;
-            }
-        }
-        if (err || total > ZSTD_BLOCK_MAX) blocks[bi].err = 1;
+    if (lane < 3) {
+        bool own = ((B.modes >> (6 - 2 * lane)) & 3) != 3;
+        S.tl[lane] = own ? build_seq_table(B, (int)lane, S) : 0xFFu;
     }
+    __syncwarp();
+    u32 *o = tabs + (size_t)slot * ZD_TAB_WORDS;
+    for (int t = 0; t < 3; t++) {
+        u32 tl = S.tl[t];
+        if (tl == 0xFF) continue;
+        u32 n = 1u << tl;
+        const u32 *src = (const u32 *)S.dt[t];
+        for (u32 i = lane; i < n; i += 32) o[512u * t + i] = src[i];
+    }
+    if (lane < 3) o[1536u + lane] = S.tl[lane];
+}
+
+// One thread per block with sequences.  slot_of[b] = table slot of block b (exclusive scan of the
+// has-sequences flags).
+__global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u32 *seqblk, u32 nsb, const u32 *slot_of, const u32 *tabs, u32 *seqbuf) {
+    u32 slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nsb) return;
+    const u32 bi = seqblk[slot];
+    const ZDBlock &B = blocks[bi];
+    u32 err = 0;
+    u32 tl[3];
+    const u32 *dt[3];
+    for (int t = 0; t < 3; t++) {
+        u32 sb = B.fse_block[t];  // == bi unless the table is repeated from an earlier block of the frame
+        const u32 *tb = tabs + (size_t)slot_of[sb] * ZD_TAB_WORDS;
+        dt[t] = tb + 512u * t;
+        tl[t] = tb[1536u + t];
+        if (tl[t] == 0xFF) err = 1;
+    }
+    const u32 nseq = B.nseq;
+    u32 *sq = seqbuf + 3ull * B.seq_off;
+    u64 total = 0;
+    if (!err) {
+        const u8 *c = (const u8 *)(uintptr_t)B.src;
+        const u32 bsz = B.csize - B.bits_pos;
+        if (bsz == 0 || c[B.csize - 1] == 0) err = 1;  // no bitstream, or its end mark is missing
+        else {
+            // same reader as the Huffman streams: aligned words prefetched ahead of the state chain,
+            // consumed bits counted and checked against the stream size at the end.  Every group of
+            // reads between two refills takes at most 32 bits (offset extra bits <= 31; match + literal
+            // length extra bits <= 16 + 16; three state updates <= 9 + 9 + 8).
+            HufBits br;
+            const u32 avail = br.init(c + B.bits_pos, bsz);
+            u32 used = tl[0] + tl[1] + tl[2];
+            br.refill();
+            u32 sLL = br.take(tl[0]), sOF = br.take(tl[1]), sML = br.take(tl[2]);
+            for (u32 i = 0; i < nseq; i++) {
+                u32 eLL = dt[0][sLL], eOF = dt[1][sOF], eML = dt[2][sML];  // FseDEnt: base | sym << 16 | nb << 24
+                u32 ofc = (eOF >> 16) & 0xFFu, mlc = (eML >> 16) & 0xFFu, llc = (eLL >> 16) & 0xFFu;
+                if (ofc > 31 || mlc > 52 || llc > 35) { err = 1; break; }
+                br.refill();
+                u32 ofv = (1u << ofc) + br.take(ofc);
+                br.refill();
+                u32 mlb = kMLBits[mlc], llb = kLLBits[llc];
+                u32 ml = kMLBase[mlc] + br.take(mlb);
+                u32 ll = kLLBase[llc] + br.take(llb);
+                used += ofc + mlb + llb;
+                sq[3 * i] = ll;
+                sq[3 * i + 1] = ml;
+                sq[3 * i + 2] = ofv;
+                total += (u64)ll + ml;
+                if (i + 1 < nseq) {
+                    br.refill();
+                    u32 nLL = eLL >> 24, nML = eML >> 24, nOF = eOF >> 24;
+                    sLL = (eLL & 0xFFFFu) + br.take(nLL);
+                    sML = (eML & 0xFFFFu) + br.take(nML);
+                    sOF = (eOF & 0xFFFFu) + br.take(nOF);
+                    used += nLL + nML + nOF;
+                }
+                if (used > avail) { err = 1; break; }
+            }
+            if (used != avail) err = 1;
+        }
+    }
+    if (err || total > ZSTD_BLOCK_MAX) blocks[bi].err = 1;
 }
 
 // ---------------------------------------------------------------------------------- execution
@@ -1082,41 +1131,91 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
             else if ((u64)B.out_off != o) { err = 1; break; }
             o += B.lit_regen;
         } else {
+            // Sequences are taken 32 at a time, one per lane.  Offsets are resolved against the repeat
+            // history in a short uniform loop, a warp scan of the lengths gives every lane its place,
+            // all literal runs are copied at once, and the matches complete in rounds: a lane copies as
+            // soon as everything its source range needs is final — always true for the first unfinished
+            // lane, and true for many at once when the offsets reach back beyond the group (round trip
+            // through memory per round instead of per sequence).  Long matches are left to the whole warp.
             const u8 *lit = litbuf + B.lit_off;
             const u32 *sq = seqbuf + 3ull * B.seq_off;
             u32 lp = 0;
             u64 o0 = o;
-            for (u32 i = 0; i < B.nseq; i++) {
-                u32 ll = sq[3 * i], ml = sq[3 * i + 1], ofv = sq[3 * i + 2];
-                // repeat offsets (RFC 8878 §3.1.1.5)
-                u32 off;
-                if (ofv > 3) {
-                    off = ofv - 3;
-                    rep2 = rep1; rep1 = rep0; rep0 = off;
-                } else {
-                    u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
-                    if (idx == 0) off = rep0;
-                    else {
-                        off = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
-                        if (idx != 1) rep2 = rep1;
-                        rep1 = rep0;
-                        rep0 = off;
+            for (u32 sb = 0; sb < B.nseq && !err; sb += 32) {
+                const u32 cn = min(32u, B.nseq - sb);
+                const bool live = lane < cn;
+                u32 ll = 0, ml = 0, ofv = 0;
+                if (live) {
+                    ll = sq[3 * (sb + lane)];
+                    ml = sq[3 * (sb + lane) + 1];
+                    ofv = sq[3 * (sb + lane) + 2];
+                }
+                // repeat offsets (RFC 8878 §3.1.1.5), uniform
+                u32 off = 0;
+                for (u32 j = 0; j < cn; j++) {
+                    u32 v = __shfl_sync(FULL, ofv, (int)j), l = __shfl_sync(FULL, ll, (int)j);
+                    u32 f;
+                    if (v > 3) {
+                        f = v - 3;
+                        rep2 = rep1; rep1 = rep0; rep0 = f;
+                    } else {
+                        u32 idx = v - 1 + (l == 0 ? 1u : 0u);
+                        if (idx == 0) f = rep0;
+                        else {
+                            f = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
+                            if (idx != 1) rep2 = rep1;
+                            rep1 = rep0;
+                            rep0 = f;
+                        }
                     }
+                    if (lane == j) off = f;
                 }
-                if (lp + ll > B.lit_regen || off == 0 || off > o + ll || o + ll + ml > F.out_cap) { err = 1; break; }
-                warp_copy(base + o, lit + lp, ll, lane);
-                lp += ll;
-                o += ll;
-                __syncwarp();
-                u8 *d = base + o;
-                const u8 *s = d - off;
-                if (off >= ml) {
-                    for (u32 k = lane; k < ml; k += 32) d[k] = s[k];
-                } else {  // overlapping match: the source is the last `off` bytes, repeated
-                    for (u32 k = lane; k < ml; k += 32) d[k] = s[k % off];
+                u32 tot = ll + ml;
+                u32 incl = group_incl_scan(tot, FULL, 32), lincl = group_incl_scan(ll, FULL, 32);
+                u32 gtot = __shfl_sync(FULL, incl, 31), gll = __shfl_sync(FULL, lincl, 31);
+                u64 lstart = o + incl - tot, mstart = lstart + ll;
+                u32 lsrc = lp + lincl - ll;
+                bool bad = live && (off == 0 || (u64)off > mstart);
+                if (__any_sync(FULL, bad) || lp + gll > B.lit_regen || o + gtot > F.out_cap) { err = 1; break; }
+                if (live) {
+                    u8 *d = base + lstart;
+                    const u8 *sp = lit + lsrc;
+                    for (u32 k = 0; k < ll; k++) d[k] = sp[k];
                 }
-                o += ml;
                 __syncwarp();
+                bool done = !live || ml == 0;
+                const u64 need = (off >= ml) ? (mstart - off + ml) : mstart;  // output that must be final before this lane copies
+                for (;;) {
+                    u32 pend = __ballot_sync(FULL, !done);
+                    if (!pend) break;
+                    int hw = __ffs((int)pend) - 1;
+                    u64 hwpos = __shfl_sync(FULL, mstart, hw);  // everything below is final
+                    u32 hml = __shfl_sync(FULL, ml, hw);
+                    if (hml > 64u) {  // long match at the front: the whole warp copies it
+                        u32 hoff = __shfl_sync(FULL, off, hw);
+                        u8 *d = base + hwpos;
+                        const u8 *sp = d - hoff;
+                        if (hoff >= hml) {
+                            for (u32 k = lane; k < hml; k += 32) d[k] = sp[k];
+                        } else if (hoff >= 32u) {  // overlapping, but 32 bytes at a time never overtake the source
+                            for (u32 k0 = 0; k0 < hml; k0 += 32) {
+                                if (k0 + lane < hml) d[k0 + lane] = sp[k0 + lane];
+                                __syncwarp();
+                            }
+                        } else {
+                            for (u32 k = lane; k < hml; k += 32) d[k] = sp[k % hoff];  // the source is the last `off` bytes, repeated
+                        }
+                        if ((int)lane == hw) done = true;
+                    } else if (!done && ml <= 64u && ((int)lane == hw || need <= hwpos)) {
+                        u8 *d = base + mstart;
+                        const u8 *sp = d - off;
+                        for (u32 k = 0; k < ml; k++) d[k] = sp[k];
+                        done = true;
+                    }
+                    __syncwarp();
+                }
+                o += gtot;
+                lp += gll;
             }
             if (err) break;
             u32 rest = B.lit_regen - lp;
@@ -1213,18 +1312,18 @@ void fqz_launch_zd_link(ZDFrame *frames, u32 nframes, ZDBlock *blocks, u32 *cnt,
     if (!nframes) return;
     FQZ_LAUNCH(k_zd_link, (nframes + 127) / 128, 128, 0, s, frames, nframes, blocks, cnt, cnt_stride);
 }
-void fqz_launch_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, cudaStream_t s) {
+void fqz_launch_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, u32 *seqblk, u32 *litgrp, cudaStream_t s) {
     if (!nblocks) return;
-    FQZ_LAUNCH(k_zd_offsets, (nblocks + 127) / 128, 128, 0, s, blocks, nblocks, cnt, cnt_stride);
+    FQZ_LAUNCH(k_zd_offsets, (nblocks + 127) / 128, 128, 0, s, blocks, nblocks, cnt, cnt_stride, seqblk, litgrp);
 }
-void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s) {
-    if (!nblocks) return;
-    u32 groups = (nblocks + ZD_GROUP - 1) / ZD_GROUP;
-    FQZ_LAUNCH(k_zd_literals, (groups + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, frames, litbuf, out);
+void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const u32 *litgrp, u32 ngroups, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s) {
+    if (!nblocks || !ngroups) return;
+    FQZ_LAUNCH(k_zd_literals, (ngroups + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, litgrp, ngroups, frames, litbuf, out);
 }
-void fqz_launch_zd_sequences(ZDBlock *blocks, u32 nblocks, u32 *seqbuf, cudaStream_t s) {
-    if (!nblocks) return;
-    FQZ_LAUNCH(k_zd_sequences, (nblocks + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, seqbuf);
+void fqz_launch_zd_sequences(ZDBlock *blocks, const u32 *seqblk, u32 nsb, const u32 *slot_of, u32 *tabs, u32 *seqbuf, cudaStream_t s) {
+    if (!nsb) return;
+    FQZ_LAUNCH(k_zd_seq_tables, (nsb + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, seqblk, nsb, tabs);
+    FQZ_LAUNCH(k_zd_seq_decode, (nsb + 127) / 128, 128, 0, s, blocks, seqblk, nsb, slot_of, tabs, seqbuf);
 }
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s) {
     if (!nframes) return;

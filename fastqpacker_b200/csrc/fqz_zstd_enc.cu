@@ -1828,52 +1828,54 @@ __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *fr
     if (live && q == 0) hashes[fi] = (u32)h;
 }
 
-// One warp per index frame (see FQZ_ZPOLICY_INDEX): frame fi indexes the src_len frames fi+1 ...
-__global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes) {
-    u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
-    if (wi >= nidx) return;
-    u32 fi = index[wi];
-    u32 n = frames[fi].src_len;
-    u32 *o = (u32 *)(slots + frames[fi].dst_off);  // slots are 16-byte aligned
-    if (lane == 0) {
+// One thread per frame (see FQZ_ZPOLICY_INDEX): an index frame writes its header, every frame that is
+// listed in one writes its own entry.
+__global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes) {
+    u32 f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const ZFrame &F = frames[f];
+    if (F.policy == FQZ_ZPOLICY_INDEX) {
+        u32 n = F.src_len;
+        u32 *o = (u32 *)(slots + F.dst_off);  // slots are 16-byte aligned
         o[0] = FQZ_ZINDEX_MAGIC;
         o[1] = FQZ_ZINDEX_BYTES(n) - 8u;
         o[2] = FQZ_ZINDEX_SIG;
         o[3] = n;
-        o[4] = frames[fi + 1].src_len;  // every frame but the last holds this many content bytes
-        out_sizes[fi] = FQZ_ZINDEX_BYTES(n);
+        o[4] = frames[f + 1].src_len;  // every frame but the last holds this many content bytes
+        out_sizes[f] = FQZ_ZINDEX_BYTES(n);
+        return;
     }
-    for (u32 k = lane; k < n; k += 32) {
-        const ZFrame &F = frames[fi + 1 + k];
-        u32 first = 0, cnt = 0;
-        const u32 *items = (const u32 *)(uintptr_t)F.items;
-        if (F.policy == FQZ_ZPOLICY_ITEMS && items) {
-            // items[] = start of every item in stream coordinates (ascending, last entry = end sentinel):
-            // i0 = first item starting at or after the frame's first byte, i1 = same for the frame's end
-            u32 nit = F.item_count - 1u;
-            u32 lo0 = F.item_base, lo1 = F.item_base + F.src_len;
-            u32 a = 0, b = nit;
-            while (a < b) {
-                u32 mid = (a + b) >> 1;
-                if (items[mid] < lo0) a = mid + 1; else b = mid;
-            }
-            u32 i0 = a;
-            b = nit;
-            while (a < b) {
-                u32 mid = (a + b) >> 1;
-                if (items[mid] < lo1) a = mid + 1; else b = mid;
-            }
-            cnt = a - i0;
-            if (cnt) first = items[i0] - lo0;
-            if (cnt > 0xFFFFu || first > 0xFFFFu) cnt = 0xFFFFu, first = 0xFFFFu;  // unusable hint: the decoder falls back
+    if (!F.index_of) return;
+    u32 fi = F.index_of - 1u, k = f - fi - 1u;
+    u32 *o = (u32 *)(slots + frames[fi].dst_off);
+    u32 first = 0, cnt = 0;
+    const u32 *items = (const u32 *)(uintptr_t)F.items;
+    if (F.policy == FQZ_ZPOLICY_ITEMS && items) {
+        // items[] = start of every item in stream coordinates (ascending, last entry = end sentinel):
+        // i0 = first item starting at or after the frame's first byte, i1 = same for the frame's end
+        u32 nit = F.item_count - 1u;
+        u32 lo0 = F.item_base, lo1 = F.item_base + F.src_len;
+        u32 a = 0, b = nit;
+        while (a < b) {
+            u32 mid = (a + b) >> 1;
+            if (items[mid] < lo0) a = mid + 1; else b = mid;
         }
-        o[5 + 2 * k] = out_sizes[fi + 1 + k];
-        o[6 + 2 * k] = first | (cnt << 16);
+        u32 i0 = a;
+        b = nit;
+        while (a < b) {
+            u32 mid = (a + b) >> 1;
+            if (items[mid] < lo1) a = mid + 1; else b = mid;
+        }
+        cnt = a - i0;
+        if (cnt) first = items[i0] - lo0;
+        if (cnt > 0xFFFFu || first > 0xFFFFu) cnt = 0xFFFFu, first = 0xFFFFu;  // unusable hint: the decoder falls back
     }
+    o[5 + 2 * k] = out_sizes[f];
+    o[6 + 2 * k] = first | (cnt << 16);
 }
-void fqz_launch_zindex(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, u32 *out_sizes, cudaStream_t s) {
-    if (!nidx) return;
-    FQZ_LAUNCH(k_zindex, (nidx * 32 + 127) / 128, 128, 0, s, frames, index, nidx, slots, out_sizes);
+void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+    if (!nframes) return;
+    FQZ_LAUNCH(k_zindex, (nframes + 127) / 128, 128, 0, s, frames, nframes, slots, out_sizes);
 }
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
