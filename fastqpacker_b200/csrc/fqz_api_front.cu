@@ -17,7 +17,7 @@ __global__ void k_gather_bounds(const u32 *offs, u64 stride, u64 R, u32 nblocks,
 
 static const int kErrOfKind[5] = {0, FQZ_E_HEADER_AT, FQZ_E_PLUS, FQZ_E_LEN_MISMATCH, FQZ_E_LONG_N};
 
-int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out) {
+int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out, u32 skip) {
     out = FrontOut();
     cudaStream_t s = c->stream;
     if (n >= ((u64)1 << 32) - 65536) return FQZ_E_TOO_LARGE;
@@ -40,7 +40,13 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     u32 *h = (u32 *)c->h_pin;
     FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_tiles + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, s));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    // skip > 0: the window starts inside the 16-byte word that still holds the end of the previous
+    // window's last line, '\n' included (windows are cut behind a newline): that line is line -1
     u64 nlines = h[0];
+    if (skip) {
+        if (nlines == 0) return FQZ_E_INVALID_ARG;
+        nlines -= 1;
+    }
     u64 R_all = nlines / 4;
     u64 R = R_all;
     u32 tail_lines = 0;
@@ -55,14 +61,17 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     out.nblocks = (u32)((R + FQZ_BLOCK_RECORDS - 1) / FQZ_BLOCK_RECORDS);
     // ---- 2. line_end[]
     u64 want_lines = 4 * R + tail_lines;
-    u32 *d_line_end = (u32 *)c->arena.alloc((size_t)(want_lines + 4) * sizeof(u32));
-    if (!d_line_end) {
+    u32 *d_line_alloc = (u32 *)c->arena.alloc((size_t)(want_lines + 8) * sizeof(u32));
+    if (!d_line_alloc) {
         c->err = "arena: out of device memory (line_end)";
         return FQZ_E_CUDA;
     }
+    // entry -1 of line_end[]: end of the line in front of record 0 (0xFFFFFFFF + 1 = 0 when there is none)
+    u32 *d_line_end = d_line_alloc + 4;
+    if (!skip) FQZ_CUDA_TRY(c, cudaMemsetAsync(d_line_end - 1, 0xFF, sizeof(u32), s));
     {
         StageScope sc(c, ST_NL_INDEX, n + 4 * want_lines);
-        fqz_launch_newline_index(d_text, n, d_tiles, ntiles, d_line_end, (u32)want_lines, s);
+        fqz_launch_newline_index(d_text, n, d_tiles, ntiles, skip ? d_line_end - 1 : d_line_end, (u32)want_lines + (skip ? 1u : 0u), s);
     }
     // ---- 3. per-record sizes + validation + Phred min, then five scans
     u64 stride = ((R + 1 + 63) / 64) * 64;
@@ -157,7 +166,7 @@ extern "C" int fqz_encode_streams(fqz_ctx *c, const uint8_t *fastq, size_t n, in
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_text + (n & ~(size_t)15), 0, 64, c->stream));  // defined bytes in the slack
     if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_text, fastq, n, cudaMemcpyHostToDevice, c->stream));
     FrontOut fo;
-    int rc = fqz_run_frontend(c, d_text, n, true, 0, phred64 < 0 ? -1 : (phred64 ? 1 : 0), FQZ_BLOCK_RECORDS, fo);
+    int rc = fqz_run_frontend(c, d_text, n, true, 0, phred64 < 0 ? -1 : (phred64 ? 1 : 0), FQZ_BLOCK_RECORDS, fo, 0);
     if (rc != FQZ_OK) {
         info[5] = fo.consumed;
         return rc;

@@ -1,6 +1,7 @@
 // fqz_api_zstd.cu — host orchestration of the zstd encode stage, container assembly
 // (block headers + payload order of internal/compress/compress.go:530-552,
 // internal/fqformat/container.go:83-113) and the compress entry points.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -212,10 +213,10 @@ static const int kStreamPolicy[6] = {FQZ_ZPOLICY_ENTROPY, FQZ_ZPOLICY_ENTROPY, F
 // Compresses the whole blocks of d_text[0..n) into d_out.  Emits the 10-byte file header first
 // when `with_file_header`.  Returns bytes written in *out_len, text consumed in *consumed.
 int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, bool with_file_header,
-                        u32 header_block_size, u8 *d_out, size_t out_cap, size_t *out_len, u64 *consumed, u64 *records, u32 *phred_out) {
+                        u32 header_block_size, u8 *d_out, size_t out_cap, size_t *out_len, u64 *consumed, u64 *records, u32 *phred_out, u32 skip) {
     cudaStream_t s = c->stream;
     FrontOut fo;
-    FQZ_TRY(fqz_run_frontend(c, d_text, n, is_last, rec_base, phred_mode, 0, fo));
+    FQZ_TRY(fqz_run_frontend(c, d_text, n, is_last, rec_base, phred_mode, 0, fo, skip));
     *consumed = fo.consumed;
     *records = fo.R;
     *phred_out = fo.phred64;
@@ -308,7 +309,11 @@ struct CompState {
 // h_out on the copy stream while the next window is coded.
 static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_last, CompState &st, u32 header_block_size, u8 *d_out,
                                 size_t out_cap, size_t *out_len, u64 *consumed, u8 *h_out = nullptr, size_t h_cap = 0) {
-    const u64 WIN = (u64)1 << 30;  // the entropy kernels are latency-bound per frame: large windows keep every SM busy
+    u64 WIN = (u64)1 << 30;  // the entropy kernels are latency-bound per frame: large windows keep every SM busy
+    if (const char *e = getenv("FQZ_WINDOW_BYTES")) {  // test hook: small windows exercise the window hand-over
+        u64 v = strtoull(e, nullptr, 10);
+        if (v >= ((u64)1 << 20)) WIN = std::min(v, WIN);
+    }
     u64 pos = 0;
     size_t written = 0;
     *out_len = 0;
@@ -323,22 +328,27 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
             last = false;
         }
         if (h_out) FQZ_TRY(fqz_io_gate(c, pos + take, nullptr));
-        // windows must start 16-byte aligned for the vector loads: copy the unaligned remainder
+        // windows must start 16-byte aligned for the vector loads: start at the aligned address below and
+        // tell the front end how many bytes to skip (they end the previous window's last line)
         const u8 *wptr = d_fastq + pos;
-        if (((uintptr_t)wptr & 15u) != 0) {
+        u32 skip = (u32)((uintptr_t)wptr & 15u);
+        if (skip > pos) {  // only the caller's own pointer can be misaligned at pos == 0: copy (rare)
             u8 *tmp = (u8 *)c->arena.alloc(take + 64);
             if (!tmp) return FQZ_E_CUDA;
             StageScope sc(c, ST_COPY, 2 * take);
             FQZ_CUDA_TRY(c, cudaMemcpyAsync(tmp, wptr, take, cudaMemcpyDeviceToDevice, c->stream));
             FQZ_CUDA_TRY(c, cudaMemsetAsync(tmp + take, 0, 64, c->stream));
             wptr = tmp;
+            skip = 0;
         }
+        wptr -= skip;
         size_t wl = 0;
         u64 used = 0, recs = 0;
         u32 ph = 0;
         int pmode = st.first ? (st.forced_phred >= 0 ? st.forced_phred : -1) : (int)st.phred64;
-        int rc = fqz_compress_window(c, wptr, take, last, st.rec_base, pmode, st.first && st.emit_header, header_block_size,
-                                     d_out + written, out_cap - written, &wl, &used, &recs, &ph);
+        int rc = fqz_compress_window(c, wptr, take + skip, last, st.rec_base, pmode, st.first && st.emit_header, header_block_size,
+                                     d_out + written, out_cap - written, &wl, &used, &recs, &ph, skip);
+        if (rc == FQZ_OK) used -= skip;
         if (rc == FQZ_E_NEED_MORE) {
             if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside a full device window
             break;                                    // streaming: the tail waits for more data

@@ -115,7 +115,7 @@ __device__ __forceinline__ u32 strip_cr(const u8 *text, u32 s, u32 e) { return (
 __device__ __forceinline__ LineSpan record_lines(const u8 *text, const u32 *line_end, u64 r) {
     LineSpan t;
     u64 l = 4 * r;
-    u32 e0 = (l == 0) ? 0xFFFFFFFFu : line_end[l - 1];
+    u32 e0 = line_end[(long long)l - 1];  // entry -1 exists: 0xFFFFFFFF, or the end of the previous window's last line
     u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
     t.hs = e0 + 1u;
     t.he = strip_cr(text, t.hs, e1);
@@ -175,7 +175,7 @@ k_record_meta(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail
         // meets EOF (parser.go:138-166), e.g. a trailing blank line is a header error.
         if (g == 0 && tail_lines > 0) {
             u64 l = 4 * R;
-            u32 hs = (l == 0) ? 0u : line_end[l - 1] + 1u;
+            u32 hs = line_end[(long long)l - 1] + 1u;
             u32 he = strip_cr(text, hs, line_end[l]);
             u32 kind = 0;
             if (he == hs || text[hs] != '@') kind = FQZ_K_HEADER_AT;
@@ -253,7 +253,7 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
     u64 r0 = (u64)blockIdx.x * FQZ_SC_RPC;
     u64 r1 = min(r0 + (u64)FQZ_SC_RPC, R);
     // contiguous text chunk of this CTA's records, widened to 16-byte boundaries for the bulk copy
-    u32 c0 = (r0 == 0) ? 0u : line_end[4 * r0 - 1] + 1u;
+    u32 c0 = line_end[4ll * (long long)r0 - 1] + 1u;
     u32 c1 = line_end[4 * r1 - 1] + 1u;
     u32 a0 = c0 & ~15u;
     u32 a1 = (c1 + 15u) & ~15u;
@@ -276,7 +276,7 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
         LineSpan t;
         {
             u64 l = 4 * r;
-            u32 e0 = (l == 0) ? 0xFFFFFFFFu : line_end[l - 1];
+            u32 e0 = line_end[(long long)l - 1];
             u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
             t.hs = e0 + 1u;
             t.he = (e1 > t.hs && *src.at(e1 - 1) == '\r') ? e1 - 1 : e1;

@@ -150,4 +150,6 @@ struct FrontOut {
 };
 // phred_mode: -1 detect on the first block of the file (rec_base must be 0), -2 use c->d_phred as
 // already decided, 0/1 force.  max_records: cap on records taken (0 = all whole blocks / all).
-int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out);
+// skip: bytes in front of the window's first record inside d_text (d_text is 16-byte aligned; the byte at skip - 1 is the '\n' that
+// ended the previous window); out.consumed counts from d_text.
+int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_base, int phred_mode, u64 max_records, FrontOut &out, u32 skip);

@@ -158,3 +158,16 @@ def test_sharded_compress(ctx, oracle):
         merged = head + tail
         assert oracle.decompress(merged) == text.tobytes()
         assert merged == ctx.compress(text)  # sharding does not change a single byte of the file
+
+
+def test_window_hand_over(ctx, oracle, monkeypatch):
+    """Several device windows per call (FQZ_WINDOW_BYTES test hook): every window but the first starts
+    at an arbitrary byte, is entered at the aligned address below it and skips the tail of the
+    previous window's last line.  Same bytes as one big window."""
+    text = oracle.synth(1, 77, 0, 320_000).tobytes()  # variable-length records: window cuts land on every alignment
+    whole = ctx.compress(text)
+    monkeypatch.setenv("FQZ_WINDOW_BYTES", str(45 << 20))
+    cut = ctx.compress(text)
+    monkeypatch.delenv("FQZ_WINDOW_BYTES")
+    assert cut == whole
+    assert ctx.decompress(cut) == text
