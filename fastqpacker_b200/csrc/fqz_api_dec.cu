@@ -26,7 +26,7 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
         c->err = "arena: out of device memory (zstd decode)";
         return FQZ_E_CUDA;
     }
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_streams, hp, in_b, cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, d_streams, hp, in_b));
     u64 cbytes = 0;
     for (auto &st : streams) cbytes += st.csize;
     {
@@ -34,7 +34,7 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
         fqz_launch_zd_hop(d_streams, ns, d_info, nullptr, nullptr, 0, s);
     }
     ZDStreamInfo *hinfo = (ZDStreamInfo *)(hp + in_b);
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hinfo, d_info, info_b, cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, hinfo, d_info, info_b));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     u64 nframes = 0, nblocks = 0, obytes = 0;
     for (u32 i = 0; i < ns; i++) {
@@ -54,7 +54,7 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
         obytes += (hinfo[i].out_bytes + 63) & ~(u64)63;  // each stream starts 64-byte aligned
     }
     if (nframes >= (1ull << 31) || nblocks >= (1ull << 31) || obytes >= (1ull << 32) || (max_out && obytes > max_out)) return FQZ_E_TOO_LARGE;
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_info, hinfo, info_b, cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, d_info, hinfo, info_b));
     ZDFrame *d_frames = (ZDFrame *)c->arena.alloc((size_t)(nframes + 1) * sizeof(ZDFrame));
     ZDBlock *d_blocks = (ZDBlock *)c->arena.alloc((size_t)(nblocks + 1) * sizeof(ZDBlock));
     const u32 cstride = (u32)nblocks + 1;
@@ -79,10 +79,10 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
         FQZ_TRY(fqz_scan_excl_u32(c, d_cnt, cstride, cstride, 4));
         fqz_launch_zd_offsets(d_blocks, (u32)nblocks, d_cnt, cstride, d_seqblk, d_litgrp, s);
         u32 *htot = (u32 *)c->h_pin;
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot, d_cnt + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 1, d_cnt + cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 2, d_cnt + 2 * (size_t)cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot + 3, d_cnt + 3 * (size_t)cstride + nblocks, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_TRY(fqz_pin_copy(c, htot, d_cnt + nblocks, sizeof(u32)));
+        FQZ_TRY(fqz_pin_copy(c, htot + 1, d_cnt + cstride + nblocks, sizeof(u32)));
+        FQZ_TRY(fqz_pin_copy(c, htot + 2, d_cnt + 2 * (size_t)cstride + nblocks, sizeof(u32)));
+        FQZ_TRY(fqz_pin_copy(c, htot + 3, d_cnt + 3 * (size_t)cstride + nblocks, sizeof(u32)));
         FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
         lbytes = htot[0];  // <= obytes < 2^32 (k_zd_link rejects frames that claim more than their output)
         nseq = htot[1];
@@ -115,7 +115,7 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
     fqz_launch_zd_finish(d_frames, d_info, ns, d_res, s);
     fqz_launch_zd_compact(d_frames, d_info, d_res, ns, d_out, s);
     ZDStreamResult *hres = (ZDStreamResult *)(hp + in_b + info_b);
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hres, d_res, res_b, cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, hres, d_res, res_b));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     for (u32 i = 0; i < ns; i++) {
         if (hres[i].err) {

@@ -83,8 +83,8 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
         c->err = "arena: out of device memory (back end tables)";
         return FQZ_E_CUDA;
     }
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_blks, hp, blk_b, cudaMemcpyHostToDevice, s));
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_st, hst, sizeof(FqzDecStatus), cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, d_blks, hp, blk_b));
+    FQZ_TRY(fqz_pin_copy(c, d_st, hst, sizeof(FqzDecStatus)));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_tot, 0, tot_b, s));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_ok, 0, (size_t)nb * 3 * sizeof(u32), s));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_sz, 0, (size_t)(3 * stride) * sizeof(u32), s));
@@ -100,8 +100,8 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
     }
     BkTotals *htot = (BkTotals *)(hp + blk_b);
     FqzDecStatus *hst2 = (FqzDecStatus *)(c->h_pin + 64);
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(htot, d_tot, tot_b, cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
+    FQZ_TRY(fqz_pin_copy(c, htot, d_tot, tot_b));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     if (hst2->err_key != ~0ull) {
         // a sequence / quality stream may run short at an earlier record than the failure seen so far
@@ -110,7 +110,7 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
         if (!wrap) {
             FQZ_TRY(fqz_scan_excl_u32(c, d_sz, R + 1, stride, 3));
             fqz_launch_check_seq_qual(d_blks, nb, max_nrec, d_sz, stride, d_st, s);
-            FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
+            FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
             FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
         }
         return backend_error(c, blks, hst2->err_key, block_base);
@@ -143,7 +143,7 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
         StageScope sc(c, ST_EMIT, stream_bytes + total);
         fqz_launch_emit(d_blks, nb, max_nrec, d_offs, d_sz, stride, phred64, d_out, d_st, s);
     }
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, d_st, sizeof(FqzDecStatus), cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     FQZ_CUDA_TRY(c, cudaGetLastError());
     if (hst2->err_key != ~0ull) return backend_error(c, blks, hst2->err_key, block_base);
@@ -203,7 +203,7 @@ static int parse_file_header(fqz_ctx *c, const u8 *h, u64 n, DecState &st);
 static int read_file_header(fqz_ctx *c, const u8 *d_fqz, u64 n, DecState &st) {
     u8 *h = c->h_pin + 128;
     size_t take = (size_t)std::min<u64>(n, 10);
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_fqz, take, cudaMemcpyDeviceToHost, c->stream));
+    FQZ_TRY(fqz_pin_copy(c, h, d_fqz, take));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return parse_file_header(c, h, n, st);
 }
@@ -254,11 +254,11 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
         FQZ_TRY(fqz_pin_reserve(c, 8192 + DEC_TABLE_CAP * sizeof(FqzBlockEntry)));
         FqzWalkResult *hwr = (FqzWalkResult *)(c->h_pin + 256);
         FqzBlockEntry *htab = (FqzBlockEntry *)(c->h_pin + 4096);
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(hwr, d_wr, sizeof(FqzWalkResult), cudaMemcpyDeviceToHost, s));
+        FQZ_TRY(fqz_pin_copy(c, hwr, d_wr, sizeof(FqzWalkResult)));
         FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
         FqzWalkResult wr = *hwr;
         if (wr.nblocks) {
-            FQZ_CUDA_TRY(c, cudaMemcpyAsync(htab, d_tab, (size_t)wr.nblocks * sizeof(FqzBlockEntry), cudaMemcpyDeviceToHost, s));
+            FQZ_TRY(fqz_pin_copy(c, htab, d_tab, (size_t)wr.nblocks * sizeof(FqzBlockEntry)));
             FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
             ent.assign(htab, htab + wr.nblocks);
         } else

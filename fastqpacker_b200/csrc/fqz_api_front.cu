@@ -38,7 +38,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
         FQZ_TRY(fqz_scan_excl_u32(c, d_tiles, (u64)ntiles + 1, (u64)ntiles + 1, 1));
     }
     u32 *h = (u32 *)c->h_pin;
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, d_tiles + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, h, d_tiles + ntiles, sizeof(u32)));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     // skip > 0: the window starts inside the 16-byte word that still holds the end of the previous
     // window's last line, '\n' included (windows are cut behind a newline): that line is line -1
@@ -86,7 +86,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     hst->err_key = ~0ull;
     hst->qual_min = 255u;
     hst->pad = 0;
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(c->d_status, hst, sizeof(FqzWinStatus), cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, c->d_status, hst, sizeof(FqzWinStatus)));
     u64 phred_records = (phred_mode == -1) ? (u64)FQZ_BLOCK_RECORDS : 0;
     {
         StageScope sc(c, ST_RECORD_META, 0);
@@ -97,7 +97,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     } else if (phred_mode >= 0) {
         u32 *hv = (u32 *)(c->h_pin + 1280);
         *hv = phred_mode ? 1u : 0u;
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(c->d_phred, hv, sizeof(u32), cudaMemcpyHostToDevice, s));
+        FQZ_TRY(fqz_pin_copy(c, c->d_phred, hv, sizeof(u32)));
     }
     {
         StageScope sc(c, ST_SCAN, 0);
@@ -112,10 +112,10 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     u32 *hphred = (u32 *)(c->h_pin + 1600);
     u32 *hcons = (u32 *)(c->h_pin + 1664);
     u32 *hb = (u32 *)(c->h_pin + 2048);
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hst2, c->d_status, sizeof(FqzWinStatus), cudaMemcpyDeviceToHost, s));
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hphred, c->d_phred, sizeof(u32), cudaMemcpyDeviceToHost, s));
-    if (R) FQZ_CUDA_TRY(c, cudaMemcpyAsync(hcons, d_line_end + 4 * R - 1, sizeof(u32), cudaMemcpyDeviceToHost, s));
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(hb, d_bounds, (size_t)nb * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, hst2, c->d_status, sizeof(FqzWinStatus)));
+    FQZ_TRY(fqz_pin_copy(c, hphred, c->d_phred, sizeof(u32)));
+    if (R) FQZ_TRY(fqz_pin_copy(c, hcons, d_line_end + 4 * R - 1, sizeof(u32)));
+    FQZ_TRY(fqz_pin_copy(c, hb, d_bounds, (size_t)nb * sizeof(u32)));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     if (hst2->err_key != ~0ull) {
         u32 kind = (u32)(hst2->err_key & 0xFF);

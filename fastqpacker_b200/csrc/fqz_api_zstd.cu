@@ -136,7 +136,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
         c->err = "arena: out of device memory (zstd stage)";
         return FQZ_E_CUDA;
     }
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_up, hp, up, cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, d_up, hp, up));
     ze.d_frames = (ZFrame *)d_up;
     u32 *d_idx = (u32 *)(d_up + (size_t)nf * sizeof(ZFrame));
     FQZ_CUDA_TRY(c, cudaMemsetAsync(ze.d_scan + nf, 0, sizeof(u32), s));
@@ -185,7 +185,7 @@ extern "C" int fqz_zstd_compress(fqz_ctx *c, const uint8_t *src, size_t n, int p
     FQZ_TRY(zbatch_encode(c, zb, ze, n));
     u32 nf = ze.nframes;
     u32 *h = (u32 *)c->h_pin;
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, ze.d_scan + nf, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    FQZ_TRY(fqz_pin_copy(c, h, ze.d_scan + nf, sizeof(u32)));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     size_t total = h[0];
     *out_len = total;
@@ -262,12 +262,12 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
     if (nb) memcpy(hp + nf + first.size() + nb, fo.orig.data(), (size_t)nb * 4);
     u32 *d_tab = (u32 *)c->arena.alloc(up_words * 4 + 16);
     if (!d_tab) return FQZ_E_CUDA;
-    FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_tab, hp, up_words * 4, cudaMemcpyHostToDevice, s));
+    FQZ_TRY(fqz_pin_copy(c, d_tab, hp, up_words * 4));
     u32 *d_fixed = d_tab, *d_first = d_tab + nf, *d_nrec = d_first + first.size(), *d_orig = d_nrec + nb;
     size_t total = hdr0;
     if (nf) {
         u32 *h = (u32 *)c->h_pin;
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(h, ze.d_scan + nf, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        FQZ_TRY(fqz_pin_copy(c, h, ze.d_scan + nf, sizeof(u32)));
         FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
         total = (size_t)hdr0 + 36ull * nb + h[0];
     }
@@ -280,7 +280,7 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
         u32 bs = header_block_size ? header_block_size : FQZ_BLOCK_RECORDS;  // compress.go:129-131
         fh[5] = (u8)bs; fh[6] = (u8)(bs >> 8); fh[7] = (u8)(bs >> 16); fh[8] = (u8)(bs >> 24);
         fh[9] = fo.phred64 ? 2 : 0;  // FlagPhred64, compress.go:162-164
-        FQZ_CUDA_TRY(c, cudaMemcpyAsync(d_out, fh, 10, cudaMemcpyHostToDevice, s));
+        FQZ_TRY(fqz_pin_copy(c, d_out, fh, 10));
     }
     if (nf) {
         StageScope sc(c, ST_ASSEMBLE, 2 * (total - hdr0));

@@ -109,6 +109,27 @@ int fqz_pin_reserve(fqz_ctx *c, size_t bytes) {
     c->h_pin_cap = cap;
     return FQZ_OK;
 }
+__global__ void __launch_bounds__(256) k_pin_copy(u8 *dst, const u8 *src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+        size_t nv = n >> 4;
+        for (size_t k = i; k < nv; k += step) ((uint4 *)dst)[k] = ((const uint4 *)src)[k];
+        for (size_t k = (nv << 4) + i; k < n; k += step) dst[k] = src[k];
+    } else if ((((uintptr_t)dst | (uintptr_t)src) & 3u) == 0) {
+        size_t nw = n >> 2;
+        for (size_t k = i; k < nw; k += step) ((u32 *)dst)[k] = ((const u32 *)src)[k];
+        for (size_t k = (nw << 2) + i; k < n; k += step) dst[k] = src[k];
+    } else
+        for (size_t k = i; k < n; k += step) dst[k] = src[k];
+}
+int fqz_pin_copy(fqz_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return FQZ_OK;
+    size_t units = (bytes + 15) / 16;
+    u32 grid = (u32)((units + 255) / 256);
+    if (grid > 128) grid = 128;
+    FQZ_LAUNCH(k_pin_copy, grid, 256, 0, c->stream, (u8 *)dst, (const u8 *)src, bytes);
+    return FQZ_OK;
+}
 int fqz_io_reserve(fqz_ctx *c, size_t bytes) {
     if (bytes <= c->h_io_cap) return FQZ_OK;
     if (c->h_io) cudaFreeHost(c->h_io);

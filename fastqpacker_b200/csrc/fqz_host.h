@@ -116,6 +116,11 @@ struct StageScope {
 };
 
 int fqz_pin_reserve(fqz_ctx *c, size_t bytes);
+// Small stream-ordered copy between device memory and the PINNED scratch (c->h_pin) done by a kernel
+// over the mapped host memory instead of cudaMemcpyAsync: copy-engine queues are served in submission
+// order, so a 4-byte readback queued behind gigabytes of pipelined upload would stall the compute
+// stream until the whole upload has drained.  Never pass pageable memory.
+int fqz_pin_copy(fqz_ctx *c, void *dst, const void *src, size_t bytes);
 int fqz_io_reserve(fqz_ctx *c, size_t bytes);
 // ---- copy pipeline (fqz_ctx.cu)
 int fqz_io_upload(fqz_ctx *c, const u8 *host, size_t n);             // starts the chunked upload into c->io.d_in
