@@ -38,6 +38,15 @@ FULL_RECORDS = 25_000_000  # BASELINE config 2: ~9 GB of 150 bp Phred+33 reads
 CPU_SAMPLE_RECORDS = 3_000_000  # ~1.1 GB: a few seconds on all host cores
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -275,6 +284,23 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- compressed bytes per stream class (block headers of the container, container.go:97-109): the
+    #      algorithmic bytes of an entropy kernel are stream bytes read + compressed bytes written
+    import struct
+
+    hdrs = d_out[:m].cpu().numpy()
+    z_ent = z_lz = 0
+    pos = 10
+    while pos < m:
+        v = struct.unpack_from("<9I", hdrs, pos)
+        z_ent += v[1] + v[2]
+        z_lz += v[3] + v[4] + v[5] + v[6]
+        pos += 36 + sum(v[1:7])
+    del hdrs
+    if "zstd_enc_lz" in stages:
+        stages["zstd_enc_lz"]["bytes"] += z_lz
+    if "zstd_enc_entropy" in stages:
+        stages["zstd_enc_entropy"]["bytes"] += z_ent
     # ---- roofline of the dominant kernel (largest share of the compress step)
     comp_stages = ["newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "xxh64", "assemble", "copy"]
     cs = {k: v for k, v in stages.items() if k in comp_stages}
@@ -284,7 +310,18 @@ def run_ours(args):
         v = cs[top]
         # algorithmic bytes of the entropy kernels: stream bytes read + compressed bytes written (SURVEY §8d A2 = S + Z)
         ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0  # bytes per launch / time per launch
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                t = json.load(f).get(top)
+            if t:  # DRAM bytes of one launch over one full window, from the committed ncu --set full capture
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+                traffic_src = t["source"]
+        except OSError:
+            pass
+        nl = max(1, v["launches"])
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": v["bytes"] / nl, "ms_per_launch": v["ms"] / nl,
                 "peak_source": peak_src, "launches_per_step": v["launches"], "kernel_ms_per_step": v["ms"],
                 "share_of_step": v["ms"] / sum(x["ms"] for x in cs.values())}
     step_s = t_c / args.steps
@@ -325,7 +362,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -369,6 +406,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, ...) write there too, so
+    # everything but that line is sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
