@@ -102,10 +102,11 @@ int fqz_zdecode_batch(fqz_ctx *c, const std::vector<ZDStream> &streams, u64 max_
     }
     {
         StageScope sc(c, ST_ZDEC_SEQUENCES, nseq * 12);
-        fqz_launch_zd_sequences(d_blocks, d_seqblk, nsb, d_cnt + 2 * (size_t)cstride, d_tabs, d_seq, s);
+        fqz_launch_zd_sequences(d_blocks, d_frames, d_seqblk, nsb, d_cnt + 2 * (size_t)cstride, d_tabs, d_seq, s);
     }
     {
         StageScope sc(c, ST_ZDEC_EXECUTE, obytes);
+        fqz_launch_zd_rawcopy(d_blocks, (u32)nblocks, d_frames, d_out, s);
         fqz_launch_zd_execute(d_frames, (u32)nframes, d_blocks, d_lit, d_seq, d_out, s);
     }
     {

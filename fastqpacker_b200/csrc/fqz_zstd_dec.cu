@@ -1035,7 +1035,8 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_seq_tables(const ZDBlock *
 
 // One thread per block with sequences.  slot_of[b] = table slot of block b (exclusive scan of the
 // has-sequences flags).
-__global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u32 *seqblk, u32 nsb, const u32 *slot_of, const u32 *tabs, u32 *seqbuf) {
+__global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const ZDFrame *frames, const u32 *seqblk, u32 nsb, const u32 *slot_of, const u32 *tabs,
+                                                       u32 *seqbuf) {
     u32 slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= nsb) return;
     const u32 bi = seqblk[slot];
@@ -1053,6 +1054,10 @@ __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u3
     const u32 nseq = B.nseq;
     u32 *sq = seqbuf + 3ull * B.seq_off;
     u64 total = 0;
+    // the only block of its frame starts from the initial repeat history: resolve the offsets here, where
+    // the chain is serial anyway, and spare k_zd_execute its per-sequence loop (RFC 8878 §3.1.1.5)
+    const bool resolve = frames[B.frame].nblocks == 1;
+    u32 rep0 = 1, rep1 = 4, rep2 = 8;
     if (!err) {
         const u8 *c = (const u8 *)(uintptr_t)B.src;
         const u32 bsz = B.csize - B.bits_pos;
@@ -1078,6 +1083,23 @@ __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u3
                 u32 ml = kMLBase[mlc] + br.take(mlb);
                 u32 ll = kLLBase[llc] + br.take(llb);
                 used += ofc + mlb + llb;
+                if (resolve) {
+                    u32 f;
+                    if (ofv > 3) {
+                        f = ofv - 3;
+                        rep2 = rep1; rep1 = rep0; rep0 = f;
+                    } else {
+                        u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
+                        if (idx == 0) f = rep0;
+                        else {
+                            f = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
+                            if (idx != 1) rep2 = rep1;
+                            rep1 = rep0;
+                            rep0 = f;
+                        }
+                    }
+                    ofv = f;
+                }
                 sq[3 * i] = ll;
                 sq[3 * i + 1] = ml;
                 sq[3 * i + 2] = ofv;
@@ -1096,6 +1118,7 @@ __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u3
         }
     }
     if (err || total > ZSTD_BLOCK_MAX) blocks[bi].err = 1;
+    else if (resolve) blocks[bi].pad[0] = 1;  // sq[3i+2] holds real offsets
 }
 
 // ---------------------------------------------------------------------------------- execution
@@ -1103,12 +1126,69 @@ __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const u3
 __device__ __forceinline__ void warp_copy(u8 *dst, const u8 *src, u32 n, u32 lane) {
     for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
 }
+// Raw and RLE blocks whose place in the frame is known from the headers alone (k_zd_link) are
+// regenerated here, one warp per block with 16-byte stores, instead of by the frame's single warp in
+// k_zd_execute (incompressible streams — 2-bit packed bases of random reads — are all raw blocks).
+__global__ void __launch_bounds__(256) k_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *out) {
+    u32 bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (bi >= nblocks) return;
+    const ZDBlock &B = blocks[bi];
+    if (B.type > 1 || B.out_off == 0xFFFFFFFFu || B.err) return;
+    const ZDFrame &F = frames[B.frame];
+    const u32 n = B.rsize;
+    if ((u64)B.out_off + n > F.out_cap) return;  // k_zd_execute reports it
+    u8 *dst = out + F.dst_off + B.out_off;
+    const u8 *src = (const u8 *)(uintptr_t)B.src;
+    u32 head = (u32)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    const u32 v0 = src[0];
+    const u32 fill = v0 * 0x01010101u;
+    const bool rle = B.type == 1;
+    if (lane < head) dst[lane] = rle ? (u8)v0 : src[lane];
+    u32 nv = (n - head) >> 4;
+    uint4 *d16 = (uint4 *)(dst + head);
+    const u8 *s16 = src + head;
+    for (u32 v = lane; v < nv; v += 32) {
+        uint4 x;
+        if (rle) x = make_uint4(fill, fill, fill, fill);
+        else {
+            const u8 *sp = s16 + 16u * v;
+            x = make_uint4(ld_u32_unaligned(sp), ld_u32_unaligned(sp + 4), ld_u32_unaligned(sp + 8), ld_u32_unaligned(sp + 12));
+        }
+        d16[v] = x;
+    }
+    u32 t0 = head + 16u * nv;
+    if (lane < n - t0) dst[t0 + lane] = rle ? (u8)v0 : src[t0 + lane];
+}
+
+// n bytes from s to d by ONE lane, forward.  d and s may overlap when d - s >= 4 (an LZ match whose
+// offset is at least 4): words are read before they are written.  Destination-aligned 32-bit stores,
+// source words assembled from aligned loads.
+__device__ __forceinline__ void lane_copy_fwd(u8 *d, const u8 *s, u32 n) {
+    u32 k = 0;
+    u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+    if (head > n) head = n;
+    for (; k < head; k++) d[k] = s[k];
+    for (; k + 4 <= n; k += 4) *(u32 *)(d + k) = ld_u32_unaligned(s + k);
+    for (; k < n; k++) d[k] = s[k];
+}
+
+// Frames of one block with sequences and at most ZX_STAGE bytes of content (the 16 KiB item frames
+// this library writes) are executed in shared memory — the dependency rounds then cost a shared-memory
+// round trip instead of one through L2 — and written out with wide coalesced stores.
+#define ZX_ENABLE 1
+#define ZX_STAGE 16384u
+#define ZX_SMEM (ZX_ENABLE ? ZD_WARPS * (ZX_STAGE + 64u) : 0u)
 __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out) {
+    FQZ_DYN_SMEM(u8, smem);
     u32 warp = threadIdx.x >> 5, lane = lane_id();
     u32 fi = blockIdx.x * ZD_WARPS + warp;
     if (fi >= nframes) return;
     ZDFrame F = frames[fi];
-    u8 *base = out + F.dst_off;
+    u8 *const gbase = out + F.dst_off;
+    u8 *base = gbase;
+    const bool staged = ZX_ENABLE && F.nblocks == 1 && F.out_cap <= ZX_STAGE && blocks[F.first_block].type == 2 && blocks[F.first_block].nseq > 0;
+    if (staged) base = smem + (size_t)warp * (ZX_STAGE + 64u);
     u64 o = 0;  // bytes regenerated so far in this frame
     u32 rep0 = 1, rep1 = 4, rep2 = 8;
     u32 err = 0;
@@ -1116,7 +1196,10 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
         ZDBlock B = blocks[F.first_block + b];
         if (B.err) { err = 1; break; }
         const u8 *c = (const u8 *)(uintptr_t)B.src;
-        if (B.type == 0) {
+        if (B.type <= 1 && B.out_off != 0xFFFFFFFFu) {  // regenerated by k_zd_rawcopy
+            if (o + B.rsize > F.out_cap || (u64)B.out_off != o) { err = 1; break; }
+            o += B.rsize;
+        } else if (B.type == 0) {
             if (o + B.rsize > F.out_cap) { err = 1; break; }
             warp_copy(base + o, c, B.rsize, lane);
             o += B.rsize;
@@ -1150,8 +1233,9 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
                     ml = sq[3 * (sb + lane) + 1];
                     ofv = sq[3 * (sb + lane) + 2];
                 }
-                // repeat offsets (RFC 8878 §3.1.1.5), uniform
-                u32 off = 0;
+                // repeat offsets (RFC 8878 §3.1.1.5), uniform — unless k_zd_seq_decode resolved them already
+                u32 off = ofv;
+                if (!B.pad[0])
                 for (u32 j = 0; j < cn; j++) {
                     u32 v = __shfl_sync(FULL, ofv, (int)j), l = __shfl_sync(FULL, ll, (int)j);
                     u32 f;
@@ -1177,42 +1261,61 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
                 u32 lsrc = lp + lincl - ll;
                 bool bad = live && (off == 0 || (u64)off > mstart);
                 if (__any_sync(FULL, bad) || lp + gll > B.lit_regen || o + gtot > F.out_cap) { err = 1; break; }
-                if (live) {
-                    u8 *d = base + lstart;
-                    const u8 *sp = lit + lsrc;
-                    for (u32 k = 0; k < ll; k++) d[k] = sp[k];
-                }
+                if (live) lane_copy_fwd(base + lstart, lit + lsrc, ll);
                 __syncwarp();
-                bool done = !live || ml == 0;
-                const u64 need = (off >= ml) ? (mstart - off + ml) : mstart;  // output that must be final before this lane copies
-                for (;;) {
-                    u32 pend = __ballot_sync(FULL, !done);
-                    if (!pend) break;
-                    int hw = __ffs((int)pend) - 1;
-                    u64 hwpos = __shfl_sync(FULL, mstart, hw);  // everything below is final
-                    u32 hml = __shfl_sync(FULL, ml, hw);
-                    if (hml > 64u) {  // long match at the front: the whole warp copies it
-                        u32 hoff = __shfl_sync(FULL, off, hw);
-                        u8 *d = base + hwpos;
+                if (staged) {
+                    // shared memory: one sequence after the other, every match copied by the whole warp
+                    // (a shared-memory round trip per sequence, ~14 instructions)
+                    for (u32 j = 0; j < cn; j++) {
+                        u32 hm = (u32)__shfl_sync(FULL, mstart, (int)j), hoff = __shfl_sync(FULL, off, (int)j), hml = __shfl_sync(FULL, ml, (int)j);
+                        u8 *d = base + hm;
                         const u8 *sp = d - hoff;
                         if (hoff >= hml) {
                             for (u32 k = lane; k < hml; k += 32) d[k] = sp[k];
-                        } else if (hoff >= 32u) {  // overlapping, but 32 bytes at a time never overtake the source
+                        } else if (hoff >= 32u) {
                             for (u32 k0 = 0; k0 < hml; k0 += 32) {
                                 if (k0 + lane < hml) d[k0 + lane] = sp[k0 + lane];
                                 __syncwarp();
                             }
                         } else {
-                            for (u32 k = lane; k < hml; k += 32) d[k] = sp[k % hoff];  // the source is the last `off` bytes, repeated
+                            for (u32 k = lane; k < hml; k += 32) d[k] = sp[k % hoff];
                         }
-                        if ((int)lane == hw) done = true;
-                    } else if (!done && ml <= 64u && ((int)lane == hw || need <= hwpos)) {
-                        u8 *d = base + mstart;
-                        const u8 *sp = d - off;
-                        for (u32 k = 0; k < ml; k++) d[k] = sp[k];
-                        done = true;
+                        __syncwarp();
                     }
-                    __syncwarp();
+                } else {
+                bool done = !live || ml == 0;
+                    const u64 need = (off >= ml) ? (mstart - off + ml) : mstart;  // output that must be final before this lane copies
+                    for (;;) {
+                        u32 pend = __ballot_sync(FULL, !done);
+                        if (!pend) break;
+                        int hw = __ffs((int)pend) - 1;
+                        u64 hwpos = __shfl_sync(FULL, mstart, hw);  // everything below is final
+                        u32 hml = __shfl_sync(FULL, ml, hw);
+                        if (hml > 64u) {  // long match at the front: the whole warp copies it
+                            u32 hoff = __shfl_sync(FULL, off, hw);
+                            u8 *d = base + hwpos;
+                            const u8 *sp = d - hoff;
+                            if (hoff >= hml) {
+                                for (u32 k = lane; k < hml; k += 32) d[k] = sp[k];
+                            } else if (hoff >= 32u) {  // overlapping, but 32 bytes at a time never overtake the source
+                                for (u32 k0 = 0; k0 < hml; k0 += 32) {
+                                    if (k0 + lane < hml) d[k0 + lane] = sp[k0 + lane];
+                                    __syncwarp();
+                                }
+                            } else {
+                                for (u32 k = lane; k < hml; k += 32) d[k] = sp[k % hoff];  // the source is the last `off` bytes, repeated
+                            }
+                            if ((int)lane == hw) done = true;
+                        } else if (!done && ml <= 64u && ((int)lane == hw || need <= hwpos)) {
+                            u8 *d = base + mstart;
+                            const u8 *sp = d - off;
+                            if (off >= 4u) lane_copy_fwd(d, sp, ml);
+                            else
+                                for (u32 k = 0; k < ml; k++) d[k] = sp[k];
+                            done = true;
+                        }
+                        __syncwarp();
+                    }
                 }
                 o += gtot;
                 lp += gll;
@@ -1227,6 +1330,16 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
         __syncwarp();
     }
     if (!err && F.content_size != ~0ull && o != F.content_size) err = 1;
+    if (staged && !err) {  // shared memory -> output
+        __syncwarp();
+        u32 n = (u32)o;
+        if ((((uintptr_t)gbase) & 15u) == 0) {
+            u32 nv = n >> 4;
+            for (u32 v = lane; v < nv; v += 32) ((uint4 *)gbase)[v] = ((const uint4 *)base)[v];
+            for (u32 k = (nv << 4) + lane; k < n; k += 32) gbase[k] = base[k];
+        } else
+            for (u32 k = lane; k < n; k += 32) gbase[k] = base[k];
+    }
     if (lane == 0) {
         frames[fi].out_size = o;
         frames[fi].err = err;
@@ -1320,14 +1433,23 @@ void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const u32 *litgrp, u32
     if (!nblocks || !ngroups) return;
     FQZ_LAUNCH(k_zd_literals, (ngroups + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, nblocks, litgrp, ngroups, frames, litbuf, out);
 }
-void fqz_launch_zd_sequences(ZDBlock *blocks, const u32 *seqblk, u32 nsb, const u32 *slot_of, u32 *tabs, u32 *seqbuf, cudaStream_t s) {
+void fqz_launch_zd_sequences(ZDBlock *blocks, const ZDFrame *frames, const u32 *seqblk, u32 nsb, const u32 *slot_of, u32 *tabs, u32 *seqbuf, cudaStream_t s) {
     if (!nsb) return;
     FQZ_LAUNCH(k_zd_seq_tables, (nsb + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, blocks, seqblk, nsb, tabs);
-    FQZ_LAUNCH(k_zd_seq_decode, (nsb + 127) / 128, 128, 0, s, blocks, seqblk, nsb, slot_of, tabs, seqbuf);
+    FQZ_LAUNCH(k_zd_seq_decode, (nsb + 127) / 128, 128, 0, s, blocks, frames, seqblk, nsb, slot_of, tabs, seqbuf);
 }
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s) {
     if (!nframes) return;
-    FQZ_LAUNCH(k_zd_execute, (nframes + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, 0, s, frames, nframes, blocks, litbuf, seqbuf, out);
+    static bool attr_done = false;
+    if (!attr_done && ZX_SMEM) {
+        cudaFuncSetAttribute(k_zd_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, ZX_SMEM);
+        attr_done = true;
+    }
+    FQZ_LAUNCH(k_zd_execute, (nframes + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, ZX_SMEM, s, frames, nframes, blocks, litbuf, seqbuf, out);
+}
+void fqz_launch_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *out, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_zd_rawcopy, (nblocks * 32 + 255) / 256, 256, 0, s, blocks, nblocks, frames, out);
 }
 void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s) {
     if (!nframes) return;

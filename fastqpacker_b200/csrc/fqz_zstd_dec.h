@@ -60,7 +60,8 @@ void fqz_launch_zd_link(ZDFrame *frames, u32 nframes, ZDBlock *blocks, u32 *cnt,
 void fqz_launch_zd_offsets(ZDBlock *blocks, u32 nblocks, const u32 *cnt, u32 cnt_stride, u32 *seqblk, u32 *litgrp, cudaStream_t s);
 void fqz_launch_zd_literals(ZDBlock *blocks, u32 nblocks, const u32 *litgrp, u32 ngroups, const ZDFrame *frames, u8 *litbuf, u8 *out, cudaStream_t s);
 #define FQZ_ZD_TAB_BYTES ((3u * 512u + 4u) * 4u)  // decode tables of one block with sequences (k_zd_seq_tables)
-void fqz_launch_zd_sequences(ZDBlock *blocks, const u32 *seqblk, u32 nsb, const u32 *slot_of, u32 *tabs, u32 *seqbuf, cudaStream_t s);
+void fqz_launch_zd_sequences(ZDBlock *blocks, const ZDFrame *frames, const u32 *seqblk, u32 nsb, const u32 *slot_of, u32 *tabs, u32 *seqbuf, cudaStream_t s);
+void fqz_launch_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *out, cudaStream_t s);
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s);
 void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s);
 void fqz_launch_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res, cudaStream_t s);

@@ -1339,7 +1339,7 @@ __device__ __forceinline__ void write_block_header(u8 *o, u32 type, u32 size) {
 
 // MODE 0: literals-only (legacy, superseded by k_zenc_huf), 1: hash-table LZ77, 2: item matcher
 template <int MODE>
-__global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
+__global__ void __launch_bounds__(ZENC_WARPS * 32, 7) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
                                                           u8 *ws, u32 *out_sizes) {
     constexpr bool LZ = MODE != 0;
     typedef typename std::conditional<MODE == 1, WarpScratchLZ, typename std::conditional<MODE == 2, WarpScratchItems, WarpScratchEnt>::type>::type WS;
