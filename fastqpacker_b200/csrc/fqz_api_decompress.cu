@@ -24,8 +24,11 @@ static const int kErrOfBk[8] = {0,
 static const char *kStreamWhat[6] = {"sequences", "quality", "headers", "plus-line payload", "N positions", "lengths"};
 
 #define DEC_TABLE_CAP 1024u                  // fqz blocks per container-walk pass
-#define DEC_WINDOW_BYTES ((u64)256 << 20)    // compressed bytes per device window
-#define DEC_WINDOW_OUT ((u64)1280 << 20)     // decoded stream bytes per device window (keeps FASTQ offsets below 2^32)
+#define DEC_WINDOW_BYTES ((u64)640 << 20)    // compressed bytes per device window (device-resident calls; large windows amortise kernel tails)
+#define DEC_WINDOW_HOST ((u64)256 << 20)     // ... of the host pipeline, whose first window cannot start before it has been uploaded
+// decoded stream bytes per device window: FASTQ is at most 1.6 x the stream bytes (2 L text bytes per 1.25 L
+// of packed bases + qualities), so FASTQ offsets stay below 2^32
+#define DEC_WINDOW_OUT ((u64)2400 << 20)
 
 static int backend_error(fqz_ctx *c, const std::vector<BkBlock> &blks, u64 key, u64 block_base) {
     u32 kind = (u32)(key & 0xFF);
@@ -239,18 +242,19 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
     u64 n_all = n;
     u64 want = 0;
     int win = 0;
+    const u64 win_bytes = host_io ? DEC_WINDOW_HOST : DEC_WINDOW_BYTES;
     while (pos < n_all) {
         c->arena.reset();
         if (host_io) {  // the walk must not look at bytes that have not arrived yet
             size_t avail = 0;
-            want = std::max<u64>(want, pos + DEC_WINDOW_BYTES + ((u64)32 << 20));
+            want = std::max<u64>(want, pos + win_bytes + ((u64)32 << 20));
             FQZ_TRY(fqz_io_gate(c, (size_t)std::min<u64>(n_all, want), &avail));
             n = avail;
         }
         FqzBlockEntry *d_tab = (FqzBlockEntry *)c->arena.alloc(DEC_TABLE_CAP * sizeof(FqzBlockEntry));
         FqzWalkResult *d_wr = (FqzWalkResult *)c->arena.alloc(sizeof(FqzWalkResult));
         if (!d_tab || !d_wr) return FQZ_E_CUDA;
-        fqz_launch_walk_container(d_fqz, n, pos, st.version, d_tab, DEC_TABLE_CAP, DEC_WINDOW_BYTES, d_wr, s);
+        fqz_launch_walk_container(d_fqz, n, pos, st.version, d_tab, DEC_TABLE_CAP, win_bytes, d_wr, s);
         FQZ_TRY(fqz_pin_reserve(c, 8192 + DEC_TABLE_CAP * sizeof(FqzBlockEntry)));
         FqzWalkResult *hwr = (FqzWalkResult *)(c->h_pin + 256);
         FqzBlockEntry *htab = (FqzBlockEntry *)(c->h_pin + 4096);
@@ -308,7 +312,7 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
             *out_len = written;
         }
         if (wr.status && n < n_all) {  // ran into bytes still in flight, not a truncated file: widen the gate
-            if (wr.nblocks == 0) want = std::max<u64>(want, n + DEC_WINDOW_BYTES);
+            if (wr.nblocks == 0) want = std::max<u64>(want, n + win_bytes);
             continue;
         }
         if (wr.status) {  // truncated block header / payload after the blocks just decoded
