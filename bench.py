@@ -368,7 +368,18 @@ def run_ours(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(args)
+        cb, text, ref_fqz = cpu_baseline(args)
+        line["cpu_baseline"] = cb
+        # BASELINE config 3, second half: the REFERENCE-SHAPED file of the same sample (oracle container: one
+        # libzstd level-1 frame per stream, 128 KiB blocks) decoded on the device.  Such frames are one serial
+        # chain each: correctness path, reported for completeness.
+        d_ref = torch.from_numpy(ref_fqz).cuda()
+        d_txt = torch.empty(text.size + (1 << 16), dtype=torch.uint8, device="cuda")
+        ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_txt.data_ptr(), d_txt.numel())
+        t_r = timed(lambda: ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_txt.data_ptr(), d_txt.numel()), 1, 0)
+        same = bool(torch.equal(d_txt[: text.size], torch.from_numpy(text).cuda()))
+        line["decompress"]["reference_written"] = {"value": text.size / t_r / 1e9, "unit": UNIT, "bit_exact": same, "sample": cb["sample"],
+                                                   "input": "oracle-written .fqz (reference-shaped: one libzstd-1 frame per stream)"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -398,7 +409,7 @@ def cpu_baseline(args):
         "decompress_value": n / ddt / 1e9,
         "ratio": n / fqz.size,
         "note": "restated CPU baseline (oracle + libzstd level 1 + frame checksum), not fqpack: no Go toolchain in this image (SURVEY F7)",
-    }
+    }, text, fqz
 
 
 def main():
