@@ -49,6 +49,8 @@ struct WarpScratchLZ {
     } u;
     u8 tmpsym[512];  // FSE symbol spreading
     short norm[64];
+    u8 tsym_b[512];    // second / third scratch so that the three sequence tables are built by three lanes at once
+    short norm_b[128];
 };
 #define ZI_MAXM 8  // matches kept per item and lane (the rest of a pathological item stays literal)
 struct WarpScratchItems {
@@ -60,6 +62,8 @@ struct WarpScratchItems {
     } u;
     u8 tmpsym[512];
     short norm[64];
+    u8 tsym_b[512];
+    short norm_b[128];
 };
 struct WarpScratchEnt {
     u32 hist[256];
@@ -69,6 +73,8 @@ struct WarpScratchEnt {
     } u;
     u8 tmpsym[512];
     short norm[64];
+    u8 tsym_b[512];
+    short norm_b[128];
 };
 
 // ---------------------------------------------------------------------------------- bit writer (one lane)
@@ -759,55 +765,70 @@ __device__ static u32 warp_write_sequences(u16 *sll, u16 *sml, u32 *sof, u32 nse
     __syncwarp();
     u32 total = 0;
     bool over = false;
+    // the three tables (LL, OF, ML) are independent: lanes 0 / 1 / 2 choose the mode, normalise, build the
+    // encoding table and write the table description of one each (into their scratch; lane 0 strings
+    // the descriptions together afterwards)
+    if (lane < 3) {
+        const u32 t = lane;
+        u8 *ts = (t == 0) ? S.tmpsym : (t == 1 ? (u8 *)S.hlut : S.tsym_b);  // the literals are written: the Huffman LUT is free
+        short *nm = (t == 0) ? S.norm : S.norm_b + 64 * (t - 1);
+        const u32 *h = S.hist + 64 * t;
+        const u32 maxLog = (t == 0) ? ZSTD_LL_MAXLOG : (t == 1 ? ZSTD_OF_MAXLOG : ZSTD_ML_MAXLOG);
+        const u32 defLog = (t == 0) ? ZSTD_LL_DEFLOG : (t == 1 ? ZSTD_OF_DEFLOG : ZSTD_ML_DEFLOG);
+        const u32 defMax = (t == 0) ? 35u : (t == 1 ? 28u : 52u);
+        u32 maxSym = 0, most = 0, mostSym = 0;
+        for (u32 sy = 0; sy < 64; sy++) {
+            u32 c = h[sy];
+            if (c) {
+                maxSym = sy;
+                if (c > most) { most = c; mostSym = sy; }
+            }
+        }
+        // selection rule modelled on zstd's fast strategies: RLE if one symbol, predefined for
+        // short or flat blocks, dynamic FSE otherwise
+        u32 dynMin = ((1u << defLog) * 9u) >> 3;
+        u32 m;
+        if (most == nseq) m = (nseq <= 2 && maxSym <= defMax) ? 0u : 1u;
+        else if (maxSym <= defMax && (nseq < dynMin || most < (nseq >> (defLog - 1)))) m = 0;
+        else m = 2;
+        FseCT &ct = S.u.e.fse[t];
+        u32 tl = 0, dlen = 0;
+        if (m == 1) {
+            ts[0] = (u8)mostSym;
+            dlen = 1;
+        } else if (m == 0) {
+            const short *dn = (t == 0) ? kLLDefNorm : (t == 1 ? kOFDefNorm : kMLDefNorm);
+            for (u32 sy = 0; sy <= defMax; sy++) nm[sy] = dn[sy];
+            tl = defLog;
+            fse_build_ctable(nm, defMax, tl, ct.tab, ct.dnb, ct.dfs, ts);
+        } else {
+            tl = fse_optimal_log(maxLog, nseq, maxSym);
+            fse_normalize(h, maxSym, nseq, tl, nm);
+            fse_build_ctable(nm, maxSym, tl, ct.tab, ct.dnb, ct.dfs, ts);
+            dlen = fse_write_ncount(ts, nm, maxSym, tl);  // the spreading scratch is free again; a description is < 80 bytes
+        }
+        S.hist[194 + t] = tl;
+        S.hist[200 + t] = m;
+        S.hist[204 + t] = dlen;
+    }
+    __syncwarp();
     if (lane == 0) {
         u32 o = 0;
         if (nseq < 128) out[o++] = (u8)nseq;
         else if (nseq < 0x7F00) { out[o++] = (u8)((nseq >> 8) + 0x80); out[o++] = (u8)nseq; }
         else { out[o++] = 0xFF; out[o++] = (u8)(nseq - 0x7F00); out[o++] = (u8)((nseq - 0x7F00) >> 8); }
-        u32 modes_at = o++;
-        u32 mode[3], tlog[3];
-        const u32 *hh[3] = {hLL, hOF, hML};
-        const u32 maxLog[3] = {ZSTD_LL_MAXLOG, ZSTD_OF_MAXLOG, ZSTD_ML_MAXLOG};
-        const u32 defLog[3] = {ZSTD_LL_DEFLOG, ZSTD_OF_DEFLOG, ZSTD_ML_DEFLOG};
-        const u32 defMax[3] = {35, 28, 52};
-        for (int t = 0; t < 3; t++) {
-            u32 maxSym = 0, most = 0, mostSym = 0;
-            for (u32 s = 0; s < 64; s++)
-                if (hh[t][s]) {
-                    maxSym = s;
-                    if (hh[t][s] > most) { most = hh[t][s]; mostSym = s; }
-                }
-            // selection rule modelled on zstd's fast strategies: RLE if one symbol, predefined for
-            // short or flat blocks, dynamic FSE otherwise
-            u32 dynMin = ((1u << defLog[t]) * 9u) >> 3;
-            u32 m;
-            if (most == nseq) m = (nseq <= 2 && maxSym <= defMax[t]) ? 0u : 1u;
-            else if (maxSym <= defMax[t] && (nseq < dynMin || most < (nseq >> (defLog[t] - 1)))) m = 0;
-            else m = 2;
-            mode[t] = m;
-            FseCT &ct = S.u.e.fse[t];
-            if (m == 1) {
-                out[o++] = (u8)mostSym;
-                tlog[t] = 0;
-            } else if (m == 0) {
-                const short *dn = (t == 0) ? kLLDefNorm : (t == 1 ? kOFDefNorm : kMLDefNorm);
-                for (u32 s = 0; s <= defMax[t]; s++) S.norm[s] = dn[s];
-                tlog[t] = defLog[t];
-                fse_build_ctable(S.norm, defMax[t], tlog[t], ct.tab, ct.dnb, ct.dfs, S.tmpsym);
-            } else {
-                tlog[t] = fse_optimal_log(maxLog[t], nseq, maxSym);
-                fse_normalize(hh[t], maxSym, nseq, tlog[t], S.norm);
-                if (o + 80 < cap) o += fse_write_ncount(out + o, S.norm, maxSym, tlog[t]);
-                else over = true;
-                fse_build_ctable(S.norm, maxSym, tlog[t], ct.tab, ct.dnb, ct.dfs, S.tmpsym);
-            }
+        out[o++] = (u8)((S.hist[200] << 6) | (S.hist[201] << 4) | (S.hist[202] << 2));
+        for (u32 t = 0; t < 3; t++) {
+            const u8 *ts = (t == 0) ? S.tmpsym : (t == 1 ? (const u8 *)S.hlut : S.tsym_b);
+            u32 dlen = S.hist[204 + t];
+            if (o + 80 < cap) {
+                for (u32 k = 0; k < dlen; k++) out[o + k] = ts[k];
+                o += dlen;
+            } else
+                over = true;
         }
-        out[modes_at] = (u8)((mode[0] << 6) | (mode[1] << 4) | (mode[2] << 2));
         S.hist[192] = o;
         S.hist[193] = over ? 1u : 0u;
-        S.hist[194] = tlog[0];
-        S.hist[195] = tlog[1];
-        S.hist[196] = tlog[2];
     }
     __syncwarp();
     // 3. interleaved FSE bitstream, written backwards (last sequence first), 32 sequences per round:
@@ -1339,7 +1360,7 @@ __device__ __forceinline__ void write_block_header(u8 *o, u32 type, u32 size) {
 
 // MODE 0: literals-only (legacy, superseded by k_zenc_huf), 1: hash-table LZ77, 2: item matcher
 template <int MODE>
-__global__ void __launch_bounds__(ZENC_WARPS * 32, 7) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
+__global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
                                                           u8 *ws, u32 *out_sizes) {
     constexpr bool LZ = MODE != 0;
     typedef typename std::conditional<MODE == 1, WarpScratchLZ, typename std::conditional<MODE == 2, WarpScratchItems, WarpScratchEnt>::type>::type WS;
