@@ -7,11 +7,16 @@
 // fqz_zstd_enc.cu.  No dictionaries (the reference uses none, compress.go:523-528).
 //
 // Pipeline over a batch of streams (each a chain of frames):
-//   k_zd_walk      1 thread / stream : frame + block headers -> frame / block tables
-//   k_zd_literals  1 warp  / block   : Huffman (4 lanes = 4 streams) / raw / RLE literals
-//   k_zd_sequences 1 warp  / block   : FSE tables + serial sequence decode
-//   k_zd_execute   1 warp  / frame   : repeat-offset resolution + LZ77 copies, block after block
-//   k_zd_checksum  4 lanes / frame   : XXH64 of the regenerated content
+//   k_zd_hop        1 warp   / stream : frame + block positions (32 frames at a time behind an index frame)
+//   k_zd_parse      1 thread / block  : literals header, sequence count, table positions
+//   k_zd_link       1 thread / frame  : treeless / repeat provenance, output offsets known from headers
+//   k_zd_offsets    1 thread / block  : arena offsets, table slots, literal groups (after the scans)
+//   k_zd_literals   1 warp   / group  : <= 8 blocks of one frame, lane = (block, Huffman stream)
+//   k_zd_seq_tables 1 warp   / block  : FSE decode tables into L2 (lanes 0-2)
+//   k_zd_seq_decode 1 thread / block  : the serial FSE chain, 32 blocks per warp
+//   k_zd_rawcopy    1 warp   / block  : raw / RLE blocks whose place is known from the headers
+//   k_zd_execute    1 warp   / frame  : LZ77 copies (single-block frames staged in shared memory)
+//   k_zd_checksum   4 lanes  / frame  : XXH64 of the regenerated content
 #include "fqz_zstd.h"
 #include "fqz_zstd_dec.h"
 #include "fqz_zstd_tables.cuh"

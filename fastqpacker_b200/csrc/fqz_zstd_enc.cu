@@ -5,11 +5,15 @@
 // pinned by any reference test, so the contract is: valid RFC 8878 frames with content checksums
 // that the reference's decoder accepts, ratio within 2 % of the CPU path.
 //
-// One WARP encodes one frame (<= 64 KiB of one stream) start to finish; thousands of frames are in
-// flight per launch.  Two policies:
-//   ENTROPY : literals-only compressed block (Huffman, 4 streams) / RLE block / raw block
-//   AUTO    : greedy LZ77 (32 positions per step: ballot + match_any candidate search, hash table
-//             in shared memory), Huffman literals, FSE sequences (predefined / RLE / dynamic)
+// Three kernels, thousands of frames in flight per launch:
+//   k_zenc_huf : literals-only frames (packed bases, qualities): one CTA per 128 KiB frame of eight
+//                16 KiB blocks sharing one Huffman tree; RLE / raw fallbacks
+//   k_zenc<2>  : item streams (headers, plus lines, N positions, lengths): one warp per 16 KiB frame:
+//                item matcher, Huffman literals, FSE sequences (predefined / RLE / dynamic)
+//   k_zenc<1>  : generic data (fqz_zstd_compress, policy AUTO): one warp per 64 KiB frame, greedy
+//                LZ77 (32 positions per step: ballot + match_any candidate search, hash table in
+//                shared memory), same entropy back end
+//   k_zindex   : the skippable index frame in front of every stream of >= 4 frames (fqz_zstd.h)
 #include <type_traits>
 
 #include "fqz_zstd.h"
