@@ -1233,10 +1233,143 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
         __syncwarp();
     }
     __syncwarp();
-    // serial clean-up (lane 0): fuse / trim what the rounds left overlapping, turn positions into
-    // literal lengths, resolve repeat offsets.  The list is read and written through shared-memory
-    // chunks of 32 entries so that the serial chain never waits for global memory.
+    // Clean-up: fuse / trim what the rounds left overlapping, turn positions into literal lengths,
+    // resolve repeat offsets.  The fuse / trim state machine looks serial, but its state — the pending
+    // match — is re-established by the first entry that starts a new match, so the list is cut into 32
+    // segments that the lanes process in lockstep: pass A finds every segment's final pending match
+    // from a cold start, pass B reruns the segment with the previous segment's pending as input and
+    // PROVES that its own final state is what pass A promised the next lane (any mismatch — tiny lists,
+    // runs that swallow a whole segment — falls back to the serial pass), pass C turns the survivors into
+    // sequences with warp scans.  Only the repeat-offset history stays serial.
     u32 nseq = 0, nlit = 0;
+    bool par_done = false;
+    if (nm >= 256u && 8u * (nm + 1u) <= len) {
+        u32 *toff = (u32 *)lit;  // the literal buffer is free until the literals are gathered below
+        u16 *tpos = (u16 *)(toff + nm + 1u), *tlen = tpos + nm + 1u;
+        const u32 seg = (nm + 31u) >> 5, ea = min(nm, lane * seg), eb = min(nm, ea + seg);
+        // ---- pass A
+        u32 kpos = 0, klen = 0, koff = 0;
+        bool have = false;
+        for (u32 e = ea; e < eb; e++) {
+            u32 p = sll[e], l = sml[e], o = sof[e];
+            if (have && o == koff && p <= kpos + klen) {
+                klen = max(kpos + klen, p + l) - kpos;
+                continue;
+            }
+            if (have && p < kpos + klen) {
+                u32 cut = kpos + klen - p;
+                if (l < cut + ZI_MINMATCH) continue;
+                p += cut;
+                l -= cut;
+            }
+            kpos = p; klen = l; koff = o; have = true;
+        }
+        const u32 a_pos = kpos, a_len = klen, a_off = koff;
+        const bool a_have = have;
+        // ---- pass B: incoming pending = what pass A left in the segment before
+        {
+            u32 ipos = __shfl_up_sync(FULL, a_pos, 1), ilen = __shfl_up_sync(FULL, a_len, 1), ioff = __shfl_up_sync(FULL, a_off, 1);
+            bool ihave = __shfl_up_sync(FULL, a_have ? 1u : 0u, 1) != 0;
+            if (lane == 0) ihave = false;
+            kpos = ipos; klen = ilen; koff = ioff; have = ihave;
+        }
+        u32 w = ea;
+        for (u32 e = ea; e < eb; e++) {
+            u32 p = sll[e], l = sml[e], o = sof[e];
+            if (have && o == koff && p <= kpos + klen) {
+                klen = max(kpos + klen, p + l) - kpos;
+                continue;
+            }
+            if (have && p < kpos + klen) {
+                u32 cut = kpos + klen - p;
+                if (l < cut + ZI_MINMATCH) continue;
+                p += cut;
+                l -= cut;
+            }
+            if (have) {
+                tpos[w] = (u16)kpos; tlen[w] = (u16)klen; toff[w] = koff;
+                w++;
+            }
+            kpos = p; klen = l; koff = o; have = true;
+        }
+        const bool last_seg = (ea < nm) && (eb == nm);
+        bool bad = (ea < nm) && !last_seg && !(have == a_have && kpos == a_pos && klen == a_len && koff == a_off);
+        if (last_seg && have) {  // nobody takes the last pending over
+            tpos[w] = (u16)kpos; tlen[w] = (u16)klen; toff[w] = koff;
+            w++;
+        }
+        if (!__any_sync(FULL, bad)) {
+            // ---- pass C: sequence numbers, literal lengths and literal offsets
+            const u32 cnt = w - ea;
+            u32 cincl = group_incl_scan(cnt, FULL, 32);
+            nseq = __shfl_sync(FULL, cincl, 31);
+            const u32 g0 = cincl - cnt;
+            u32 lastend = cnt ? (u32)tpos[w - 1] + tlen[w - 1] : 0u;
+            for (int d = 1; d < 32; d <<= 1) {  // ends grow with the position in the list: prefix maximum
+                u32 t = __shfl_up_sync(FULL, lastend, (unsigned)d);
+                if ((int)lane >= d) lastend = max(lastend, t);
+            }
+            u32 prev0 = __shfl_up_sync(FULL, lastend, 1);
+            if (lane == 0) prev0 = 0;
+            u32 sumll = 0;
+            {
+                u32 pe = prev0;
+                for (u32 k = ea; k < w; k++) {
+                    sumll += (u32)tpos[k] - pe;
+                    pe = (u32)tpos[k] + tlen[k];
+                }
+            }
+            u32 lincl = group_incl_scan(sumll, FULL, 32);
+            nlit = __shfl_sync(FULL, lincl, 31);
+            u32 lo = lincl - sumll;
+            __syncwarp();  // every lane has read the uncompacted entries of its segment; the arrays may be overwritten
+            {
+                u32 pe = prev0;
+                for (u32 k = ea, g = g0; k < w; k++, g++) {
+                    u32 p = tpos[k], l = tlen[k];
+                    sll[g] = (u16)(p - pe);
+                    sml[g] = (u16)(l - 3u);
+                    sof[g] = toff[k];
+                    slo[g] = (u16)lo;
+                    lo += p - pe;
+                    pe = p + l;
+                }
+            }
+            const u32 pend_all = __shfl_sync(FULL, lastend, 31);
+            __syncwarp();
+            // ---- repeat offsets: serial by nature (lane 0), staged through shared memory
+            {
+                u32 *inb = mbuf, *outb = mbuf + 64;
+                u32 rep0 = 1, rep1 = 4, rep2 = 8;
+                for (u32 base = 0; base < nseq; base += 32) {
+                    u32 cn = min(32u, nseq - base);
+                    __syncwarp();
+                    if (lane < cn) {
+                        inb[lane] = sof[base + lane];
+                        inb[32 + lane] = sll[base + lane];
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        for (u32 k = 0; k < cn; k++) outb[k] = zstd_off_base(inb[k], inb[32 + k] == 0, rep0, rep1, rep2);
+                    __syncwarp();
+                    if (lane < cn) sof[base + lane] = outb[lane];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbuf[0] = nseq;
+                mbuf[1] = nlit;
+                mbuf[2] = pend_all;
+            }
+            par_done = true;
+        }
+        __syncwarp();
+    }
+    if (!par_done) {
+    // serial pass (lane 0): the list is read and written through shared-memory chunks of 32 entries so
+    // that the serial chain never waits for global memory
+    nseq = 0;
+    nlit = 0;
     {
         u32 *inb = mbuf;             // 32 x (pos | len << 16), 32 x offset
         u32 *outb = mbuf + 64;       // 64 x (ll | (ml-3) << 16), 64 x offBase, 64 x literal offset
@@ -1312,6 +1445,7 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
             mbuf[1] = outb[193];
             mbuf[2] = outb[194];
         }
+    }
     }
     __syncwarp();
     nseq = mbuf[0];
