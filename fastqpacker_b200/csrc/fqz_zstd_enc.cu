@@ -1615,22 +1615,44 @@ struct ZhShared {
     u32 stage[ZH_WARPS][ZH_STAGE_WORDS];
 };
 
-// histogram of src[a, b) (one Huffman stream) by one warp
+// histogram of src[a, b) (one Huffman stream) by one warp.  The body is read as aligned 16-byte
+// vectors, two per lane in flight, so that the counting never waits for a 4-byte load; zero — by far
+// the most frequent byte of delta-coded qualities — is counted in a register.
+__device__ __forceinline__ void hist_word(u32 x, u32 *h2, u32 &zeros) {
+#pragma unroll
+    for (u32 k = 0; k < 4; k++) {
+        u32 sy = (x >> (8u * k)) & 0xFFu;
+        if (sy == 0) zeros++;
+        else atomicAdd(&h2[sy >> 1], 1u << (16u * (sy & 1u)));
+    }
+}
 __device__ static void warp_stream_hist(const u8 *src, u32 a, u32 b, u32 *h2) {
     u32 lane = lane_id();
     u32 zeros = 0;
-#pragma unroll 4
-    for (u32 p = a + 4u * lane; p < b; p += 128u) {
-        u32 x = ld_u32_unaligned(src + p);
-        u32 nv = min(4u, b - p);
-#pragma unroll
-        for (u32 k = 0; k < 4; k++) {
-            u32 sy = (x >> (8u * k)) & 0xFFu;
-            if (k < nv) {
-                if (sy == 0) zeros++;
-                else atomicAdd(&h2[sy >> 1], 1u << (16u * (sy & 1u)));
-            }
-        }
+    // head: bytes in front of the first 16-byte boundary, tail: bytes behind the last one
+    u32 a16 = a + (u32)((16u - ((uintptr_t)(src + a) & 15u)) & 15u);
+    if (a16 > b) a16 = b;
+    u32 nv = (b - a16) >> 4, b16 = a16 + 16u * nv;
+    for (u32 p = a + lane; p < a16; p += 32) {
+        u32 sy = src[p];
+        if (sy == 0) zeros++;
+        else atomicAdd(&h2[sy >> 1], 1u << (16u * (sy & 1u)));
+    }
+    const uint4 *v = (const uint4 *)(src + a16);
+    u32 i = lane;
+    for (; i + 32 < nv; i += 64) {
+        uint4 x0 = v[i], x1 = v[i + 32];
+        hist_word(x0.x, h2, zeros); hist_word(x0.y, h2, zeros); hist_word(x0.z, h2, zeros); hist_word(x0.w, h2, zeros);
+        hist_word(x1.x, h2, zeros); hist_word(x1.y, h2, zeros); hist_word(x1.z, h2, zeros); hist_word(x1.w, h2, zeros);
+    }
+    if (i < nv) {
+        uint4 x0 = v[i];
+        hist_word(x0.x, h2, zeros); hist_word(x0.y, h2, zeros); hist_word(x0.z, h2, zeros); hist_word(x0.w, h2, zeros);
+    }
+    for (u32 p = b16 + lane; p < b; p += 32) {
+        u32 sy = src[p];
+        if (sy == 0) zeros++;
+        else atomicAdd(&h2[sy >> 1], 1u << (16u * (sy & 1u)));
     }
     zeros = __reduce_add_sync(FULL, zeros);
     if (lane == 0 && zeros) atomicAdd(&h2[0], zeros);
@@ -1737,12 +1759,23 @@ __device__ static void warp_stream_encode(const u8 *src, u32 a, u32 b, const u16
     u32 P = 8u * al;
     bool first = true;
     u32 m = b - a, T = (m + 127u) >> 7;
+    // the word of the next step is loaded while this one is coded
+    u32 xn = 0;
+    {
+        int i0 = (int)b - 4 * (int)(lane + 1u);
+        if (i0 >= (int)a) xn = ld_u32_unaligned(src + i0);
+    }
     for (u32 t = 0; t < T; t++) {
         int idx0 = (int)(b - 128u * t) - 4 * (int)(lane + 1u);  // lane 0 owns the highest indices = lowest bits
         u64 v = 0;
         u32 L = 0;
+        const u32 xc = xn;
+        {
+            int i1 = idx0 - 128;
+            if (t + 1 < T && i1 >= (int)a) xn = ld_u32_unaligned(src + i1);
+        }
         if (idx0 >= (int)a) {
-            u32 x = ld_u32_unaligned(src + idx0);
+            u32 x = xc;
 #pragma unroll
             for (int k = 3; k >= 0; k--) {
                 u32 e = hlut[(x >> (8 * k)) & 0xFFu];
