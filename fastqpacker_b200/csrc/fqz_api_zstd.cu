@@ -131,8 +131,9 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     ze.d_slots = (u8 *)c->arena.alloc(zb.slot_bytes + 16);
     u8 *d_ws = (u8 *)c->arena.alloc(zb.ws_bytes + 16);
     u32 *d_hash = (u32 *)c->arena.alloc((size_t)(nf + 1) * sizeof(u32));
+    u32 *d_parsed = (u32 *)c->arena.alloc((zb.idx_items.size() + 1) * 2 * sizeof(u32));
     ze.d_scan = (u32 *)c->arena.alloc((size_t)(nf + 2) * sizeof(u32));
-    if (!d_up || !ze.d_slots || !d_ws || !d_hash || !ze.d_scan) {
+    if (!d_up || !ze.d_slots || !d_ws || !d_hash || !d_parsed || !ze.d_scan) {
         c->err = "arena: out of device memory (zstd stage)";
         return FQZ_E_CUDA;
     }
@@ -150,9 +151,9 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     }
     {
         StageScope sc(c, ST_ZENC_LZ, lz_bytes);
-        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, s);
+        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, nullptr, s);
         fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size() + zb.idx_lz.size(), (u32)zb.idx_items.size(), d_hash, ze.d_slots, d_ws, ze.d_scan,
-                        2, s);
+                        2, d_parsed, s);
     }
     {
         StageScope sc(c, ST_ZENC_ENTROPY, ent_bytes);

@@ -52,5 +52,6 @@ void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream
 void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s);
+// parsed: 2 u32 per work item, scratch between the item matcher and the entropy kernel (lz == 2 only)
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
-                     cudaStream_t s);
+                     u32 *parsed, cudaStream_t s);
