@@ -1525,9 +1525,13 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zitems_parse(const ZFrame *
     }
 }
 
-template <int MODE>
+// PHASE 0: the whole frame in one kernel.  PHASE 1 / 2 (item frames): literals, then sequences and the
+// frame's closing steps, as two kernels — `parsed` carries (sequences, literals) from the item matcher to
+// phase 1 and (sequences, literals-section size | RLE mark) from phase 1 to phase 2.
+#define ZENC_RLE_MARK 0xFFFFFFFFu
+template <int MODE, int PHASE>
 __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
-                                                          u8 *ws, u32 *out_sizes, const u32 *parsed) {
+                                                          u8 *ws, u32 *out_sizes, u32 *parsed) {
     constexpr bool LZ = MODE != 0;
     typedef typename std::conditional<MODE == 1, WarpScratchLZ, typename std::conditional<MODE == 2, WarpScratchItems, WarpScratchEnt>::type>::type WS;
     __shared__ WS scratch[ZENC_WARPS];
@@ -1541,14 +1545,14 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
     u8 *out = slots + fr.dst_off;
     u32 len = fr.src_len;
     u32 cap = (u32)FQZ_ZSLOT(len);
-    if (lane == 0) write_frame_header(out, len);
+    if (PHASE != 2 && lane == 0) write_frame_header(out, len);
     u8 *blk = out + 10;       // 3-byte block header, then content
     u8 *body = blk + 3;
     u32 body_cap = cap - 13 - 4;
     u32 bsize = 0, btype = 0;  // 0 raw, 1 rle, 2 compressed
     bool done = false;
     // RLE block: every byte equal
-    {
+    if constexpr (PHASE != 2) {
         u32 b0 = src[0];
         bool same = true;
         for (u32 i = lane; i < len && same; i += 32) same = (src[i] == b0);
@@ -1557,6 +1561,16 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
             btype = 1;
             bsize = len;  // block header carries the regenerated size
             done = true;
+        }
+    } else if (parsed[2 * wi + 1] == ZENC_RLE_MARK) {
+        btype = 1;
+        bsize = len;
+        done = true;
+    }
+    if constexpr (PHASE == 1) {
+        if (done) {
+            if (lane == 0) parsed[2 * wi + 1] = ZENC_RLE_MARK;
+            return;
         }
     }
     if (!done) {
@@ -1574,19 +1588,31 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
                 u32 nseq;
                 if constexpr (MODE == 2) {  // parsed by k_zitems_parse
                     nseq = parsed[2 * wi];
-                    nlit = parsed[2 * wi + 1];
+                    nlit = parsed[2 * wi + 1];  // phase 2: the size of the literals section instead
                 } else
                     nseq = warp_lz_parse(src, len, S.u.htab, lit, sll, sml, sof, &nlit);
                 __syncwarp();
-                u32 lsz = warp_write_literals(nseq ? (const u8 *)lit : src, nlit, body, S);
+                u32 lsz;
+                if constexpr (PHASE == 2) lsz = nlit;
+                else lsz = warp_write_literals(nseq ? (const u8 *)lit : src, nlit, body, S);
                 __syncwarp();
+                if constexpr (PHASE == 1) {
+                    if (lane == 0) parsed[2 * wi + 1] = lsz;
+                    return;
+                }
                 u32 ssz = 0;
                 if (lsz + 16 < body_cap) ssz = warp_write_sequences(sll, sml, sof, nseq, body + lsz, body_cap - lsz, S, &ovf, MODE == 2);
                 else ovf = true;
                 total = lsz + ssz;
             }
         } else {
-            u32 lsz = warp_write_literals(src, len, body, S);
+            u32 lsz;
+            if constexpr (PHASE == 2) lsz = parsed[2 * wi + 1];
+            else lsz = warp_write_literals(src, len, body, S);
+            if constexpr (PHASE == 1) {
+                if (lane == 0) parsed[2 * wi + 1] = lsz;
+                return;
+            }
             if (lane == 0) body[lsz] = 0;  // no sequences
             total = lsz + 1;
         }
@@ -2116,7 +2142,8 @@ void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32
     u32 grid = (nidx + ZENC_WARPS - 1) / ZENC_WARPS;
     if (lz == 2) {
         FQZ_LAUNCH(k_zitems_parse, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, ws, parsed);
-        FQZ_LAUNCH(k_zenc<2>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
-    } else if (lz) FQZ_LAUNCH(k_zenc<1>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
-    else FQZ_LAUNCH(k_zenc<0>, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+        FQZ_LAUNCH((k_zenc<2, 1>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+        FQZ_LAUNCH((k_zenc<2, 2>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+    } else if (lz) FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+    else FQZ_LAUNCH((k_zenc<0, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
 }
