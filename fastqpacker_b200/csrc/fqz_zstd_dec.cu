@@ -643,10 +643,16 @@ struct LitScratch {
 // tableLog (0 on error) and *tree_size = bytes of the tree description.
 __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 *tree_size) {
     u32 lane = lane_id();
-    const u8 *p = (const u8 *)(uintptr_t)hb.src + hb.lit_hdr;
+    const u8 *gp = (const u8 *)(uintptr_t)hb.src + hb.lit_hdr;
     u32 avail = hb.lit_csize;
     u32 nsym = 0, tsz = 0, bad = 0;
     for (u32 i = lane; i < 256; i += 32) S.weights[i] = 0;
+    // the tree description (at most 1 + 128 bytes) is parsed by one lane: stage it in shared memory (in
+    // the decode table's space, which is only filled afterwards) so that the serial parse never waits
+    // for global memory
+    u8 *stage = (u8 *)S.dt + 16;  // 16 readable bytes in front: the bit reader loads aligned words around its window
+    for (u32 i = lane; i < min(avail, 144u); i += 32) stage[i] = gp[i];
+    const u8 *p = stage;
     __syncwarp();
     if (lane == 0) {
         if (avail < 1) bad = 1;
@@ -771,7 +777,7 @@ struct HufBits {
     u32 nb;         // valid bits in `bits`
     const u32 *lo;  // aligned word that holds the first byte of the stream
     u32 wi;         // index (from lo) of the next word to prefetch; sticks at 0
-    u32 w0, w1, w2; // prefetched words, nearest first
+    u32 w0, w1, w2, w3; // prefetched words, nearest first; w3 is the load in flight
     // src[csize - 1] != 0 (it holds the end mark).  Returns the payload bits of the stream.
     __device__ __forceinline__ u32 init(const u8 *src, u32 csize) {
         u32 hb = hibit32(src[csize - 1]);
@@ -791,20 +797,24 @@ struct HufBits {
         wi = wi ? wi - 1u : 0u;
         w2 = lo[wi];
         wi = wi ? wi - 1u : 0u;
+        w3 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
         return (csize - 1u) * 8u + hb;
     }
     // Afterwards nb >= 32 (bits past the stream start are whatever memory holds).  Branch-free on
     // purpose: the 32 lanes of a warp run 32 different streams and would otherwise take this path at
-    // different times, every one of them paying for all the others.
+    // different times, every one of them paying for all the others.  The word loaded here is first
+    // looked at by the NEXT refill that shifts the queue, several symbols later, so the chain never
+    // waits for it; a refill that does not shift loads nothing (predicated load).
     __device__ __forceinline__ void refill() {
         const bool need = nb <= 32u;
-        const u32 v = lo[wi];  // always a valid address; only used when `need`
         const u64 add = (u64)w0 << ((32u - nb) & 63u);
         bits |= need ? add : 0ull;
         nb += need ? 32u : 0u;
         w0 = need ? w1 : w0;
         w1 = need ? w2 : w1;
-        w2 = need ? v : w2;
+        w2 = need ? w3 : w2;
+        if (need) w3 = lo[wi];
         wi = (need && wi) ? wi - 1u : wi;
     }
     __device__ __forceinline__ u32 peek(u32 n) const { return (u32)(bits >> 32) >> (32u - n); }  // 1 <= n <= 32
