@@ -349,7 +349,18 @@ def run_ours(args):
         except OSError:
             pass
         nl = max(1, v["launches"])
-        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+        stage_kernels = {
+            "zstd_enc_lz": "k_zitems_parse + k_zenc<2,1> + k_zenc<2,2> (item streams: matcher, Huffman literals, FSE sequences)",
+            "zstd_enc_entropy": "k_zenc_huf (packed bases, qualities: Huffman frames)",
+            "scatter_streams": "k_scatter_streams",
+            "record_meta": "k_record_meta",
+            "newline_count": "k_newline_count",
+            "newline_index": "k_newline_index",
+            "xxh64": "k_xxh64_frames",
+            "assemble": "k_zassemble + k_write_block_headers",
+            "scan": "k_scan_partial + k_scan_apply + k_zindex",
+        }
+        roof = {"bound": "hbm", "kernel": top, "kernels": stage_kernels.get(top, top), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": v["bytes"] / nl, "ms_per_launch": v["ms"] / nl,
                 "peak_source": peak_src, "launches_per_step": v["launches"], "kernel_ms_per_step": v["ms"],
                 "share_of_step": v["ms"] / sum(x["ms"] for x in cs.values())}
