@@ -242,8 +242,10 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
     u64 n_all = n;
     u64 want = 0;
     int win = 0;
-    const u64 win_bytes = host_io ? DEC_WINDOW_HOST : DEC_WINDOW_BYTES;
     while (pos < n_all) {
+        // host pipeline: nothing is downloaded before the first window has been uploaded and decoded, so the
+        // pipeline is started with a small one
+        const u64 win_bytes = host_io ? (win == 0 ? DEC_WINDOW_HOST / 4 : DEC_WINDOW_HOST) : DEC_WINDOW_BYTES;
         c->arena.reset();
         if (host_io) {  // the walk must not look at bytes that have not arrived yet
             size_t avail = 0;

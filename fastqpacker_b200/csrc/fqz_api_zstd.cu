@@ -323,6 +323,7 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
     size_t written = 0;
     *out_len = 0;
     *consumed = 0;
+    bool no_split = false;  // a halved tail window held no complete block (very long reads): take the tail whole
     while (st.first || pos < n) {
         c->arena.reset();
         u64 left = n - pos;
@@ -330,6 +331,11 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
         bool last = is_last;
         if (left > WIN + (WIN >> 2)) {
             take = WIN;
+            last = false;
+        } else if (h_out && !no_split && left > ((u64)384 << 20)) {
+            // host pipeline: the compute and the download of the LAST window are not hidden behind any
+            // upload, so the end of the input is taken in halving windows
+            take = left / 2;
             last = false;
         }
         if (h_out) FQZ_TRY(fqz_io_gate(c, pos + take, nullptr));
@@ -354,6 +360,10 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
         int rc = fqz_compress_window(c, wptr, take + skip, last, st.rec_base, pmode, st.first && st.emit_header, header_block_size,
                                      d_out + written, out_cap - written, &wl, &used, &recs, &ph, skip);
         if (rc == FQZ_OK) used -= skip;
+        if (rc == FQZ_E_NEED_MORE && take < left && left <= WIN + (WIN >> 2) && !no_split) {
+            no_split = true;
+            continue;
+        }
         if (rc == FQZ_E_NEED_MORE) {
             if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside a full device window
             break;                                    // streaming: the tail waits for more data
