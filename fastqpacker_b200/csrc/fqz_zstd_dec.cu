@@ -751,15 +751,30 @@ __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 
     }
     __syncwarp();
     if (S.rank[0] != (1u << tl)) return 0;
-    for (u32 s = lane; s < nsym; s += 32) {
-        u32 w = S.weights[s];
-        if (!w) continue;
-        u32 idx = 0;
-        for (u32 t = 0; t < s; t++) idx += (S.weights[t] == w) ? 1u : 0u;
-        u32 len = 1u << (w - 1);
-        u32 at = S.rank[w] + idx * len;
-        u16 e = (u16)(((tl + 1 - w) << 8) | s);
-        for (u32 k = 0; k < len; k++) S.dt[at + k] = e;
+    // Fill: a symbol of weight w owns 2^(w-1) consecutive cells.  Short runs are written by the lane that
+    // owns the symbol; long runs (the few frequent symbols own most of the table — up to half of it each)
+    // are handed to the whole warp, 32 cells per step, so that no lane writes a thousand cells alone.
+    for (u32 s0 = 0; s0 < nsym; s0 += 32) {
+        u32 s = s0 + lane;
+        u32 w = (s < nsym) ? S.weights[s] : 0u;
+        u32 len = 0, at = 0;
+        u32 e = 0;
+        if (w) {
+            u32 idx = 0;
+            for (u32 t = 0; t < s; t++) idx += (S.weights[t] == w) ? 1u : 0u;
+            len = 1u << (w - 1);
+            at = S.rank[w] + idx * len;
+            e = ((tl + 1 - w) << 8) | s;
+            if (len < 32u)
+                for (u32 k = 0; k < len; k++) S.dt[at + k] = (u16)e;
+        }
+        u32 big = __ballot_sync(FULL, len >= 32u);
+        while (big) {
+            int l = __ffs((int)big) - 1;
+            big &= big - 1u;
+            u32 blen = __shfl_sync(FULL, len, l), bat = __shfl_sync(FULL, at, l), be = __shfl_sync(FULL, e, l);
+            for (u32 k = lane; k < blen; k += 32) S.dt[bat + k] = (u16)be;
+        }
     }
     __syncwarp();
     return tl;
