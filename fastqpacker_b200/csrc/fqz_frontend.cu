@@ -298,9 +298,30 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
         group_copy<W>(s_hdr + o_hdr + 2, src.at(t.hs + 1u), H, g);
         if (g == 0) st_u16_unaligned(s_plus + o_plus, P & 0xFFFFu);
         group_copy<W>(s_plus + o_plus + 2, src.at(t.ps + 1u), P, g);
-        // seqPacked + nPositions (sequence.go:139-184): 16 bases per lane per round
+        // seqPacked + nPositions (sequence.go:139-184): 16 bases per lane per round.  k_record_meta has
+        // already counted the record's non-ACGT bases (that count sized the N-position stream): the 99 % of
+        // reads without any take a path with no N test, no position bookkeeping and no group scan.
         u32 units = (L + 15u) >> 4, rounds = (units + W - 1) / W;
         u32 nbase = 0;
+        const bool has_n = (offs[4 * stride + r + 1] - o_npos) > 2u;
+        if (!has_n) {
+            for (u32 u = g; u < units; u += W) {
+                const u8 *sp = src.at(t.ss + 16u * u);
+                u32 out = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
+                    if (bp < L) {
+                        u32 x = ld_u32_unaligned(sp + 4 * k);
+                        u32 codes = base_codes4(x, 0u);
+                        if (bp + 4u > L) codes &= 0xFFFFFFFFu >> (8u * (bp + 4u - L));  // bytes past the read
+                        out |= pack_codes4(codes) << (8 * k);
+                    }
+                }
+                u32 vb = min(16u, L - 16u * u);
+                st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
+            }
+        } else
         for (u32 j = 0; j < rounds; j++) {
             u32 u = j * W + g;
             u32 nmask16 = 0;
