@@ -137,8 +137,15 @@ __device__ __forceinline__ u32 partial_count_n(const u8 *text, u32 a, u32 b, u32
         u32 w0 = a >> 2, w1 = (b - 1) >> 2;
         for (u32 w = w0 + g; w <= w1; w += W) {
             u32 x = *(const u32 *)(text + 4ull * w);
-            u32 nm = nonacgt_mask4(x) & range_mask4(4u * w, a, b);
-            c += (u32)__popc(nm & 0x01010101u);
+            // A byte is one of ACGTacgt exactly when, with bit 5 cleared, it equals the letter that its
+            // bits 1-2 select from "ACTG" (the same two bits the packer uses as the base code): one
+            // byte_perm lookup and one XOR test four bytes, and almost every word of a read passes
+            u32 t = (x >> 1) & 0x03030303u;
+            u32 u2 = (t | (t >> 4)) & 0x00330033u;          // two selector nibbles per half word
+            u32 sel = (u2 | (u2 >> 8)) & 0x3333u;           // four selector nibbles
+            u32 y = (x & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, sel);
+            if (4u * w < a || 4u * w + 4u > b) y &= range_mask4(4u * w, a, b);  // first / last word of the line
+            if (y) c += (u32)__popc((((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u);
         }
     }
     return c;
