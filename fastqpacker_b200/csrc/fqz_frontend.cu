@@ -130,22 +130,32 @@ __device__ __forceinline__ LineSpan record_lines(const u8 *text, const u32 *line
 
 // Count bytes that are not ACGTacgt in text[a,b) with a group of `W` lanes (lane index g) using
 // aligned 32-bit words.  Returns the lane's partial count.
+// A byte is one of ACGTacgt exactly when, with bit 5 cleared, it equals the letter that its bits 1-2
+// select from "ACTG" (the same two bits the packer uses as the base code): one byte_perm lookup and one
+// XOR test four bytes.  Returns a word that is non-zero in exactly the byte lanes that are NOT ACGTacgt.
+__device__ __forceinline__ u32 nonacgt_diff4(u32 x) {
+    u32 t = (x >> 1) & 0x03030303u;
+    u32 u2 = (t | (t >> 4)) & 0x00330033u;  // two selector nibbles per half word
+    u32 sel = (u2 | (u2 >> 8)) & 0x3333u;   // four selector nibbles
+    return (x & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, sel);
+}
+// text must be 16-byte aligned (window bases are): every lane of the group reads whole 16-byte vectors, so a
+// 150-base line is two load round trips for the group instead of five.
 template <int W>
 __device__ __forceinline__ u32 partial_count_n(const u8 *text, u32 a, u32 b, u32 g) {
     u32 c = 0;
     if (b > a) {
-        u32 w0 = a >> 2, w1 = (b - 1) >> 2;
-        for (u32 w = w0 + g; w <= w1; w += W) {
-            u32 x = *(const u32 *)(text + 4ull * w);
-            // A byte is one of ACGTacgt exactly when, with bit 5 cleared, it equals the letter that its
-            // bits 1-2 select from "ACTG" (the same two bits the packer uses as the base code): one
-            // byte_perm lookup and one XOR test four bytes, and almost every word of a read passes
-            u32 t = (x >> 1) & 0x03030303u;
-            u32 u2 = (t | (t >> 4)) & 0x00330033u;          // two selector nibbles per half word
-            u32 sel = (u2 | (u2 >> 8)) & 0x3333u;           // four selector nibbles
-            u32 y = (x & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, sel);
-            if (4u * w < a || 4u * w + 4u > b) y &= range_mask4(4u * w, a, b);  // first / last word of the line
-            if (y) c += (u32)__popc((((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u);
+        u32 v0 = a >> 4, v1 = (b - 1) >> 4;
+        for (u32 v = v0 + g; v <= v1; v += W) {
+            uint4 q = *(const uint4 *)(text + 16ull * v);
+            u32 xs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (u32 k = 0; k < 4; k++) {
+                u32 wp = 16u * v + 4u * k;
+                u32 y = nonacgt_diff4(xs[k]);
+                if (wp < a || wp + 4u > b) y &= range_mask4(wp, a, b);  // words at or beyond the ends of the line
+                if (y) c += (u32)__popc((((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u);
+            }
         }
     }
     return c;
