@@ -72,6 +72,7 @@ class FqzLibrary:
         L.fqz_get_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.fqz_get_stream.argtypes = [vp]
         L.fqz_get_stream.restype = vp
+        self._opt(L, "fqz_set_option", [vp, i32, C.c_uint64])
         self._opt(L, "fqz_decode_streams", [vp, vp, vp, u32, i32, vp, sz, szp])
         self._opt(L, "fqz_zstd_compress", [vp, vp, sz, i32, vp, sz, szp])
         self._opt(L, "fqz_zstd_decompress", [vp, vp, sz, vp, sz, szp])
@@ -257,6 +258,12 @@ class FqzContext:
 
     def decompress_stream(self):
         return _DStream(self)
+
+    # ---- tuning -------------------------------------------------------------------------------
+    OPT_WINDOW_BYTES, OPT_HOST_WINDOW_BYTES, OPT_FRONTEND = 1, 2, 3
+
+    def set_option(self, key: int, value: int):
+        self._check(self.lib.L.fqz_set_option(self.h, key, value))
 
     # ---- measurement --------------------------------------------------------------------------
     def stream_handle(self) -> int:

@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 
 #include "fqz_host.h"
 
@@ -31,7 +32,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     FQZ_CUDA_TRY(c, cudaMemsetAsync(d_tiles + ntiles, 0, sizeof(u32), s));
     {
         StageScope sc(c, ST_NL_COUNT, n);
-        fqz_launch_newline_count(d_text, n, d_tiles, ntiles, s);
+        fqz_launch_newline_count(d_text, n, skip ? skip - 1u : 0u, d_tiles, ntiles, s);
     }
     {
         StageScope sc(c, ST_SCAN, 0);
@@ -71,7 +72,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     if (!skip) FQZ_CUDA_TRY(c, cudaMemsetAsync(d_line_end - 1, 0xFF, sizeof(u32), s));
     {
         StageScope sc(c, ST_NL_INDEX, n + 4 * want_lines);
-        fqz_launch_newline_index(d_text, n, d_tiles, ntiles, skip ? d_line_end - 1 : d_line_end, (u32)want_lines + (skip ? 1u : 0u), s);
+        fqz_launch_newline_index(d_text, n, skip ? skip - 1u : 0u, d_tiles, ntiles, skip ? d_line_end - 1 : d_line_end, (u32)want_lines + (skip ? 1u : 0u), s);
     }
     // ---- 3. per-record sizes + validation + Phred min, then five scans
     u64 stride = ((R + 1 + 63) / 64) * 64;
@@ -120,9 +121,37 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     if (hst2->err_key != ~0ull) {
         u32 kind = (u32)(hst2->err_key & 0xFF);
         u64 rec = hst2->err_key >> 8;
-        char msg[160];
+        char msg[640];
         snprintf(msg, sizeof msg, "record %llu: %s", (unsigned long long)rec, fqz_strerror(kErrOfKind[kind < 5 ? kind : 0]));
         c->err = msg;
+        if (kind == FQZ_K_LONG_N && rec >= rec_base && rec - rec_base < R) {
+            // the reference names the record and its length (compress.go:484): fetch the header line
+            u32 *le = (u32 *)(c->h_pin + 1792);
+            u8 *hb = c->h_pin + 3072;
+            u64 rr = rec - rec_base;
+            if (fqz_pin_copy(c, le, d_line_end + 4 * rr - 1, 3 * sizeof(u32)) == FQZ_OK && cudaStreamSynchronize(s) == cudaSuccess) {
+                u32 hs = le[0] + 1u, he = le[1], se = le[2];
+                u32 hl = he > hs ? he - hs : 0u, show = hl > 256u ? 256u : hl;
+                // lines are cut at '\n'; one trailing '\r' is not part of the field (parser.go:213-215)
+                u8 *tmp = c->h_pin + 2048;
+                if (fqz_pin_copy(c, hb, d_text + hs, show + 1u) == FQZ_OK && fqz_pin_copy(c, tmp, d_text + (se ? se - 1u : 0u), 1) == FQZ_OK &&
+                    cudaStreamSynchronize(s) == cudaSuccess) {
+                    u32 L = se - he - 1u;
+                    if (L && tmp[0] == '\r') L--;
+                    if (show == hl && show && hb[show - 1] == '\r') show--;
+                    std::string q;
+                    for (u32 i = 1; i < show; i++) {  // skip the '@'
+                        u8 ch = hb[i];
+                        if (ch == '"' || ch == '\\') { q += '\\'; q += (char)ch; }
+                        else if (ch < 0x20 || ch >= 0x7f) { char e[8]; snprintf(e, sizeof e, "\\x%02x", ch); q += e; }
+                        else q += (char)ch;
+                    }
+                    snprintf(msg, sizeof msg, "record \"%s\": sequence length %u has ambiguous bases beyond position %u; N-position tracking is limited to %u bp",
+                             q.c_str(), L, FQZ_MAX_SEQ_LEN, FQZ_MAX_SEQ_LEN);
+                    c->err = msg;
+                }
+            }
+        }
         out.consumed = rec;  // callers read the offending record index here
         return kErrOfKind[kind < 5 ? kind : 0];
     }

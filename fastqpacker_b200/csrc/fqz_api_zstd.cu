@@ -314,11 +314,10 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
     // large windows amortise it (131 -> 146 GB/s from 1 GiB to 3 GB windows on config 2).  Window offsets
     // are u32: take + take / 4 must stay below 4 GiB.  The host pipeline keeps 1 GiB windows — its first
     // window cannot start before it has been uploaded.
+    const u64 MAXWIN = (u64)3 << 30;
     u64 WIN = h_out ? (u64)1 << 30 : 3000000000ull;
-    if (const char *e = getenv("FQZ_WINDOW_BYTES")) {  // test hook: small windows exercise the window hand-over
-        u64 v = strtoull(e, nullptr, 10);
-        if (v >= ((u64)1 << 20)) WIN = std::min(v, (u64)3 << 30);  // window offsets are u32: take + take / 4 must stay below 4 GiB
-    }
+    if (h_out && c->opt_host_window_bytes) WIN = c->opt_host_window_bytes;
+    if (!h_out && c->opt_window_bytes) WIN = c->opt_window_bytes;
     u64 pos = 0;
     size_t written = 0;
     *out_len = 0;
@@ -364,8 +363,15 @@ static int compress_device_impl(fqz_ctx *c, const u8 *d_fastq, u64 n, bool is_la
             no_split = true;
             continue;
         }
+        if (rc == FQZ_E_NEED_MORE && take < left && WIN < MAXWIN) {
+            // no complete 100 000-record block inside the window (long reads: a block of 10 kb reads is ~2 GB of
+            // text): grow the window up to what u32 offsets allow before giving up
+            WIN = std::min(MAXWIN, WIN * 2);
+            no_split = true;
+            continue;
+        }
         if (rc == FQZ_E_NEED_MORE) {
-            if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside a full device window
+            if (take < left) return FQZ_E_TOO_LARGE;  // no complete block inside the largest device window
             break;                                    // streaming: the tail waits for more data
         }
         if (rc != FQZ_OK) {

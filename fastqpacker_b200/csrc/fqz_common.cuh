@@ -14,7 +14,9 @@
     type *name = reinterpret_cast<type *>(fqz_dyn_smem_raw)
 #endif
 
-extern unsigned long long g_fqz_launches;  // kernels launched by this library (bench.py "gpu_launches")
+// kernels launched by this library on the calling thread (bench.py "gpu_launches"); a context is driven by one
+// thread at a time, so per-thread counting keeps the contexts of a multi-GPU process apart
+extern thread_local unsigned long long g_fqz_launches;
 
 #define FQZ_BLOCK_RECORDS 100000u  // reference: internal/compress/compress.go:71 + batchPool :48-52
 #define FQZ_MAX_SEQ_LEN 65536u     // reference: internal/encoder/sequence.go:11

@@ -4,7 +4,7 @@
 
 #include "fqz_host.h"
 
-unsigned long long g_fqz_launches = 0;
+thread_local unsigned long long g_fqz_launches = 0;
 
 // ---------------------------------------------------------------------------------- arena
 void *Arena::alloc(size_t bytes) {
@@ -273,6 +273,12 @@ extern "C" int fqz_init(int device, fqz_ctx **out) {
         return FQZ_E_CUDA;
     }
     cudaMemset(c->d_phred, 0, 256);
+    // dynamic shared-memory limits are per device: set them for every context (one process may drive several GPUs)
+    if (fqz_frontend_init_device() | fqz_zstd_enc_init_device() | fqz_zstd_dec_init_device()) {
+        cudaGetLastError();
+        delete c;
+        return FQZ_E_CUDA;
+    }
     if (fqz_pin_reserve(c, 65536) != FQZ_OK) {
         delete c;
         return FQZ_E_CUDA;
@@ -324,6 +330,25 @@ extern "C" const char *fqz_strerror(int code) {
     case FQZ_E_NEED_MORE: return "window holds no complete block";
     case FQZ_E_TOO_LARGE: return "input larger than one device window; use the streaming calls";
     default: return "unknown error";
+    }
+}
+
+extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
+    if (!c) return FQZ_E_INVALID_ARG;
+    switch (key) {
+    case FQZ_OPT_WINDOW_BYTES:
+        if (value && value < ((u64)1 << 20)) return FQZ_E_INVALID_ARG;
+        c->opt_window_bytes = value > ((u64)3 << 30) ? ((u64)3 << 30) : value;  // window offsets are u32
+        return FQZ_OK;
+    case FQZ_OPT_HOST_WINDOW_BYTES:
+        if (value && value < ((u64)1 << 20)) return FQZ_E_INVALID_ARG;
+        c->opt_host_window_bytes = value > ((u64)3 << 30) ? ((u64)3 << 30) : value;
+        return FQZ_OK;
+    case FQZ_OPT_FRONTEND:
+        if (value > 2) return FQZ_E_INVALID_ARG;
+        c->opt_frontend = (int)value;
+        return FQZ_OK;
+    default: return FQZ_E_INVALID_ARG;
     }
 }
 

@@ -19,7 +19,10 @@
 
 // ---------------------------------------------------------------------------------- newline scan
 // One CTA = one tile of FQZ_NL_TILE bytes; each thread owns 64 contiguous bytes (4 x 128-bit loads).
-__device__ __forceinline__ u32 nl_mask64(const u8 *text, u64 n, u64 pos, u64 &m_out) {
+// lo: newlines at window offsets below lo do not count (a window that starts inside the 16-byte word holding
+// the tail of the previous window's last record may see several short lines there; only the '\n' at
+// skip - 1 is line -1)
+__device__ __forceinline__ u32 nl_mask64(const u8 *text, u64 n, u64 pos, u64 lo, u64 &m_out) {
     u64 m = 0;  // bit k set <=> text[pos+k] == '\n'
     if (pos < n) {
         const uint4 *v = (const uint4 *)(text + pos);
@@ -37,27 +40,28 @@ __device__ __forceinline__ u32 nl_mask64(const u8 *text, u64 n, u64 pos, u64 &m_
             }
         }
         if (pos + 64 > n) m &= (~0ull) >> (64 - (n - pos));  // bytes past the end do not count
+        if (pos < lo) m = (lo - pos >= 64) ? 0ull : (m & ((~0ull) << (lo - pos)));
     }
     m_out = m;
     return (u32)__popcll(m);
 }
 
-__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_count(const u8 *text, u64 n, u32 *tile_counts) {
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts) {
     __shared__ u32 ws[33];
     u64 pos = (u64)blockIdx.x * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
     u64 m;
-    u32 c = nl_mask64(text, n, pos, m);
+    u32 c = nl_mask64(text, n, pos, lo, m);
     u32 total;
     block_excl_scan(c, ws, &total);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
 // tile_prefix = exclusive scan of tile_counts.  line_end[i] = byte offset of the i-th '\n'.
-__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_index(const u8 *text, u64 n, const u32 *tile_prefix, u32 *line_end, u32 max_lines) {
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 *line_end, u32 max_lines) {
     __shared__ u32 ws[33];
     u64 pos = (u64)blockIdx.x * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
     u64 m;
-    u32 c = nl_mask64(text, n, pos, m);
+    u32 c = nl_mask64(text, n, pos, lo, m);
     u32 ex = block_excl_scan(c, ws, nullptr);
     u32 idx = tile_prefix[blockIdx.x] + ex;
     while (m) {
@@ -399,11 +403,11 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
 }
 
 // ---------------------------------------------------------------------------------- host launchers
-void fqz_launch_newline_count(const u8 *text, u64 n, u32 *tile_counts, u32 ntiles, cudaStream_t s) {
-    if (ntiles) FQZ_LAUNCH(k_newline_count, ntiles, FQZ_NL_THREADS, 0, s, text, n, tile_counts);
+void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_newline_count, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, tile_counts);
 }
-void fqz_launch_newline_index(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s) {
-    if (ntiles) FQZ_LAUNCH(k_newline_index, ntiles, FQZ_NL_THREADS, 0, s, text, n, tile_prefix, line_end, max_lines);
+void fqz_launch_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_newline_index, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, tile_prefix, line_end, max_lines);
 }
 void fqz_launch_scan_partial(const u32 *data, u64 n, u64 stride, u32 narr, u32 *sums, u32 ntiles, cudaStream_t s) {
     FQZ_LAUNCH(k_scan_partial, dim3(ntiles, narr), FQZ_SCAN_THREADS, 0, s, data, n, stride, sums, ntiles);
@@ -421,12 +425,11 @@ void fqz_launch_decide_phred(const FqzWinStatus *st, u32 *phred64, cudaStream_t 
 void fqz_launch_scatter(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u64 stride, const u32 *phred64, u8 *const streams[6],
                         cudaStream_t s) {
     if (!R) return;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_scatter_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
-        attr_done = true;
-    }
     u32 grid = (u32)((R + FQZ_SC_RPC - 1) / FQZ_SC_RPC);
     FQZ_LAUNCH(k_scatter_streams, grid, FQZ_SC_THREADS, FQZ_SC_SMEM, s, text, line_end, R, offs, stride, phred64, streams[0], streams[1],
                streams[2], streams[3], streams[4], streams[5], (u32)(FQZ_SC_SMEM - 128));
+}
+// per-device kernel attributes: called once per context (the attribute is per device, and one process may drive several GPUs)
+int fqz_frontend_init_device() {
+    return (int)cudaFuncSetAttribute(k_scatter_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
 }

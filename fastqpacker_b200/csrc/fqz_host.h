@@ -103,7 +103,15 @@ struct fqz_ctx {
     int sm_count = 148;
     u64 launches_base = 0;
     IoPipe io;
+    // fqz_set_option
+    u64 opt_window_bytes = 0;       // device window of the compress calls (0 = default)
+    u64 opt_host_window_bytes = 0;  // window of the host-buffer compress calls (0 = default)
+    int opt_frontend = 0;           // 0 auto (fused single pass, legacy on bail), 1 legacy multi-pass, 2 fused only (bail = error)
+    u64 fused_windows = 0, legacy_windows = 0;
 };
+int fqz_frontend_init_device();
+int fqz_zstd_enc_init_device();
+int fqz_zstd_dec_init_device();
 
 // RAII stage marker: CUDA events around the launches of one pipeline stage when profiling is on
 struct StageScope {

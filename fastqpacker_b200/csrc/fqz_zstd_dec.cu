@@ -1470,11 +1470,6 @@ void fqz_launch_zd_sequences(ZDBlock *blocks, const ZDFrame *frames, const u32 *
 }
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s) {
     if (!nframes) return;
-    static bool attr_done = false;
-    if (!attr_done && ZX_SMEM) {
-        cudaFuncSetAttribute(k_zd_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, ZX_SMEM);
-        attr_done = true;
-    }
     FQZ_LAUNCH(k_zd_execute, (nframes + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, ZX_SMEM, s, frames, nframes, blocks, litbuf, seqbuf, out);
 }
 void fqz_launch_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *out, cudaStream_t s) {
@@ -1483,15 +1478,16 @@ void fqz_launch_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *fr
 }
 void fqz_launch_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out, cudaStream_t s) {
     if (!nframes) return;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_zd_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
-        attr_done = true;
-    }
     u32 threads = XX_WARPS * 32;
     FQZ_LAUNCH(k_zd_checksum, (nframes * 4 + threads - 1) / threads, threads, XX_SMEM, s, frames, nframes, out);
 }
 void fqz_launch_zd_finish(const ZDFrame *frames, const ZDStreamInfo *info, u32 nstreams, ZDStreamResult *res, cudaStream_t s) {
     if (!nstreams) return;
     FQZ_LAUNCH(k_zd_finish, (nstreams + 63) / 64, 64, 0, s, frames, info, nstreams, res);
+}
+int fqz_zstd_dec_init_device() {
+    int e = 0;
+    if (ZX_SMEM) e |= (int)cudaFuncSetAttribute(k_zd_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, ZX_SMEM);
+    e |= (int)cudaFuncSetAttribute(k_zd_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+    return e;
 }

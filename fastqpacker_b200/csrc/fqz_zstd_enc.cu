@@ -2124,11 +2124,6 @@ void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_si
 }
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
-        attr_done = true;
-    }
     u32 threads = XX_WARPS * 32, grid = (nframes * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes);
 }
@@ -2146,4 +2141,7 @@ void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32
         FQZ_LAUNCH((k_zenc<2, 2>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
     } else if (lz) FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
     else FQZ_LAUNCH((k_zenc<0, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+}
+int fqz_zstd_enc_init_device() {
+    return (int)cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
 }

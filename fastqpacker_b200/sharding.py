@@ -129,8 +129,10 @@ def block_cut_candidates(local_newlines: Sequence[int], lines_before: int) -> Li
 
 def merge_compressed(parts: Sequence[bytes]) -> bytes:
     """Ordered host gather (collectAndWriteResults, compress.go:365-403): rank 0's part keeps the file
-    header, the others contribute their blocks only."""
+    header, the others contribute their blocks only.  Later parts may come with a file header of their
+    own (a stand-alone .fqz) or without (`fqz_compress_shard(emit_file_header=0)`); a block header starts
+    with NumRecords <= 100 000, which can never read as the magic, so the two are told apart safely."""
     out = bytearray(parts[0])
     for p in parts[1:]:
-        out += p[10:]
+        out += p[10:] if p[:4] == MAGIC else p
     return bytes(out)

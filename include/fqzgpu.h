@@ -59,6 +59,13 @@ const char *fqz_strerror(int code);
 const char *fqz_last_error(const fqz_ctx *ctx);
 int fqz_abi_version(void);
 
+/* Tuning knobs (all optional; 0 restores the default).  The codec's results do not depend on them, only where
+ * windows are cut and which front-end kernels run. */
+#define FQZ_OPT_WINDOW_BYTES 1      /* FASTQ bytes per device pass of the compress calls (default 3e9, min 1 MiB) */
+#define FQZ_OPT_HOST_WINDOW_BYTES 2 /* same for the host-buffer calls (default 1 GiB: their first window must be uploaded first) */
+#define FQZ_OPT_FRONTEND 3          /* 0 auto: fused single-pass front end, legacy kernels when it bails out; 1 legacy; 2 fused only */
+int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
+
 /* ---- whole buffer, HOST memory: replaces the bodies of compress.Compress / compress.Decompress
  *      (compress.go:125-192, 558-604).  Output = complete .fqz file (10-byte header + blocks of
  *      100 000 records, F2) / complete FASTQ text.  header_block_size is echoed into the file

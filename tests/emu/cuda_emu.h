@@ -108,7 +108,7 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 }
 static inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = 1ull << 34; return cudaSuccess; }
 
-extern unsigned long long g_fqz_launches;
+extern thread_local unsigned long long g_fqz_launches;
 #define FQZ_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (++g_fqz_launches, emu::launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); }))
 #define FQZ_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emu::dyn_smem)

@@ -67,3 +67,23 @@ def long_read(n_at=None, length=70000):
     if n_at is not None:
         seq[n_at] = ord("N")
     return b"@SEQ_LONG\n" + bytes(seq) + b"\n+\n" + b"I" * length + b"\n"
+
+
+def short_read_handover(nrec=230_000, want_mod=12):
+    """1-6 base reads; record 99 999 (the last of block 0) is a 1-base read that ends at an offset with
+    (offset & 15) == want_mod, so that the next device window is entered `want_mod` bytes in front of its
+    first record and those bytes hold more than one newline."""
+    rnd = random.Random(99)
+    recs = []
+    for i in range(nrec):
+        L = 1 if i == 99_999 else rnd.randint(1, 6)
+        seq = bytes(rnd.choice(b"ACGT") for _ in range(L))
+        qual = bytes(rnd.randint(35, 74) for _ in range(L))
+        hdr = b"@r" if i == 99_999 else b"@r%d" % i
+        recs.append(hdr + b"\n" + seq + b"\n+\n" + qual + b"\n")
+    end = sum(len(r) for r in recs[:100_000])
+    pad = (want_mod - end) % 16
+    recs[0] = b"@" + b"p" * pad + recs[0][1:]
+    text = b"".join(recs)
+    assert sum(len(r) for r in recs[:100_000]) % 16 == want_mod
+    return text

@@ -53,3 +53,21 @@ def test_forced_phred(emu, oracle):
     text = GOOD_CASES["three"]
     for p in (0, 1):
         assert emu.encode_streams(text, phred64=p)["streams"] == oracle.encode_streams(text, phred64=p)["streams"]
+
+
+def test_window_hand_over_short_reads(emu, oracle):
+    """a window cut behind a 1-base record; the next window is entered 12 bytes in front
+    of its first record and those bytes hold three newlines.  Device path with 2 MiB windows."""
+    from tests.fastq_cases import short_read_handover
+
+    text = short_read_handover(nrec=205_000)
+    try:
+        emu.set_option(emu.OPT_FRONTEND, 1)
+        emu.set_option(emu.OPT_WINDOW_BYTES, 2 << 20)
+        emu.set_option(emu.OPT_HOST_WINDOW_BYTES, 2 << 20)
+        cut = emu.compress(text)
+    finally:
+        emu.set_option(emu.OPT_WINDOW_BYTES, 0)
+        emu.set_option(emu.OPT_HOST_WINDOW_BYTES, 0)
+        emu.set_option(emu.OPT_FRONTEND, 0)
+    assert oracle.decompress(cut) == text

@@ -160,14 +160,38 @@ def test_sharded_compress(ctx, oracle):
         assert merged == ctx.compress(text)  # sharding does not change a single byte of the file
 
 
-def test_window_hand_over(ctx, oracle, monkeypatch):
-    """Several device windows per call (FQZ_WINDOW_BYTES test hook): every window but the first starts
+def test_window_hand_over(ctx, oracle):
+    """Several device windows per call (fqz_set_option window sizes): every window but the first starts
     at an arbitrary byte, is entered at the aligned address below it and skips the tail of the
     previous window's last line.  Same bytes as one big window."""
     text = oracle.synth(1, 77, 0, 320_000).tobytes()  # variable-length records: window cuts land on every alignment
     whole = ctx.compress(text)
-    monkeypatch.setenv("FQZ_WINDOW_BYTES", str(45 << 20))
-    cut = ctx.compress(text)
-    monkeypatch.delenv("FQZ_WINDOW_BYTES")
+    try:
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 45 << 20)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 45 << 20)
+        cut = ctx.compress(text)
+    finally:
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 0)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
     assert cut == whole
+    assert ctx.decompress(cut) == text
+
+
+@pytest.mark.parametrize("frontend", [0, 1])
+def test_window_hand_over_short_reads(ctx, oracle, frontend):
+    """A window cut behind a record of a few bytes: the 16-byte word the next window is entered at holds
+    several newlines, only the last of which ends the previous window."""
+    from tests.fastq_cases import short_read_handover
+
+    text = short_read_handover()
+    try:
+        ctx.set_option(ctx.OPT_FRONTEND, frontend)
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 2 << 20)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 2 << 20)
+        cut = ctx.compress(text)
+    finally:
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 0)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
+        ctx.set_option(ctx.OPT_FRONTEND, 0)
+    assert oracle.decompress(cut) == text
     assert ctx.decompress(cut) == text

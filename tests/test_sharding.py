@@ -43,8 +43,17 @@ def _worker(rank, world, port, tmp):
     dist.all_gather_object(allc, cand)
     plan = sharding.plan_compress(allc, n, world)
     lo, hi = plan[rank]
-    # 2. every rank codes its own whole blocks; rank 0 owns block 0 and therefore the Phred decision
+    # 2. every rank codes its own whole blocks; rank 0 owns block 0 and therefore the Phred decision,
+    #    which is broadcast (the other ranks must not detect on their own first block, compress.go:146-164)
+    flag = [None]
+    if rank == 0:
+        es = oracle.encode_streams(text[lo:hi].tobytes(), max_records=100000)
+        flag[0] = int(es["phred64"])
+    dist.broadcast_object_list(flag, src=0)
     part = oracle.compress(text[lo:hi].tobytes(), threads=2) if hi > lo else b"FQZ\x00\x02\xa0\x86\x01\x00\x00"
+    assert part[9] == (2 if flag[0] else 0)  # the shard was coded with the broadcast flag
+    if rank == 1:
+        part = part[10:]  # headerless, as fqz_compress_shard(emit_file_header=0) emits it
     parts = [None] * world
     dist.all_gather_object(parts, part)  # ordered host gather
     if rank == 0:
