@@ -60,9 +60,14 @@ __global__ void k_write_block_headers(u32 nblocks, const u32 *first, const u32 *
 struct ZBatch {
     std::vector<ZFrame> frames;
     std::vector<u32> idx_ent, idx_lz, idx_items, idx_index;
+    std::vector<ZRStream> rstreams;  // literals-only streams with record boundaries (duplicate-record search)
+    u32 rblocks = 0, rmax_records = 0, rmax_blocks = 0;
     size_t slot_bytes = 0, ws_bytes = 0;
     // items / item_base / item_count: see ZFrame (policy FQZ_ZPOLICY_ITEMS only)
-    void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0) {
+    // rec0 / nrec (policy ENTROPY with items): the block's records inside items[]
+    void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0, u32 rec0 = 0,
+                    u32 nrec = 0) {
+        const u32 rs_no = (policy == FQZ_ZPOLICY_ENTROPY && items && len) ? (u32)rstreams.size() + 1u : 0u;
         const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : (policy == FQZ_ZPOLICY_ITEMS ? FQZ_ZFRAME_ITEMS : FQZ_ZFRAME);
         const size_t nfr = (len + fsz - 1) / fsz;
         if (nfr >= FQZ_ZINDEX_MIN) {  // frame index in front of the stream (FQZ_ZPOLICY_INDEX)
@@ -76,12 +81,29 @@ struct ZBatch {
             f.item_base = 0;
             f.item_count = 0;
             f.index_of = 0;
-            f.pad = 0;
+            f.pad = rs_no;
             slot_bytes += (FQZ_ZINDEX_BYTES(nfr) + 15u) & ~(size_t)15;
             idx_index.push_back((u32)frames.size());
             frames.push_back(f);
         }
         const u32 index_of = (nfr >= FQZ_ZINDEX_MIN) ? (u32)frames.size() : 0u;  // 1 + number of the index frame just added
+        if (rs_no) {
+            ZRStream r;
+            r.src = (u64)(uintptr_t)d_src;
+            r.items = (u64)(uintptr_t)items;
+            r.len = (u32)len;
+            r.item_base = item_base;
+            r.rec0 = rec0;
+            r.nrec = nrec;
+            r.first_frame = (u32)frames.size();
+            r.blk0 = rblocks;
+            r.nblk = (u32)((len + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT);
+            r.pad = 0;
+            rblocks += r.nblk;
+            rmax_records = std::max(rmax_records, nrec);
+            rmax_blocks = std::max(rmax_blocks, r.nblk);
+            rstreams.push_back(r);
+        }
         for (size_t o = 0; o < len; o += fsz) {
             u32 l = (u32)std::min<size_t>(fsz, len - o);
             ZFrame f;
@@ -94,7 +116,7 @@ struct ZBatch {
             f.item_base = item_base + (u32)o;
             f.item_count = item_count;
             f.index_of = index_of;
-            f.pad = 0;
+            f.pad = rs_no;
             slot_bytes += FQZ_ZSLOT(l);
             if (policy == FQZ_ZPOLICY_AUTO || policy == FQZ_ZPOLICY_ITEMS) {
                 f.ws_off = ws_bytes;
@@ -113,11 +135,16 @@ struct ZEncoded {
     u32 nframes = 0;
 };
 
-static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
+// offs_base / offs_words: the scanned per-record offset arrays of the window (FrontOut::d_offs), when the
+// literals-only frames carry item boundaries: enables the record matcher on them
+static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, const u32 *offs_base = nullptr, size_t offs_words = 0) {
     cudaStream_t s = c->stream;
     u32 nf = (u32)zb.frames.size();
     ze.nframes = nf;
-    size_t up = (size_t)nf * sizeof(ZFrame) + (zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size() + zb.idx_index.size()) * sizeof(u32);
+    const u32 nrs = (offs_base && !c->opt_no_record_match) ? (u32)zb.rstreams.size() : 0u;
+    const size_t idx_words = zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size() + zb.idx_index.size();
+    const size_t rs_at = ((size_t)nf * sizeof(ZFrame) + idx_words * sizeof(u32) + 15u) & ~(size_t)15;
+    size_t up = rs_at + (size_t)nrs * sizeof(ZRStream);
     FQZ_TRY(fqz_pin_reserve(c, 8192 + up));
     u8 *hp = c->h_pin + 4096;
     memcpy(hp, zb.frames.data(), (size_t)nf * sizeof(ZFrame));
@@ -127,6 +154,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
     if (!zb.idx_items.empty()) memcpy(hidx + zb.idx_ent.size() + zb.idx_lz.size(), zb.idx_items.data(), zb.idx_items.size() * sizeof(u32));
     const size_t index_at = zb.idx_ent.size() + zb.idx_lz.size() + zb.idx_items.size();
     if (!zb.idx_index.empty()) memcpy(hidx + index_at, zb.idx_index.data(), zb.idx_index.size() * sizeof(u32));
+    if (nrs) memcpy(hp + rs_at, zb.rstreams.data(), (size_t)nrs * sizeof(ZRStream));
     u8 *d_up = (u8 *)c->arena.alloc(up + 16);
     ze.d_slots = (u8 *)c->arena.alloc(zb.slot_bytes + 16);
     u8 *d_ws = (u8 *)c->arena.alloc(zb.ws_bytes + 16);
@@ -155,13 +183,44 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes) {
         fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size() + zb.idx_lz.size(), (u32)zb.idx_items.size(), d_hash, ze.d_slots, d_ws, ze.d_scan,
                         2, d_parsed, s);
     }
+    u32 *d_lzflags = nullptr;
+    const u32 nent = (u32)zb.idx_ent.size();
+    const ZRStream *d_rs = (const ZRStream *)(d_up + rs_at);
+    u32 *d_rhash = nullptr, *d_bsizes = nullptr;
+    u8 *pool_out = nullptr;
+    if (nrs) {
+        // duplicated records: pair them up, flag the streams that hold enough of them and code those with
+        // sequences as one frame each; the blocks go through a workspace pool in batches (a launch over
+        // unflagged streams returns at once)
+        StageScope sc(c, ST_ZENC_DUP, ent_bytes);
+        const u32 BB = std::min<u32>(zb.rblocks, 8192u);
+        u32 *d_keys = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
+        u32 *d_cand = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
+        d_lzflags = (u32 *)c->arena.alloc((size_t)(nrs + 1) * sizeof(u32));
+        d_rhash = (u32 *)c->arena.alloc((size_t)(nrs + 1) * sizeof(u32));
+        d_bsizes = (u32 *)c->arena.alloc((size_t)(zb.rblocks + 1) * sizeof(u32));
+        u8 *pool_ws = (u8 *)c->arena.alloc(fqz_lzrec_pool_ws(BB) + 64);
+        pool_out = (u8 *)c->arena.alloc(fqz_lzrec_pool_out(zb.rblocks) + 64);
+        u32 *d_rparsed = (u32 *)c->arena.alloc((size_t)BB * 2 * sizeof(u32));
+        if (!d_keys || !d_cand || !d_lzflags || !d_rhash || !d_bsizes || !pool_ws || !pool_out || !d_rparsed) {
+            c->err = "arena: out of device memory (record matcher)";
+            return FQZ_E_CUDA;
+        }
+        fqz_launch_rec_match(d_rs, nrs, zb.rmax_records, offs_base, d_keys, d_cand, d_lzflags, d_rhash, s);
+        for (u32 g0 = 0; g0 < zb.rblocks; g0 += BB)
+            fqz_launch_lzrec(d_rs, nrs, d_lzflags, offs_base, d_cand, pool_ws, pool_out, g0, std::min<u32>(zb.rblocks, g0 + BB), d_rparsed, d_bsizes, s);
+    }
     {
         StageScope sc(c, ST_ZENC_ENTROPY, ent_bytes);
-        fqz_launch_zenc_huf(ze.d_frames, d_idx, (u32)zb.idx_ent.size(), d_hash, ze.d_slots, ze.d_scan, s);
+        fqz_launch_zenc_huf(ze.d_frames, d_idx, nent, d_hash, ze.d_slots, ze.d_scan, d_lzflags, s);
+    }
+    if (nrs) {
+        StageScope sc(c, ST_ZENC_DUP, 0);
+        fqz_launch_lzrec_close(d_rs, nrs, zb.rmax_blocks, d_lzflags, d_rhash, pool_out, d_bsizes, ze.d_frames, ze.d_slots, ze.d_scan, s);
     }
     {
         StageScope sc(c, ST_SCAN, 0);
-        if (!zb.idx_index.empty()) fqz_launch_zindex(ze.d_frames, nf, ze.d_slots, ze.d_scan, s);
+        if (!zb.idx_index.empty()) fqz_launch_zindex(ze.d_frames, nf, ze.d_slots, ze.d_scan, d_lzflags, s);
         FQZ_TRY(fqz_scan_excl_u32(c, ze.d_scan, (u64)nf + 1, (u64)nf + 1, 1));
     }
     return FQZ_OK;
@@ -234,8 +293,9 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
                 // headers / plus lines / N positions: item starts = the scanned per-record offsets; lengths: 4-byte items
                 if (a < 5) zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride, (u32)o0, (u32)fo.R + 1);
                 else zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], nullptr, 0, 4);
-            } else
-                zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a]);
+            } else  // packed bases / qualities: literals-only, with the record boundaries for the duplicate search
+                zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride, (u32)o0, (u32)fo.R + 1,
+                              b * FQZ_BLOCK_RECORDS, nrec[b]);
             stream_bytes += o1 - o0;
         }
     }
@@ -247,7 +307,7 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
         if (hdr0 > out_cap) return FQZ_E_NOSPACE;
     }
     ZEncoded ze;
-    if (nf) FQZ_TRY(zbatch_encode(c, zb, ze, stream_bytes));
+    if (nf) FQZ_TRY(zbatch_encode(c, zb, ze, stream_bytes, fo.d_offs, (size_t)2 * fo.offs_stride));
     // fixed offsets (headers in front of each frame) + small tables, one upload
     std::vector<u32> fixed(nf);
     for (u32 b = 0; b < nb; b++)

@@ -49,7 +49,7 @@ size_t Arena::capacity() const {
 
 // ---------------------------------------------------------------------------------- profiler
 static const char *k_stage_names[ST_COUNT_] = {
-    "newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "xxh64",
+    "newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "zstd_enc_dup", "xxh64",
     "assemble", "zstd_dec_scan", "zstd_dec_literals", "zstd_dec_sequences", "zstd_dec_execute", "prefix_walk", "record_offsets",
     "emit_fastq", "copy"};
 
@@ -344,9 +344,9 @@ extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
         if (value && value < ((u64)1 << 20)) return FQZ_E_INVALID_ARG;
         c->opt_host_window_bytes = value > ((u64)3 << 30) ? ((u64)3 << 30) : value;
         return FQZ_OK;
-    case FQZ_OPT_FRONTEND:
-        if (value > 2) return FQZ_E_INVALID_ARG;
-        c->opt_frontend = (int)value;
+    case FQZ_OPT_RECORD_MATCH:
+        if (value > 1) return FQZ_E_INVALID_ARG;
+        c->opt_no_record_match = value ? 0 : 1;
         return FQZ_OK;
     default: return FQZ_E_INVALID_ARG;
     }

@@ -42,6 +42,7 @@ enum FqzStage {
     ST_SCATTER,
     ST_ZENC_ENTROPY,
     ST_ZENC_LZ,
+    ST_ZENC_DUP,
     ST_XXH64,
     ST_ASSEMBLE,
     ST_ZDEC_SCAN,
@@ -106,8 +107,7 @@ struct fqz_ctx {
     // fqz_set_option
     u64 opt_window_bytes = 0;       // device window of the compress calls (0 = default)
     u64 opt_host_window_bytes = 0;  // window of the host-buffer compress calls (0 = default)
-    int opt_frontend = 0;           // 0 auto (fused single pass, legacy on bail), 1 legacy multi-pass, 2 fused only (bail = error)
-    u64 fused_windows = 0, legacy_windows = 0;
+    int opt_no_record_match = 0;    // 1: packed bases / qualities always literals-only (no duplicate-record search)
 };
 int fqz_frontend_init_device();
 int fqz_zstd_enc_init_device();

@@ -26,7 +26,7 @@ struct ZFrame {
     u32 item_base;  // offset of this frame's first byte in the coordinates of items[]
     u32 item_count; // entries of items[] including the end sentinel; fixed stride: the stride in bytes
     u32 index_of;   // 1 + number of the FQZ_ZPOLICY_INDEX frame that lists this frame (0 = none)
-    u32 pad;
+    u32 pad;        // 1 + number of the frame's ZRStream (0 = none)
 };
 #define FQZ_ZPOLICY_ITEMS 2  // internal: LZ by item matcher (needs the item boundaries of the stream)
 // internal: not a zstd frame but a SKIPPABLE frame (RFC 8878 §3.1.2) in front of a stream that was cut
@@ -49,9 +49,36 @@ struct ZFrame {
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
 // fills the index frames (FQZ_ZPOLICY_INDEX) from the sizes of the frames behind them
-void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, cudaStream_t s);
+void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, const u32 *lzflags, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
-void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s);
+// lzflags: optional per-stream flags of fqz_launch_rec_match (frames of flagged streams are left to fqz_launch_lzrec)
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
+                         cudaStream_t s);
+// One literals-only stream of one fqz block that carries its record boundaries (packed bases, qualities):
+// the unit of the duplicate-record search (fqz_zstd_enc.cu, "duplicated records").  Its frames carry
+// pad = 1 + the stream's number in this table.
+struct ZRStream {
+    u64 src;           // device address of the stream's bytes
+    u64 items;         // device address of the scanned record offsets of the whole window (u32)
+    u32 len;           // bytes
+    u32 item_base;     // items[rec0] : stream coordinates of the first byte
+    u32 rec0, nrec;    // the block's records inside items[]
+    u32 first_frame;   // number of the stream's first zstd frame in the frame table (its slots are contiguous)
+    u32 blk0, nblk;    // 16 KiB blocks of the stream, numbered through all streams of the batch
+    u32 pad;
+};
+// pairs duplicated records (cand, laid out like the scanned offset arrays `offs_base`; keys = scratch of the same
+// shape), flags the streams that hold enough of them and hashes their content
+void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
+                          u32 *hashes, cudaStream_t s);
+// codes blocks [g0, gend) of the flagged streams (parse, literals, sequences) into their staging (pool_out: all
+// blocks of the batch, pool_ws / parsed: gend - g0 blocks); _close strings the blocks of every flagged stream together
+size_t fqz_lzrec_pool_ws(u32 nblocks);
+size_t fqz_lzrec_pool_out(u32 nblocks);
+void fqz_launch_lzrec(const ZRStream *rs, u32 ns, const u32 *flags, const u32 *offs_base, const u32 *cand_base, u8 *pool_ws, u8 *pool_out, u32 g0,
+                      u32 gend, u32 *parsed, u32 *bsizes, cudaStream_t s);
+void fqz_launch_lzrec_close(const ZRStream *rs, u32 ns, u32 max_blocks, const u32 *flags, const u32 *hashes, const u8 *pool_out, const u32 *bsizes,
+                            const ZFrame *frames, u8 *slots, u32 *out_sizes, cudaStream_t s);
 // parsed: 2 u32 per work item, scratch between the item matcher and the entropy kernel (lz == 2 only)
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
                      u32 *parsed, cudaStream_t s);

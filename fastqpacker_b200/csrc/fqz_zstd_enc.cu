@@ -1079,6 +1079,9 @@ __device__ static u32 warp_lz_parse(const u8 *src, u32 len, u16 *htab, u8 *lit, 
 //   d2 = length of this item          (aligned at their ends: what follows a variable-width field)
 // A match may run up to ZI_AHEAD bytes past its item, so that equal neighbours fuse into one long
 // match in the serial clean-up pass.  All 32 lanes work on 32 consecutive items at a time.
+#define ZR_MAXDIST ((8u << 20) - 1u)  // record matcher: matches stay inside the 8 MiB window every zstd decoder must support
+#define ZR_MINMATCH 8u
+#define ZR_MINRUN 12u
 #define ZI_AHEAD 32u
 #define ZI_MINMATCH 3u
 
@@ -1102,8 +1105,15 @@ __device__ __forceinline__ u32 zi_match_len(const u8 *S, u32 p, u32 d, u32 lim) 
 // Parse of src[0..len) with item boundaries.  items != nullptr: items[i] - item_base is the frame
 // position of item i (monotonic, nitems entries, the last one an end sentinel); items == nullptr:
 // fixed stride `nitems` bytes.  Emits sequences into sll/sml/sof (raw offsets) and literals into lit.
+// back: bytes of the same zstd frame in front of src (earlier blocks of a multi-block frame) that
+// matches may reach into; cand: optional, per item 1 + the number of an earlier item with the same
+// leading bytes (k_rec_match), whose offset is tried before the predecessor's;
+// rep_known: false for a block that does not open its frame — the decoder's repeat-offset history is
+// then whatever the block before left, which this warp does not know: it starts from three values no
+// offset can equal, so repeat codes are only used for offsets this block has itself emitted.
 __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, u32 item_base, u32 nitems, u32 *mbuf, u8 *lit, u16 *sll,
-                                      u16 *sml, u32 *sof, u16 *slo, u32 *nlit_out) {
+                                      u16 *sml, u32 *sof, u16 *slo, u32 *nlit_out, u32 back = 0, const u32 *cand = nullptr,
+                                      bool rep_known = true) {
     u32 lane = lane_id();
     // first item that overlaps the frame
     long long i0 = 0, iend = 0;  // items [i0, iend) overlap [0, len)
@@ -1134,6 +1144,12 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
                 e = (long long)items[i + 1] - item_base;
                 d2 = (u32)(e - s);
                 d1 = (i > 0) ? (u32)(items[i] - items[i - 1]) : 0u;
+                if (cand) {
+                    u32 ci = cand[i];  // 1 + number of the partner item
+                    u32 dh = ci ? items[i] - items[ci - 1u] : 0u;
+                    if (dh) d1 = dh;
+                    d2 = 1;  // runs of one byte (equal qualities are zeros after the delta, poly-A / poly-G tails)
+                }
             } else {
                 s = i * nitems;
                 e = s + nitems;
@@ -1147,11 +1163,17 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
         if (live) {
             u32 p = (u32)max(s, 0ll), stop = (u32)min(e, (long long)len);
             u32 lim = (u32)min((long long)len, e + (long long)ZI_AHEAD);
-            if (d1 > 65535u) d1 = 0;
-            if (d2 > 65535u || d2 == d1) d2 = 0;
+            const u32 dmax = cand ? ZR_MAXDIST : 65535u;  // inside the frame's window
+            if (d1 > dmax) d1 = 0;
+            if (d2 > dmax || d2 == d1) d2 = 0;
+            // record streams: unlike the item streams their literals are cheap (2 bits per base, a bit per zero),
+            // so only matches that clearly beat them are taken
+            const u32 min1 = cand ? ZR_MINMATCH : ZI_MINMATCH, min2 = cand ? ZR_MINRUN : ZI_MINMATCH;
             while (p < stop && cnt < ZI_MAXM) {
-                u32 la = (d1 && p >= d1) ? zi_match_len(src, p, d1, lim) : 0u;
-                u32 lb = (d2 && p >= d2) ? zi_match_len(src, p, d2, lim) : 0u;
+                u32 la = (d1 && p + back >= d1) ? zi_match_len(src, p, d1, lim) : 0u;
+                u32 lb = (d2 && p + back >= d2) ? zi_match_len(src, p, d2, lim) : 0u;
+                if (la < min1) la = 0;
+                if (lb < min2) lb = 0;
                 u32 best = max(la, lb);
                 if (best >= ZI_MINMATCH) {
                     mbuf[(lane * ZI_MAXM + cnt) * 2] = p | (best << 16);
@@ -1340,7 +1362,7 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
             // ---- repeat offsets: serial by nature (lane 0), staged through shared memory
             {
                 u32 *inb = mbuf, *outb = mbuf + 64;
-                u32 rep0 = 1, rep1 = 4, rep2 = 8;
+                u32 rep0 = rep_known ? 1u : 0xFFFFFFF1u, rep1 = rep_known ? 4u : 0xFFFFFFE1u, rep2 = rep_known ? 8u : 0xFFFFFFD1u;
                 for (u32 base = 0; base < nseq; base += 32) {
                     u32 cn = min(32u, nseq - base);
                     __syncwarp();
@@ -1376,7 +1398,7 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
         u32 pend = 0;                // end of the last flushed match
         u32 kpos = 0, klen = 0, koff = 0;
         bool have = false;
-        u32 rep0 = 1, rep1 = 4, rep2 = 8;
+        u32 rep0 = rep_known ? 1u : 0xFFFFFFF1u, rep1 = rep_known ? 4u : 0xFFFFFFE1u, rep2 = rep_known ? 8u : 0xFFFFFFD1u;
         for (u32 base = 0; base <= nm; base += 32) {  // one extra iteration flushes the pending match
             u32 cn = min(32u, nm - min(nm, base));
             __syncwarp();
@@ -1903,10 +1925,16 @@ __device__ static void warp_stream_encode(const u8 *src, u32 a, u32 b, const u16
 }
 
 __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots,
-                                                         u32 *out_sizes) {
+                                                         u32 *out_sizes, const u32 *lzflags) {
     __shared__ ZhShared S;
     u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     u32 fi = index ? index[blockIdx.x] : blockIdx.x;
+    if (lzflags && frames[fi].pad && lzflags[frames[fi].pad - 1u]) {
+        // a stream with duplicated records is coded as ONE frame by the record matcher (k_lzrec_*), which writes
+        // the size of the whole stream into its first frame's entry afterwards
+        if (tid == 0) out_sizes[fi] = 0;
+        return;
+    }
     ZFrame fr = frames[fi];
     const u8 *src = (const u8 *)(uintptr_t)fr.src;
     u8 *out = slots + fr.dst_off;
@@ -2056,6 +2084,301 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
     }
 }
 
+// ---------------------------------------------------------------------------------- duplicated records in the literals-only streams
+// Packed bases and qualities of i.i.d. reads hold no matches worth coding (k_zenc_huf), but real runs do:
+// PCR / optical duplicates, identical test records, all-'F' quality lines.  They are looked for at RECORD
+// granularity — one hash per record, not per byte:
+//   k_rec_keys   one thread per record: key = hash of its first 8..16 stream bytes
+//   k_rec_match  one warp per (block, stream): walks the keys in order, 32 records per step, and pairs every
+//                record with the nearest earlier record of the same key (two-probe table of the last ~8 K
+//                records in shared memory for the earlier steps, __match_any inside the step; the last lane
+//                that wants a slot gets it, so the result does not depend on scheduling).  A stream in which
+//                at least 1/16 of the records found a partner is flagged.
+//   k_lzrec_*    a flagged stream is NOT cut into independent frames (every frame would have to send the
+//                recurring reads again): it becomes ONE zstd frame of 16 KiB blocks, like the reference's own
+//                output, but all blocks are parsed and entropy-coded in parallel, one warp each — the item
+//                matcher at the partner's offset and at the predecessor's (matches reach back up to 8 MiB into
+//                the earlier blocks), then the literals / sequences writers of the item streams.  Only the
+//                repeat-offset history of the block in front is unknown to a warp: see warp_item_parse.
+// Unflagged streams keep the literals-only frames; the cost there is the key + pairing passes.
+#define ZR_HLOG 13
+__global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 *offs_base, u32 *keys_base) {
+    const ZRStream &R = rs[blockIdx.y];
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R.nrec) return;
+    const u32 *items = (const u32 *)(uintptr_t)R.items + R.rec0;
+    u32 s = items[r], n = items[r + 1] - s, key = 0;
+    if (n >= 8u) {
+        const u8 *P = (const u8 *)(uintptr_t)R.src + (s - R.item_base);
+        u32 w0 = ld_u32_unaligned(P), w1 = ld_u32_unaligned(P + 4), w2 = 0, w3 = 0;
+        if (n >= 12u) w2 = ld_u32_unaligned(P + 8);
+        if (n >= 16u) w3 = ld_u32_unaligned(P + 12);
+        u32 h = (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u);
+        h = (h << 13 | h >> 19) * 0xC2B2AE3Du;
+        h ^= (w2 * 0x27D4EB2Fu) ^ (w3 * 0x165667B1u);
+        h ^= h >> 15;
+        h *= 0x2C1B3C6Du;
+        h ^= h >> 12;
+        key = h | 1u;
+    }
+    keys_base[(items - offs_base) + r] = key;
+}
+// cand[r] = 1 + number (inside the stream's block) of the partner record, 0 = none
+__global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, const u32 *offs_base, const u32 *keys_base, u32 *cand_base, u32 *flags) {
+    __shared__ u32 tab[1 << ZR_HLOG];  // key bits 17.. | 1 + record number (17 bits: a block holds 100 000 records)
+    const u32 si = blockIdx.x, lane = lane_id();
+    if (si >= ns) return;
+    const ZRStream R = rs[si];
+    const size_t at = ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0;
+    const u32 *keys = keys_base + at;
+    u32 *cand = cand_base + at;
+    const u32 nrec = R.nrec;
+    // records of 20 bytes or more on average (the match list of a block holds one entry per two bytes)
+    if (nrec < 8u || (u64)nrec * 20u > R.len || nrec >= (1u << 17)) {
+        if (lane == 0) flags[si] = 0;
+        return;
+    }
+    for (u32 i = lane; i < (1u << ZR_HLOG); i += 32) tab[i] = 0;
+    __syncwarp();
+    u32 hits = 0;
+    u32 knext = lane < nrec ? keys[lane] : 0u;
+    for (u32 ib = 0; ib < nrec; ib += 32) {
+        const u32 i = ib + lane;
+        const bool live = i < nrec;
+        const u32 key = knext;
+        knext = (i + 32 < nrec) ? keys[i + 32] : 0u;
+        // two probes per key (a direct-mapped table loses ~4 % of the partners to slot collisions, and a lost
+        // partner costs a whole record of literals)
+        const u32 s1 = (key >> 1) & ((1u << ZR_HLOG) - 1u), s2 = ((key >> 14) ^ (key >> 25) ^ 0x555u) & ((1u << ZR_HLOG) - 1u);
+        const u32 khi = key & 0xFFFE0000u;
+        u32 c = 0, t1 = 0, t2 = 0;
+        if (key) {
+            t1 = tab[s1];
+            t2 = tab[s2];
+            if (t1 && (t1 & 0xFFFE0000u) == khi) c = t1 & 0x1FFFFu;
+            else if (t2 && (t2 & 0xFFFE0000u) == khi) c = t2 & 0x1FFFFu;
+        }
+        u32 m = __match_any_sync(FULL, key);
+        if (key) {
+            u32 lower = m & ((1u << lane) - 1u);
+            if (lower) c = ib + (31u - (u32)__clz((int)lower)) + 1u;
+        }
+        if (live) {
+            cand[i] = c;
+            hits += c ? 1u : 0u;
+        }
+        // insert: the key's own slot if it has one, else a free one, else the slot whose record is older; all lanes
+        // decide on the table as the step found it, the last lane that wants a slot gets it (same result on every run)
+        u32 slot = s1;
+        if (key) {
+            if (t1 && (t1 & 0xFFFE0000u) == khi) slot = s1;
+            else if (t2 && (t2 & 0xFFFE0000u) == khi) slot = s2;
+            else if (!t1) slot = s1;
+            else if (!t2) slot = s2;
+            else slot = ((t1 & 0x1FFFFu) <= (t2 & 0x1FFFFu)) ? s1 : s2;
+        }
+        u32 ms = __match_any_sync(FULL, key ? slot : (0x10000u + lane));
+        __syncwarp();
+        if (key && (ms >> lane) == 1u) tab[slot] = khi | (i + 1u);
+        __syncwarp();
+    }
+    hits = __reduce_add_sync(FULL, hits);
+#ifdef FQZ_EMU
+    if (lane == 0 && getenv("FQZ_DEBUG")) fprintf(stderr, "rec_match stream %u len %u records %u hits %u\n", si, R.len, nrec, hits);
+#endif
+    if (lane == 0) flags[si] = (hits * 16u >= nrec) ? 1u : 0u;
+}
+// content checksum of the flagged streams (one quad per stream; unflagged streams cost nothing)
+__global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_streams(const ZRStream *rs, u32 ns, const u32 *flags, u32 *hashes) {
+    FQZ_DYN_SMEM(u8, smem);
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 si = t >> 2, q = t & 3;
+    u32 gmask = group_mask(4);
+    bool live = si < ns;
+    u32 sj = live ? si : ns - 1;
+    u8 *rows;
+    u64 *bars;
+    xx_quad_smem(smem, &rows, &bars);
+    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)rs[sj].src, (live && flags[sj]) ? rs[sj].len : 0u, q, gmask, rows, bars);
+    if (live && q == 0) hashes[si] = (u32)h;
+}
+
+// per-block staging of the flagged streams
+#define ZR_OUT_STRIDE ((size_t)FQZ_ZBLOCK_ENT + 64u)
+struct ZRBlock {
+    const u8 *src;
+    u32 len, back, k, nblk, si;
+    u8 *lit, *out;
+    u16 *sll, *sml, *slo;
+    u32 *sof;
+};
+// block g (numbered through all streams of the batch) -> its stream and place; false: nothing to do
+__device__ __forceinline__ bool zr_block(const ZRStream *rs, u32 ns, const u32 *flags, u8 *pool_ws, u8 *pool_out, u32 g0, u32 g, u32 gend, ZRStream &R,
+                                         ZRBlock &B) {
+    if (g >= gend) return false;
+    u32 lo = 0, hi = ns - 1;  // largest s with rs[s].blk0 <= g
+    while (lo < hi) {
+        u32 mid = (lo + hi + 1) >> 1;
+        if (rs[mid].blk0 <= g) lo = mid; else hi = mid - 1;
+    }
+    if (!flags[lo]) return false;
+    R = rs[lo];
+    B.si = lo;
+    B.k = g - R.blk0;
+    B.nblk = R.nblk;
+    if (B.k >= B.nblk) return false;
+    B.back = B.k * FQZ_ZBLOCK_ENT;
+    B.len = min(FQZ_ZBLOCK_ENT, R.len - B.back);
+    B.src = (const u8 *)(uintptr_t)R.src + B.back;
+    B.lit = pool_ws + (size_t)(g - g0) * FQZ_ZWS(FQZ_ZBLOCK_ENT);
+    u32 maxseq = ((B.len / 2) + 2u) & ~1u;
+    B.sll = (u16 *)(B.lit + ((B.len + 15u) & ~15u));
+    B.sml = B.sll + maxseq;
+    B.sof = (u32 *)(B.sml + maxseq);
+    B.slo = (u16 *)(B.sof + maxseq);
+    B.out = pool_out + (size_t)g * ZR_OUT_STRIDE;
+    return true;
+}
+__device__ __forceinline__ u32 zr_lower_bound(const u32 *items, u32 n, u32 v) {  // first i in [0, n] with items[i] >= v (items[n] = sentinel)
+    u32 a = 0, b = n;
+    while (a < b) {
+        u32 mid = (a + b) >> 1;
+        if (items[mid] < v) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+__global__ void __launch_bounds__(ZENC_WARPS * 32) k_lzrec_parse(const ZRStream *rs, u32 ns, const u32 *flags, const u32 *offs_base, const u32 *cand_base,
+                                                                 u8 *pool_ws, u8 *pool_out, u32 g0, u32 gend, u32 *parsed) {
+    __shared__ u32 mbufs[ZENC_WARPS][32 * ZI_MAXM * 2];
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 g = g0 + blockIdx.x * ZENC_WARPS + warp;
+    ZRStream R;
+    ZRBlock B;
+    if (!zr_block(rs, ns, flags, pool_ws, pool_out, g0, g, gend, R, B)) return;
+    u32 *pr = parsed + 2 * (size_t)(g - g0);
+    // the stream's own records: items[0 .. nrec] in stream coordinates, cand[] alongside
+    const u32 *items = (const u32 *)(uintptr_t)R.items + R.rec0;
+    const u32 *cand = cand_base + (items - offs_base);
+    // one repeated byte: RLE block
+    {
+        u32 b0 = B.src[0];
+        bool same = true;
+        for (u32 i = lane; i < B.len && same; i += 32) same = (B.src[i] == b0);
+        if (__all_sync(FULL, same) && B.len > 1) {
+            if (lane == 0) {
+                pr[0] = 0;
+                pr[1] = ZENC_RLE_MARK;
+            }
+            return;
+        }
+    }
+    u32 nseq = 0, nlit = 0;
+    // the match list holds one entry per two bytes: only blocks whose records are >= 20 bytes on average are parsed
+    const u32 b0 = R.item_base + B.back;
+    const u32 ia = zr_lower_bound(items, R.nrec, b0), ib = zr_lower_bound(items, R.nrec, b0 + B.len);
+    if (B.len >= 64 && (ib - ia + 1u) * 20u <= B.len + 256u)
+        nseq = warp_item_parse(B.src, B.len, items, b0, R.nrec + 1u, mbufs[warp], B.lit, B.sll, B.sml, B.sof, B.slo, &nlit, B.back, cand, B.k == 0);
+    if (lane == 0) {
+        pr[0] = nseq;
+        pr[1] = nseq ? nlit : B.len;
+    }
+}
+// PHASE 1: literals section, PHASE 2: sequences section + block header (same split as the item frames)
+template <int PHASE>
+__global__ void __launch_bounds__(ZENC_WARPS * 32) k_lzrec_code(const ZRStream *rs, u32 ns, const u32 *flags, u8 *pool_ws, u8 *pool_out, u32 g0, u32 gend,
+                                                                u32 *parsed, u32 *bsizes) {
+    __shared__ WarpScratchItems scratch[ZENC_WARPS];
+    u32 warp = threadIdx.x >> 5, lane = lane_id();
+    u32 g = g0 + blockIdx.x * ZENC_WARPS + warp;
+    ZRStream R;
+    ZRBlock B;
+    if (!zr_block(rs, ns, flags, pool_ws, pool_out, g0, g, gend, R, B)) return;
+    u32 *pr = parsed + 2 * (size_t)(g - g0);
+    WarpScratchItems &S = scratch[warp];
+    u8 *body = B.out + 3;
+    const u32 body_cap = (u32)ZR_OUT_STRIDE - 3u - 8u;
+    const u32 nseq = pr[0];
+    const bool rle = pr[1] == ZENC_RLE_MARK;
+    if constexpr (PHASE == 1) {
+        if (rle) return;
+        u32 nlit = pr[1];
+        u32 lsz = warp_write_literals(nseq ? (const u8 *)B.lit : B.src, nlit, body, S);
+        __syncwarp();
+        if (lane == 0) pr[1] = lsz;
+        return;
+    } else {
+        u32 btype, bsize;
+        if (rle) {
+            if (lane == 0) body[0] = B.src[0];
+            btype = 1;
+            bsize = B.len;
+        } else {
+            u32 lsz = pr[1], ssz = 0;
+            bool ovf = false;
+            if (nseq == 0) {
+                if (lane == 0) body[lsz] = 0;
+                ssz = 1;
+            } else if (lsz + 16 < body_cap) ssz = warp_write_sequences(B.sll, B.sml, B.sof, nseq, body + lsz, body_cap - lsz, S, &ovf, true);
+            else ovf = true;
+            __syncwarp();
+            u32 total = lsz + ssz;
+            if (!ovf && total < B.len) {
+                btype = 2;
+                bsize = total;
+            } else {
+                for (u32 i = lane; i < B.len; i += 32) body[i] = B.src[i];
+                btype = 0;
+                bsize = B.len;
+            }
+        }
+        if (lane == 0) {
+            u32 h = ((B.k + 1u == B.nblk) ? 1u : 0u) | (btype << 1) | (bsize << 3);
+            B.out[0] = (u8)h; B.out[1] = (u8)(h >> 8); B.out[2] = (u8)(h >> 16);
+            bsizes[g] = 3u + ((btype == 1) ? 1u : bsize);
+        }
+    }
+}
+// strings the blocks of a flagged stream together in the output slots of its frames (one contiguous span):
+// frame header, blocks, checksum.  grid (streams, chunks of ZR_CLOSE_BLOCKS blocks)
+#define ZR_CLOSE_BLOCKS 32u
+__global__ void __launch_bounds__(256) k_lzrec_close(const ZRStream *rs, const u32 *flags, const u32 *hashes, const u8 *pool_out, const u32 *bsizes,
+                                                     const ZFrame *frames, u8 *slots, u32 *out_sizes) {
+    __shared__ u32 warp_sums[33];
+    const u32 si = blockIdx.x;
+    if (!flags[si]) return;
+    const ZRStream R = rs[si];
+    const u32 k0 = blockIdx.y * ZR_CLOSE_BLOCKS;
+    if (k0 >= R.nblk) return;
+    u8 *out = slots + frames[R.first_frame].dst_off;
+    // bytes of the blocks in front of this chunk
+    u32 part = 0;
+    for (u32 k = threadIdx.x; k < k0; k += blockDim.x) part += bsizes[R.blk0 + k];
+    u32 tot = 0;
+    block_excl_scan(part, warp_sums, &tot);
+    u32 pos = 10u + tot;  // frame header: magic, descriptor, window, 4-byte content size
+    const u32 kend = min(R.nblk, k0 + ZR_CLOSE_BLOCKS);
+    for (u32 k = k0; k < kend; k++) {
+        u32 sz = bsizes[R.blk0 + k];
+        const u8 *src = pool_out + (size_t)(R.blk0 + k) * ZR_OUT_STRIDE;
+        for (u32 i = threadIdx.x; i < sz; i += blockDim.x) out[pos + i] = src[i];
+        pos += sz;
+    }
+    if (threadIdx.x == 0 && k0 == 0) {
+        u32 wlog = 17;
+        while (wlog < 23 && (1u << wlog) < R.len) wlog++;
+        out[0] = 0x28; out[1] = 0xB5; out[2] = 0x2F; out[3] = 0xFD;
+        out[4] = 0x84;  // FCS 4 bytes, window descriptor present, content checksum, no dictionary
+        out[5] = (u8)((wlog - 10) << 3);
+        out[6] = (u8)R.len; out[7] = (u8)(R.len >> 8); out[8] = (u8)(R.len >> 16); out[9] = (u8)(R.len >> 24);
+    }
+    if (threadIdx.x == 0 && kend == R.nblk) {
+        u32 hsh = hashes[si];
+        u8 *ck = out + pos;
+        ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
+        out_sizes[R.first_frame] = pos + 4;
+    }
+}
+
 // ---------------------------------------------------------------------------------- XXH64 (frame content checksum)
 // see fqz_xxh64.cuh: 4 threads per frame, 8 frames per warp, frames streamed through shared memory by TMA
 __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *frames, u32 nframes, u32 *hashes) {
@@ -2075,10 +2398,14 @@ __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *fr
 
 // One thread per frame (see FQZ_ZPOLICY_INDEX): an index frame writes its header, every frame that is
 // listed in one writes its own entry.
-__global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes) {
+__global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, const u32 *lzflags) {
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const ZFrame &F = frames[f];
+    if (lzflags && F.pad && lzflags[F.pad - 1u]) {  // one frame for the whole stream: no index
+        if (F.policy == FQZ_ZPOLICY_INDEX) out_sizes[f] = 0;
+        return;
+    }
     if (F.policy == FQZ_ZPOLICY_INDEX) {
         u32 n = F.src_len;
         u32 *o = (u32 *)(slots + F.dst_off);  // slots are 16-byte aligned
@@ -2118,18 +2445,43 @@ __global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, u32 nframe
     o[5 + 2 * k] = out_sizes[f];
     o[6 + 2 * k] = first | (cnt << 16);
 }
-void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, const u32 *lzflags, cudaStream_t s) {
     if (!nframes) return;
-    FQZ_LAUNCH(k_zindex, (nframes + 127) / 128, 128, 0, s, frames, nframes, slots, out_sizes);
+    FQZ_LAUNCH(k_zindex, (nframes + 127) / 128, 128, 0, s, frames, nframes, slots, out_sizes, lzflags);
 }
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
     u32 threads = XX_WARPS * 32, grid = (nframes * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes);
 }
-void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
+                         cudaStream_t s) {
     if (!nidx) return;
-    FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes);
+    FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags);
+}
+void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
+                          u32 *hashes, cudaStream_t s) {
+    if (!ns) return;
+    FQZ_LAUNCH(k_rec_keys, dim3((max_records + 255) / 256, ns), 256, 0, s, rs, offs_base, keys_base);
+    FQZ_LAUNCH(k_rec_match, ns, 32, 0, s, rs, ns, offs_base, keys_base, cand_base, flags);
+    u32 threads = XX_WARPS * 32, grid = (ns * 4 + threads - 1) / threads;
+    FQZ_LAUNCH(k_xxh64_streams, grid, threads, XX_SMEM, s, rs, ns, flags, hashes);
+}
+size_t fqz_lzrec_pool_ws(u32 nblocks) { return (size_t)nblocks * FQZ_ZWS(FQZ_ZBLOCK_ENT); }
+size_t fqz_lzrec_pool_out(u32 nblocks) { return (size_t)nblocks * ZR_OUT_STRIDE; }
+void fqz_launch_lzrec(const ZRStream *rs, u32 ns, const u32 *flags, const u32 *offs_base, const u32 *cand_base, u8 *pool_ws, u8 *pool_out, u32 g0,
+                      u32 gend, u32 *parsed, u32 *bsizes, cudaStream_t s) {
+    if (!ns || gend <= g0) return;
+    u32 grid = (gend - g0 + ZENC_WARPS - 1) / ZENC_WARPS;
+    FQZ_LAUNCH(k_lzrec_parse, grid, ZENC_WARPS * 32, 0, s, rs, ns, flags, offs_base, cand_base, pool_ws, pool_out, g0, gend, parsed);
+    FQZ_LAUNCH(k_lzrec_code<1>, grid, ZENC_WARPS * 32, 0, s, rs, ns, flags, pool_ws, pool_out, g0, gend, parsed, bsizes);
+    FQZ_LAUNCH(k_lzrec_code<2>, grid, ZENC_WARPS * 32, 0, s, rs, ns, flags, pool_ws, pool_out, g0, gend, parsed, bsizes);
+}
+void fqz_launch_lzrec_close(const ZRStream *rs, u32 ns, u32 max_blocks, const u32 *flags, const u32 *hashes, const u8 *pool_out, const u32 *bsizes,
+                            const ZFrame *frames, u8 *slots, u32 *out_sizes, cudaStream_t s) {
+    if (!ns) return;
+    FQZ_LAUNCH(k_lzrec_close, dim3(ns, (max_blocks + ZR_CLOSE_BLOCKS - 1) / ZR_CLOSE_BLOCKS), 256, 0, s, rs, flags, hashes, pool_out, bsizes, frames,
+               slots, out_sizes);
 }
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
                      u32 *parsed, cudaStream_t s) {
@@ -2143,5 +2495,7 @@ void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32
     else FQZ_LAUNCH((k_zenc<0, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
 }
 int fqz_zstd_enc_init_device() {
-    return (int)cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_xxh64_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
+    return (int)e;
 }

