@@ -11,9 +11,20 @@ Decompress numbers (BASELINE config 3) ride along in "decompress".  Multi-GPU: o
 blocks are independent so every rank codes its own records — weak scaling, no
 data-path collective; timings are max over ranks.
 
+Extra keys of the N=1 line: "cfg4" (BASELINE config 4: 2 M Phred+64 / N-heavy / '+' payload / 50-300 bp
+records), "duplicates" (3 M reads of which 35 % are exact copies: GPU ratio next to the CPU path's),
+"decompress.reference_written" (config 3: the FULL 25 M-record file written by the CPU path, decoded on
+the GPUs — at N > 1 every rank decodes the block run sharding.plan_decompress gives it).
+
+--workload cfg5 (BASELINE config 5, N >= 2 under torchrun): ONE logical 64 GB input spread over the ranks
+as even slices that do not end on block boundaries; per-rank newline counts are exchanged, the slices are
+re-cut on block boundaries (sharding.py), every rank codes its blocks, and the parts are gathered on the
+host inside the timed region.
+
 --impl reference times the CPU restatement of the reference (oracle/, libzstd standing in for
 klauspost/compress; the Go reference cannot be built in this image — SURVEY.md F7) on the box's
-host cores, on a bounded sample of the same workload.
+host cores, on the SAME 25 M-record input (fewer timed passes than --steps asks for when a pass
+takes seconds; "steps_timed" says how many).
 """
 from __future__ import annotations
 
@@ -35,7 +46,26 @@ SEED = 0x5EED0001
 METRIC = "fastq_compress_throughput"
 UNIT = "GB/s"
 FULL_RECORDS = 25_000_000  # BASELINE config 2: ~9 GB of 150 bp Phred+33 reads
-CPU_SAMPLE_RECORDS = 3_000_000  # ~1.1 GB: a few seconds on all host cores
+CFG4_RECORDS = 2_000_000  # BASELINE config 4
+CFG4_SEED = 0x5EED0004
+DUP_RECORDS = 3_000_000
+CFG5_BYTES = 64_000_000_000  # BASELINE config 5
+WORKLOAD = "synthetic Illumina 150 bp Phred+33 reads shaped like ERR532393_1 (BASELINE config 2), compress at 1 B200 per rank"
+
+
+def _synth_host(kind, seed, first, count, threads):
+    """The CPU twin of the generator on `threads` threads (ctypes releases the GIL) -> one numpy array."""
+    import concurrent.futures as cf
+
+    import numpy as np
+
+    from oracle import fqz_oracle as oracle
+
+    step = 250_000
+    jobs = [(f, min(step, first + count - f)) for f in range(first, first + count, step)]
+    with cf.ThreadPoolExecutor(max(1, threads)) as ex:
+        parts = list(ex.map(lambda j: oracle.synth(kind, seed, j[0], j[1]), jobs))
+    return np.concatenate(parts) if len(parts) > 1 else parts[0]
 
 
 _REAL_STDOUT = None
@@ -140,21 +170,24 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: oracle (restated reference + libzstd level 1 + frame checksum) on all host cores."""
+    """CPU arm: oracle (restated reference + libzstd level 1 + frame checksum) on all host cores, on the same
+    input as the GPU arm (config 2, 25 M records)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the other ranks exit 0 without work
     from oracle import fqz_oracle as oracle
 
     cores = os.cpu_count() or 1
-    nrec = min(args.records or FULL_RECORDS, args.cpu_records or CPU_SAMPLE_RECORDS)
-    text = oracle.synth(0, SEED, 0, nrec)
+    nrec = args.records or FULL_RECORDS
+    text = _synth_host(0, SEED, 0, nrec, cores)
     n = text.size
-    fqz = None
-    for _ in range(args.warmup if args.warmup < 2 else 1):  # one warm-up pass is plenty on the CPU
-        fqz = oracle.compress_np(text, threads=cores)
+    t0 = time.perf_counter()
+    fqz = oracle.compress_np(text, threads=cores)  # warm-up pass (also sizes the timed ones)
+    one = time.perf_counter() - t0
+    # a pass over 9.2 GB takes seconds on the host: bound the whole run to about a minute of timed work
+    steps = max(1, min(args.steps, int(60.0 / max(one, 1e-3))))
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
         fqz = oracle.compress_np(text, threads=cores)
         times.append(time.perf_counter() - t0)
@@ -164,7 +197,7 @@ def run_reference(args):
     ddt = time.perf_counter() - t0
     assert back.size == n
     val = n / dt / 1e9
-    sample = f"{nrec} records ({n / 1e9:.2f} GB) of the config-2 generator per step, oracle compress with {cores} threads"
+    sample = f"all {nrec} records ({n / 1e9:.2f} GB) of the config-2 generator per step, oracle compress with {cores} threads, {steps} timed passes"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -172,6 +205,7 @@ def run_reference(args):
         "unit": UNIT,
         "n_gpus": args.gpus,
         "steps": args.steps,
+        "steps_timed": steps,
         "warmup": args.warmup,
         "ms_per_step": dt * 1e3,
         "higher_is_better": True,
@@ -179,7 +213,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "synthetic Illumina 150 bp Phred+33 reads shaped like ERR532393_1 (BASELINE config 2), compress", "sample": sample},
+        "config": {"workload": WORKLOAD, "records_per_gpu": nrec, "fastq_bytes_per_gpu": int(n), "fqz_bytes_per_gpu": int(fqz.size),
+                   "ratio": n / fqz.size, "blocks_per_gpu": (nrec + 99999) // 100000},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "decompress_value": n / ddt / 1e9, "ratio": n / fqz.size,
                          "note": "restated CPU baseline (oracle + libzstd-1), not fqpack: no Go toolchain in this image"},
@@ -306,6 +341,17 @@ def run_ours(args):
         e2e_d = {"value": world * n * e_steps / t_ed / 1e9, "unit": UNIT, "h2d_bytes_per_step": res["em"], "d2h_bytes_per_step": n,
                  "steps": e_steps, "api": "fqz_decompress (host buffers, pinned)"}
         del a_back, h_back, a_out, h_out
+    # ---- BASELINE config 3, second half: the REFERENCE-WRITTEN file of the whole workload (rank 0's 25 M records,
+    #      one libzstd level-1 frame per stream as the reference writes them), decoded by all ranks together
+    refw, cb = None, None
+    if not args.no_cpu:
+        refw, cb = reference_written(args, ctx, torch, dist, rank, world, nrec, d_in, n, d_back, timed)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras["cfg4"] = side_workload(ctx, torch, 1, CFG4_SEED, min(CFG4_RECORDS, nrec), 760, timed, None,
+                                       "synthetic Phred+64, N-heavy (5 % N), '+' payloads, 50-300 bp (BASELINE config 4)")
+        extras["duplicates"] = side_workload(ctx, torch, 2, SEED, min(DUP_RECORDS, nrec), 372, timed, os.cpu_count() or 1,
+                                             "config-2 reads of which 35 % are exact copies of one of the 400 reads in front (generator kind 2)")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -383,7 +429,7 @@ def run_ours(args):
         "dtype": "u8",
         "data": "synthetic",
         "config": {
-            "workload": "synthetic Illumina 150 bp Phred+33 reads shaped like ERR532393_1 (BASELINE config 2), compress at 1 B200 per rank",
+            "workload": WORKLOAD,
             "records_per_gpu": nrec,
             "fastq_bytes_per_gpu": n,
             "fqz_bytes_per_gpu": m,
@@ -402,49 +448,378 @@ def run_ours(args):
                        "input": "GPU-written .fqz"},
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu:
-        cb, text, ref_fqz = cpu_baseline(args)
+    if cb is not None and world == 1:
         line["cpu_baseline"] = cb
-        # BASELINE config 3, second half: the REFERENCE-SHAPED file of the same sample (oracle container: one
-        # libzstd level-1 frame per stream, 128 KiB blocks) decoded on the device.  Such frames are one serial
-        # chain each: correctness path, reported for completeness.
-        d_ref = torch.from_numpy(ref_fqz).cuda()
-        d_txt = torch.empty(text.size + (1 << 16), dtype=torch.uint8, device="cuda")
-        ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_txt.data_ptr(), d_txt.numel())
-        t_r = timed(lambda: ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_txt.data_ptr(), d_txt.numel()), 1, 0)
-        same = bool(torch.equal(d_txt[: text.size], torch.from_numpy(text).cuda()))
-        line["decompress"]["reference_written"] = {"value": text.size / t_r / 1e9, "unit": UNIT, "bit_exact": same, "sample": cb["sample"],
-                                                   "input": "oracle-written .fqz (reference-shaped: one libzstd-1 frame per stream)"}
+    if refw is not None:
+        line["decompress"]["reference_written"] = refw
+    line.update(extras)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args):
+def run_cfg5(args):
+    """BASELINE config 5: ONE logical input (default 64 GB) block-sharded over the ranks.
+
+    Rank r holds the even slice of the file's records [R*r/N, R*(r+1)/N) — slices end on record but not on
+    block boundaries — in pinned HOST memory.  A timed end-to-end step is the whole flow a multi-GPU host runs:
+      H2D of the slice -> newline count on the GPU -> counts exchanged (the one tiny exchange) -> every rank finds
+      the first block cut inside its slice -> the bytes in front of it go to the rank before (they finish ITS last
+      block; NCCL send/recv, at most one block) -> fqz_compress_shard_device on the block-aligned range (rank 0
+      decides the Phred flag on block 0 first and the flag travels with the cuts) -> D2H -> ordered gather of the
+      parts into one host file (/dev/shm).
+    "value" is the device-resident part (count ... compress), "e2e" everything.  Decompress: the gathered file is
+    walked once, plan_decompress hands every rank a run of blocks, each rank decodes its run (H2D + D2H inside
+    the e2e figure) and compares with its slice."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fastqpacker_b200 as fq
+    from fastqpacker_b200 import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa_node(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = fq.context(local)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=local)
+    peak, peak_src = _peaks()
+    total_bytes = args.total_bytes or CFG5_BYTES
+    R = int(total_bytes / 368.03)  # records of the logical file (config-2 records average 368.03 bytes)
+    r0, r1 = R * rank // world, R * (rank + 1) // world
+    nrec = r1 - r0
+    LPB = sharding.LINES_PER_BLOCK
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_ints(vals):
+        t = torch.tensor(vals, dtype=torch.int64, device="cuda")
+        if world == 1:
+            return [list(vals)]
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [[int(x) for x in o.tolist()] for o in out]
+
+    # ---- the rank's slice: generated on the device, parked in pinned host memory (one block of slack for the borrowed tail)
+    slack = 48 << 20
+    cap = nrec * 372 + (1 << 20)
+    d_slice = torch.empty(cap + slack, dtype=torch.uint8, device="cuda")
+    n = 0
+    for first in range(0, nrec, 4_000_000):
+        c = min(4_000_000, nrec - first)
+        n += ctx.synth_device(0, SEED, r0 + first, c, d_slice.data_ptr() + n, cap - n)
+    h_slice = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_slice.copy_(d_slice[:n])
+    d_out = torch.empty(n // 2 + (64 << 20), dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(n // 3 + (64 << 20), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    out_path = _shared_path(f"fqz_bench_cfg5_{os.environ.get('MASTER_PORT', '0')}.fqz")
+    st = {}
+    # the ordered collector's output file (collectAndWriteResults, compress.go:365-403): one shared host buffer that every
+    # rank maps and page-locks, so that a part goes from HBM straight to its place in the file (no second host copy)
+    out_cap = (R * 372) // 3 + (64 << 20) * world
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.truncate(out_cap)
+    barrier()
+    mm = np.memmap(out_path, dtype=np.uint8, mode="r+")
+    h_file = torch.from_numpy(mm)
+    direct = False
+    try:
+        direct = int(torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, mm.size, 0)) == 0
+    except Exception:
+        direct = False
+
+    def plan_and_compress():
+        """device-resident part: count, exchange, borrow, compress.  Leaves the part in d_out[:st['m']]."""
+        lines = ctx.count_lines_device(d_slice.data_ptr(), n)
+        ph = -1
+        if rank == 0:  # block 0 decides the Phred flag of the file (compress.go:146-164): code it alone first, read the flag
+            e0 = ctx.find_line_end_device(d_slice.data_ptr(), n, min(LPB, lines)) + 1 if lines else 0
+            _, ph = ctx.compress_shard_device(d_slice.data_ptr(), e0, d_out.data_ptr(), d_out.numel(), -1, True)
+        allv = gather_ints([lines, ph])
+        counts = [v[0] for v in allv]
+        ph = allv[0][1]
+        before = sum(counts[:rank])
+        k = (LPB - before % LPB) % LPB  # this slice's k-th newline ends the block that is open at its start
+        if k == 0:
+            start = 0
+        elif k <= lines:
+            start = ctx.find_line_end_device(d_slice.data_ptr(), n, k) + 1
+        else:
+            start = n  # no cut inside the slice: all of it belongs to the rank before (tiny slices only)
+        starts = [v[0] for v in gather_ints([start])]
+        # the head of slice r+1 finishes the last block of rank r
+        give = starts[rank] if rank > 0 else 0
+        take = starts[rank + 1] if rank + 1 < world else 0
+        assert take <= slack, "borrowed tail larger than one block of slack"
+        if world > 1 and (give or take):
+            ops = []
+            if give:
+                ops.append(dist.P2POp(dist.isend, d_slice[:give], rank - 1))
+            if take:
+                ops.append(dist.P2POp(dist.irecv, d_slice[n : n + take], rank + 1))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            torch.cuda.synchronize()
+        st["start"], st["take"] = start, take
+        m, _ = ctx.compress_shard_device(d_slice.data_ptr() + start, n - start + take, d_out.data_ptr(), d_out.numel(), ph, rank == 0)
+        st["m"] = m
+
+    def e2e_compress():
+        with torch.cuda.stream(lib_stream):
+            d_slice[:n].copy_(h_slice, non_blocking=True)
+        plan_and_compress()
+        m = st["m"]
+        sizes = [v[0] for v in gather_ints([m])]  # where this part goes in the file
+        st["sizes"] = sizes
+        off = sum(sizes[:rank])
+        assert sum(sizes) <= out_cap
+        if direct:
+            with torch.cuda.stream(lib_stream):
+                h_file[off : off + m].copy_(d_out[:m], non_blocking=True)
+            lib_stream.synchronize()
+        else:  # page-locking the shared file failed: stage through this rank's pinned buffer
+            with torch.cuda.stream(lib_stream):
+                h_out[:m].copy_(d_out[:m], non_blocking=True)
+            lib_stream.synchronize()
+            mm[off : off + m] = h_out[:m].numpy()
+
+    def timed_wall(fn, steps, warmup):
+        """end-to-end steps hold host work and exchanges: wall clock between barriers, max over ranks"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 2))
+    ctx.stats_reset()
+    t_dev = timed_wall(plan_and_compress, steps, warm)
+    launches = ctx.stats()["launches"] // (steps + warm)
+    t_e2e = timed_wall(e2e_compress, steps, 1)
+    sizes = st["sizes"]
+    fqz_total = sum(sizes)
+    totals = gather_ints([n])
+    file_bytes = sum(v[0] for v in totals)
+
+    # ---- decompress: one walk of the gathered file, block runs per rank
+    barrier()
+    del h_slice, h_out
+    fqz = mm[:fqz_total]
+    _, _, blocks = sharding.walk_container(memoryview(fqz))
+    first, last = sharding.plan_decompress(blocks, world)[rank]
+    a = blocks[first].offset if last > first else 10
+    b = blocks[last - 1].offset + blocks[last - 1].size if last > first else 10
+    h_part = torch.empty(10 + b - a, dtype=torch.uint8, pin_memory=True)
+    h_part.numpy()[:10] = fqz[:10]
+    h_part.numpy()[10:] = fqz[a:b]
+    nblocks, nrecords = len(blocks), sum(x.records for x in blocks)
+    rec_lo = sum(x.records for x in blocks[:first])
+    rec_n = sum(x.records for x in blocks[first:last])
+    del fqz
+    d_part = torch.empty(h_part.numel() + 64, dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(rec_n * 372 + (1 << 20), dtype=torch.uint8, device="cuda")
+    h_back = torch.empty(d_back.numel(), dtype=torch.uint8, pin_memory=True)
+    dd = {}
+
+    def dev_decompress():
+        dd["k"] = ctx.decompress_device(d_part.data_ptr(), h_part.numel(), d_back.data_ptr(), d_back.numel())
+
+    def e2e_decompress():
+        with torch.cuda.stream(lib_stream):
+            d_part[: h_part.numel()].copy_(h_part, non_blocking=True)
+        dev_decompress()
+        with torch.cuda.stream(lib_stream):
+            h_back[: dd["k"]].copy_(d_back[: dd["k"]], non_blocking=True)
+        lib_stream.synchronize()
+
+    d_part[: h_part.numel()].copy_(h_part)
+    t_ddev = timed_wall(dev_decompress, steps, 1)
+    t_de2e = timed_wall(e2e_decompress, steps, 1)
+    # what the run must decode to: records [rec_lo, rec_lo + rec_n) of the logical file
+    del d_slice
+    d_want = torch.empty(rec_n * 372 + (1 << 20), dtype=torch.uint8, device="cuda")
+    want = 0
+    for f0 in range(rec_lo, rec_lo + rec_n, 4_000_000):
+        c = min(4_000_000, rec_lo + rec_n - f0)
+        want += ctx.synth_device(0, SEED, f0, c, d_want.data_ptr() + want, d_want.numel() - want)
+    same = dd["k"] == want and bool(torch.equal(d_back[:want], d_want[:want])) and bool(torch.equal(h_back[:want].cuda(), d_want[:want]))
+    ok = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    if direct:
+        try:
+            torch.cuda.cudart().cudaHostUnregister(mm.ctypes.data)
+        except Exception:
+            pass
+    if rank == 0:
+        try:
+            os.unlink(out_path)
+        except OSError:
+            pass
+        gbs = lambda t: file_bytes * steps / t / 1e9
+        line = {
+            "metric": METRIC, "value": gbs(t_dev), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "one synthetic config-2 FASTQ block-sharded over the GPUs (BASELINE config 5), compress + decompress",
+                       "fastq_bytes": file_bytes, "records": nrecords, "blocks": nblocks, "fqz_bytes": fqz_total, "ratio": file_bytes / fqz_total,
+                       "slices": "even record ranges per rank, re-cut on block boundaries from exchanged newline counts (sharding.py)",
+                       "l2": "inputs (GBs) far larger than the 126 MB L2; no flush needed", "round_trip_ok": bool(ok.item() == 1.0),
+                       "timing": "wall clock between barriers, max over ranks (the steps hold exchanges and host work)",
+                       "cpus_bound_to_gpu_numa_node": numa},
+            "e2e": {"value": gbs(t_e2e), "unit": UNIT, "h2d_bytes_per_step": file_bytes, "d2h_bytes_per_step": fqz_total, "steps": steps,
+                    "api": "H2D slice, fqz_count_lines_device, exchange, fqz_compress_shard_device, D2H into the part's place in one shared host file",
+                    "gather": "direct (file page-locked by every rank)" if direct else "staged through a pinned buffer"},
+            "gpu_launches": launches * steps,
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": (file_bytes + fqz_total) * steps / t_dev / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": (file_bytes + fqz_total) * steps / t_dev / 1e9 / world / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU: (F + Z) / device time of the whole sharded step; per-kernel rooflines are in the default workload's line"},
+            "decompress": {"value": gbs(t_ddev), "unit": UNIT, "ms_per_step": t_ddev / steps * 1e3,
+                           "e2e": {"value": gbs(t_de2e), "unit": UNIT, "h2d_bytes_per_step": fqz_total, "d2h_bytes_per_step": file_bytes, "steps": steps,
+                                   "api": "H2D block run, fqz_decompress_device, D2H (per rank; the ordered write of the FASTQ is the host's)"},
+                           "input": "the gathered GPU-written .fqz, block runs from sharding.plan_decompress"},
+            "clocks": clocks,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _shared_path(name):
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    return os.path.join(d, name)
+
+
+def reference_written(args, ctx, torch, dist, rank, world, nrec, d_in, n, d_back, timed):
+    """Rank 0 times the CPU path on the box's host cores over the WHOLE workload (= cpu_baseline) and leaves the
+    file it wrote where all ranks can read it; every rank then decodes the run of blocks plan_decompress gives it
+    and compares with the generator.  Returns (reference_written dict, cpu_baseline dict) on rank 0."""
+    import numpy as np
+
+    from fastqpacker_b200 import sharding
     from oracle import fqz_oracle as oracle
 
     cores = os.cpu_count() or 1
-    nrec = min(args.records or FULL_RECORDS, args.cpu_records or CPU_SAMPLE_RECORDS)
-    text = oracle.synth(0, SEED, 0, nrec)
-    n = text.size
-    oracle.compress_np(text[: n // 8], threads=cores)  # warm the library
-    t0 = time.perf_counter()
-    fqz = oracle.compress_np(text, threads=cores)
-    dt = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    back = oracle.decompress_mt(fqz, cores, n + 4096)
-    ddt = time.perf_counter() - t0
-    assert back.size == n
-    return {
-        "value": n / dt / 1e9,
-        "unit": UNIT,
-        "cores": cores,
-        "kind": "port",
-        "sample": f"first {nrec} records ({n / 1e9:.2f} GB) of the same generator, one pass, {cores} threads",
-        "decompress_value": n / ddt / 1e9,
-        "ratio": n / fqz.size,
-        "note": "restated CPU baseline (oracle + libzstd level 1 + frame checksum), not fqpack: no Go toolchain in this image (SURVEY F7)",
-    }, text, fqz
+    path = _shared_path(f"fqz_bench_ref_{os.environ.get('MASTER_PORT', '0')}_{nrec}.fqz")
+    cb = None
+    if rank == 0:
+        text = d_in[:n].cpu().numpy()  # rank 0 owns records [0, nrec): the device generator is the CPU twin
+        oracle.compress_np(text[: max(1, n // 64)], threads=cores)  # warm the library
+        t0 = time.perf_counter()
+        fqz = oracle.compress_np(text, threads=cores)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        back = oracle.decompress_mt(fqz, cores, n + 4096)
+        ddt = time.perf_counter() - t0
+        assert back.size == n
+        del back
+        fqz.tofile(path)
+        cb = {"value": n / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+              "sample": f"all {nrec} records ({n / 1e9:.2f} GB) of the workload, one pass, {cores} threads",
+              "decompress_value": n / ddt / 1e9, "ratio": n / fqz.size,
+              "note": "restated CPU baseline (oracle + libzstd level 1 + frame checksum), not fqpack: no Go toolchain in this image (SURVEY F7)"}
+        del text, fqz
+    if world > 1:
+        dist.barrier()
+    fqz = np.fromfile(path, dtype=np.uint8)
+    _, _, blocks = sharding.walk_container(memoryview(fqz))
+    first, last = sharding.plan_decompress(blocks, world)[rank]
+    rec_lo = sum(b.records for b in blocks[:first])
+    rec_n = sum(b.records for b in blocks[first:last])
+    a = blocks[first].offset if last > first else 10
+    b = blocks[last - 1].offset + blocks[last - 1].size if last > first else 10
+    shard = np.concatenate([fqz[:10], fqz[a:b]])
+    total_records = sum(x.records for x in blocks)
+    del fqz
+    d_ref = torch.from_numpy(shard).cuda()
+    # what the shard must decode to: records [rec_lo, rec_lo + rec_n) of rank 0's generator stream
+    cap = d_in.numel()
+    want = 0
+    for f0 in range(rec_lo, rec_lo + rec_n, 4_000_000):
+        c = min(4_000_000, rec_lo + rec_n - f0)
+        want += ctx.synth_device(0, SEED, f0, c, d_in.data_ptr() + want, cap - want)
+    res = {}
+
+    def dec():
+        res["k"] = ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_back.data_ptr(), d_back.numel())
+
+    t_r = timed(dec, 1, 1)
+    same = res["k"] == want and bool(torch.equal(d_back[:want], d_in[:want]))
+    flag = torch.tensor([1.0 if same else 0.0, float(want)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(flag[:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(flag[1:], op=dist.ReduceOp.SUM)
+        dist.barrier()
+    if rank == 0:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    total = float(flag[1].item())
+    refw = {"value": total / t_r / 1e9, "unit": UNIT, "bit_exact": bool(flag[0].item() == 1.0), "n_gpus": world,
+            "records": total_records, "fastq_bytes": int(total), "blocks": len(blocks), "scaling": "strong (one file, block runs per rank)",
+            "input": "oracle-written .fqz of the whole workload (reference-shaped: one libzstd-1 frame per stream and block)"}
+    return (refw, cb) if rank == 0 else (None, None)
+
+
+def side_workload(ctx, torch, kind, seed, nrec, per_record, timed, cpu_threads, what):
+    """Device-resident compress + decompress GB/s of a second workload (N = 1); with cpu_threads also the CPU path's ratio."""
+    cap = nrec * per_record + (1 << 20)
+    d = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = 0
+    for first in range(0, nrec, 4_000_000):
+        c = min(4_000_000, nrec - first)
+        n += ctx.synth_device(kind, seed, first, c, d.data_ptr() + n, cap - n)
+    d_out = torch.empty(n // 2 + (1 << 20), dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(n + (1 << 16), dtype=torch.uint8, device="cuda")
+    res = {}
+
+    def comp():
+        res["m"] = ctx.compress_device(d.data_ptr(), n, d_out.data_ptr(), d_out.numel())
+
+    def dec():
+        res["k"] = ctx.decompress_device(d_out.data_ptr(), res["m"], d_back.data_ptr(), d_back.numel())
+
+    t_c = timed(comp, 3, 2)
+    t_d = timed(dec, 3, 2)
+    ok = res["k"] == n and bool(torch.equal(d_back[:n], d[:n]))
+    out = {"workload": what, "records": nrec, "fastq_bytes": n, "fqz_bytes": res["m"], "ratio": n / res["m"],
+           "compress": {"value": 3 * n / t_c / 1e9, "unit": UNIT}, "decompress": {"value": 3 * n / t_d / 1e9, "unit": UNIT}, "round_trip_ok": ok}
+    if cpu_threads:
+        from oracle import fqz_oracle as oracle
+
+        text = d[:n].cpu().numpy()
+        t0 = time.perf_counter()
+        fqz = oracle.compress_np(text, threads=cpu_threads)
+        dt = time.perf_counter() - t0
+        out["cpu"] = {"ratio": n / fqz.size, "compress": {"value": n / dt / 1e9, "unit": UNIT}, "cores": cpu_threads, "kind": "port"}
+        out["ratio_vs_cpu"] = (n / res["m"]) / (n / fqz.size)
+        # the CPU-written file decodes on the GPU too
+        d_ref = torch.from_numpy(fqz).cuda()
+        k = ctx.decompress_device(d_ref.data_ptr(), d_ref.numel(), d_back.data_ptr(), d_back.numel())
+        out["cpu_written_decodes_bit_exact"] = k == n and bool(torch.equal(d_back[:n], d[:n]))
+    return out
 
 
 def main():
@@ -454,7 +829,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records", type=int, default=0, help="records per GPU (default: BASELINE config 2, 25 000 000)")
-    ap.add_argument("--cpu-records", type=int, default=0, help="records of the CPU baseline sample")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg5: one 64 GB input block-sharded over the ranks")
+    ap.add_argument("--total-bytes", type=int, default=0, help="cfg5: size of the logical input (default 64e9)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-4 and duplicates side workloads")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -467,6 +844,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 

@@ -79,6 +79,9 @@ class FqzLibrary:
         self._opt(L, "fqz_compress", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress_shard", [vp, vp, sz, u32, i32, i32, vp, sz, szp, C.POINTER(C.c_int)])
+        self._opt(L, "fqz_compress_shard_device", [vp, vp, sz, u32, i32, i32, vp, sz, szp, C.POINTER(C.c_int)])
+        self._opt(L, "fqz_count_lines_device", [vp, vp, sz, C.POINTER(C.c_uint64)])
+        self._opt(L, "fqz_find_line_end_device", [vp, vp, sz, C.c_uint64, C.POINTER(C.c_uint64)])
         self._opt(L, "fqz_compress_device", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress_device", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress_bound", [sz], restype=sz)
@@ -241,6 +244,26 @@ class FqzContext:
         m = C.c_size_t(0)
         self._check(self.lib.L.fqz_compress_device(self.h, C.c_void_p(d_in), n, block_size, C.c_void_p(d_out), out_cap, C.byref(m)))
         return m.value
+
+    def compress_shard_device(self, d_in: int, n: int, d_out: int, out_cap: int, phred64: int = -1, file_header: bool = True, block_size: int = 0):
+        """fqz_compress_shard on device memory -> (bytes written, phred64 flag in force)."""
+        m, used = C.c_size_t(0), C.c_int(0)
+        self._check(
+            self.lib.L.fqz_compress_shard_device(self.h, C.c_void_p(d_in), n, block_size, phred64, 1 if file_header else 0, C.c_void_p(d_out), out_cap,
+                                                 C.byref(m), C.byref(used))
+        )
+        return m.value, used.value
+
+    def count_lines_device(self, d_in: int, n: int) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.L.fqz_count_lines_device(self.h, C.c_void_p(d_in), n, C.byref(v)))
+        return v.value
+
+    def find_line_end_device(self, d_in: int, n: int, k: int) -> int:
+        """Offset of the k-th (1-based) newline of the device buffer."""
+        v = C.c_uint64(0)
+        self._check(self.lib.L.fqz_find_line_end_device(self.h, C.c_void_p(d_in), n, k, C.byref(v)))
+        return v.value
 
     def decompress_device(self, d_in: int, n: int, d_out: int, out_cap: int) -> int:
         m = C.c_size_t(0)

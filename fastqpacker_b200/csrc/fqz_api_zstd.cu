@@ -470,6 +470,21 @@ extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, ui
     return compress_device_impl(c, (const u8 *)d_fastq, n, true, st, header_block_size, (u8 *)d_out, out_cap, out_len, &used);
 }
 
+// the device-memory twin of fqz_compress_shard: d_fastq may have any alignment (a shard starts where the plan cuts)
+extern "C" int fqz_compress_shard_device(fqz_ctx *c, const void *d_fastq, size_t n, uint32_t header_block_size, int phred64, int emit_file_header,
+                                         void *d_out, size_t out_cap, size_t *out_len, int *phred64_used) {
+    if (!c || !out_len || (!d_fastq && n) || !d_out) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    CompState st;
+    st.forced_phred = phred64 < 0 ? -1 : (phred64 ? 1 : 0);
+    st.emit_header = emit_file_header != 0;
+    u64 used = 0;
+    int rc = compress_device_impl(c, (const u8 *)d_fastq, n, true, st, header_block_size, (u8 *)d_out, out_cap, out_len, &used);
+    if (phred64_used) *phred64_used = (int)st.phred64;
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------- streaming (Seam B)
 struct fqz_cstream {
     fqz_ctx *c;

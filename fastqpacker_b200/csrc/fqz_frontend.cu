@@ -56,6 +56,32 @@ __global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_count(const u8 *text
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
+// Offset of the newline number `target` (0-based) of the text: one CTA finds the tile in the scanned tile
+// counts and rescans that tile (planning calls of the multi-GPU split, fqz_find_line_end_device).
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos) {
+    __shared__ u32 ws[33];
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) {
+        u32 lo = 0, hi = ntiles - 1;  // largest t with tile_prefix[t] <= target
+        while (lo < hi) {
+            u32 mid = (lo + hi + 1) >> 1;
+            if (tile_prefix[mid] <= target) lo = mid; else hi = mid - 1;
+        }
+        s_tile = lo;
+    }
+    __syncthreads();
+    const u32 t = s_tile;
+    u64 pos = (u64)t * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
+    u64 m;
+    u32 c = nl_mask64(text, n, pos, 0, m);
+    u32 ex = block_excl_scan(c, ws, nullptr);
+    u32 want = target - tile_prefix[t];
+    if (want >= ex && want < ex + c) {
+        for (u32 k = ex; k < want; k++) m &= m - 1;
+        *out_pos = pos + (u64)(__ffsll((long long)m) - 1);
+    }
+}
+
 // tile_prefix = exclusive scan of tile_counts.  line_end[i] = byte offset of the i-th '\n'.
 __global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 *line_end, u32 max_lines) {
     __shared__ u32 ws[33];
@@ -405,6 +431,9 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
 // ---------------------------------------------------------------------------------- host launchers
 void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s) {
     if (ntiles) FQZ_LAUNCH(k_newline_count, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, tile_counts);
+}
+void fqz_launch_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos, cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_find_newline, 1, FQZ_NL_THREADS, 0, s, text, n, tile_prefix, ntiles, target, out_pos);
 }
 void fqz_launch_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s) {
     if (ntiles) FQZ_LAUNCH(k_newline_index, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, tile_prefix, line_end, max_lines);

@@ -19,6 +19,7 @@
 #define FQZ_SC_SMEM 40960
 
 void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s);
+void fqz_launch_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos, cudaStream_t s);
 void fqz_launch_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s);
 void fqz_launch_scan_partial(const u32 *data, u64 n, u64 stride, u32 narr, u32 *sums, u32 ntiles, cudaStream_t s);
 void fqz_launch_scan_apply(u32 *data, u64 n, u64 stride, u32 narr, const u32 *sums, u32 ntiles, cudaStream_t s);

@@ -6,6 +6,8 @@
 //   kind 0: "ERR532393_1-shaped" Illumina HiSeq reads: 150 bp, Phred+33 (Q2..Q41), bare '+',
 //           N in ~1 % of reads (10 % of their bases), first-order Markov qualities.
 //   kind 1: read length 50..300, Phred+64, ~5 % N in clustered runs, '+' line repeats the header.
+//   kind 2: kind 0 with duplicates: 35 % of the records copy the bases and qualities of one of the 400 records
+//           in front of them (PCR / optical duplicates of a clustered run); read names stay unique.
 #include "fqz_host.h"
 
 __host__ __device__ static inline u64 synth_mix(u64 z) {
@@ -62,6 +64,18 @@ __host__ __device__ static inline int put_str(u8 *p, const char *s) {
     return n;
 }
 
+// kind 2: the record whose bases and qualities record `rec` carries (a copy may copy a copy)
+__host__ __device__ static inline u64 synth_dup_source(u64 seed, u64 rec) {
+    u64 body = rec;
+    for (int hop = 0; hop < 64 && body > 0; hop++) {
+        u64 h = synth_mix(seed ^ 0xD0B1E5ull ^ synth_mix(body));
+        if ((h & 0xFFFFu) >= 22938u) break;  // 35 % copy
+        u64 d = 1 + (h >> 16) % 400;
+        body = body > d ? body - d : 0;
+    }
+    return body;
+}
+
 // Writes record `rec` at p (or only measures it when p == nullptr).  Returns its byte length.
 __host__ __device__ static u32 synth_record(int kind, u64 seed, u64 rec, u8 *p) {
     SynthRng g;
@@ -78,7 +92,7 @@ __host__ __device__ static u32 synth_record(int kind, u64 seed, u64 rec, u8 *p) 
     } while (0)
     u32 L;
     u32 hdr_start, hdr_len;
-    if (kind == 0) {
+    if (kind != 1) {
         const u64 T = 250000;
         u64 t = rec / T;
         u32 tile = (u32)((1 + (t / 48) % 2) * 1000 + (1 + (t / 16) % 3) * 100 + (1 + t % 16));
@@ -115,8 +129,16 @@ __host__ __device__ static u32 synth_record(int kind, u64 seed, u64 rec, u8 *p) 
         n += L + 1 + 1 + (kind == 1 ? hdr_len : 0) + 1 + L + 1;
         return n;
     }
+    if (kind == 2) {
+        u64 body = synth_dup_source(seed, rec);
+        if (body != rec) {  // same draws as the source record made for its own header
+            g.init(seed, body);
+            g.next64();
+            g.next16();
+        }
+    }
     // ---- sequence
-    if (kind == 0) {
+    if (kind != 1) {
         bool nread = g.next16() < 655;  // ~1 % of reads carry Ns
         for (u32 i = 0; i < L; i++) {
             u32 d = g.next16();
@@ -144,7 +166,7 @@ __host__ __device__ static u32 synth_record(int kind, u64 seed, u64 rec, u8 *p) 
     EMIT('\n');
     // ---- qualities: first-order Markov chain per read
     {
-        int qmax = (kind == 0) ? 41 : 40, qmin = (kind == 0) ? 2 : 0, base = (kind == 0) ? 33 : 64;
+        int qmax = (kind != 1) ? 41 : 40, qmin = (kind != 1) ? 2 : 0, base = (kind != 1) ? 33 : 64;
         int q = qmax - 7 + (int)(g.next16() % 8);
         bool tail = false;
         for (u32 i = 0; i < L; i++) {
@@ -182,7 +204,7 @@ __global__ void k_synth_write(int kind, u64 seed, u64 first, u64 count, const u3
 
 extern "C" int fqz_synth_device(fqz_ctx *c, int kind, uint64_t seed, uint64_t first, uint64_t count, void *d_out, size_t out_cap,
                                 size_t *out_len) {
-    if (!c || !out_len || (kind != 0 && kind != 1)) return FQZ_E_INVALID_ARG;
+    if (!c || !out_len || kind < 0 || kind > 2) return FQZ_E_INVALID_ARG;
     cudaSetDevice(c->device);
     c->arena.reset();
     *out_len = 0;

@@ -2088,7 +2088,7 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
 // Packed bases and qualities of i.i.d. reads hold no matches worth coding (k_zenc_huf), but real runs do:
 // PCR / optical duplicates, identical test records, all-'F' quality lines.  They are looked for at RECORD
 // granularity — one hash per record, not per byte:
-//   k_rec_keys   one thread per record: key = hash of its first 8..16 stream bytes
+//   k_rec_keys   one thread per record: key = hash of its length and of three 16-byte windows (head, middle, tail)
 //   k_rec_match  one warp per (block, stream): walks the keys in order, 32 records per step, and pairs every
 //                record with the nearest earlier record of the same key (two-probe table of the last ~8 K
 //                records in shared memory for the earlier steps, __match_any inside the step; the last lane
@@ -2109,16 +2109,26 @@ __global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 
     const u32 *items = (const u32 *)(uintptr_t)R.items + R.rec0;
     u32 s = items[r], n = items[r + 1] - s, key = 0;
     if (n >= 8u) {
+        // three 16-byte windows (head, middle, tail; they overlap in short records) and the length: reads that merely
+        // open alike — most quality lines of a run do — must not pair up, exact and near-exact copies must
         const u8 *P = (const u8 *)(uintptr_t)R.src + (s - R.item_base);
-        u32 w0 = ld_u32_unaligned(P), w1 = ld_u32_unaligned(P + 4), w2 = 0, w3 = 0;
-        if (n >= 12u) w2 = ld_u32_unaligned(P + 8);
-        if (n >= 16u) w3 = ld_u32_unaligned(P + 12);
-        u32 h = (w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA77u);
-        h = (h << 13 | h >> 19) * 0xC2B2AE3Du;
-        h ^= (w2 * 0x27D4EB2Fu) ^ (w3 * 0x165667B1u);
+        const u32 m = min(n, 16u) & ~3u;  // whole words of a window
+        const u32 o1 = (n - m) >> 1, o2 = n - m;
+        u32 h = n * 0x9E3779B1u;
+        for (u32 k = 0; k < m; k += 4) {
+            u32 w0 = ld_u32_unaligned(P + k), w1 = ld_u32_unaligned(P + o1 + k), w2 = ld_u32_unaligned(P + o2 + k);
+            h = (h ^ w0) * 0x85EBCA77u;
+            h = (h << 13 | h >> 19);
+            h = (h ^ w1) * 0xC2B2AE3Du;
+            h = (h << 11 | h >> 21);
+            h = (h ^ w2) * 0x27D4EB2Fu;
+            h = (h << 15 | h >> 17);
+        }
         h ^= h >> 15;
         h *= 0x2C1B3C6Du;
         h ^= h >> 12;
+        h *= 0x297A2D39u;
+        h ^= h >> 15;
         key = h | 1u;
     }
     keys_base[(items - offs_base) + r] = key;

@@ -106,6 +106,17 @@ int fqz_compress_device(fqz_ctx *ctx, const void *d_fastq, size_t n, uint32_t he
                         size_t *out_len);
 int fqz_decompress_device(fqz_ctx *ctx, const void *d_fqz, size_t n, void *d_out, size_t out_cap, size_t *out_len);
 
+/* One input split across GPUs with the text in DEVICE memory (bench.py --workload cfg5): the reference's
+ * producer cuts a block every 100 000 records while parsing (compress.go:240-300); here every rank counts
+ * the newlines of its byte slice, the counts are exchanged through the host, and fastqpacker_b200/sharding.py
+ * re-cuts the slices on block boundaries.  fqz_count_lines_device: '\n' bytes in d_text[0..n).
+ * fqz_find_line_end_device: offset of the k-th (1-based) '\n'.  fqz_compress_shard_device: fqz_compress_shard
+ * on device memory (any alignment of d_fastq). */
+int fqz_count_lines_device(fqz_ctx *ctx, const void *d_text, size_t n, uint64_t *lines);
+int fqz_find_line_end_device(fqz_ctx *ctx, const void *d_text, size_t n, uint64_t k, uint64_t *offset);
+int fqz_compress_shard_device(fqz_ctx *ctx, const void *d_fastq, size_t n, uint32_t header_block_size, int phred64, int emit_file_header,
+                              void *d_out, size_t out_cap, size_t *out_len, int *phred64_used);
+
 /* ---- block level (Seam A and the parity tests) -------------------------------------------------
  * fqz_encode_streams: FASTQ chunk -> the six pre-entropy streams of its first block
  *   (<= 100 000 records), byte-identical to what compressBlockWithBuffers builds before EncodeAll

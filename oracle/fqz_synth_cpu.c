@@ -37,6 +37,18 @@ static uint32_t next16(rng_t *g) {
     return v;
 }
 
+/* kind 2: kind 0 in which 35 % of the records copy bases and qualities of one of the 400 records in front */
+static uint64_t dup_source(uint64_t seed, uint64_t rec) {
+    uint64_t body = rec;
+    for (int hop = 0; hop < 64 && body > 0; hop++) {
+        uint64_t h = mix(seed ^ 0xD0B1E5ull ^ mix(body));
+        if ((h & 0xFFFF) >= 22938) break;
+        uint64_t d = 1 + (h >> 16) % 400;
+        body = body > d ? body - d : 0;
+    }
+    return body;
+}
+
 /* one record into p (>= 1024 bytes free); returns its length */
 static size_t synth_record(int kind, uint64_t seed, uint64_t rec, uint8_t *p) {
     rng_t g;
@@ -47,7 +59,7 @@ static size_t synth_record(int kind, uint64_t seed, uint64_t rec, uint8_t *p) {
     char hdr[160];
     int hl;
     uint32_t L;
-    if (kind == 0) {
+    if (kind != 1) {
         const uint64_t T = 250000;
         uint64_t t = rec / T;
         unsigned tile = (unsigned)((1 + (t / 48) % 2) * 1000 + (1 + (t / 16) % 3) * 100 + (1 + t % 16));
@@ -65,7 +77,18 @@ static size_t synth_record(int kind, uint64_t seed, uint64_t rec, uint8_t *p) {
     o += hl;
     *o++ = '\n';
     static const char B[4] = {'A', 'C', 'G', 'T'};
-    if (kind == 0) {
+    if (kind == 2) {
+        uint64_t body = dup_source(seed, rec);
+        if (body != rec) {
+            g.s = mix(seed ^ mix(body));
+            if (!g.s) g.s = 0x1234567;
+            g.left = 0;
+            g.cur = 0;
+            next64(&g);
+            next16(&g);
+        }
+    }
+    if (kind != 1) {
         int nread = next16(&g) < 655;
         for (uint32_t i = 0; i < L; i++) {
             uint32_t d = next16(&g);
@@ -91,7 +114,7 @@ static size_t synth_record(int kind, uint64_t seed, uint64_t rec, uint8_t *p) {
         o += hl;
     }
     *o++ = '\n';
-    int qmax = kind == 0 ? 41 : 40, qmin = kind == 0 ? 2 : 0, base = kind == 0 ? 33 : 64;
+    int qmax = kind != 1 ? 41 : 40, qmin = kind != 1 ? 2 : 0, base = kind != 1 ? 33 : 64;
     int q = qmax - 7 + (int)(next16(&g) % 8);
     int tail = 0;
     for (uint32_t i = 0; i < L; i++) {

@@ -195,3 +195,44 @@ def duplicated_reads_varlen(nrec, seed, dup_rate=0.35, reach=200):
             recs.pop(0)
         out += b"@V.%d\n" % (i + 1) + seq + b"\n+\n" + qual + b"\n"
     return bytes(out)
+
+
+def check_shard_planning(ctx, oracle, full, to_device=None):
+    """fqz_count_lines_device / fqz_find_line_end_device / fqz_compress_shard_device (the device side of
+    sharding.plan_compress).  full: a three-block input cut where the plan says and coded as two shards
+    concatenates to the bytes of the unsplit call.  to_device(np.ndarray) -> (device pointer, keep-alive);
+    None: device memory is host memory (the emulated build)."""
+    import numpy as np
+
+    from fastqpacker_b200 import sharding
+
+    raw = short_read_handover(nrec=230_000) if full else rand_fastq(3000, 5, lmin=1, lmax=80)
+    text = np.frombuffer(raw + b"\0" * 64, dtype=np.uint8).copy()
+    n = text.size - 64
+    ptr, keep = to_device(text) if to_device else (text.ctypes.data, text)
+    assert ptr % 16 == 0
+    nl = np.flatnonzero(text[:n] == 10)
+    assert ctx.count_lines_device(ptr, n) == nl.size
+    for k in sorted({1, 2, 17, 4097, nl.size // 2, int(nl.size)}):
+        assert ctx.find_line_end_device(ptr, n, k) == int(nl[k - 1])
+    if not full:
+        return
+    # slice 1 starts at an arbitrary 16-byte aligned offset in the middle of the file
+    a1 = (n // 2) & ~15
+    before = ctx.count_lines_device(ptr, a1)
+    k = sharding.LINES_PER_BLOCK - before % sharding.LINES_PER_BLOCK
+    cut = a1 + ctx.find_line_end_device(ptr + a1, n - a1, k) + 1
+    assert cut == int(nl[2 * sharding.LINES_PER_BLOCK - 1]) + 1
+    out = np.zeros(n + 4096, dtype=np.uint8)
+    optr, okeep = to_device(out) if to_device else (out.ctypes.data, out)
+
+    def fetch(m):
+        return okeep[:m].cpu().numpy().tobytes() if to_device else out[:m].tobytes()
+
+    m0, ph = ctx.compress_shard_device(ptr, cut, optr, out.size, -1, True)
+    part0 = fetch(m0)
+    m1, _ = ctx.compress_shard_device(ptr + cut, n - cut, optr, out.size, ph, False)
+    part1 = fetch(m1)
+    whole = ctx.compress(text[:n])
+    assert sharding.merge_compressed([part0, part1]) == whole
+    assert oracle.decompress(whole) == text[:n].tobytes()

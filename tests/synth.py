@@ -34,9 +34,23 @@ class _Rng:
         return v
 
 
+def dup_source(seed: int, rec: int) -> int:
+    """kind 2: the record whose bases and qualities record `rec` carries (35 % copy one of the 400 in front)."""
+    body = rec
+    for _ in range(64):
+        if body == 0:
+            break
+        h = _mix(seed ^ 0xD0B1E5 ^ _mix(body))
+        if (h & 0xFFFF) >= 22938:
+            break
+        d = 1 + (h >> 16) % 400
+        body = body - d if body > d else 0
+    return body
+
+
 def record(kind: int, seed: int, rec: int) -> bytes:
     g = _Rng(seed, rec)
-    if kind == 0:
+    if kind != 1:
         T = 250000
         t = rec // T
         tile = (1 + (t // 48) % 2) * 1000 + (1 + (t // 16) % 3) * 100 + (1 + t % 16)
@@ -48,7 +62,13 @@ def record(kind: int, seed: int, rec: int) -> bytes:
         L = 50 + g.next64() % 251
         hdr = b"SRR_synth.%d %d length=%d" % (rec + 1, rec + 1, L)
     seq = bytearray()
-    if kind == 0:
+    if kind == 2:
+        body = dup_source(seed, rec)
+        if body != rec:
+            g = _Rng(seed, body)
+            g.next64()
+            g.next16()
+    if kind != 1:
         nread = g.next16() < 655
         for _ in range(L):
             d = g.next16()
@@ -66,7 +86,7 @@ def record(kind: int, seed: int, rec: int) -> bytes:
             if inrun:
                 b = ord("N")
             seq.append(b)
-    qmax, qmin, base = (41, 2, 33) if kind == 0 else (40, 0, 64)
+    qmax, qmin, base = (41, 2, 33) if kind != 1 else (40, 0, 64)
     q = qmax - 7 + g.next16() % 8
     tail = False
     qual = bytearray()

@@ -76,3 +76,9 @@ def test_duplicated_records_ratio(emu, oracle, name):
     from tests.fastq_cases import check_repetitive
 
     check_repetitive(emu, oracle, name)
+
+
+def test_shard_planning_calls(emu, oracle):
+    from tests.fastq_cases import check_shard_planning
+
+    check_shard_planning(emu, oracle, full=False)

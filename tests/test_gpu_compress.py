@@ -177,22 +177,19 @@ def test_window_hand_over(ctx, oracle):
     assert ctx.decompress(cut) == text
 
 
-@pytest.mark.parametrize("frontend", [0, 1])
-def test_window_hand_over_short_reads(ctx, oracle, frontend):
+def test_window_hand_over_short_reads(ctx, oracle):
     """A window cut behind a record of a few bytes: the 16-byte word the next window is entered at holds
     several newlines, only the last of which ends the previous window."""
     from tests.fastq_cases import short_read_handover
 
     text = short_read_handover()
     try:
-        ctx.set_option(ctx.OPT_FRONTEND, frontend)
         ctx.set_option(ctx.OPT_WINDOW_BYTES, 2 << 20)
         ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 2 << 20)
         cut = ctx.compress(text)
     finally:
         ctx.set_option(ctx.OPT_WINDOW_BYTES, 0)
         ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
-        ctx.set_option(ctx.OPT_FRONTEND, 0)
     assert oracle.decompress(cut) == text
     assert ctx.decompress(cut) == text
 
@@ -204,3 +201,15 @@ def test_duplicated_records_ratio(ctx, oracle, name):
     from tests.fastq_cases import check_repetitive
 
     check_repetitive(ctx, oracle, name)
+
+
+def test_shard_planning_calls(ctx, oracle):
+    import torch
+
+    from tests.fastq_cases import check_shard_planning
+
+    def to_device(a):
+        t = torch.from_numpy(a).cuda()
+        return t.data_ptr(), t
+
+    check_shard_planning(ctx, oracle, full=True, to_device=to_device)

@@ -67,7 +67,12 @@ def test_full_size_round_trip(ctx, oracle, kind, seed, nrec, per_record, phred64
     k = ctx.decompress_device(d_out.data_ptr(), m, d_back.data_ptr(), d_back.numel())
     assert k == n
     assert bool(torch.equal(d_back[:n], d_in[:n]))
-    # the first block decodes under the oracle too (it stands in for `fqpack -d`)
-    first = 10 + 36 + sum(blocks[0][1:7])
-    got = oracle.decompress(hdrs[:first])
-    assert got == d_in[: len(got)].cpu().numpy().tobytes() and got.count(b"\n") == 400_000
+    # the first, a middle and the last block decode under the oracle too (it stands in for `fqpack -d`): each must be
+    # the generator's records of that block (not only block 0)
+    offs = [10]
+    for b in blocks:
+        offs.append(offs[-1] + 36 + sum(b[1:7]))
+    for i in sorted({0, len(blocks) // 2, len(blocks) - 1}):
+        got = oracle.decompress(hdrs[:10] + hdrs[offs[i] : offs[i + 1]])
+        want = oracle.synth(kind, seed, i * 100_000, blocks[i][0]).tobytes()
+        assert got == want, f"block {i} differs under the oracle"
