@@ -308,6 +308,7 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI calls (pinned host memory)
     e2e = None
     e2e_d = None
+    e2e_f = None
     m = res["m"]
     if not args.no_e2e:
         import numpy as np
@@ -326,6 +327,26 @@ def run_ours(args):
 
         e_steps = max(1, min(args.steps, args.e2e_steps))
         t_ec = timed(e2e_compress, e_steps, min(args.warmup, 3))
+
+        # the same through the STREAMING calls the Go shim uses: 2 GiB windows fed one after the
+        # other, the unconsumed tail of a call (less than one block) in front of the next window
+        FEED = 2 << 30
+
+        def e2e_feed():
+            cs = ctx.compress_stream()
+            pos = outpos = 0
+            while True:
+                end = min(n, pos + FEED)
+                mm, used = cs.feed(a_in[pos:end], end == n, a_out[outpos:])
+                outpos += mm
+                pos += used
+                if end == n:
+                    break
+            cs.close()
+            res["fm"] = outpos
+
+        t_ef = timed(e2e_feed, e_steps, 1)
+        assert res["fm"] == res["em"], "the streaming calls wrote a different file"
         del a_in, h_in
         h_back = torch.empty(n + (1 << 16), dtype=torch.uint8, pin_memory=True)
         a_back = h_back.numpy()
@@ -340,6 +361,8 @@ def run_ours(args):
                "steps": e_steps, "api": "fqz_compress (host buffers, pinned)"}
         e2e_d = {"value": world * n * e_steps / t_ed / 1e9, "unit": UNIT, "h2d_bytes_per_step": res["em"], "d2h_bytes_per_step": n,
                  "steps": e_steps, "api": "fqz_decompress (host buffers, pinned)"}
+        e2e_f = {"value": world * n * e_steps / t_ef / 1e9, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": res["fm"], "steps": e_steps,
+                 "api": "fqz_compress_begin / fqz_compress_feed (2 GiB windows, pinned) / fqz_compress_end: the loop of INTEGRATION.md's shim"}
         del a_back, h_back, a_out, h_out
     # ---- BASELINE config 3, second half: the REFERENCE-WRITTEN file of the whole workload (rank 0's 25 M records,
     #      one libzstd level-1 frame per stream as the reference writes them), decoded by all ranks together
@@ -440,6 +463,7 @@ def run_ours(args):
             "cpus_bound_to_gpu_numa_node": numa,
         },
         "e2e": e2e,
+        "e2e_feed": e2e_f,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "pipeline_roofline": pipeline,

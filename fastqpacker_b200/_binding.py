@@ -85,6 +85,8 @@ class FqzLibrary:
         self._opt(L, "fqz_compress_device", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress_device", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress_bound", [sz], restype=sz)
+        self._opt(L, "fqz_host_alloc", [sz], restype=vp)
+        self._opt(L, "fqz_host_free", [vp], restype=None)
         self._opt(L, "fqz_compress_begin", [vp, u32, C.POINTER(vp)])
         self._opt(L, "fqz_compress_feed", [vp, vp, sz, i32, vp, sz, szp, szp])
         self._opt(L, "fqz_compress_end", [vp], restype=None)

@@ -368,8 +368,6 @@ extern "C" int fqz_decompress(fqz_ctx *c, const uint8_t *fqz, size_t n, uint8_t 
 struct fqz_dstream {
     fqz_ctx *c;
     DecState st;
-    u8 *d_in = nullptr;
-    size_t d_cap = 0;
 };
 extern "C" int fqz_decompress_begin(fqz_ctx *c, fqz_dstream **out) {
     if (!c || !out) return FQZ_E_INVALID_ARG;
@@ -379,10 +377,9 @@ extern "C" int fqz_decompress_begin(fqz_ctx *c, fqz_dstream **out) {
 }
 extern "C" void fqz_decompress_end(fqz_dstream *s) {
     if (!s) return;
-    cudaSetDevice(s->c->device);
-    if (s->d_in) cudaFree(s->d_in);
     delete s;
 }
+// Like fqz_compress_feed, a fed window runs through the copy pipeline of the whole-buffer call.
 extern "C" int fqz_decompress_feed(fqz_dstream *s, const uint8_t *fqz, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
                                    size_t *consumed) {
     if (!s || !out_len || !consumed || (!fqz && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
@@ -397,24 +394,18 @@ extern "C" int fqz_decompress_feed(fqz_dstream *s, const uint8_t *fqz, size_t n,
     }
     u64 pos = 0;
     if (!s->st.have_header && n < 10 && !is_last) return FQZ_E_NEED_MORE;
-    if (n + 256 > s->d_cap) {
-        if (s->d_in) cudaFree(s->d_in);
-        s->d_in = nullptr;
-        s->d_cap = 0;
-        size_t cap = n + n / 4 + 4096;
-        FQZ_CUDA_TRY(c, cudaMalloc((void **)&s->d_in, cap));
-        s->d_cap = cap;
-    }
-    FQZ_CUDA_TRY(c, cudaMemsetAsync(s->d_in + (n & ~(size_t)15), 0, 64, c->stream));
-    if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(s->d_in, fqz, n, cudaMemcpyHostToDevice, c->stream));
     if (!s->st.have_header) {
-        FQZ_TRY(read_file_header(c, s->d_in, n, s->st));
+        FQZ_TRY(parse_file_header(c, fqz, n, s->st));  // read on the host; the payload streams to the device
         pos = 10;
         *consumed = 10;
     }
     u64 used = pos;
     static u8 dummy;
-    int rc = decompress_blocks(c, s->d_in, n, pos, is_last != 0, true, s->st, nullptr, out ? out : &dummy, out_cap, out_len, &used);
+    int rc = fqz_io_upload(c, fqz, n);
+    if (rc == FQZ_OK) rc = decompress_blocks(c, c->io.d_in, n, pos, is_last != 0, true, s->st, nullptr, out ? out : &dummy, out_cap, out_len, &used, true);
+    int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
     if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *consumed = (size_t)used;
     if (rc == FQZ_OK && !is_last && used == pos && pos < n && *out_len == 0 && *consumed == 0) return FQZ_E_NEED_MORE;
     return rc;

@@ -196,7 +196,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
         const u32 BB = std::min<u32>(zb.rblocks, 8192u);
         u32 *d_keys = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
         u32 *d_cand = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
-        d_lzflags = (u32 *)c->arena.alloc((size_t)(nrs + 1) * sizeof(u32));
+        d_lzflags = (u32 *)c->arena.alloc((size_t)(2 * nrs + 2) * sizeof(u32));  // flags[nrs + 1], then the duplicate counts
         d_rhash = (u32 *)c->arena.alloc((size_t)(nrs + 1) * sizeof(u32));
         d_bsizes = (u32 *)c->arena.alloc((size_t)(zb.rblocks + 1) * sizeof(u32));
         u8 *pool_ws = (u8 *)c->arena.alloc(fqz_lzrec_pool_ws(BB) + 64);
@@ -206,7 +206,8 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
             c->err = "arena: out of device memory (record matcher)";
             return FQZ_E_CUDA;
         }
-        fqz_launch_rec_match(d_rs, nrs, zb.rmax_records, offs_base, d_keys, d_cand, d_lzflags, d_rhash, s);
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_lzflags, 0, (size_t)(2 * nrs + 2) * sizeof(u32), s));
+        fqz_launch_rec_match(d_rs, nrs, zb.rmax_records, offs_base, d_keys, d_cand, d_lzflags, d_lzflags + nrs + 1, d_rhash, s);
         for (u32 g0 = 0; g0 < zb.rblocks; g0 += BB)
             fqz_launch_lzrec(d_rs, nrs, d_lzflags, offs_base, d_cand, pool_ws, pool_out, g0, std::min<u32>(zb.rblocks, g0 + BB), d_rparsed, d_bsizes, s);
     }
@@ -490,8 +491,6 @@ struct fqz_cstream {
     fqz_ctx *c;
     CompState st;
     u32 header_block_size = 0;
-    u8 *d_in = nullptr, *d_out = nullptr;
-    size_t in_cap = 0, out_cap = 0;
 };
 extern "C" int fqz_compress_begin(fqz_ctx *c, uint32_t header_block_size, fqz_cstream **out) {
     if (!c || !out) return FQZ_E_INVALID_ARG;
@@ -502,27 +501,19 @@ extern "C" int fqz_compress_begin(fqz_ctx *c, uint32_t header_block_size, fqz_cs
 }
 extern "C" void fqz_compress_end(fqz_cstream *s) {
     if (!s) return;
-    cudaSetDevice(s->c->device);
-    if (s->d_in) cudaFree(s->d_in);
-    if (s->d_out) cudaFree(s->d_out);
     delete s;
 }
-static int dev_reserve(fqz_ctx *c, u8 **p, size_t *cap, size_t need) {
-    if (need <= *cap) return FQZ_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
-    size_t want = need + need / 8 + 4096;
-    FQZ_CUDA_TRY(c, cudaMalloc((void **)p, want));
-    *cap = want;
-    return FQZ_OK;
-}
+// One fed window goes through the same copy pipeline as fqz_compress: chunked upload on its own stream, the
+// compute stream gated chunk by chunk, every device window's output downloaded while the next one is coded
+// (the calls the Go shim uses must overlap too).  Feed large windows (>= 1 GiB) from
+// page-locked buffers (fqz_host_alloc): each call pays one pipeline fill and drain.
 extern "C" int fqz_compress_feed(fqz_cstream *s, const uint8_t *fastq, size_t n, int is_last, uint8_t *out, size_t out_cap, size_t *out_len,
                                  size_t *consumed) {
     if (!s || !out_len || !consumed || (!fastq && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
     fqz_ctx *c = s->c;
     cudaSetDevice(c->device);
     c->err.clear();
+    c->arena.reset();
     *out_len = 0;
     *consumed = 0;
     if (n > FQZ_MAX_WINDOW) {  // take a window's worth; the caller re-presents the rest
@@ -530,20 +521,21 @@ extern "C" int fqz_compress_feed(fqz_cstream *s, const uint8_t *fastq, size_t n,
         is_last = 0;
     }
     size_t ocap = fqz_compress_bound(n);
-    FQZ_TRY(dev_reserve(c, &s->d_in, &s->in_cap, n + 256));
-    FQZ_TRY(dev_reserve(c, &s->d_out, &s->out_cap, ocap + 256));
-    FQZ_CUDA_TRY(c, cudaMemsetAsync(s->d_in + (n & ~(size_t)15), 0, 64, c->stream));
-    if (n) FQZ_CUDA_TRY(c, cudaMemcpyAsync(s->d_in, fastq, n, cudaMemcpyHostToDevice, c->stream));
-    CompState trial = s->st;  // committed only when the output fits
+    u8 *d_o = nullptr;
+    static u8 dummy;
+    int rc = fqz_io_upload(c, fastq, n);
+    if (rc == FQZ_OK) rc = fqz_io_out_acquire(c, 0, ocap, &d_o);
+    CompState trial = s->st;  // committed only when the call succeeds
     size_t m = 0;
     u64 used = 0;
-    int rc = compress_device_impl(c, s->d_in, n, is_last != 0, trial, s->header_block_size, s->d_out, ocap, &m, &used);
+    if (rc == FQZ_OK) rc = compress_device_impl(c, c->io.d_in, n, is_last != 0, trial, s->header_block_size, d_o, ocap, &m, &used, out ? out : &dummy, out_cap);
+    int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_E_NOSPACE) *out_len = m;  // nothing consumed; retry with a larger buffer
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
     if (rc != FQZ_OK) return rc;
     if (used == 0 && m == 0 && !is_last) return FQZ_E_NEED_MORE;
     *out_len = m;
-    if (m > out_cap) return FQZ_E_NOSPACE;  // nothing consumed; retry with a larger buffer
-    if (m) FQZ_CUDA_TRY(c, cudaMemcpyAsync(out, s->d_out, m, cudaMemcpyDeviceToHost, c->stream));
-    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     s->st = trial;
     *consumed = (size_t)used;
     return FQZ_OK;

@@ -333,6 +333,20 @@ extern "C" const char *fqz_strerror(int code) {
     }
 }
 
+// page-locked host buffers for the shim's window buffers: copies from / to them run at PCIe rate and overlap with
+// kernels; pageable memory (a Go slice, malloc) is staged by the driver at a fraction of that
+extern "C" void *fqz_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void fqz_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
     if (!c) return FQZ_E_INVALID_ARG;
     switch (key) {

@@ -68,9 +68,9 @@ struct ZRStream {
     u32 pad;
 };
 // pairs duplicated records (cand, laid out like the scanned offset arrays `offs_base`; keys = scratch of the same
-// shape), flags the streams that hold enough of them and hashes their content
+// shape), flags the streams that hold enough of them (flags[ns] = any) and hashes their content.  dupcnt: ns zeroed words.
 void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
-                          u32 *hashes, cudaStream_t s);
+                          u32 *dupcnt, u32 *hashes, cudaStream_t s);
 // codes blocks [g0, gend) of the flagged streams (parse, literals, sequences) into their staging (pool_out: all
 // blocks of the batch, pool_ws / parsed: gend - g0 blocks); _close strings the blocks of every flagged stream together
 size_t fqz_lzrec_pool_ws(u32 nblocks);

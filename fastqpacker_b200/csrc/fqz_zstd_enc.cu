@@ -712,6 +712,11 @@ __device__ static u32 warp_write_literals(const u8 *lit, u32 n, u8 *out, WS &S) 
 // offBase of one sequence given the repeat-offset history (RFC 8878 §3.1.1.5)
 __device__ __forceinline__ u32 zstd_off_base(u32 off, bool ll0, u32 &rep0, u32 &rep1, u32 &rep2) {
     u32 ob;
+#ifdef FQZ_REP0_ONLY
+    ob = (!ll0 && off == rep0) ? 1u : off + 3u;
+    rep0 = off;
+    return ob;
+#endif
     if (!ll0) {
         if (off == rep0) ob = 1;
         else if (off == rep1) { ob = 2; rep1 = rep0; rep0 = off; }
@@ -1359,22 +1364,66 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
             }
             const u32 pend_all = __shfl_sync(FULL, lastend, 31);
             __syncwarp();
-            // ---- repeat offsets: serial by nature (lane 0), staged through shared memory
+            // ---- repeat offsets, 32 sequences per step.  The decoder's history is a move-to-front list as long as no
+            //      offset is pushed that it already holds on top, so its first two entries are known without walking it:
+            //      rep0 = the previous sequence's offset, rep1 = the offset of the run of equal offsets in front of
+            //      that one.  A sequence that continues its run codes rep0 (its literal length is > 0: touching
+            //      matches of one offset were fused above), the head of a run codes rep1 when it returns to the
+            //      offset before the previous run (the start- / end-aligned offsets of an item alternate), else
+            //      the offset itself; rep2 is not used.  The one case that would push a duplicate (ll == 0 with
+            //      the previous offset) sends the list through the serial walk below instead.
             {
-                u32 *inb = mbuf, *outb = mbuf + 64;
-                u32 rep0 = rep_known ? 1u : 0xFFFFFFF1u, rep1 = rep_known ? 4u : 0xFFFFFFE1u, rep2 = rep_known ? 8u : 0xFFFFFFD1u;
+                u32 c0 = rep_known ? 1u : 0xFFFFFFF1u, c1 = rep_known ? 4u : 0xFFFFFFE1u;
+                bool dup_push = false;
                 for (u32 base = 0; base < nseq; base += 32) {
-                    u32 cn = min(32u, nseq - base);
-                    __syncwarp();
-                    if (lane < cn) {
-                        inb[lane] = sof[base + lane];
-                        inb[32 + lane] = sll[base + lane];
+                    const u32 i = base + lane;
+                    const bool live = i < nseq;
+                    const u32 off = live ? sof[i] : 0u, ll = live ? sll[i] : 1u;
+                    u32 prev = __shfl_up_sync(FULL, off, 1);
+                    if (lane == 0) prev = c0;
+                    const bool head = live && off != prev;
+                    const u32 H = __ballot_sync(FULL, head), Lm = __ballot_sync(FULL, live);
+                    // start of the run in front of this lane's run: the highest head below this lane
+                    const u32 P = H & ((1u << lane) - 1u);
+                    const int pl = P ? 31 - __clz((int)P) : -1;
+                    u32 before = __shfl_sync(FULL, off, pl > 0 ? pl - 1 : 0);  // offset of the run in front of that one
+                    if (pl < 0) before = c1;
+                    else if (pl == 0) before = c0;
+                    u32 ob;
+                    if (!head) {
+                        ob = 1u;
+                        if (live && ll == 0) dup_push = true;
+                    } else if (off == before) ob = ll ? 2u : 1u;
+                    else ob = off + 3u;
+                    if (live) toff[i] = ob;  // the scratch of the clean-up is free again; sof keeps the raw offsets for the fallback
+                    // carry: last offset of the step and the offset of the run in front of its last run
+                    const int last = 31 - __clz((int)Lm);
+                    const int ql = H ? 31 - __clz((int)H) : -1;
+                    u32 n1 = __shfl_sync(FULL, off, ql > 0 ? ql - 1 : 0);
+                    if (ql < 0) n1 = c1;
+                    else if (ql == 0) n1 = c0;
+                    c1 = n1;
+                    c0 = __shfl_sync(FULL, off, last);
+                }
+                __syncwarp();
+                if (!__any_sync(FULL, dup_push)) {
+                    for (u32 i = lane; i < nseq; i += 32) sof[i] = toff[i];
+                } else {  // exact walk of the history (lane 0), staged through shared memory
+                    u32 *inb = mbuf, *outb = mbuf + 64;
+                    u32 rep0 = rep_known ? 1u : 0xFFFFFFF1u, rep1 = rep_known ? 4u : 0xFFFFFFE1u, rep2 = rep_known ? 8u : 0xFFFFFFD1u;
+                    for (u32 base = 0; base < nseq; base += 32) {
+                        u32 cn = min(32u, nseq - base);
+                        __syncwarp();
+                        if (lane < cn) {
+                            inb[lane] = sof[base + lane];
+                            inb[32 + lane] = sll[base + lane];
+                        }
+                        __syncwarp();
+                        if (lane == 0)
+                            for (u32 k = 0; k < cn; k++) outb[k] = zstd_off_base(inb[k], inb[32 + k] == 0, rep0, rep1, rep2);
+                        __syncwarp();
+                        if (lane < cn) sof[base + lane] = outb[lane];
                     }
-                    __syncwarp();
-                    if (lane == 0)
-                        for (u32 k = 0; k < cn; k++) outb[k] = zstd_off_base(inb[k], inb[32 + k] == 0, rep0, rep1, rep2);
-                    __syncwarp();
-                    if (lane < cn) sof[base + lane] = outb[lane];
                 }
             }
             __syncwarp();
@@ -2133,8 +2182,43 @@ __global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 
     }
     keys_base[(items - offs_base) + r] = key;
 }
-// cand[r] = 1 + number (inside the stream's block) of the partner record, 0 = none
-__global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, const u32 *offs_base, const u32 *keys_base, u32 *cand_base, u32 *flags) {
+// Cheap, fully parallel look for repeated keys, so that the serial pairing pass only runs on streams that need it:
+// one CTA per 2048 records counts the records whose key occurs earlier in the same chunk.  Order-independent
+// (every slot keeps the LARGEST key that hashes to it, then counts its occurrences), hence the same on every run;
+// keys that lose their slot are not counted, so this is a lower bound.  dupcnt[stream] += sum of (occurrences - 1).
+#define ZR_DET_RECORDS 2048u
+#define ZR_DET_SLOTS 4096u
+__global__ void __launch_bounds__(256) k_rec_detect(const ZRStream *rs, const u32 *offs_base, const u32 *keys_base, u32 *dupcnt) {
+    __shared__ u32 tkey[ZR_DET_SLOTS], tcnt[ZR_DET_SLOTS];
+    __shared__ u32 ws[33];
+    const ZRStream &R = rs[blockIdx.y];
+    const u32 r0 = blockIdx.x * ZR_DET_RECORDS;
+    if (r0 >= R.nrec) return;
+    const u32 r1 = min(R.nrec, r0 + ZR_DET_RECORDS);
+    const u32 *keys = keys_base + ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0;
+    for (u32 i = threadIdx.x; i < ZR_DET_SLOTS; i += blockDim.x) tkey[i] = 0, tcnt[i] = 0;
+    __syncthreads();
+    u32 k[ZR_DET_RECORDS / 256];
+#pragma unroll
+    for (u32 j = 0; j < ZR_DET_RECORDS / 256; j++) {
+        u32 r = r0 + j * 256u + threadIdx.x;
+        k[j] = r < r1 ? keys[r] : 0u;
+        if (k[j]) atomicMax(&tkey[(k[j] >> 1) & (ZR_DET_SLOTS - 1u)], k[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (u32 j = 0; j < ZR_DET_RECORDS / 256; j++)
+        if (k[j] && tkey[(k[j] >> 1) & (ZR_DET_SLOTS - 1u)] == k[j]) atomicAdd(&tcnt[(k[j] >> 1) & (ZR_DET_SLOTS - 1u)], 1u);
+    __syncthreads();
+    u32 d = 0;
+    for (u32 i = threadIdx.x; i < ZR_DET_SLOTS; i += blockDim.x) d += tcnt[i] > 1u ? tcnt[i] - 1u : 0u;
+    u32 tot = 0;
+    block_excl_scan(d, ws, &tot);
+    if (threadIdx.x == 0 && tot) atomicAdd(&dupcnt[blockIdx.y], tot);
+}
+// cand[r] = 1 + number (inside the stream's block) of the partner record, 0 = none.  flags[ns] = any stream flagged.
+__global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, const u32 *offs_base, const u32 *keys_base, u32 *cand_base, u32 *flags,
+                                                  const u32 *dupcnt) {
     __shared__ u32 tab[1 << ZR_HLOG];  // key bits 17.. | 1 + record number (17 bits: a block holds 100 000 records)
     const u32 si = blockIdx.x, lane = lane_id();
     if (si >= ns) return;
@@ -2143,8 +2227,9 @@ __global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, co
     const u32 *keys = keys_base + at;
     u32 *cand = cand_base + at;
     const u32 nrec = R.nrec;
-    // records of 20 bytes or more on average (the match list of a block holds one entry per two bytes)
-    if (nrec < 8u || (u64)nrec * 20u > R.len || nrec >= (1u << 17)) {
+    // records of 20 bytes or more on average (the match list of a block holds one entry per two bytes), and enough
+    // repeated keys for the 1/16 below to be in reach (the chunk-local count misses the far pairs: ask for half)
+    if (nrec < 8u || (u64)nrec * 20u > R.len || nrec >= (1u << 17) || dupcnt[si] * 32u < nrec) {
         if (lane == 0) flags[si] = 0;
         return;
     }
@@ -2196,11 +2281,16 @@ __global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, co
 #ifdef FQZ_EMU
     if (lane == 0 && getenv("FQZ_DEBUG")) fprintf(stderr, "rec_match stream %u len %u records %u hits %u\n", si, R.len, nrec, hits);
 #endif
-    if (lane == 0) flags[si] = (hits * 16u >= nrec) ? 1u : 0u;
+    if (lane == 0) {
+        const u32 f = (hits * 16u >= nrec) ? 1u : 0u;
+        flags[si] = f;
+        if (f) flags[ns] = 1u;
+    }
 }
 // content checksum of the flagged streams (one quad per stream; unflagged streams cost nothing)
 __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_streams(const ZRStream *rs, u32 ns, const u32 *flags, u32 *hashes) {
     FQZ_DYN_SMEM(u8, smem);
+    if (!flags[ns]) return;  // no stream flagged
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 si = t >> 2, q = t & 3;
     u32 gmask = group_mask(4);
@@ -2225,7 +2315,7 @@ struct ZRBlock {
 // block g (numbered through all streams of the batch) -> its stream and place; false: nothing to do
 __device__ __forceinline__ bool zr_block(const ZRStream *rs, u32 ns, const u32 *flags, u8 *pool_ws, u8 *pool_out, u32 g0, u32 g, u32 gend, ZRStream &R,
                                          ZRBlock &B) {
-    if (g >= gend) return false;
+    if (g >= gend || !flags[ns]) return false;  // flags[ns]: any stream flagged
     u32 lo = 0, hi = ns - 1;  // largest s with rs[s].blk0 <= g
     while (lo < hi) {
         u32 mid = (lo + hi + 1) >> 1;
@@ -2470,10 +2560,11 @@ void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const
     FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags);
 }
 void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
-                          u32 *hashes, cudaStream_t s) {
+                          u32 *dupcnt, u32 *hashes, cudaStream_t s) {
     if (!ns) return;
     FQZ_LAUNCH(k_rec_keys, dim3((max_records + 255) / 256, ns), 256, 0, s, rs, offs_base, keys_base);
-    FQZ_LAUNCH(k_rec_match, ns, 32, 0, s, rs, ns, offs_base, keys_base, cand_base, flags);
+    FQZ_LAUNCH(k_rec_detect, dim3((max_records + ZR_DET_RECORDS - 1) / ZR_DET_RECORDS, ns), 256, 0, s, rs, offs_base, keys_base, dupcnt);
+    FQZ_LAUNCH(k_rec_match, ns, 32, 0, s, rs, ns, offs_base, keys_base, cand_base, flags, dupcnt);
     u32 threads = XX_WARPS * 32, grid = (ns * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_streams, grid, threads, XX_SMEM, s, rs, ns, flags, hashes);
 }

@@ -66,6 +66,12 @@ int fqz_abi_version(void);
 #define FQZ_OPT_RECORD_MATCH 3      /* 1 (default): search packed bases / qualities for duplicated records and code them as matches; 0: literals only */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
+/* Page-locked host memory for the caller's window buffers (the Go shim reads the file into these instead of Go
+ * slices): transfers from / to them run at PCIe rate and overlap with the kernels.  Any host memory is accepted
+ * by the calls below; pageable memory is simply slower.  NULL when the allocation fails. */
+void *fqz_host_alloc(size_t bytes);
+void fqz_host_free(void *p);
+
 /* ---- whole buffer, HOST memory: replaces the bodies of compress.Compress / compress.Decompress
  *      (compress.go:125-192, 558-604).  Output = complete .fqz file (10-byte header + blocks of
  *      100 000 records, F2) / complete FASTQ text.  header_block_size is echoed into the file

@@ -213,3 +213,48 @@ def test_shard_planning_calls(ctx, oracle):
         return t.data_ptr(), t
 
     check_shard_planning(ctx, oracle, full=True, to_device=to_device)
+
+
+def _two_contexts(oracle, dev_a, dev_b):
+    """Two contexts in ONE process driven from two threads at the same time (the Go host is one process driving all
+    GPUs): two shards of one file coded concurrently must concatenate to the bytes of the unsplit call."""
+    import threading
+
+    import numpy as np
+
+    import fastqpacker_b200 as fq
+    from fastqpacker_b200 import sharding
+
+    ca, cb = fq.library().context(dev_a), fq.library().context(dev_b)
+    text = oracle.synth(0, 0x5EED0001, 0, 330_000).tobytes()
+    nl = np.flatnonzero(np.frombuffer(text, dtype=np.uint8) == 10)
+    cut = int(nl[2 * sharding.LINES_PER_BLOCK - 1]) + 1  # two blocks for the first shard, 1.3 for the second
+    whole = ca.compress(text)
+    for _ in range(3):
+        out, err = [None, None], []
+
+        def work(i, c, data, phred, header):
+            try:
+                out[i] = c.compress_shard(data, phred, header)[0]
+                assert c.decompress(whole) == text
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+
+        ts = [threading.Thread(target=work, args=(0, ca, text[:cut], -1, True)), threading.Thread(target=work, args=(1, cb, text[cut:], 0, False))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not err, err
+        assert sharding.merge_compressed(out) == whole
+    assert cb.compress(text) == whole
+
+
+def test_two_contexts_one_device(oracle):
+    _two_contexts(oracle, 0, 0)
+
+
+def test_two_contexts_two_devices(oracle):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    _two_contexts(oracle, 0, 1)
