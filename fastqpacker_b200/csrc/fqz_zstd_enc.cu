@@ -1107,6 +1107,110 @@ __device__ __forceinline__ u32 zi_match_len(const u8 *S, u32 p, u32 d, u32 lim) 
     return l;
 }
 
+// ---- equality masks: the whole item is compared with its two candidate offsets up front — one pass of
+//      independent loads (every source word is loaded once and reused by both offsets, a rolling funnel shift
+//      serves the unaligned positions) instead of a compare loop whose every step waits for its own loads — and
+//      the matches are then read off 128-bit masks with bit scans.  Items of more than ZM_SPAN positions
+//      (with the look-ahead) keep the byte loop.
+#define ZM_SPAN 128u
+#ifdef FQZ_EMU
+#define ZM_DEBUG_TOGGLE &&!getenv("FQZ_NOMASK")
+#else
+#define ZM_DEBUG_TOGGLE
+#endif
+struct Mask128 {
+    u64 lo, hi;
+};
+__device__ __forceinline__ Mask128 m128_shr(Mask128 m, u32 k) {  // 0 < k < 64
+    Mask128 r;
+    r.lo = (m.lo >> k) | (m.hi << (64u - k));
+    r.hi = m.hi >> k;
+    return r;
+}
+__device__ __forceinline__ Mask128 m128_and(Mask128 a, Mask128 b) {
+    Mask128 r;
+    r.lo = a.lo & b.lo;
+    r.hi = a.hi & b.hi;
+    return r;
+}
+// positions from which at least `k` ones follow (k = 3, 8 or 12)
+__device__ __forceinline__ Mask128 m128_runs(Mask128 m, u32 k) {
+    Mask128 m2 = m128_and(m, m128_shr(m, 1));
+    if (k == 3u) return m128_and(m2, m128_shr(m, 2));
+    Mask128 m4 = m128_and(m2, m128_shr(m2, 2));
+    Mask128 m8 = m128_and(m4, m128_shr(m4, 4));
+    if (k == 8u) return m8;
+    return m128_and(m8, m128_shr(m4, 8));  // 12
+}
+// number of ones from bit q upwards
+__device__ __forceinline__ u32 m128_runlen(Mask128 m, u32 q) {
+    if (q < 64u) {
+        u64 x = ~(m.lo >> q);  // the q bits shifted in are zeros -> ones: the run ends at 64 - q at the latest
+        u32 r = x ? (u32)__ffsll((long long)x) - 1u : 64u;
+        if (r < 64u - q) return r;
+        u64 y = ~m.hi;
+        return (64u - q) + (y ? (u32)__ffsll((long long)y) - 1u : 64u);
+    }
+    u64 x = ~(m.hi >> (q - 64u));
+    return x ? (u32)__ffsll((long long)x) - 1u : 64u;
+}
+// first set bit at or above q, ZM_SPAN if none
+__device__ __forceinline__ u32 m128_next(Mask128 m, u32 q) {
+    if (q < 64u) {
+        u64 x = m.lo & (~0ull << q);
+        if (x) return (u32)__ffsll((long long)x) - 1u;
+        return m.hi ? 64u + (u32)__ffsll((long long)m.hi) - 1u : ZM_SPAN;
+    }
+    u64 x = m.hi & (~0ull << (q - 64u));
+    return x ? 64u + (u32)__ffsll((long long)x) - 1u : ZM_SPAN;
+}
+// four flag bits of the byte lanes in which a and b agree
+__device__ __forceinline__ u32 eq_bits4(u32 a, u32 b) { return (((__vcmpeq4(a, b) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }
+// masks of S[p0 + i] == S[p0 + i - d] for i < n (n <= ZM_SPAN), d = d1 / d2 (0 = no such offset)
+__device__ __forceinline__ void zi_eq_masks(const u8 *S, u32 p0, u32 n, u32 d1, u32 d2, Mask128 &A, Mask128 &B) {
+    const u8 *c = S + p0, *a = c - d1, *b = c - d2;
+    const u32 *cw = (const u32 *)((uintptr_t)c & ~(uintptr_t)3), *aw = (const u32 *)((uintptr_t)a & ~(uintptr_t)3),
+              *bw = (const u32 *)((uintptr_t)b & ~(uintptr_t)3);
+    const u32 cs = ((u32)(uintptr_t)c & 3u) * 8u, as = ((u32)(uintptr_t)a & 3u) * 8u, bs = ((u32)(uintptr_t)b & 3u) * 8u;
+    u32 cp = cw[0], ap = d1 ? aw[0] : 0u, bp = d2 ? bw[0] : 0u;
+    A.lo = A.hi = B.lo = B.hi = 0;
+    const u32 nw = (n + 3u) >> 2;
+#pragma unroll 4
+    for (u32 j = 0; j < nw; j++) {
+        u32 cn = cw[j + 1];
+        u32 cv = __funnelshift_r(cp, cn, cs);
+        cp = cn;
+        u32 ea = 0, eb = 0;
+        if (d1) {
+            u32 an = aw[j + 1];
+            ea = eq_bits4(cv, __funnelshift_r(ap, an, as));
+            ap = an;
+        }
+        if (d2) {
+            u32 bn = bw[j + 1];
+            eb = eq_bits4(cv, __funnelshift_r(bp, bn, bs));
+            bp = bn;
+        }
+        const u32 sh = (4u * j) & 63u;
+        if (j < 16u) {
+            A.lo |= (u64)ea << sh;
+            B.lo |= (u64)eb << sh;
+        } else {
+            A.hi |= (u64)ea << sh;
+            B.hi |= (u64)eb << sh;
+        }
+    }
+    // positions at or beyond n do not count
+    if (n < 64u) {
+        const u64 keep = (1ull << n) - 1ull;
+        A.lo &= keep; B.lo &= keep;
+        A.hi = B.hi = 0;
+    } else if (n < 128u) {
+        const u64 keep = (n == 64u) ? 0ull : (1ull << (n - 64u)) - 1ull;
+        A.hi &= keep; B.hi &= keep;
+    }
+}
+
 // Parse of src[0..len) with item boundaries.  items != nullptr: items[i] - item_base is the frame
 // position of item i (monotonic, nitems entries, the last one an end sentinel); items == nullptr:
 // fixed stride `nitems` bytes.  Emits sequences into sll/sml/sof (raw offsets) and literals into lit.
@@ -1174,6 +1278,33 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
             // record streams: unlike the item streams their literals are cheap (2 bits per base, a bit per zero),
             // so only matches that clearly beat them are taken
             const u32 min1 = cand ? ZR_MINMATCH : ZI_MINMATCH, min2 = cand ? ZR_MINRUN : ZI_MINMATCH;
+            // (an offset that reaches in front of the frame at the item's start — the first items of a frame — takes the byte loop)
+            if (lim - p <= ZM_SPAN && (!d1 || p + back >= d1) && (!d2 || p + back >= d2) ZM_DEBUG_TOGGLE) {
+                const u32 e1 = d1, e2 = d2;
+                if (e1 | e2) {
+                    Mask128 A, B;
+                    zi_eq_masks(src, p, lim - p, e1, e2, A, B);
+                    const Mask128 RA = m128_runs(A, min1), RB = m128_runs(B, min2);
+                    Mask128 C;
+                    C.lo = RA.lo | RB.lo;
+                    C.hi = RA.hi | RB.hi;
+                    const u32 qstop = stop - p;
+                    u32 q = 0;
+                    while (cnt < ZI_MAXM) {
+                        q = m128_next(C, q);
+                        if (q >= qstop) break;
+                        const bool ina = q < 64u ? (RA.lo >> q) & 1ull : (RA.hi >> (q - 64u)) & 1ull;
+                        const bool inb = q < 64u ? (RB.lo >> q) & 1ull : (RB.hi >> (q - 64u)) & 1ull;
+                        const u32 la = ina ? m128_runlen(A, q) : 0u, lb = inb ? m128_runlen(B, q) : 0u;
+                        const u32 best = max(la, lb);
+                        mbuf[(lane * ZI_MAXM + cnt) * 2] = (p + q) | (best << 16);
+                        mbuf[(lane * ZI_MAXM + cnt) * 2 + 1] = (la >= lb) ? e1 : e2;
+                        cnt++;
+                        q += best;
+                        if (q >= ZM_SPAN) break;
+                    }
+                }
+            } else
             while (p < stop && cnt < ZI_MAXM) {
                 u32 la = (d1 && p + back >= d1) ? zi_match_len(src, p, d1, lim) : 0u;
                 u32 lb = (d2 && p + back >= d2) ? zi_match_len(src, p, d2, lim) : 0u;
@@ -1721,8 +1852,9 @@ __global__ void __launch_bounds__(ZENC_WARPS * 32) k_zenc(const ZFrame *frames, 
 // Decoders see ordinary multi-block frames; the GPU decoder decodes the 32 streams of a frame in parallel.
 #define ZH_THREADS 256
 #define ZH_WARPS 8
-#define ZH_STAGE_WORDS 192
-#define ZH_FLUSH_BITS 4096u
+#define ZH_STAGE_WORDS 360  // a round of 32 lanes x ZH_CHUNK symbols x 11 bits, plus the carried partial word
+#define ZH_CHUNK 32u        // symbols per lane and round
+#define ZH_LANE_WORDS 12u
 #define ZH_MIN_HUF 1024u  // blocks / frames below this are stored raw
 
 struct ZhShared {
@@ -1874,79 +2006,105 @@ __device__ static u32 cta_huf_build(const u32 *hist, u32 total, u16 *hlut, HufTm
 
 // One warp encodes the Huffman stream of src[a, b) to dst (exactly ((bits + 1) + 7) / 8 bytes).
 // The LAST symbol goes to the lowest bits (the decoder reads the stream backwards).
-__device__ static void warp_stream_encode(const u8 *src, u32 a, u32 b, const u16 *hlut, u8 *dst, u32 *stage) {
+// Rounds of ZH_CHUNK symbols per lane: every lane codes ITS run of symbols into a private bit buffer with a
+// plain serial loop (table lookup, shift, or — no warp scan per handful of symbols), one warp scan of the lanes'
+// bit counts then places the 32 buffers in the warp's stage (whole words by funnel shift, only the two words a
+// lane shares with its neighbours by atomicOr), and the complete words go out with coalesced 32-bit stores.
+// lbuf: ZH_LANE_WORDS x 32 words, word j of lane l at lbuf[32 j + l] (conflict free).
+__device__ static void warp_stream_encode(const u8 *src, u32 a, u32 b, const u16 *hlut, u8 *dst, u32 *stage, u32 *lbuf) {
     u32 lane = lane_id();
     const u32 al = (u32)((uintptr_t)dst & 3u);  // stage byte i <-> global byte gbase[i]
     u8 *gbase = dst - al;
     for (u32 i = lane; i < ZH_STAGE_WORDS; i += 32) stage[i] = 0;
     __syncwarp();
-    u32 P = 8u * al;
+    u32 P = 8u * al;  // bits in the stage (the first 8 al of the first word are not ours)
     bool first = true;
-    u32 m = b - a, T = (m + 127u) >> 7;
-    // the word of the next step is loaded while this one is coded
-    u32 xn = 0;
-    {
-        int i0 = (int)b - 4 * (int)(lane + 1u);
-        if (i0 >= (int)a) xn = ld_u32_unaligned(src + i0);
-    }
+    const u32 m = b - a, T = (m + 32u * ZH_CHUNK - 1u) / (32u * ZH_CHUNK);
     for (u32 t = 0; t < T; t++) {
-        int idx0 = (int)(b - 128u * t) - 4 * (int)(lane + 1u);  // lane 0 owns the highest indices = lowest bits
-        u64 v = 0;
-        u32 L = 0;
-        const u32 xc = xn;
-        {
-            int i1 = idx0 - 128;
-            if (t + 1 < T && i1 >= (int)a) xn = ld_u32_unaligned(src + i1);
-        }
-        if (idx0 >= (int)a) {
-            u32 x = xc;
+        // this lane's symbols: [lo, hi), coded from hi - 1 downwards (lane 0 owns the highest indices = lowest bits)
+        const int top = (int)(b - 32u * ZH_CHUNK * t) - (int)(ZH_CHUNK * lane);
+        const int hi = max(top, (int)a), lo = max(top - (int)ZH_CHUNK, (int)a);
+        u64 acc = 0;
+        u32 nb = 0, nwd = 0;
+        if (hi > lo) {
+            // whole words from the top through a rolling pair of aligned loads, then the bytes left at the bottom
+            const u8 *pt = src + hi;
+            const u32 *wp = (const u32 *)((uintptr_t)pt & ~(uintptr_t)3);
+            const u32 sh = ((u32)(uintptr_t)pt & 3u) * 8u;
+            u32 whi = sh ? wp[0] : 0u;  // bytes of the word that holds pt (only its low part is ours)
+            int i = hi;
+            for (; i - 4 >= lo; i -= 4) {
+                wp--;
+                const u32 wlo = wp[0];
+                const u32 x = sh ? __funnelshift_r(wlo, whi, sh) : wlo;  // src[i-4 .. i-1]
+                whi = wlo;
+                // two symbols (<= 22 bits) on top of < 32 pending bits fit the 64-bit accumulator
 #pragma unroll
-            for (int k = 3; k >= 0; k--) {
-                u32 e = hlut[(x >> (8 * k)) & 0xFFu];
-                v |= (u64)(e >> 4) << L;
-                L += e & 15u;
-            }
-        } else {
-            for (int k = 3; k >= 0; k--) {
-                int idx = idx0 + k;
-                if (idx >= (int)a) {
-                    u32 e = hlut[src[idx]];
-                    v |= (u64)(e >> 4) << L;
-                    L += e & 15u;
+                for (int k = 3; k >= 1; k -= 2) {
+                    const u32 e1 = hlut[(x >> (8 * k)) & 0xFFu], e0 = hlut[(x >> (8 * (k - 1))) & 0xFFu];
+                    const u32 l1 = e1 & 15u;
+                    const u32 pair = (e1 >> 4) | ((e0 >> 4) << l1);
+                    acc |= (u64)pair << nb;
+                    nb += l1 + (e0 & 15u);
+                    if (nb >= 32u) {
+                        lbuf[32u * nwd + lane] = (u32)acc;
+                        nwd++;
+                        acc >>= 32;
+                        nb -= 32u;
+                    }
                 }
             }
+            for (; i > lo; i--) {  // at most three
+                const u32 e = hlut[src[i - 1]];
+                acc |= (u64)(e >> 4) << nb;
+                nb += e & 15u;
+                if (nb >= 32u) {
+                    lbuf[32u * nwd + lane] = (u32)acc;
+                    nwd++;
+                    acc >>= 32;
+                    nb -= 32u;
+                }
+            }
+            if (nb) lbuf[32u * nwd + lane] = (u32)acc;
         }
-        u32 incl = group_incl_scan(L, FULL, 32);
-        u32 tot = __shfl_sync(FULL, incl, 31);
-        u32 bit = P + incl - L;
+        const u32 L = 32u * nwd + nb;  // bits of this lane
+        const u32 incl = group_incl_scan(L, FULL, 32);
+        const u32 tot = __shfl_sync(FULL, incl, 31);
         if (L) {
-            u32 w = bit >> 5, sh = bit & 31u;
-            u32 v0 = (u32)v, v1 = (u32)(v >> 32);
-            atomicOr(&stage[w], v0 << sh);
-            u32 mid = __funnelshift_l(v0, v1, sh);
-            if (mid) atomicOr(&stage[w + 1], mid);
-            u32 hi = sh ? (v1 >> (32u - sh)) : 0u;
-            if (hi) atomicOr(&stage[w + 2], hi);
+            const u32 bit = P + incl - L, w0 = bit >> 5, s2 = bit & 31u;
+            const u32 nws = (L + 31u) >> 5;                // words of the lane buffer in use
+            const u32 nst = ((s2 + L - 1u) >> 5) + 1u;     // stage words the lane's bits fall into
+            // stage word w0 + k = low part of buffer word k | high part of buffer word k - 1; the first and the last
+            // one may hold bits of the neighbouring lanes too
+            u32 prev = 0;
+            for (u32 k = 0; k < nst; k++) {
+                const u32 cur = k < nws ? lbuf[32u * k + lane] : 0u;
+                const u32 v = s2 ? __funnelshift_l(prev, cur, s2) : cur;
+                if (k == 0 || k + 1u == nst) atomicOr(&stage[w0 + k], v);
+                else stage[w0 + k] = v;
+                prev = cur;
+            }
         }
         __syncwarp();
         P += tot;
-        if (P >= ZH_FLUSH_BITS) {  // flush the complete words, keep the partial one
-            u32 nw = P >> 5;
-            for (u32 i = lane; i < nw; i += 32) {
-                u32 wv = stage[i];
-                u8 *g = gbase + 4u * i;
-                if (i == 0 && first && al) {
-                    for (u32 k = al; k < 4; k++) g[k] = (u8)(wv >> (8u * k));
-                } else
-                    *(u32 *)g = wv;
-            }
-            __syncwarp();
-            u32 carry = stage[nw];
-            __syncwarp();
-            for (u32 i = lane; i < nw + 4u; i += 32) stage[i] = 0;
-            __syncwarp();
-            if (lane == 0) stage[0] = carry;
-            __syncwarp();
+        // flush the complete words, keep the partial one
+        const u32 nw = P >> 5;
+        for (u32 i = lane; i < nw; i += 32) {
+            u32 wv = stage[i];
+            u8 *g = gbase + 4u * i;
+            if (i == 0 && first && al) {
+                for (u32 k = al; k < 4; k++) g[k] = (u8)(wv >> (8u * k));
+            } else
+                *(u32 *)g = wv;
+        }
+        __syncwarp();
+        const u32 carry = stage[nw];
+        __syncwarp();
+        for (u32 i = lane; i < nw + 3u; i += 32) stage[i] = 0;
+        __syncwarp();
+        if (lane == 0) stage[0] = carry;
+        __syncwarp();
+        if (nw) {
             gbase += 4u * nw;
             P &= 31u;
             first = false;
@@ -2092,7 +2250,11 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
             ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
             out_sizes[fi] = S.misc[2];
         }
-        // ---- 4. encode
+        // ---- 4. encode.  The per-stream histograms (and the code builder's arrays behind them) are done with: their
+        //      memory becomes the lanes' bit buffers
+        __syncthreads();
+        u32 *lbuf = &S.shist[0][0] + warp * (ZH_LANE_WORDS * 32u);
+        static_assert(ZH_WARPS * ZH_LANE_WORDS * 32u <= 32u * 128u, "lane buffers must fit into the stream histograms");
         if (warp < nblk) {
             u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
             if (bn < ZH_MIN_HUF) {
@@ -2101,7 +2263,7 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
             } else {
                 for (u32 k = 0; k < 4; k++) {
                     u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
-                    warp_stream_encode(src, a, b, S.hlut, out + S.sdst[4 * warp + k], S.stage[warp]);
+                    warp_stream_encode(src, a, b, S.hlut, out + S.sdst[4 * warp + k], S.stage[warp], lbuf);
                 }
             }
         }
