@@ -2167,7 +2167,11 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
     // ---- 2. code
     u32 mode = 0;  // 0 raw block, 1 RLE block, 2 Huffman blocks
     u32 maxBits = 0;
-    if (n >= ZH_MIN_HUF) maxBits = cta_huf_build(S.hist, n, S.hlut, S.huf, S.keys, S.misc);
+    // all 256 byte values within 25 % of n / 256 (2-bit packed random bases): a Huffman code cannot gain a percent,
+    // so the frame is stored without building one
+    const u32 hc = S.hist[tid];
+    const bool flat = !__syncthreads_or(4u * 256u * hc > 5u * n || 4u * 256u * hc < 3u * n);
+    if (n >= ZH_MIN_HUF && !flat) maxBits = cta_huf_build(S.hist, n, S.hlut, S.huf, S.keys, S.misc);
     else {
         u32 distinct = (u32)__syncthreads_count(S.hist[tid] != 0);
         if (tid == 0) S.misc[3] = distinct;
