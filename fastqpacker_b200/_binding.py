@@ -51,6 +51,20 @@ def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data if a.size else None)
 
 
+class _FileInfo(C.Structure):
+    _fields_ = [
+        ("version", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("header_block_size", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("blocks", C.c_uint64),
+        ("records", C.c_uint64),
+        ("compressed", C.c_uint64 * 6),
+        ("original_seq", C.c_uint64),
+        ("original_qual", C.c_uint64),
+    ]
+
+
 class FqzLibrary:
     def __init__(self, path: str):
         self.path = path
@@ -84,6 +98,8 @@ class FqzLibrary:
         self._opt(L, "fqz_find_line_end_device", [vp, vp, sz, C.c_uint64, C.POINTER(C.c_uint64)])
         self._opt(L, "fqz_compress_device", [vp, vp, sz, u32, vp, sz, szp])
         self._opt(L, "fqz_decompress_device", [vp, vp, sz, vp, sz, szp])
+        self._opt(L, "fqz_info", [vp, vp, sz, C.POINTER(_FileInfo)])
+        self._opt(L, "fqz_check", [vp, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
         self._opt(L, "fqz_compress_bound", [sz], restype=sz)
         self._opt(L, "fqz_host_alloc", [sz], restype=vp)
         self._opt(L, "fqz_host_free", [vp], restype=None)
@@ -235,6 +251,22 @@ class FqzContext:
                 continue
             self._check(rc)
             return out[: m.value].tobytes()
+
+    def info(self, fqz) -> dict:
+        """`fqpack info`: version, flags, blocks, records, per-stream compressed sizes (header walk only)."""
+        a = _as_u8(fqz)
+        fi = _FileInfo()
+        self._check(self.lib.L.fqz_info(self.h, _ptr(a), a.size, C.byref(fi)))
+        return dict(version=fi.version, flags=fi.flags, phred64=bool(fi.flags & 2), header_block_size=fi.header_block_size, blocks=int(fi.blocks),
+                    records=int(fi.records), compressed=[int(x) for x in fi.compressed], original_seq=int(fi.original_seq),
+                    original_qual=int(fi.original_qual))
+
+    def check(self, fqz):
+        """`fqpack check`: full decode on the GPU without output -> (records, FASTQ bytes); raises FqzError on a bad file."""
+        a = _as_u8(fqz)
+        r, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.L.fqz_check(self.h, _ptr(a), a.size, C.byref(r), C.byref(b)))
+        return r.value, b.value
 
     def decompress_into(self, fqz: np.ndarray, out: np.ndarray) -> int:
         m = C.c_size_t(0)

@@ -231,8 +231,9 @@ static int parse_file_header(fqz_ctx *c, const u8 *h, u64 n, DecState &st) {
 // the last block decoded.  A partial trailing block is an error only when is_last.
 // host_io: d_fqz is c->io.d_in still being uploaded; windows gate on the chunks they read and
 // every window's FASTQ is downloaded from an alternating staging slot while the next one is decoded.
+// discard: the FASTQ of every window is produced in device memory and dropped (fqz_check); out_cap is ignored.
 static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool is_last, bool partial_ok, DecState &st, u8 *d_out, u8 *h_out,
-                             size_t out_cap, size_t *out_len, u64 *consumed, bool host_io = false) {
+                             size_t out_cap, size_t *out_len, u64 *consumed, bool host_io = false, bool discard = false) {
     cudaStream_t s = c->stream;
     u64 pos = pos0;
     size_t written = 0;
@@ -276,7 +277,8 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
             c->arena.reset();  // the table lives on in `ent`
             size_t wl = 0;
             u8 *d_res = nullptr;
-            int slot = host_io ? (win & 1) : -1;
+            int slot = (host_io && !discard) ? (win & 1) : -1;
+            if (discard) out_cap = written + ((size_t)1 << 40);
             int rc = decode_blocks(c, d_fqz, ent.data() + done, take, st.phred64, d_out ? d_out + written : nullptr, out_cap - written,
                                    &d_res, &wl, st.block_base, slot);
             if (rc == FQZ_E_TOO_LARGE && take > 1) {  // the window decodes to more than one device pass holds
@@ -293,7 +295,7 @@ static int decompress_blocks(fqz_ctx *c, const u8 *d_fqz, u64 n, u64 pos0, bool 
                 return FQZ_E_NOSPACE;
             }
             if (rc != FQZ_OK) return rc;
-            if (!d_out && wl) {
+            if (!d_out && wl && !discard) {
                 if (host_io) {
                     FQZ_TRY(fqz_io_download(c, slot, h_out + written, d_res, wl));
                     win++;
@@ -362,6 +364,79 @@ extern "C" int fqz_decompress(fqz_ctx *c, const uint8_t *fqz, size_t n, uint8_t 
     if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *out_len = m;
     if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
     return rc;
+}
+
+// ---------------------------------------------------------------------------------- info / check (ROADMAP.md PR-008, PR-009)
+// fqz_info: what `fqpack info` would print — version, flags, block count, record count, stream sizes — from one hop
+// over the block headers (container.go:48-152; the format has no index, compress.go:721-736).  Header arithmetic
+// on the caller's host buffer: no device work.
+extern "C" int fqz_info(fqz_ctx *c, const uint8_t *fqz, size_t n, fqz_file_info *out) {
+    if (!c || !out || (!fqz && n)) return FQZ_E_INVALID_ARG;
+    c->err.clear();
+    memset(out, 0, sizeof *out);
+    DecState st;
+    FQZ_TRY(parse_file_header(c, fqz, n, st));
+    out->version = st.version;
+    out->flags = fqz[9];
+    out->header_block_size = (u32)fqz[5] | ((u32)fqz[6] << 8) | ((u32)fqz[7] << 16) | ((u32)fqz[8] << 24);
+    const size_t hsz = st.version == 1 ? 32 : 36;
+    const int ns = st.version == 1 ? 5 : 6;
+    size_t pos = 10;
+    while (pos < n) {
+        if (n - pos < hsz) {
+            c->err = "reading block header: unexpected EOF";
+            return FQZ_E_TRUNC_FILE;
+        }
+        u32 v[9];
+        for (size_t i = 0; i < hsz / 4; i++) v[i] = (u32)fqz[pos + 4 * i] | ((u32)fqz[pos + 4 * i + 1] << 8) | ((u32)fqz[pos + 4 * i + 2] << 16) | ((u32)fqz[pos + 4 * i + 3] << 24);
+        u64 payload = 0;
+        // v1: seq, qual, headers, N positions, lengths (container.go:128-152); v2 adds the plus-line payload in front of N positions
+        static const int k_v1_slot[5] = {0, 1, 2, 4, 5};
+        for (int a = 0; a < ns; a++) {
+            payload += v[1 + a];
+            out->compressed[st.version == 1 ? k_v1_slot[a] : a] += v[1 + a];
+        }
+        if (n - pos - hsz < payload) {
+            c->err = "reading compressed data: unexpected EOF";
+            return FQZ_E_TRUNC_FILE;
+        }
+        out->blocks++;
+        out->records += v[0];
+        out->original_seq += v[1 + ns];
+        out->original_qual += v[2 + ns];
+        pos += hsz + payload;
+    }
+    return FQZ_OK;
+}
+
+// fqz_check: what `fqpack check` would do — walk the container, decode every stream of every block (frame checksums
+// verified), rebuild every record, and report pass / fail without writing the FASTQ anywhere: the text of each
+// device window is produced in HBM and dropped, so the check runs at the device-resident decompress rate plus
+// the upload of the compressed file.  Returns the first error the decoder meets (same codes and texts as
+// fqz_decompress); *records / *fastq_bytes (optional) = what the file holds.
+extern "C" int fqz_check(fqz_ctx *c, const uint8_t *fqz, size_t n, uint64_t *records, uint64_t *fastq_bytes) {
+    if (!c || (!fqz && n)) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    if (records) *records = 0;
+    if (fastq_bytes) *fastq_bytes = 0;
+    fqz_file_info fi;
+    FQZ_TRY(fqz_info(c, fqz, n, &fi));
+    DecState st;
+    FQZ_TRY(parse_file_header(c, fqz, n, st));
+    int rc = fqz_io_upload(c, fqz, n);
+    size_t m = 0;
+    if (rc == FQZ_OK) {
+        u64 used = 0;
+        rc = decompress_blocks(c, c->io.d_in, n, 10, true, false, st, nullptr, nullptr, 0, &m, &used, true, true);
+    }
+    int rc2 = fqz_io_finish(c);
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
+    if (rc != FQZ_OK) return rc;
+    if (records) *records = fi.records;
+    if (fastq_bytes) *fastq_bytes = m;
+    return FQZ_OK;
 }
 
 // ---------------------------------------------------------------------------------- streaming (Seam B)

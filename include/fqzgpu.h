@@ -79,6 +79,23 @@ void fqz_host_free(void *p);
 size_t fqz_compress_bound(size_t fastq_bytes);
 int fqz_compress(fqz_ctx *ctx, const uint8_t *fastq, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap, size_t *out_len);
 int fqz_decompress(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
+/* ---- archive introspection and verification (the reference's ROADMAP.md PR-009 `fqpack info`, PR-008 `fqpack check`)
+ * fqz_info: version, flags, block / record counts and per-stream compressed sizes from one hop over the block
+ *   headers (container.go:48-152); header arithmetic on the host buffer, no device work.
+ * fqz_check: decodes every stream of every block (frame checksums verified) and rebuilds every record on the GPU
+ *   without writing the FASTQ anywhere; same error codes and texts as fqz_decompress. */
+typedef struct fqz_file_info {
+    uint32_t version;            /* 1 or 2 */
+    uint32_t flags;              /* bit 1 = Phred+64 (container.go:28) */
+    uint32_t header_block_size;  /* records per block as written in the file header */
+    uint32_t reserved;
+    uint64_t blocks, records;
+    uint64_t compressed[6];      /* seqPacked, quality, headers, plusLines (0 in v1 files), nPositions, seqLengths */
+    uint64_t original_seq, original_qual; /* sums of OriginalSeqSize / OriginalQualSize */
+} fqz_file_info;
+int fqz_info(fqz_ctx *ctx, const uint8_t *fqz, size_t n, fqz_file_info *out);
+int fqz_check(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t *records, uint64_t *fastq_bytes);
+
 /* One shard of a file that is split across GPUs on block boundaries (blocks are independent,
  * compress.go:523-528).  phred64: -1 = detect on this shard's first block (the shard
  * holding block 0 of the file, compress.go:146-164), 0 / 1 = the file-global decision made there.

@@ -223,6 +223,12 @@ def check_file_errors(ctx, oracle):
         with pytest.raises(FqzError) as ge:
             ctx.decompress(blob)
         assert ge.value.code == code, name
+        with pytest.raises(FqzError) as ce:  # `fqpack check` (fqz_check) rejects the same files the same way
+            ctx.check(blob)
+        assert ce.value.code == code, name
+        with pytest.raises(FqzError) as ie:  # ... and so does the header walk of `fqpack info`
+            ctx.info(blob)
+        assert ie.value.code == code, name
     # corrupt frames: flip one byte inside each stream's payload in turn
     sizes = struct.unpack("<9I", fqz[10:46])[1:7]
     pos = 46
@@ -240,9 +246,23 @@ def check_file_errors(ctx, oracle):
             got = e.code
         if isinstance(want, int):
             assert isinstance(got, int) and got < 0, (i, want, got)  # both reject (the first check that trips may differ)
+            with pytest.raises(FqzError):
+                ctx.check(bytes(bad))
         else:
             assert got == want
     assert ctx.decompress(fqz[:10]) == b""  # header-only file (compress_test.go:160-173)
+    assert ctx.check(fqz[:10]) == (0, 0)
+    # info / check of good files, reference-written (v2, v1) and GPU-written
+    text = GOOD_CASES["rand_small"]
+    nrec = text.count(b"\n") // 4
+    for blob, ver in ((fqz, 2), (oracle.compress(text, version=1), 1), (ctx.compress(text), 2)):
+        fi = ctx.info(blob)
+        hdr = struct.unpack("<8I" if ver == 1 else "<9I", blob[10 : 10 + (32 if ver == 1 else 36)])
+        assert (fi["version"], fi["blocks"], fi["records"], fi["phred64"], fi["header_block_size"]) == (ver, 1, nrec, False, 100000)
+        want_sizes = list(hdr[1:6]) if ver == 2 else [hdr[1], hdr[2], hdr[3], 0, hdr[4]]
+        assert fi["compressed"][:5] == want_sizes and fi["compressed"][5] == hdr[6 if ver == 2 else 5]
+        assert fi["original_seq"] == fi["original_qual"] == sum(len(l) for l in text.split(b"\n")[1::4])
+        assert ctx.check(blob) == (nrec, len(oracle.decompress(blob)))
 
 
 def check_item_hints(ctx, oracle, nrec=3000):
