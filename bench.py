@@ -542,24 +542,9 @@ def run_cfg5(args):
     h_slice = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     h_slice.copy_(d_slice[:n])
     d_out = torch.empty(n // 2 + (64 << 20), dtype=torch.uint8, device="cuda")
-    h_out = torch.empty(n // 3 + (64 << 20), dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
     out_path = _shared_path(f"fqz_bench_cfg5_{os.environ.get('MASTER_PORT', '0')}.fqz")
     st = {}
-    # the ordered collector's output file (collectAndWriteResults, compress.go:365-403): one shared host buffer that every
-    # rank maps and page-locks, so that a part goes from HBM straight to its place in the file (no second host copy)
-    out_cap = (R * 372) // 3 + (64 << 20) * world
-    if rank == 0:
-        with open(out_path, "wb") as f:
-            f.truncate(out_cap)
-    barrier()
-    mm = np.memmap(out_path, dtype=np.uint8, mode="r+")
-    h_file = torch.from_numpy(mm)
-    direct = False
-    try:
-        direct = int(torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, mm.size, 0)) == 0
-    except Exception:
-        direct = False
 
     def plan_and_compress():
         """device-resident part: count, exchange, borrow, compress.  Leaves the part in d_out[:st['m']]."""
@@ -603,9 +588,8 @@ def run_cfg5(args):
         plan_and_compress()
         m = st["m"]
         sizes = [v[0] for v in gather_ints([m])]  # where this part goes in the file
-        st["sizes"] = sizes
+        assert sizes == st["sizes"], "part sizes changed between steps"
         off = sum(sizes[:rank])
-        assert sum(sizes) <= out_cap
         if direct:
             with torch.cuda.stream(lib_stream):
                 h_file[off : off + m].copy_(d_out[:m], non_blocking=True)
@@ -639,6 +623,32 @@ def run_cfg5(args):
     ctx.stats_reset()
     t_dev = timed_wall(plan_and_compress, steps, warm)
     launches = ctx.stats()["launches"] // (steps + warm)
+    # the ordered collector's output file (collectAndWriteResults, compress.go:365-403): one shared host file that every
+    # rank maps; a rank page-locks the pages its own part lands in (the sizes are known from the passes above and do
+    # not change), so that the part goes from HBM straight to its place in the file — no second host copy
+    st["sizes"] = [v[0] for v in gather_ints([st["m"]])]
+    total_out = sum(st["sizes"])
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.truncate(total_out)
+    barrier()
+    mm = np.memmap(out_path, dtype=np.uint8, mode="r+")
+    h_file = torch.from_numpy(mm)
+    my_off, my_m = sum(st["sizes"][:rank]), st["m"]
+    page = 4096
+    reg_lo = (mm.ctypes.data + my_off) & ~(page - 1)
+    reg_hi = (mm.ctypes.data + my_off + my_m + page - 1) & ~(page - 1)
+    direct = False
+    try:
+        direct = int(torch.cuda.cudart().cudaHostRegister(reg_lo, reg_hi - reg_lo, 0)) == 0
+    except Exception:
+        direct = False
+    if not direct:
+        try:
+            torch.cuda.cudart().cudaGetLastError()  # a refused registration must not poison the next CUDA call
+        except Exception:
+            pass
+    h_out = None if direct else torch.empty(my_m + (1 << 20), dtype=torch.uint8, pin_memory=True)
     t_e2e = timed_wall(e2e_compress, steps, 1)
     sizes = st["sizes"]
     fqz_total = sum(sizes)
@@ -694,7 +704,7 @@ def run_cfg5(args):
     barrier()
     if direct:
         try:
-            torch.cuda.cudart().cudaHostUnregister(mm.ctypes.data)
+            torch.cuda.cudart().cudaHostUnregister(reg_lo)
         except Exception:
             pass
     if rank == 0:

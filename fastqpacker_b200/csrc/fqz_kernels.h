@@ -14,9 +14,15 @@
 #define FQZ_META_GROUP 8
 // stream scatter: 16 lanes per record, 64 records per CTA staged through 40 KiB of shared memory
 #define FQZ_SC_THREADS 256
+#ifndef FQZ_SC_GROUP
 #define FQZ_SC_GROUP 16
+#endif
+#ifndef FQZ_SC_RPC
 #define FQZ_SC_RPC 64
+#endif
+#ifndef FQZ_SC_SMEM
 #define FQZ_SC_SMEM 40960
+#endif
 
 void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s);
 void fqz_launch_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos, cudaStream_t s);
