@@ -381,6 +381,9 @@ __global__ void __launch_bounds__(256) k_check_seq_qual(const BkBlock *blks, u32
 }
 
 // ---------------------------------------------------------------------------------- emit
+#ifndef FQZ_EM_GROUP
+#define FQZ_EM_GROUP 16  // lanes per record
+#endif
 template <int W>
 __device__ __forceinline__ void bk_group_copy(u8 *dst, const u8 *src, u32 n, u32 g) {
     u32 head = (u32)((4u - ((uintptr_t)dst & 3u)) & 3u);
@@ -407,7 +410,7 @@ __device__ __forceinline__ u32 prefix4(u32 x) {
 
 __global__ void __launch_bounds__(256)
 k_emit_fastq(const BkBlock *blks, u32 nblocks, const u32 *offs_base, const u32 *sc, u64 stride, u32 phred64, u8 *out, FqzDecStatus *st) {
-    const int W = 16;
+    const int W = FQZ_EM_GROUP;
     u32 b = blockIdx.y;
     BkBlock B = blks[b];
     u32 g = threadIdx.x & (W - 1);
@@ -569,5 +572,6 @@ void fqz_launch_check_seq_qual(const BkBlock *blks, u32 nblocks, u32 max_nrec, c
 void fqz_launch_emit(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, const u32 *sc, u64 stride, u32 phred64, u8 *out,
                      FqzDecStatus *st, cudaStream_t s) {
     if (!nblocks || !max_nrec) return;
-    FQZ_LAUNCH(k_emit_fastq, dim3((max_nrec + 15) / 16, nblocks), 256, 0, s, blks, nblocks, offs, sc, stride, phred64, out, st);
+    const u32 per = 256 / FQZ_EM_GROUP;  // records per CTA
+    FQZ_LAUNCH(k_emit_fastq, dim3((max_nrec + per - 1) / per, nblocks), 256, 0, s, blks, nblocks, offs, sc, stride, phred64, out, st);
 }

@@ -290,6 +290,103 @@ __device__ __forceinline__ void group_copy(u8 *dst, const u8 *src, u32 n, u32 g)
     if (g < n - t0) dst[t0 + g] = src[t0 + g];
 }
 
+// Writes one record into the six streams (a W-lane group).  t: its four lines; L, H, P: sequence / header / plus
+// payload lengths as sized by the meta pass; o_*: the record's offsets in the streams; has_n: it holds non-ACGT bases.
+struct ScStreams {
+    u8 *seq, *qual, *hdr, *plus, *npos, *len;
+};
+template <int W>
+__device__ __forceinline__ void scatter_record(const Src &src, const LineSpan &t, u64 r, u32 L, u32 H, u32 P, u32 o_seq, u32 o_qual, u32 o_hdr,
+                                               u32 o_plus, u32 o_npos, bool has_n, u8 off, const ScStreams &S, u32 g, u32 gm) {
+    u8 *s_seq = S.seq, *s_qual = S.qual, *s_hdr = S.hdr, *s_plus = S.plus, *s_npos = S.npos, *s_len = S.len;
+    // seqLengths: u32 L (compress.go:501)
+    if (g == 0) *(u32 *)(s_len + 4ull * r) = L;
+    // headers / plusLines: u16 length prefix + bytes without the leading '@' / '+' (compress.go:514-519)
+    if (g == 0) st_u16_unaligned(s_hdr + o_hdr, H & 0xFFFFu);
+    group_copy<W>(s_hdr + o_hdr + 2, src.at(t.hs + 1u), H, g);
+    if (g == 0) st_u16_unaligned(s_plus + o_plus, P & 0xFFFFu);
+    group_copy<W>(s_plus + o_plus + 2, src.at(t.ps + 1u), P, g);
+    // seqPacked + nPositions (sequence.go:139-184): 16 bases per lane per round.  k_record_meta has
+    // already counted the record's non-ACGT bases (that count sized the N-position stream): the 99 % of
+    // reads without any take a path with no N test, no position bookkeeping and no group scan.
+    u32 units = (L + 15u) >> 4, rounds = (units + W - 1) / W;
+    u32 nbase = 0;
+    if (!has_n) {
+        for (u32 u = g; u < units; u += W) {
+            const u8 *sp = src.at(t.ss + 16u * u);
+            u32 out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
+                if (bp < L) {
+                    u32 x = ld_u32_unaligned(sp + 4 * k);
+                    u32 codes = base_codes4(x, 0u);
+                    if (bp + 4u > L) codes &= 0xFFFFFFFFu >> (8u * (bp + 4u - L));  // bytes past the read
+                    out |= pack_codes4(codes) << (8 * k);
+                }
+            }
+            u32 vb = min(16u, L - 16u * u);
+            st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
+        }
+    } else
+    for (u32 j = 0; j < rounds; j++) {
+        u32 u = j * W + g;
+        u32 nmask16 = 0;
+        if (u < units) {
+            const u8 *sp = src.at(t.ss + 16u * u);
+            u32 out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
+                if (bp < L) {
+                    u32 x = ld_u32_unaligned(sp + 4 * k);
+                    u32 rm = range_mask4(bp, 0u, L);
+                    u32 nm = nonacgt_mask4(x) & rm;
+                    u32 codes = base_codes4(x, nm) & rm;
+                    out |= pack_codes4(codes) << (8 * k);
+                    nmask16 |= ((((nm & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+                }
+            }
+            u32 vb = min(16u, L - 16u * u);
+            st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
+            if (16u * u >= FQZ_MAX_SEQ_LEN) nmask16 = 0;  // positions >= 65536 are not tracked
+        }
+        u32 cnt = (u32)__popc(nmask16);
+        u32 incl = group_incl_scan(cnt, gm, W);
+        u32 tot = __shfl_sync(gm, incl, W - 1, W);
+        u32 k = nbase + incl - cnt;
+        while (nmask16) {
+            int b = __ffs((int)nmask16) - 1;
+            nmask16 &= nmask16 - 1;
+            st_u16_unaligned(s_npos + o_npos + 2u + 2u * k, 16u * u + (u32)b);
+            k++;
+        }
+        nbase += tot;
+    }
+    if (g == 0) st_u16_unaligned(s_npos + o_npos, nbase & 0xFFFFu);  // compress.go:495 (silent u16 truncation)
+    // quality: normalise + per-record delta (compress.go:506-510; quality.go:53-103)
+    {
+        u8 *dq = s_qual + o_qual;
+        const u8 *sq = src.at(t.qs);
+        u32 head = (u32)((4u - ((uintptr_t)dq & 3u)) & 3u);
+        if (head == 0) head = 4;  // keeps every body word at index >= 1 so q[i-1] exists
+        if (head > L) head = L;
+        if (g < head) dq[g] = (u8)(sq[g] - (g ? sq[g - 1] : off));
+        u32 nw = (L - head) >> 2;
+        for (u32 w = g; w < nw; w += W) {
+            u32 i = head + 4u * w;
+            u32 cur = ld_u32_unaligned(sq + i);
+            u32 prv = ld_u32_unaligned(sq + i - 1);
+            *(u32 *)(dq + i) = __vsub4(cur, prv);
+        }
+        u32 t0 = head + 4u * nw;
+        if (g < L - t0) {
+            u32 i = t0 + g;
+            dq[i] = (u8)(sq[i] - (i ? sq[i - 1] : off));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FQZ_SC_THREADS)
 k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u64 stride, const u32 *phred64, u8 *s_seq, u8 *s_qual,
                   u8 *s_hdr, u8 *s_plus, u8 *s_npos, u8 *s_len, u32 stage_cap) {
@@ -316,6 +413,7 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
         src.bias = 0;
     }
     const u8 off = *phred64 ? 64 : 33;
+    ScStreams S = {s_seq, s_qual, s_hdr, s_plus, s_npos, s_len};
     u32 g = threadIdx.x & (W - 1);
     u32 gm = group_mask(W);
     for (u64 r = r0 + threadIdx.x / W; r < r1; r += FQZ_SC_THREADS / W) {
@@ -338,93 +436,201 @@ k_scatter_streams(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u
         u32 H = t.he - t.hs - 1u, P = t.pe - t.ps - 1u;
         u32 o_seq = offs[0 * stride + r], o_qual = offs[1 * stride + r], o_hdr = offs[2 * stride + r];
         u32 o_plus = offs[3 * stride + r], o_npos = offs[4 * stride + r];
-        // seqLengths: u32 L (compress.go:501)
-        if (g == 0) *(u32 *)(s_len + 4ull * r) = L;
-        // headers / plusLines: u16 length prefix + bytes without the leading '@' / '+' (compress.go:514-519)
-        if (g == 0) st_u16_unaligned(s_hdr + o_hdr, H & 0xFFFFu);
-        group_copy<W>(s_hdr + o_hdr + 2, src.at(t.hs + 1u), H, g);
-        if (g == 0) st_u16_unaligned(s_plus + o_plus, P & 0xFFFFu);
-        group_copy<W>(s_plus + o_plus + 2, src.at(t.ps + 1u), P, g);
-        // seqPacked + nPositions (sequence.go:139-184): 16 bases per lane per round.  k_record_meta has
-        // already counted the record's non-ACGT bases (that count sized the N-position stream): the 99 % of
-        // reads without any take a path with no N test, no position bookkeeping and no group scan.
-        u32 units = (L + 15u) >> 4, rounds = (units + W - 1) / W;
-        u32 nbase = 0;
         const bool has_n = (offs[4 * stride + r + 1] - o_npos) > 2u;
-        if (!has_n) {
-            for (u32 u = g; u < units; u += W) {
-                const u8 *sp = src.at(t.ss + 16u * u);
-                u32 out = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
-                    if (bp < L) {
-                        u32 x = ld_u32_unaligned(sp + 4 * k);
-                        u32 codes = base_codes4(x, 0u);
-                        if (bp + 4u > L) codes &= 0xFFFFFFFFu >> (8u * (bp + 4u - L));  // bytes past the read
-                        out |= pack_codes4(codes) << (8 * k);
-                    }
-                }
-                u32 vb = min(16u, L - 16u * u);
-                st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
-            }
-        } else
-        for (u32 j = 0; j < rounds; j++) {
-            u32 u = j * W + g;
-            u32 nmask16 = 0;
-            if (u < units) {
-                const u8 *sp = src.at(t.ss + 16u * u);
-                u32 out = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 bp = 16u * u + 4u * k;  // base index of this word's first byte
-                    if (bp < L) {
-                        u32 x = ld_u32_unaligned(sp + 4 * k);
-                        u32 rm = range_mask4(bp, 0u, L);
-                        u32 nm = nonacgt_mask4(x) & rm;
-                        u32 codes = base_codes4(x, nm) & rm;
-                        out |= pack_codes4(codes) << (8 * k);
-                        nmask16 |= ((((nm & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
-                    }
-                }
-                u32 vb = min(16u, L - 16u * u);
-                st_bytes(s_seq + o_seq + 4u * u, out, (vb + 3u) >> 2);
-                if (16u * u >= FQZ_MAX_SEQ_LEN) nmask16 = 0;  // positions >= 65536 are not tracked
-            }
-            u32 cnt = (u32)__popc(nmask16);
-            u32 incl = group_incl_scan(cnt, gm, W);
-            u32 tot = __shfl_sync(gm, incl, W - 1, W);
-            u32 k = nbase + incl - cnt;
-            while (nmask16) {
-                int b = __ffs((int)nmask16) - 1;
-                nmask16 &= nmask16 - 1;
-                st_u16_unaligned(s_npos + o_npos + 2u + 2u * k, 16u * u + (u32)b);
-                k++;
-            }
-            nbase += tot;
+        scatter_record<W>(src, t, r, L, H, P, o_seq, o_qual, o_hdr, o_plus, o_npos, has_n, off, S, g, gm);
+    }
+}
+
+// ---------------------------------------------------------------------------------- fused metadata + scatter (one pass over the text)
+// k_record_meta + five device-wide scans + k_scatter_streams read the text twice and keep the per-record sizes in HBM
+// in between.  Here a CTA stages its 64 records once (TMA), sizes them out of shared memory (validation, N count,
+// long-read guard: same rules as k_record_meta), scans the 64 x 5 sizes locally, gets the five stream offsets of its
+// first record by a decoupled look-back over the CTAs in front of it (each CTA publishes its five totals, then the
+// running prefix; CTA numbers are handed out by an atomic ticket so that a CTA only ever waits for CTAs that are
+// already running), writes the scanned offsets (the entropy stage wants them) and scatters.  The streams are
+// allocated at fixed generous sizes before anything is known: a window whose streams do not fit says so in the
+// status word and is redone by the separate kernels.  Phred detection (block 0 of the file) and the check of a
+// trailing partial record run as two small kernels in front.
+struct ScCaps {
+    u32 cap[5];
+};
+#define SC_FLAG_AGG (1ull << 62)
+#define SC_FLAG_INC (2ull << 62)
+#define SC_VAL_MASK ((1ull << 62) - 1ull)
+__global__ void __launch_bounds__(FQZ_META_THREADS) k_phred_min(const u8 *text, const u32 *line_end, u64 nrec, FqzWinStatus *st) {
+    const int W = FQZ_META_GROUP;
+    u32 g = threadIdx.x & (W - 1);
+    u32 gm = group_mask(W);
+    u64 r = (u64)blockIdx.x * (FQZ_META_THREADS / W) + (threadIdx.x / W);
+    if (r >= nrec) return;
+    LineSpan t = record_lines(text, line_end, r);
+    u32 mn = group_min(partial_min_byte<W>(text, t.qs, t.qe, g), gm, W);
+    if (g == 0 && mn < 255u) atomicMin(&st->qual_min, mn);
+}
+// trailing partial record: the reference still validates the lines it can read before it meets EOF (parser.go:138-166)
+__global__ void k_tail_check(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, FqzWinStatus *st) {
+    if (threadIdx.x || blockIdx.x || tail_lines == 0) return;
+    u64 l = 4 * R;
+    u32 hs = line_end[(long long)l - 1] + 1u;
+    u32 he = strip_cr(text, hs, line_end[l]);
+    u32 kind = 0;
+    if (he == hs || text[hs] != '@') kind = FQZ_K_HEADER_AT;
+    else if (tail_lines >= 3) {
+        u32 ps = line_end[l + 1] + 1u;
+        u32 pe = strip_cr(text, ps, line_end[l + 2]);
+        if (pe == ps || text[ps] != '+') kind = FQZ_K_PLUS;
+    }
+    if (kind) atomicMin(&st->err_key, ((rec_base + R) << 8) | kind);
+}
+__global__ void __launch_bounds__(FQZ_SC_THREADS)
+k_scatter_fused(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 *offs, u64 stride, const u32 *phred64, ScStreams S, ScCaps caps,
+                FqzWinStatus *st, unsigned long long *look, u32 *ticket, u32 stage_cap) {
+    FQZ_DYN_SMEM(u8, smem);
+    const int W = FQZ_SC_GROUP;
+    __shared__ u32 s_cta;
+    __shared__ u32 s_sz[5][FQZ_SC_RPC + 1];  // sizes, then exclusive offsets inside the CTA
+    __shared__ u32 s_own[FQZ_SC_RPC];        // bytes of the record's N-position item
+    __shared__ u32 s_len[3][FQZ_SC_RPC];     // L, H, P as sized
+    __shared__ u32 s_base[5], s_tot[5];
+    __shared__ u32 s_skip;
+    if (threadIdx.x == 0) {
+        s_cta = atomicAdd(ticket, 1u);
+        s_skip = 0;
+    }
+    __syncthreads();
+    const u32 cta = s_cta;
+    u64 *bar = (u64 *)smem;
+    u8 *stage = smem + 128;
+    u64 r0 = (u64)cta * FQZ_SC_RPC;
+    u64 r1 = min(r0 + (u64)FQZ_SC_RPC, R);
+    // contiguous text chunk of this CTA's records, widened to 16-byte boundaries for the bulk copy
+    u32 c0 = line_end[4ll * (long long)r0 - 1] + 1u;
+    u32 c1 = line_end[4 * r1 - 1] + 1u;
+    u32 a0 = c0 & ~15u;
+    u32 a1 = (c1 + 15u) & ~15u;
+    Src src;
+    if (a1 - a0 + 16u <= stage_cap) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        cta_stage_bulk(stage, text + a0, a1 - a0, bar, 0);
+        src.p = stage;
+        src.bias = a0;
+    } else {  // chunk larger than the staging buffer (long reads): read HBM/L2 directly
+        src.p = text;
+        src.bias = 0;
+    }
+    u32 g = threadIdx.x & (W - 1);
+    u32 gm = group_mask(W);
+    // ---- 1. size the records (rules of k_record_meta)
+    for (u64 r = r0 + threadIdx.x / W; r < r1; r += FQZ_SC_THREADS / W) {
+        const u32 i = (u32)(r - r0);
+        u64 l = 4 * r;
+        u32 e0 = line_end[(long long)l - 1];
+        u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
+        u32 hs = e0 + 1u, he = (e1 > hs && *src.at(e1 - 1) == '\r') ? e1 - 1 : e1;
+        u32 ss = e1 + 1u, se = (e2 > ss && *src.at(e2 - 1) == '\r') ? e2 - 1 : e2;
+        u32 ps = e2 + 1u, pe = (e3 > ps && *src.at(e3 - 1) == '\r') ? e3 - 1 : e3;
+        u32 qs = e3 + 1u, qe = (e4 > qs && *src.at(e4 - 1) == '\r') ? e4 - 1 : e4;
+        u32 L = se - ss;
+        u32 kind = 0;
+        if (he == hs || *src.at(hs) != '@') kind = FQZ_K_HEADER_AT;
+        else if (pe == ps || *src.at(ps) != '+') kind = FQZ_K_PLUS;
+        else if (L != qe - qs) kind = FQZ_K_LEN;
+        // non-ACGT bases inside the tracked range, and the guard beyond it: src.p - src.bias is 16-byte aligned like the text
+        const u8 *tb = src.p - src.bias;
+        u32 lim = ss + min(L, FQZ_MAX_SEQ_LEN);
+        u32 nn = group_sum(partial_count_n<W>(tb, ss, lim, g), gm, W);
+        if (L > FQZ_MAX_SEQ_LEN) {
+            u32 beyond = group_sum(partial_count_n<W>(tb, lim, se, g), gm, W);
+            if (beyond && !kind) kind = FQZ_K_LONG_N;
         }
-        if (g == 0) st_u16_unaligned(s_npos + o_npos, nbase & 0xFFFFu);  // compress.go:495 (silent u16 truncation)
-        // quality: normalise + per-record delta (compress.go:506-510; quality.go:53-103)
+        if (g == 0) {
+            if (kind) atomicMin(&st->err_key, ((rec_base + r) << 8) | kind);
+            u32 H = (kind == FQZ_K_HEADER_AT) ? 0u : (he - hs - 1u);
+            u32 P = (kind == FQZ_K_HEADER_AT || kind == FQZ_K_PLUS) ? 0u : (pe - ps - 1u);
+            s_sz[0][i] = (L + 3u) >> 2;
+            s_sz[1][i] = L;
+            s_sz[2][i] = 2u + H;
+            s_sz[3][i] = 2u + P;
+            s_sz[4][i] = 2u + 2u * nn;
+            s_own[i] = 2u + 2u * nn;
+            s_len[0][i] = L;
+            s_len[1][i] = H;
+            s_len[2][i] = P;
+        }
+    }
+    __syncthreads();
+    // ---- 2. local scan (five threads, 64 entries each) and 3. look-back
+    if (threadIdx.x < 5) {
+        const u32 a = threadIdx.x, cnt = (u32)(r1 - r0);
+        u32 run = 0;
+        for (u32 i = 0; i < cnt; i++) {
+            u32 v = s_sz[a][i];
+            s_sz[a][i] = run;
+            run += v;
+        }
+        s_tot[a] = run;
+        volatile unsigned long long *L5 = look;
+        unsigned long long base = 0;
+        if (cta == 0) {
+            L5[(u64)cta * 5 + a] = SC_FLAG_INC | run;
+        } else {
+            L5[(u64)cta * 5 + a] = SC_FLAG_AGG | run;
+            __threadfence();
+            long long p = (long long)cta - 1;
+            for (;;) {
+                unsigned long long v = L5[(u64)p * 5 + a];
+                if ((v >> 62) == 0) {
+#ifdef FQZ_EMU
+                    emu::yield();
+#endif
+                    continue;
+                }
+                base += v & SC_VAL_MASK;
+                if ((v >> 62) == 2) break;
+                p--;
+            }
+            __threadfence();
+            L5[(u64)cta * 5 + a] = SC_FLAG_INC | (base + run);
+        }
+        s_base[a] = (u32)base;
+        if (base + run > (unsigned long long)caps.cap[a]) {  // the fixed-size stream is too small: the window is redone
+            s_skip = 1;
+            atomicOr(&st->pad, 1u);
+        }
+    }
+    __syncthreads();
+    if (r1 == R && threadIdx.x < 5) offs[threadIdx.x * stride + R] = s_base[threadIdx.x] + s_tot[threadIdx.x];
+    // ---- 4. offsets out, then the scatter proper
+    const bool skip = s_skip != 0;
+    const u8 off = *phred64 ? 64 : 33;
+    for (u64 r = r0 + threadIdx.x / W; r < r1; r += FQZ_SC_THREADS / W) {
+        const u32 i = (u32)(r - r0);
+        u32 o_seq = s_base[0] + s_sz[0][i], o_qual = s_base[1] + s_sz[1][i], o_hdr = s_base[2] + s_sz[2][i];
+        u32 o_plus = s_base[3] + s_sz[3][i], o_npos = s_base[4] + s_sz[4][i];
+        if (g == 0) {
+            offs[0 * stride + r] = o_seq;
+            offs[1 * stride + r] = o_qual;
+            offs[2 * stride + r] = o_hdr;
+            offs[3 * stride + r] = o_plus;
+            offs[4 * stride + r] = o_npos;
+        }
+        if (skip) continue;
+        LineSpan t;
         {
-            u8 *dq = s_qual + o_qual;
-            const u8 *sq = src.at(t.qs);
-            u32 head = (u32)((4u - ((uintptr_t)dq & 3u)) & 3u);
-            if (head == 0) head = 4;  // keeps every body word at index >= 1 so q[i-1] exists
-            if (head > L) head = L;
-            if (g < head) dq[g] = (u8)(sq[g] - (g ? sq[g - 1] : off));
-            u32 nw = (L - head) >> 2;
-            for (u32 w = g; w < nw; w += W) {
-                u32 i = head + 4u * w;
-                u32 cur = ld_u32_unaligned(sq + i);
-                u32 prv = ld_u32_unaligned(sq + i - 1);
-                *(u32 *)(dq + i) = __vsub4(cur, prv);
-            }
-            u32 t0 = head + 4u * nw;
-            if (g < L - t0) {
-                u32 i = t0 + g;
-                dq[i] = (u8)(sq[i] - (i ? sq[i - 1] : off));
-            }
+            u64 l = 4 * r;
+            u32 e0 = line_end[(long long)l - 1];
+            u32 e1 = line_end[l], e2 = line_end[l + 1], e3 = line_end[l + 2], e4 = line_end[l + 3];
+            t.hs = e0 + 1u;
+            t.he = (e1 > t.hs && *src.at(e1 - 1) == '\r') ? e1 - 1 : e1;
+            t.ss = e1 + 1u;
+            t.se = (e2 > t.ss && *src.at(e2 - 1) == '\r') ? e2 - 1 : e2;
+            t.ps = e2 + 1u;
+            t.pe = (e3 > t.ps && *src.at(e3 - 1) == '\r') ? e3 - 1 : e3;
+            t.qs = e3 + 1u;
+            t.qe = (e4 > t.qs && *src.at(e4 - 1) == '\r') ? e4 - 1 : e4;
         }
+        scatter_record<W>(src, t, r, s_len[0][i], s_len[1][i], s_len[2][i], o_seq, o_qual, o_hdr, o_plus, o_npos, s_own[i] > 2u, off, S, g, gm);
     }
 }
 
@@ -459,6 +665,24 @@ void fqz_launch_scatter(const u8 *text, const u32 *line_end, u64 R, const u32 *o
                streams[2], streams[3], streams[4], streams[5], (u32)(FQZ_SC_SMEM - 128));
 }
 // per-device kernel attributes: called once per context (the attribute is per device, and one process may drive several GPUs)
+void fqz_launch_phred_min(const u8 *text, const u32 *line_end, u64 nrec, FqzWinStatus *st, cudaStream_t s) {
+    if (!nrec) return;
+    u32 per = FQZ_META_THREADS / FQZ_META_GROUP;
+    FQZ_LAUNCH(k_phred_min, (u32)((nrec + per - 1) / per), FQZ_META_THREADS, 0, s, text, line_end, nrec, st);
+}
+void fqz_launch_scatter_fused(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, u32 *offs, u64 stride, const u32 *phred64,
+                              u8 *const streams[6], const u32 caps[5], FqzWinStatus *st, unsigned long long *look, u32 *ticket, cudaStream_t s) {
+    if (tail_lines) FQZ_LAUNCH(k_tail_check, 1, 32, 0, s, text, line_end, R, rec_base, tail_lines, st);
+    if (!R) return;
+    u32 grid = (u32)((R + FQZ_SC_RPC - 1) / FQZ_SC_RPC);
+    ScStreams S = {streams[0], streams[1], streams[2], streams[3], streams[4], streams[5]};
+    ScCaps C;
+    for (int a = 0; a < 5; a++) C.cap[a] = caps[a];
+    FQZ_LAUNCH(k_scatter_fused, grid, FQZ_SC_THREADS, FQZ_SC_SMEM, s, text, line_end, R, rec_base, offs, stride, phred64, S, C, st, look, ticket,
+               (u32)(FQZ_SC_SMEM - 128));
+}
 int fqz_frontend_init_device() {
-    return (int)cudaFuncSetAttribute(k_scatter_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_scatter_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scatter_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, FQZ_SC_SMEM);
+    return (int)e;
 }

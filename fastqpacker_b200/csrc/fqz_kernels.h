@@ -32,5 +32,10 @@ void fqz_launch_scan_apply(u32 *data, u64 n, u64 stride, u32 narr, const u32 *su
 void fqz_launch_record_meta(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, u32 *sizes, u64 stride,
                             FqzWinStatus *st, u64 phred_records, cudaStream_t s);
 void fqz_launch_decide_phred(const FqzWinStatus *st, u32 *phred64, cudaStream_t s);
+// fused single pass: sizes + look-back scan + scatter (fqz_frontend.cu); look: 5 zeroed u64 per CTA of FQZ_SC_RPC records, ticket: one zeroed u32;
+// st->pad bit 0 is set when a stream outgrew caps[] (the window must then be redone by the separate kernels)
+void fqz_launch_phred_min(const u8 *text, const u32 *line_end, u64 nrec, FqzWinStatus *st, cudaStream_t s);
+void fqz_launch_scatter_fused(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 tail_lines, u32 *offs, u64 stride, const u32 *phred64,
+                              u8 *const streams[6], const u32 caps[5], FqzWinStatus *st, unsigned long long *look, u32 *ticket, cudaStream_t s);
 void fqz_launch_scatter(const u8 *text, const u32 *line_end, u64 R, const u32 *offs, u64 stride, const u32 *phred64, u8 *const streams[6],
                         cudaStream_t s);
