@@ -49,6 +49,11 @@ GOOD_CASES = {
     "rand_plus": rand_fastq(300, 3, plus_payload=True, phred=64),
     "rand_lower": rand_fastq(100, 4, lower=True, n_rate=0.2),
     "rand_long": rand_fastq(12, 5, lmin=900, lmax=5000),
+    # names far longer than the reads: the header stream outgrows the room the fused front end gives it (the window is
+    # then redone by the separate kernels)
+    "long_names": b"".join(b"@" + (b"name-%d-" % i) * 12 + b"\nAC\n+\nII\n" for i in range(300)),
+    "long_plus": b"".join(b"@r%d\nACGT\n+" % i + (b"payload%d" % i) * 9 + b"\nIIII\n" for i in range(300)),
+    "all_n_reads": b"".join(b"@r%d\n" % i + b"N" * 90 + b"\n+\n" + b"#" * 90 + b"\n" for i in range(200)),
 }
 
 BAD_CASES = {
