@@ -867,7 +867,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg5: one 64 GB input block-sharded over the ranks")
     ap.add_argument("--total-bytes", type=int, default=0, help="cfg5: size of the logical input (default 64e9)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 and duplicates side workloads")
-    ap.add_argument("--frontend", type=int, default=0, choices=[0, 1], help="A/B: 0 fused single-pass front end (default), 1 separate kernels")
+    ap.add_argument("--frontend", type=int, default=0, choices=[0, 1, 2], help="A/B of the front-end kernels: see FQZ_OPT_FRONTEND")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -62,9 +62,41 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     out = FrontOut();
     cudaStream_t s = c->stream;
     if (n >= ((u64)1 << 32) - 65536) return FQZ_E_TOO_LARGE;
-    // ---- 1. count newlines per 16 KiB tile, scan, read the total
     u32 ntiles = (u32)((n + FQZ_NL_TILE - 1) / FQZ_NL_TILE);
-    u32 *d_tiles = (u32 *)c->arena.alloc(((size_t)ntiles + 1) * sizeof(u32));
+    u32 *h = (u32 *)c->h_pin;
+    u64 nlines = 0;
+    u32 *d_line_end = nullptr;
+    u32 *d_tiles = nullptr;
+    bool indexed = false;
+    // ---- 1'. single pass: count and index together (look-back over the tiles), line_end[] sized for lines of 16 bytes
+    //      or more on average; texts with shorter lines take the two passes below
+    if (c->opt_frontend != 1 && ntiles) {  // 0 and 2
+        const u64 cap_lines = n / 16 + 4096;
+        u32 *d_alloc = (u32 *)c->arena.alloc((size_t)(cap_lines + 8) * sizeof(u32));
+        unsigned long long *d_look = (unsigned long long *)c->arena.alloc(((size_t)ntiles + 2) * sizeof(unsigned long long));
+        if (!d_alloc || !d_look) {
+            c->err = "arena: out of device memory (line_end)";
+            return FQZ_E_CUDA;
+        }
+        u32 *d_total = (u32 *)(d_look + ntiles + 1);
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_look, 0, ((size_t)ntiles + 2) * sizeof(unsigned long long), s));
+        u32 *le = d_alloc + 4;
+        if (!skip) FQZ_CUDA_TRY(c, cudaMemsetAsync(le - 1, 0xFF, sizeof(u32), s));
+        {
+            StageScope sc(c, ST_NL_INDEX, n);
+            fqz_launch_newline_scan(d_text, n, skip ? skip - 1u : 0u, skip ? le - 1 : le, (u32)cap_lines, d_look, ntiles, d_total, s);
+        }
+        FQZ_TRY(fqz_pin_copy(c, h, d_total, sizeof(u32)));
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if ((u64)h[0] <= cap_lines) {
+            nlines = h[0];
+            d_line_end = le;
+            indexed = true;
+        }
+    }
+    if (!indexed) {
+    // ---- 1. count newlines per 16 KiB tile, scan, read the total
+    d_tiles = (u32 *)c->arena.alloc(((size_t)ntiles + 1) * sizeof(u32));
     if (!d_tiles) {
         c->err = "arena: out of device memory (tiles)";
         return FQZ_E_CUDA;
@@ -78,12 +110,12 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
         StageScope sc(c, ST_SCAN, 0);
         FQZ_TRY(fqz_scan_excl_u32(c, d_tiles, (u64)ntiles + 1, (u64)ntiles + 1, 1));
     }
-    u32 *h = (u32 *)c->h_pin;
     FQZ_TRY(fqz_pin_copy(c, h, d_tiles + ntiles, sizeof(u32)));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+    nlines = h[0];
+    }
     // skip > 0: the window starts inside the 16-byte word that still holds the end of the previous
     // window's last line, '\n' included (windows are cut behind a newline): that line is line -1
-    u64 nlines = h[0];
     if (skip) {
         if (nlines == 0) return FQZ_E_INVALID_ARG;
         nlines -= 1;
@@ -100,6 +132,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     }
     out.R = R;
     out.nblocks = (u32)((R + FQZ_BLOCK_RECORDS - 1) / FQZ_BLOCK_RECORDS);
+    if (!indexed) {
     // ---- 2. line_end[]
     u64 want_lines = 4 * R + tail_lines;
     u32 *d_line_alloc = (u32 *)c->arena.alloc((size_t)(want_lines + 8) * sizeof(u32));
@@ -108,16 +141,17 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
         return FQZ_E_CUDA;
     }
     // entry -1 of line_end[]: end of the line in front of record 0 (0xFFFFFFFF + 1 = 0 when there is none)
-    u32 *d_line_end = d_line_alloc + 4;
+    d_line_end = d_line_alloc + 4;
     if (!skip) FQZ_CUDA_TRY(c, cudaMemsetAsync(d_line_end - 1, 0xFF, sizeof(u32), s));
     {
         StageScope sc(c, ST_NL_INDEX, n + 4 * want_lines);
         fqz_launch_newline_index(d_text, n, skip ? skip - 1u : 0u, d_tiles, ntiles, skip ? d_line_end - 1 : d_line_end, (u32)want_lines + (skip ? 1u : 0u), s);
     }
+    }
     // ---- 3'. fused path: one kernel sizes the records, scans the sizes by look-back and scatters (one pass over the
     //      text instead of two, no size arrays through HBM); the streams are allocated at fixed generous sizes and a
     //      window whose streams outgrow them is redone by the separate kernels below
-    if (c->opt_frontend != 1 && R > 0) {
+    if (c->opt_frontend == 2 && R > 0) {
         const size_t arena_mark_unused = 0;
         (void)arena_mark_unused;
         u64 stride = ((R + 1 + 63) / 64) * 64;

@@ -359,7 +359,7 @@ extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
         c->opt_host_window_bytes = value > ((u64)3 << 30) ? ((u64)3 << 30) : value;
         return FQZ_OK;
     case FQZ_OPT_FRONTEND:
-        if (value > 1) return FQZ_E_INVALID_ARG;
+        if (value > 2) return FQZ_E_INVALID_ARG;
         c->opt_frontend = (int)value;
         return FQZ_OK;
     case FQZ_OPT_RECORD_MATCH:

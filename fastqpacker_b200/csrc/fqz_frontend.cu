@@ -98,6 +98,60 @@ __global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_index(const u8 *text
     }
 }
 
+// Count and index in ONE pass over the text: a tile counts its newlines, gets the number of newlines in front of it by
+// a decoupled look-back over the tiles before it (tile numbers come from an atomic ticket, so a tile only waits for
+// tiles that are already running), and writes its line ends straight from the masks it still holds in registers.
+// look: one zeroed u64 per tile (+1: the ticket).  line_end has room for cap_lines entries; *total_lines = all newlines.
+#define NS_FLAG_AGG (1ull << 62)
+#define NS_FLAG_INC (2ull << 62)
+__global__ void __launch_bounds__(FQZ_NL_THREADS) k_newline_scan(const u8 *text, u64 n, u64 lo, u32 *line_end, u32 cap_lines, unsigned long long *look,
+                                                                 u32 ntiles, u32 *total_lines) {
+    __shared__ u32 ws[33];
+    __shared__ u32 s_tile, s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd((u32 *)(look + ntiles), 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    u64 pos = (u64)tile * FQZ_NL_TILE + (u64)threadIdx.x * 64u;
+    u64 m;
+    u32 c = nl_mask64(text, n, pos, lo, m);
+    u32 total;
+    u32 ex = block_excl_scan(c, ws, &total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *L = look;
+        unsigned long long base = 0;
+        if (tile == 0) L[0] = NS_FLAG_INC | total;
+        else {
+            L[tile] = NS_FLAG_AGG | total;
+            __threadfence();
+            long long p = (long long)tile - 1;
+            for (;;) {
+                unsigned long long v = L[p];
+                if ((v >> 62) == 0) {
+#ifdef FQZ_EMU
+                    emu::yield();
+#endif
+                    continue;
+                }
+                base += v & ((1ull << 62) - 1ull);
+                if ((v >> 62) == 2) break;
+                p--;
+            }
+            __threadfence();
+            L[tile] = NS_FLAG_INC | (base + total);
+        }
+        s_base = (u32)base;
+        if (tile == ntiles - 1) *total_lines = (u32)(base + total);
+    }
+    __syncthreads();
+    u32 idx = s_base + ex;
+    while (m) {
+        int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (idx < cap_lines) line_end[idx] = (u32)(pos + (u64)b);
+        idx++;
+    }
+}
+
 // ---------------------------------------------------------------------------------- device-wide exclusive scan (u32, in place)
 // data holds `narr` arrays of n elements, array a at data + a*stride.  2048 elements per CTA.
 __device__ __forceinline__ u32 scan_tile_load(const u32 *d, u64 n, u64 base, u32 v[FQZ_SCAN_PER_THREAD]) {
@@ -637,6 +691,10 @@ k_scatter_fused(const u8 *text, const u32 *line_end, u64 R, u64 rec_base, u32 *o
 // ---------------------------------------------------------------------------------- host launchers
 void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s) {
     if (ntiles) FQZ_LAUNCH(k_newline_count, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, tile_counts);
+}
+void fqz_launch_newline_scan(const u8 *text, u64 n, u64 lo, u32 *line_end, u32 cap_lines, unsigned long long *look, u32 ntiles, u32 *total_lines,
+                             cudaStream_t s) {
+    if (ntiles) FQZ_LAUNCH(k_newline_scan, ntiles, FQZ_NL_THREADS, 0, s, text, n, lo, line_end, cap_lines, look, ntiles, total_lines);
 }
 void fqz_launch_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos, cudaStream_t s) {
     if (ntiles) FQZ_LAUNCH(k_find_newline, 1, FQZ_NL_THREADS, 0, s, text, n, tile_prefix, ntiles, target, out_pos);

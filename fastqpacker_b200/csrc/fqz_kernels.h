@@ -25,6 +25,9 @@
 #endif
 
 void fqz_launch_newline_count(const u8 *text, u64 n, u64 lo, u32 *tile_counts, u32 ntiles, cudaStream_t s);
+// single pass count + index (look-back over the tiles); look: ntiles + 1 zeroed u64
+void fqz_launch_newline_scan(const u8 *text, u64 n, u64 lo, u32 *line_end, u32 cap_lines, unsigned long long *look, u32 ntiles, u32 *total_lines,
+                             cudaStream_t s);
 void fqz_launch_find_newline(const u8 *text, u64 n, const u32 *tile_prefix, u32 ntiles, u32 target, u64 *out_pos, cudaStream_t s);
 void fqz_launch_newline_index(const u8 *text, u64 n, u64 lo, const u32 *tile_prefix, u32 ntiles, u32 *line_end, u32 max_lines, cudaStream_t s);
 void fqz_launch_scan_partial(const u32 *data, u64 n, u64 stride, u32 narr, u32 *sums, u32 ntiles, cudaStream_t s);

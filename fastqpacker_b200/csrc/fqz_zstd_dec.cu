@@ -787,32 +787,14 @@ __device__ static u32 warp_huf_read_table(const ZDBlock &hb, LitScratch &S, u32 
 // the start of the stream, the bits consumed are counted: a valid stream is consumed exactly
 // (RFC 8878 §4.2.2), anything else is corrupt.  Word loads are clamped to the aligned word that
 // holds src[0], so a corrupt stream never reads outside the block either.
-// cp.async of one aligned word, global -> shared: the copy is in flight without any register waiting for it
-__device__ __forceinline__ void zd_async_word(u32 *smem_dst, const u32 *gsrc) {
-#ifdef FQZ_EMU
-    *smem_dst = *gsrc;
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\ncp.async.commit_group;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-#endif
-}
-__device__ __forceinline__ void zd_async_wait_oldest() {  // all but the ZD_RING - 1 most recent copies of this thread have landed
-#ifndef FQZ_EMU
-    asm volatile("cp.async.wait_group 7;" ::: "memory");
-#endif
-}
-#define ZD_RING 8u
 struct HufBits {
     u64 bits;       // unread bits, left-aligned
     u32 nb;         // valid bits in `bits`
     const u32 *lo;  // aligned word that holds the first byte of the stream
     u32 wi;         // index (from lo) of the next word to prefetch; sticks at 0
-    u32 *ring;      // this thread's ring of ZD_RING prefetched words in shared memory: slot k at ring[k * stride]
-    u32 stride, slot;
+    u32 w0, w1, w2, w3; // prefetched words, nearest first; w3 is the load in flight
     // src[csize - 1] != 0 (it holds the end mark).  Returns the payload bits of the stream.
-    __device__ __forceinline__ u32 init(const u8 *src, u32 csize, u32 *ring_, u32 stride_) {
-        ring = ring_;
-        stride = stride_;
-        slot = 0;
+    __device__ __forceinline__ u32 init(const u8 *src, u32 csize) {
         u32 hb = hibit32(src[csize - 1]);
         const u8 *endp = src + csize;
         lo = (const u32 *)((uintptr_t)src & ~(uintptr_t)3);
@@ -823,28 +805,32 @@ struct HufBits {
         bits = (u64)v << (64u - 8u * k);
         bits <<= (8u - hb);  // padding and end mark
         nb = 8u * k - (8u - hb);
-        for (u32 j = 0; j < ZD_RING; j++) {
-            wi = wi ? wi - 1u : 0u;
-            zd_async_word(ring + j * stride, lo + wi);
-        }
+        wi = wi ? wi - 1u : 0u;
+        w0 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
+        w1 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
+        w2 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
+        w3 = lo[wi];
+        wi = wi ? wi - 1u : 0u;
         return (csize - 1u) * 8u + hb;
     }
-    // Afterwards nb >= 32 (bits past the stream start are whatever memory holds).  The 32 lanes of a warp read 32
-    // different streams, each a chain of dependent 4-byte loads a kilobyte apart from its neighbours': the words are
-    // therefore fetched ZD_RING refills ahead by cp.async into a per-thread ring in shared memory — no register
-    // waits for a load in flight (a register queue did: its newest word was touched by the very next refill, 46 % of
-    // the literal kernel's stall samples) — and a refill only waits for the OLDEST copy.
+    // Afterwards nb >= 32 (bits past the stream start are whatever memory holds).  Branch-free on
+    // purpose: the 32 lanes of a warp run 32 different streams and would otherwise take this path at
+    // different times, every one of them paying for all the others.  The word loaded here is first
+    // looked at by the NEXT refill that shifts the queue, several symbols later, so the chain never
+    // waits for it; a refill that does not shift loads nothing (predicated load).
     __device__ __forceinline__ void refill() {
-        if (nb <= 32u) {
-            zd_async_wait_oldest();
-            u32 *p = ring + slot * stride;
-            const u32 w = *(volatile u32 *)p;
-            bits |= (u64)w << (32u - nb);
-            nb += 32u;
-            wi = wi ? wi - 1u : 0u;
-            zd_async_word(p, lo + wi);
-            slot = (slot + 1u) & (ZD_RING - 1u);
-        }
+        const bool need = nb <= 32u;
+        const u64 add = (u64)w0 << ((32u - nb) & 63u);
+        bits |= need ? add : 0ull;
+        nb += need ? 32u : 0u;
+        w0 = need ? w1 : w0;
+        w1 = need ? w2 : w1;
+        w2 = need ? w3 : w2;
+        if (need) w3 = lo[wi];
+        wi = (need && wi) ? wi - 1u : wi;
     }
     __device__ __forceinline__ u32 peek(u32 n) const { return (u32)(bits >> 32) >> (32u - n); }  // 1 <= n <= 32
     __device__ __forceinline__ void drop(u32 n) {
@@ -859,10 +845,10 @@ struct HufBits {
     }
 };
 
-__device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 n, const u16 *dt, u32 tl, u32 *ring, u32 ring_stride) {
+__device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 n, const u16 *dt, u32 tl) {
     if (csize == 0 || src[csize - 1] == 0) return false;  // empty, or the end mark is missing
     HufBits hb;
-    const u32 total = hb.init(src, csize, ring, ring_stride);
+    const u32 total = hb.init(src, csize);
     u32 used = 0;
     u32 i = 0;
     while (i < n && ((uintptr_t)(dst + i) & 3u)) {
@@ -918,10 +904,7 @@ __device__ static bool huf_decode_stream(const u8 *src, u32 csize, u8 *dst, u32 
 __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, u32 nblocks, const u32 *litgrp, u32 ngroups, const ZDFrame *frames,
                                                                u8 *litbuf, u8 *out) {
     __shared__ LitScratch scratch[ZD_WARPS];
-    __shared__ u32 rings[ZD_RING * ZD_WARPS * 32];
     u32 warp = threadIdx.x >> 5, lane = lane_id();
-    u32 *ring = rings + threadIdx.x;  // slot k of this thread at ring[k * blockDim.x]
-    const u32 ring_stride = ZD_WARPS * 32;
     u32 g = blockIdx.x * ZD_WARPS + warp;
     if (g >= ngroups) return;
     const u32 b0 = litgrp[g];  // first block of the group; the group never leaves its frame
@@ -980,7 +963,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, 
                 else {
                     u32 avail = B.lit_csize - tsz;
                     if (B.lit_streams == 1) {
-                        if (q == 0 && !huf_decode_stream(sp, avail, dst, n, S.dt, tl, ring, ring_stride)) err = 1;
+                        if (q == 0 && !huf_decode_stream(sp, avail, dst, n, S.dt, tl)) err = 1;
                     } else if (avail < 10) err = 1;
                     else {
                         u32 s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
@@ -990,7 +973,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_literals(ZDBlock *blocks, 
                             u32 off = 6 + (q > 0 ? s1 : 0) + (q > 1 ? s2 : 0) + (q > 2 ? s3 : 0);
                             u32 cs = q == 0 ? s1 : q == 1 ? s2 : q == 2 ? s3 : avail - 6 - s1 - s2 - s3;
                             u32 cnt = q < 3 ? seg : n - 3 * seg;
-                            if (!huf_decode_stream(sp + off, cs, dst + q * seg, cnt, S.dt, tl, ring, ring_stride)) err = 1;
+                            if (!huf_decode_stream(sp + off, cs, dst + q * seg, cnt, S.dt, tl)) err = 1;
                         }
                     }
                 }
@@ -1084,7 +1067,6 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_seq_tables(const ZDBlock *
 // has-sequences flags).
 __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const ZDFrame *frames, const u32 *seqblk, u32 nsb, const u32 *slot_of, const u32 *tabs,
                                                        u32 *seqbuf) {
-    __shared__ u32 rings[ZD_RING * 128];
     u32 slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= nsb) return;
     const u32 bi = seqblk[slot];
@@ -1116,7 +1098,7 @@ __global__ void __launch_bounds__(128) k_zd_seq_decode(ZDBlock *blocks, const ZD
             // reads between two refills takes at most 32 bits (offset extra bits <= 31; match + literal
             // length extra bits <= 16 + 16; three state updates <= 9 + 9 + 8).
             HufBits br;
-            const u32 avail = br.init(c + B.bits_pos, bsz, rings + threadIdx.x, 128);
+            const u32 avail = br.init(c + B.bits_pos, bsz);
             u32 used = tl[0] + tl[1] + tl[2];
             br.refill();
             u32 sLL = br.take(tl[0]), sOF = br.take(tl[1]), sML = br.take(tl[2]);

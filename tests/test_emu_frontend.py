@@ -13,27 +13,37 @@ def emu():
     return emu_context()
 
 
+@pytest.mark.parametrize("frontend", [0, 1, 2])  # FQZ_OPT_FRONTEND: the three sets of front-end kernels give the same bytes
 @pytest.mark.parametrize("name", sorted(GOOD_CASES))
-def test_streams_match_oracle(emu, oracle, name):
+def test_streams_match_oracle(emu, oracle, name, frontend):
     text = GOOD_CASES[name]
     want = oracle.encode_streams(text)
-    got = emu.encode_streams(text)
+    try:
+        emu.set_option(emu.OPT_FRONTEND, frontend)
+        got = emu.encode_streams(text)
+    finally:
+        emu.set_option(emu.OPT_FRONTEND, 0)
     for k in ("nrec", "phred64", "orig_seq", "orig_qual", "consumed"):
         assert got[k] == want[k], k
     for nm, a, b in zip(oracle.STREAM_NAMES, got["streams"], want["streams"]):
         assert a == b, nm
 
 
+@pytest.mark.parametrize("frontend", [0, 2])
 @pytest.mark.parametrize("name", sorted(BAD_CASES))
-def test_errors_match_oracle(emu, oracle, name):
+def test_errors_match_oracle(emu, oracle, name, frontend):
     text, code, rec = BAD_CASES[name]
     with pytest.raises(oracle.OracleError) as oe:
         oracle.encode_streams(text)
     assert oe.value.code == code
     from fastqpacker_b200._binding import FqzError
 
-    with pytest.raises(FqzError) as ge:
-        emu.encode_streams(text)
+    try:
+        emu.set_option(emu.OPT_FRONTEND, frontend)
+        with pytest.raises(FqzError) as ge:
+            emu.encode_streams(text)
+    finally:
+        emu.set_option(emu.OPT_FRONTEND, 0)
     assert ge.value.code == code and ge.value.record == rec
 
 

@@ -258,3 +258,22 @@ def test_two_contexts_two_devices(oracle):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     _two_contexts(oracle, 0, 1)
+
+
+@pytest.mark.parametrize("frontend", [1, 2])
+def test_frontend_variants_write_the_same_file(ctx, oracle, frontend):
+    """FQZ_OPT_FRONTEND: two newline passes / fused metadata + scatter (look-back scans across CTAs) against the default
+    kernels, over several blocks and several device windows."""
+    text = oracle.synth(1, 0x5EED0004, 0, 260_000).tobytes()
+    want = ctx.compress(text)
+    try:
+        ctx.set_option(ctx.OPT_FRONTEND, frontend)
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 60 << 20)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 60 << 20)
+        got = ctx.compress(text)
+    finally:
+        ctx.set_option(ctx.OPT_FRONTEND, 0)
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, 0)
+        ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
+    assert got == want
+    assert oracle.decompress(got) == text

@@ -19,11 +19,16 @@ def ctx():
     return fq.context(0)
 
 
+@pytest.mark.parametrize("frontend", [0, 1, 2])  # FQZ_OPT_FRONTEND: the three sets of front-end kernels give the same bytes
 @pytest.mark.parametrize("name", sorted(GOOD_CASES))
-def test_streams_match_oracle(ctx, oracle, name):
+def test_streams_match_oracle(ctx, oracle, name, frontend):
     text = GOOD_CASES[name]
     want = oracle.encode_streams(text)
-    got = ctx.encode_streams(text)
+    try:
+        ctx.set_option(ctx.OPT_FRONTEND, frontend)
+        got = ctx.encode_streams(text)
+    finally:
+        ctx.set_option(ctx.OPT_FRONTEND, 0)
     for k in ("nrec", "phred64", "orig_seq", "orig_qual", "consumed"):
         assert got[k] == want[k], k
     for nm, a, b in zip(oracle.STREAM_NAMES, got["streams"], want["streams"]):
