@@ -70,7 +70,7 @@ int fqz_run_frontend(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 rec_
     bool indexed = false;
     // ---- 1'. single pass: count and index together (look-back over the tiles), line_end[] sized for lines of 16 bytes
     //      or more on average; texts with shorter lines take the two passes below
-    if (c->opt_frontend != 1 && ntiles) {  // 0 and 2
+    if (c->opt_frontend != 0 && ntiles) {  // 1 and 2
         const u64 cap_lines = n / 16 + 4096;
         u32 *d_alloc = (u32 *)c->arena.alloc((size_t)(cap_lines + 8) * sizeof(u32));
         unsigned long long *d_look = (unsigned long long *)c->arena.alloc(((size_t)ntiles + 2) * sizeof(unsigned long long));

@@ -107,7 +107,7 @@ struct fqz_ctx {
     // fqz_set_option
     u64 opt_window_bytes = 0;       // device window of the compress calls (0 = default)
     u64 opt_host_window_bytes = 0;  // window of the host-buffer compress calls (0 = default)
-    int opt_frontend = 0;           // 0: single-pass newline scan + separate metadata / scatter kernels, 1: all separate (two newline passes), 2: fused metadata + scatter too
+    int opt_frontend = 0;           // 0: separate kernels (count, index, metadata, scans, scatter); 1: count + index in one pass (look-back); 2: metadata + scatter fused as well
     u64 fused_windows = 0, legacy_windows = 0;
     int opt_no_record_match = 0;    // 1: packed bases / qualities always literals-only (no duplicate-record search)
 };

@@ -45,7 +45,9 @@ struct ZFrame {
 #define FQZ_ZINDEX_HDR 20u
 #define FQZ_ZINDEX_BYTES(n) (FQZ_ZINDEX_HDR + 8u * (u32)(n))
 
+#ifndef ZENC_WARPS
 #define ZENC_WARPS 4
+#endif
 
 void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
 // fills the index frames (FQZ_ZPOLICY_INDEX) from the sizes of the frames behind them

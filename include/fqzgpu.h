@@ -64,8 +64,9 @@ int fqz_abi_version(void);
 #define FQZ_OPT_WINDOW_BYTES 1      /* FASTQ bytes per device pass of the compress calls (default 3e9, min 1 MiB) */
 #define FQZ_OPT_HOST_WINDOW_BYTES 2 /* same for the host-buffer calls (default 1 GiB: their first window must be uploaded first) */
 #define FQZ_OPT_RECORD_MATCH 3      /* 1 (default): search packed bases / qualities for duplicated records and code them as matches; 0: literals only */
-#define FQZ_OPT_FRONTEND 4          /* front-end kernels (results identical): 0 (default) newline count + index in one pass, then metadata, scans, scatter;
-                                     * 1 two newline passes; 2 metadata and scatter fused into one kernel as well (measured slower on B200) */
+#define FQZ_OPT_FRONTEND 4          /* front-end kernels (results identical): 0 (default) newline count, index, metadata, scans, scatter as
+                                     * separate kernels; 1 count + index in one pass (look-back over the tiles); 2 metadata + scatter
+                                     * fused as well.  1 and 2 read the text less often but measured slower on B200 */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
 /* Page-locked host memory for the caller's window buffers (the Go shim reads the file into these instead of Go

@@ -435,6 +435,28 @@ int orc_zstd_compress(const uint8_t *src, size_t n, int level, uint8_t *dst, siz
     free(b.p);
     return rc;
 }
+/* TEST SUPPORT: frames shaped like other encoders' (klauspost's EncodeAll / streaming writer are not in the reference
+ * tree): explicit window log (4 MiB windows with matches across > 100 blocks), with or without the frame content size
+ * (a streaming encoder writes none) and the checksum.  window_log 0 / flags < 0 leave libzstd's defaults. */
+int orc_zstd_compress_adv(const uint8_t *src, size_t n, int level, int window_log, int content_size, int checksum, uint8_t *dst, size_t cap,
+                          size_t *out_len) {
+    if (libs()) return ORC_E_NOLIB;
+    void *c = L.createCCtx();
+    L.setParam(c, 100, level);
+    if (window_log > 0) L.setParam(c, 101, window_log); /* ZSTD_c_windowLog */
+    if (content_size >= 0) L.setParam(c, 200, content_size);
+    if (checksum >= 0) L.setParam(c, 201, checksum);
+    buf_t b = {0};
+    int rc = zstd_encode(c, src, n, &b);
+    L.freeCCtx(c);
+    if (rc == 0) {
+        *out_len = b.n;
+        if (b.n > cap) rc = ORC_E_NOSPACE;
+        else if (b.n) memcpy(dst, b.p, b.n);
+    }
+    free(b.p);
+    return rc;
+}
 /* DecodeAll: concatenated frames decode back to back; zero bytes -> empty. */
 static int zstd_decode_all(const uint8_t *src, size_t n, buf_t *out) {
     size_t pos = 0;

@@ -77,6 +77,8 @@ def lib():
         L.orc_zstd_bound.restype = sz
         L.orc_zstd_compress.argtypes = [u8p, sz, C.c_int, u8p, sz, szp]
         L.orc_zstd_compress.restype = C.c_int
+        L.orc_zstd_compress_adv.argtypes = [u8p, sz, C.c_int, C.c_int, C.c_int, C.c_int, u8p, sz, szp]
+        L.orc_zstd_compress_adv.restype = C.c_int
         L.orc_zstd_decompress.argtypes = [u8p, sz, u8p, sz, szp]
         L.orc_zstd_decompress.restype = C.c_int
         L.orc_xxh64.argtypes = [u8p, sz, C.c_ulonglong]
@@ -222,6 +224,18 @@ def zstd_compress(data, level: int = 1) -> bytes:
     out = C.create_string_buffer(cap)
     m = C.c_size_t(0)
     rc = lib().orc_zstd_compress(p, n, level, C.cast(out, C.c_void_p), cap, C.byref(m))
+    if rc:
+        raise OracleError(rc)
+    return out.raw[: m.value]
+
+
+def zstd_compress_adv(data, level: int = 1, window_log: int = 0, content_size: int = -1, checksum: int = -1) -> bytes:
+    """libzstd frame with an explicit window log and with / without content size and checksum (test support)."""
+    p, n, k = _in(data)
+    cap = lib().orc_zstd_bound(n) + 64
+    out = C.create_string_buffer(cap)
+    m = C.c_size_t(0)
+    rc = lib().orc_zstd_compress_adv(p, n, level, window_log, content_size, checksum, C.cast(out, C.c_void_p), cap, C.byref(m))
     if rc:
         raise OracleError(rc)
     return out.raw[: m.value]

@@ -18,6 +18,7 @@ from tests.decode_cases import (
     check_item_hints,
     check_zstd_libzstd_frames,
     check_zstd_round_trip,
+    check_zstd_frame_shapes,
 )
 from tests.fastq_cases import GOOD_CASES
 
@@ -44,6 +45,10 @@ def test_zstd_round_trip(emu, oracle, name, policy):
 @pytest.mark.parametrize("n", ENT_SIZES)
 def test_zstd_entropy_policy_sizes(emu, oracle, n):
     check_zstd_ent_sizes(emu, oracle, n)
+
+
+def test_zstd_frame_shapes(emu, oracle):
+    check_zstd_frame_shapes(emu, oracle, 700_000, shapes=[(19, 0, 1, 1), (20, 1, 0, 3), (18, 0, 0, 1)])
 
 
 def test_item_hints(emu, oracle):
