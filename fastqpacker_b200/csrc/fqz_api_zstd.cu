@@ -67,7 +67,9 @@ struct ZBatch {
     // rec0 / nrec (policy ENTROPY with items): the block's records inside items[]
     void add_stream(const u8 *d_src, size_t len, int policy, const u32 *items = nullptr, u32 item_base = 0, u32 item_count = 0, u32 rec0 = 0,
                     u32 nrec = 0) {
-        const u32 rs_no = (policy == FQZ_ZPOLICY_ENTROPY && items && len) ? (u32)rstreams.size() + 1u : 0u;
+        // literals-only stream with record boundaries: cut into segments of FQZ_ZSEG bytes, the units of the duplicate search
+        const bool rseg = policy == FQZ_ZPOLICY_ENTROPY && items && len;
+        const u32 rs_base = (u32)rstreams.size(), nseg = rseg ? (u32)((len + FQZ_ZSEG - 1) / FQZ_ZSEG) : 0u;
         const size_t fsz = (policy == FQZ_ZPOLICY_ENTROPY) ? FQZ_ZFRAME_ENT : (policy == FQZ_ZPOLICY_ITEMS ? FQZ_ZFRAME_ITEMS : FQZ_ZFRAME);
         const size_t nfr = (len + fsz - 1) / fsz;
         if (nfr >= FQZ_ZINDEX_MIN) {  // frame index in front of the stream (FQZ_ZPOLICY_INDEX)
@@ -81,23 +83,25 @@ struct ZBatch {
             f.item_base = 0;
             f.item_count = 0;
             f.index_of = 0;
-            f.pad = rs_no;
+            f.pad = rseg ? rs_base + 1u : 0u;  // the stream's segments: rs_base .. rs_base + item_count - 1
+            f.item_count = nseg;
             slot_bytes += (FQZ_ZINDEX_BYTES(nfr) + 15u) & ~(size_t)15;
             idx_index.push_back((u32)frames.size());
             frames.push_back(f);
         }
         const u32 index_of = (nfr >= FQZ_ZINDEX_MIN) ? (u32)frames.size() : 0u;  // 1 + number of the index frame just added
-        if (rs_no) {
+        for (u32 sg = 0; sg < nseg; sg++) {
+            const size_t so = (size_t)sg * FQZ_ZSEG, sl = std::min<size_t>(FQZ_ZSEG, len - so);
             ZRStream r;
-            r.src = (u64)(uintptr_t)d_src;
+            r.src = (u64)(uintptr_t)(d_src + so);
             r.items = (u64)(uintptr_t)items;
-            r.len = (u32)len;
-            r.item_base = item_base;
+            r.len = (u32)sl;
+            r.item_base = item_base + (u32)so;
             r.rec0 = rec0;
             r.nrec = nrec;
-            r.first_frame = (u32)frames.size();
+            r.first_frame = (u32)frames.size() + (u32)(so / fsz);
             r.blk0 = rblocks;
-            r.nblk = (u32)((len + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT);
+            r.nblk = (u32)((sl + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT);
             r.pad = 0;
             rblocks += r.nblk;
             rmax_records = std::max(rmax_records, nrec);
@@ -116,7 +120,7 @@ struct ZBatch {
             f.item_base = item_base + (u32)o;
             f.item_count = item_count;
             f.index_of = index_of;
-            f.pad = rs_no;
+            f.pad = rseg ? rs_base + (u32)(o / FQZ_ZSEG) + 1u : 0u;
             slot_bytes += FQZ_ZSLOT(l);
             if (policy == FQZ_ZPOLICY_AUTO || policy == FQZ_ZPOLICY_ITEMS) {
                 f.ws_off = ws_bytes;
@@ -196,7 +200,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
         const u32 BB = std::min<u32>(zb.rblocks, 8192u);
         u32 *d_keys = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
         u32 *d_cand = (u32 *)c->arena.alloc(offs_words * sizeof(u32));
-        d_lzflags = (u32 *)c->arena.alloc((size_t)(2 * nrs + 2) * sizeof(u32));  // flags[nrs + 1], then the duplicate counts
+        d_lzflags = (u32 *)c->arena.alloc((size_t)(4 * nrs + 4) * sizeof(u32));  // flags[nrs + 1], the duplicate counts, the record ranges
         d_rhash = (u32 *)c->arena.alloc((size_t)(nrs + 1) * sizeof(u32));
         d_bsizes = (u32 *)c->arena.alloc((size_t)(zb.rblocks + 1) * sizeof(u32));
         u8 *pool_ws = (u8 *)c->arena.alloc(fqz_lzrec_pool_ws(BB) + 64);
@@ -206,8 +210,9 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
             c->err = "arena: out of device memory (record matcher)";
             return FQZ_E_CUDA;
         }
-        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_lzflags, 0, (size_t)(2 * nrs + 2) * sizeof(u32), s));
-        fqz_launch_rec_match(d_rs, nrs, zb.rmax_records, offs_base, d_keys, d_cand, d_lzflags, d_lzflags + nrs + 1, d_rhash, s);
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_lzflags, 0, (size_t)(4 * nrs + 4) * sizeof(u32), s));
+        FQZ_CUDA_TRY(c, cudaMemsetAsync(d_cand, 0, offs_words * sizeof(u32), s));  // a record that straddles into a segment is looked up there too
+        fqz_launch_rec_match(d_rs, nrs, zb.rmax_records, offs_base, d_keys, d_cand, d_lzflags, d_lzflags + nrs + 1, d_lzflags + 2 * nrs + 2, d_rhash, s);
         for (u32 g0 = 0; g0 < zb.rblocks; g0 += BB)
             fqz_launch_lzrec(d_rs, nrs, d_lzflags, offs_base, d_cand, pool_ws, pool_out, g0, std::min<u32>(zb.rblocks, g0 + BB), d_rparsed, d_bsizes, s);
     }

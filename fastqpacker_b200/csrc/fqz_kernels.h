@@ -12,12 +12,12 @@
 // record metadata: 8 lanes per record
 #define FQZ_META_THREADS 256
 #ifndef FQZ_META_GROUP
-#define FQZ_META_GROUP 8
+#define FQZ_META_GROUP 4  // lanes per record (4: 2.1 ms per 9.2 GB step, 8: 3.3 ms, 16: 5.2 ms on B200)
 #endif
 // stream scatter: 8 lanes per record, 64 records per CTA staged through 40 KiB of shared memory
 #define FQZ_SC_THREADS 256
 #ifndef FQZ_SC_GROUP
-#define FQZ_SC_GROUP 8  // lanes per record (8: 6.1 ms per 9.2 GB step, 16: 7.7 ms on B200)
+#define FQZ_SC_GROUP 4  // lanes per record (4: 5.1 ms per 9.2 GB step, 8: 6.1 ms, 16: 7.7 ms on B200)
 #endif
 #ifndef FQZ_SC_RPC
 #define FQZ_SC_RPC 64

@@ -13,6 +13,10 @@
 // literals-only policy: frames of up to eight 16 KiB blocks sharing one Huffman tree (k_zenc_huf)
 #define FQZ_ZFRAME_ENT 131072u
 #define FQZ_ZBLOCK_ENT 16384u
+// duplicate-record search: a stream is searched, and — when it holds duplicates — coded as ONE frame, per segment of this
+// many bytes (16 literals-only frames): long enough that a recurring read is sent again only every 2 MiB, short enough
+// that a 15 MB quality stream is eight frames that decode (and checksum) side by side instead of one serial chain
+#define FQZ_ZSEG (16u * FQZ_ZFRAME_ENT)
 #define FQZ_ZSLOT(len) ((((size_t)(len) + 512) + 15) & ~(size_t)15)  // output slot of one frame: raw fallback + table scratch always fit
 #define FQZ_ZWS(len) (((size_t)(len)*6 + 1023) & ~(size_t)63)  // LZ workspace: literals + match / sequence arrays (<= len/2 + 2 entries, 10 B each)
 
@@ -56,23 +60,24 @@ void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_si
 // lzflags: optional per-stream flags of fqz_launch_rec_match (frames of flagged streams are left to fqz_launch_lzrec)
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
                          cudaStream_t s);
-// One literals-only stream of one fqz block that carries its record boundaries (packed bases, qualities):
-// the unit of the duplicate-record search (fqz_zstd_enc.cu, "duplicated records").  Its frames carry
-// pad = 1 + the stream's number in this table.
+// One segment (<= FQZ_ZSEG bytes) of a literals-only stream of one fqz block that carries its record boundaries
+// (packed bases, qualities): the unit of the duplicate-record search (fqz_zstd_enc.cu, "duplicated records").
+// Its frames carry pad = 1 + the segment's number in this table.
 struct ZRStream {
-    u64 src;           // device address of the stream's bytes
+    u64 src;           // device address of the segment's bytes
     u64 items;         // device address of the scanned record offsets of the whole window (u32)
     u32 len;           // bytes
-    u32 item_base;     // items[rec0] : stream coordinates of the first byte
-    u32 rec0, nrec;    // the block's records inside items[]
+    u32 item_base;     // stream coordinates of the segment's first byte
+    u32 rec0, nrec;    // the BLOCK's records inside items[] (the segment's own are found by binary search: k_rec_ranges)
     u32 first_frame;   // number of the stream's first zstd frame in the frame table (its slots are contiguous)
     u32 blk0, nblk;    // 16 KiB blocks of the stream, numbered through all streams of the batch
     u32 pad;
 };
 // pairs duplicated records (cand, laid out like the scanned offset arrays `offs_base`; keys = scratch of the same
 // shape), flags the streams that hold enough of them (flags[ns] = any) and hashes their content.  dupcnt: ns zeroed words.
+// ranges: 2 * ns words of scratch (first record / record count of every segment)
 void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
-                          u32 *dupcnt, u32 *hashes, cudaStream_t s);
+                          u32 *dupcnt, u32 *ranges, u32 *hashes, cudaStream_t s);
 // codes blocks [g0, gend) of the flagged streams (parse, literals, sequences) into their staging (pool_out: all
 // blocks of the batch, pool_ws / parsed: gend - g0 blocks); _close strings the blocks of every flagged stream together
 size_t fqz_lzrec_pool_ws(u32 nblocks);

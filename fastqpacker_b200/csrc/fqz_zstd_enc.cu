@@ -14,6 +14,7 @@
 //                LZ77 (32 positions per step: ballot + match_any candidate search, hash table in
 //                shared memory), same entropy back end
 //   k_zindex   : the skippable index frame in front of every stream of >= 4 frames (fqz_zstd.h)
+#include <algorithm>
 #include <type_traits>
 
 #include "fqz_zstd.h"
@@ -1279,29 +1280,34 @@ __device__ static u32 warp_item_parse(const u8 *src, u32 len, const u32 *items, 
             // so only matches that clearly beat them are taken
             const u32 min1 = cand ? ZR_MINMATCH : ZI_MINMATCH, min2 = cand ? ZR_MINRUN : ZI_MINMATCH;
             // (an offset that reaches in front of the frame at the item's start — the first items of a frame — takes the byte loop)
-            if (lim - p <= ZM_SPAN && (!d1 || p + back >= d1) && (!d2 || p + back >= d2) ZM_DEBUG_TOGGLE) {
+            // items of up to four spans go through the masks span by span (a match that runs into the next span
+            // is found again there with the same offset and fused by the clean-up)
+            if (lim - p <= 4u * ZM_SPAN && (!d1 || p + back >= d1) && (!d2 || p + back >= d2) ZM_DEBUG_TOGGLE) {
                 const u32 e1 = d1, e2 = d2;
                 if (e1 | e2) {
-                    Mask128 A, B;
-                    zi_eq_masks(src, p, lim - p, e1, e2, A, B);
-                    const Mask128 RA = m128_runs(A, min1), RB = m128_runs(B, min2);
-                    Mask128 C;
-                    C.lo = RA.lo | RB.lo;
-                    C.hi = RA.hi | RB.hi;
-                    const u32 qstop = stop - p;
-                    u32 q = 0;
-                    while (cnt < ZI_MAXM) {
-                        q = m128_next(C, q);
-                        if (q >= qstop) break;
-                        const bool ina = q < 64u ? (RA.lo >> q) & 1ull : (RA.hi >> (q - 64u)) & 1ull;
-                        const bool inb = q < 64u ? (RB.lo >> q) & 1ull : (RB.hi >> (q - 64u)) & 1ull;
-                        const u32 la = ina ? m128_runlen(A, q) : 0u, lb = inb ? m128_runlen(B, q) : 0u;
-                        const u32 best = max(la, lb);
-                        mbuf[(lane * ZI_MAXM + cnt) * 2] = (p + q) | (best << 16);
-                        mbuf[(lane * ZI_MAXM + cnt) * 2 + 1] = (la >= lb) ? e1 : e2;
-                        cnt++;
-                        q += best;
-                        if (q >= ZM_SPAN) break;
+                    for (u32 cb = p; cb < stop && cnt < ZI_MAXM; cb += ZM_SPAN) {
+                        const u32 n = min(ZM_SPAN, lim - cb);
+                        Mask128 A, B;
+                        zi_eq_masks(src, cb, n, e1, e2, A, B);
+                        const Mask128 RA = m128_runs(A, min1), RB = m128_runs(B, min2);
+                        Mask128 C;
+                        C.lo = RA.lo | RB.lo;
+                        C.hi = RA.hi | RB.hi;
+                        const u32 qstop = min(stop - cb, n);
+                        u32 q = 0;
+                        while (cnt < ZI_MAXM) {
+                            q = m128_next(C, q);
+                            if (q >= qstop) break;
+                            const bool ina = q < 64u ? (RA.lo >> q) & 1ull : (RA.hi >> (q - 64u)) & 1ull;
+                            const bool inb = q < 64u ? (RB.lo >> q) & 1ull : (RB.hi >> (q - 64u)) & 1ull;
+                            const u32 la = ina ? m128_runlen(A, q) : 0u, lb = inb ? m128_runlen(B, q) : 0u;
+                            const u32 best = max(la, lb);
+                            mbuf[(lane * ZI_MAXM + cnt) * 2] = (cb + q) | (best << 16);
+                            mbuf[(lane * ZI_MAXM + cnt) * 2 + 1] = (la >= lb) ? e1 : e2;
+                            cnt++;
+                            q += best;
+                            if (q >= ZM_SPAN) break;
+                        }
                     }
                 }
             } else
@@ -2304,29 +2310,49 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
 // PCR / optical duplicates, identical test records, all-'F' quality lines.  They are looked for at RECORD
 // granularity — one hash per record, not per byte:
 //   k_rec_keys   one thread per record: key = hash of its length and of three 16-byte windows (head, middle, tail)
-//   k_rec_match  one warp per (block, stream): walks the keys in order, 32 records per step, and pairs every
-//                record with the nearest earlier record of the same key (two-probe table of the last ~8 K
-//                records in shared memory for the earlier steps, __match_any inside the step; the last lane
-//                that wants a slot gets it, so the result does not depend on scheduling).  A stream in which
-//                at least 1/16 of the records found a partner is flagged.
-//   k_lzrec_*    a flagged stream is NOT cut into independent frames (every frame would have to send the
-//                recurring reads again): it becomes ONE zstd frame of 16 KiB blocks, like the reference's own
-//                output, but all blocks are parsed and entropy-coded in parallel, one warp each — the item
-//                matcher at the partner's offset and at the predecessor's (matches reach back up to 8 MiB into
-//                the earlier blocks), then the literals / sequences writers of the item streams.  Only the
-//                repeat-offset history of the block in front is unknown to a warp: see warp_item_parse.
-// Unflagged streams keep the literals-only frames; the cost there is the key + pairing passes.
+//   k_rec_match  one warp per segment (FQZ_ZSEG = 2 MiB of one stream of one block): walks the keys in order, 32
+//                records per step, and pairs every record with the nearest earlier record of the same key
+//                (two-probe table of the last ~8 K records in shared memory for the earlier steps, __match_any
+//                inside the step; the last lane that wants a slot gets it, so the result does not depend on
+//                scheduling).  A segment in which at least 1/16 of the records found a partner is flagged.
+//   k_lzrec_*    a flagged segment is NOT cut into independent 128 KiB frames (every frame would have to send
+//                the recurring reads again): it becomes ONE zstd frame of 16 KiB blocks, but all blocks are
+//                parsed and entropy-coded in parallel, one warp each — the item matcher at the partner's offset
+//                and at offset 1 (matches reach back into the earlier blocks of the segment), then the literals
+//                / sequences writers of the item streams.  Only the repeat-offset history of the block in front
+//                is unknown to a warp: see warp_item_parse.  2 MiB per frame keeps eight frames of a quality
+//                stream decoding side by side (a frame with sequences is one serial chain for any decoder).
+// Unflagged segments keep the literals-only frames; the cost there is the key pass and the parallel count.
 #define ZR_HLOG 13
-__global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 *offs_base, u32 *keys_base) {
+__device__ __forceinline__ u32 zr_lower_bound(const u32 *items, u32 n, u32 v) {  // first i in [0, n] with items[i] >= v (items[n] = sentinel)
+    u32 a = 0, b = n;
+    while (a < b) {
+        u32 mid = (a + b) >> 1;
+        if (items[mid] < v) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+// records that START inside the segment: ranges[2 si] = number of the first one inside the block, ranges[2 si + 1] = count
+__global__ void k_rec_ranges(const ZRStream *rs, u32 ns, u32 *ranges) {
+    u32 si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= ns) return;
+    const ZRStream &R = rs[si];
+    const u32 *items = (const u32 *)(uintptr_t)R.items + R.rec0;
+    u32 lo = zr_lower_bound(items, R.nrec, R.item_base), hi = zr_lower_bound(items, R.nrec, R.item_base + R.len);
+    ranges[2 * si] = lo;
+    ranges[2 * si + 1] = hi - lo;
+}
+__global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 *ranges, const u32 *offs_base, u32 *keys_base) {
     const ZRStream &R = rs[blockIdx.y];
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R.nrec) return;
+    if (r >= ranges[2 * blockIdx.y + 1]) return;
+    r += ranges[2 * blockIdx.y];
     const u32 *items = (const u32 *)(uintptr_t)R.items + R.rec0;
     u32 s = items[r], n = items[r + 1] - s, key = 0;
     if (n >= 8u) {
         // three 16-byte windows (head, middle, tail; they overlap in short records) and the length: reads that merely
         // open alike — most quality lines of a run do — must not pair up, exact and near-exact copies must
-        const u8 *P = (const u8 *)(uintptr_t)R.src + (s - R.item_base);
+        const u8 *P = (const u8 *)(uintptr_t)R.src + (s - R.item_base);  // the record starts inside the segment (it may end behind it)
         const u32 m = min(n, 16u) & ~3u;  // whole words of a window
         const u32 o1 = (n - m) >> 1, o2 = n - m;
         u32 h = n * 0x9E3779B1u;
@@ -2354,14 +2380,15 @@ __global__ void __launch_bounds__(256) k_rec_keys(const ZRStream *rs, const u32 
 // keys that lose their slot are not counted, so this is a lower bound.  dupcnt[stream] += sum of (occurrences - 1).
 #define ZR_DET_RECORDS 2048u
 #define ZR_DET_SLOTS 4096u
-__global__ void __launch_bounds__(256) k_rec_detect(const ZRStream *rs, const u32 *offs_base, const u32 *keys_base, u32 *dupcnt) {
+__global__ void __launch_bounds__(256) k_rec_detect(const ZRStream *rs, const u32 *ranges, const u32 *offs_base, const u32 *keys_base, u32 *dupcnt) {
     __shared__ u32 tkey[ZR_DET_SLOTS], tcnt[ZR_DET_SLOTS];
     __shared__ u32 ws[33];
     const ZRStream &R = rs[blockIdx.y];
+    const u32 nseg = ranges[2 * blockIdx.y + 1];
     const u32 r0 = blockIdx.x * ZR_DET_RECORDS;
-    if (r0 >= R.nrec) return;
-    const u32 r1 = min(R.nrec, r0 + ZR_DET_RECORDS);
-    const u32 *keys = keys_base + ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0;
+    if (r0 >= nseg) return;
+    const u32 r1 = min(nseg, r0 + ZR_DET_RECORDS);
+    const u32 *keys = keys_base + ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0 + ranges[2 * blockIdx.y];
     for (u32 i = threadIdx.x; i < ZR_DET_SLOTS; i += blockDim.x) tkey[i] = 0, tcnt[i] = 0;
     __syncthreads();
     u32 k[ZR_DET_RECORDS / 256];
@@ -2384,15 +2411,16 @@ __global__ void __launch_bounds__(256) k_rec_detect(const ZRStream *rs, const u3
 }
 // cand[r] = 1 + number (inside the stream's block) of the partner record, 0 = none.  flags[ns] = any stream flagged.
 __global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, const u32 *offs_base, const u32 *keys_base, u32 *cand_base, u32 *flags,
-                                                  const u32 *dupcnt) {
+                                                  const u32 *dupcnt, const u32 *ranges) {
     __shared__ u32 tab[1 << ZR_HLOG];  // key bits 17.. | 1 + record number (17 bits: a block holds 100 000 records)
     const u32 si = blockIdx.x, lane = lane_id();
     if (si >= ns) return;
     const ZRStream R = rs[si];
-    const size_t at = ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0;
+    const u32 first = ranges[2 * si];  // the segment's records inside the block
+    const size_t at = ((const u32 *)(uintptr_t)R.items - offs_base) + R.rec0 + first;
     const u32 *keys = keys_base + at;
     u32 *cand = cand_base + at;
-    const u32 nrec = R.nrec;
+    const u32 nrec = ranges[2 * si + 1];
     // records of 20 bytes or more on average (the match list of a block holds one entry per two bytes), and enough
     // repeated keys for the 1/16 below to be in reach (the chunk-local count misses the far pairs: ask for half)
     if (nrec < 8u || (u64)nrec * 20u > R.len || nrec >= (1u << 17) || dupcnt[si] * 32u < nrec) {
@@ -2425,7 +2453,7 @@ __global__ void __launch_bounds__(32) k_rec_match(const ZRStream *rs, u32 ns, co
             if (lower) c = ib + (31u - (u32)__clz((int)lower)) + 1u;
         }
         if (live) {
-            cand[i] = c;
+            cand[i] = c ? first + c : 0u;  // numbered inside the block, like items[]
             hits += c ? 1u : 0u;
         }
         // insert: the key's own slot if it has one, else a free one, else the slot whose record is older; all lanes
@@ -2504,14 +2532,6 @@ __device__ __forceinline__ bool zr_block(const ZRStream *rs, u32 ns, const u32 *
     B.slo = (u16 *)(B.sof + maxseq);
     B.out = pool_out + (size_t)g * ZR_OUT_STRIDE;
     return true;
-}
-__device__ __forceinline__ u32 zr_lower_bound(const u32 *items, u32 n, u32 v) {  // first i in [0, n] with items[i] >= v (items[n] = sentinel)
-    u32 a = 0, b = n;
-    while (a < b) {
-        u32 mid = (a + b) >> 1;
-        if (items[mid] < v) a = mid + 1; else b = mid;
-    }
-    return a;
 }
 __global__ void __launch_bounds__(ZENC_WARPS * 32) k_lzrec_parse(const ZRStream *rs, u32 ns, const u32 *flags, const u32 *offs_base, const u32 *cand_base,
                                                                  u8 *pool_ws, u8 *pool_out, u32 g0, u32 gend, u32 *parsed) {
@@ -2668,9 +2688,16 @@ __global__ void __launch_bounds__(128) k_zindex(const ZFrame *frames, u32 nframe
     u32 f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const ZFrame &F = frames[f];
-    if (lzflags && F.pad && lzflags[F.pad - 1u]) {  // one frame for the whole stream: no index
-        if (F.policy == FQZ_ZPOLICY_INDEX) out_sizes[f] = 0;
-        return;
+    if (lzflags && F.pad) {
+        // a stream of which any segment is coded as one frame carries no index (its frames are no longer one per entry)
+        const ZFrame &X = (F.policy == FQZ_ZPOLICY_INDEX) ? F : (F.index_of ? frames[F.index_of - 1u] : F);
+        bool any = false;
+        if (X.policy == FQZ_ZPOLICY_INDEX)
+            for (u32 k = 0; k < X.item_count; k++) any |= lzflags[X.pad - 1u + k] != 0;
+        if (any) {
+            if (F.policy == FQZ_ZPOLICY_INDEX) out_sizes[f] = 0;
+            return;
+        }
     }
     if (F.policy == FQZ_ZPOLICY_INDEX) {
         u32 n = F.src_len;
@@ -2726,11 +2753,14 @@ void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const
     FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags);
 }
 void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
-                          u32 *dupcnt, u32 *hashes, cudaStream_t s) {
+                          u32 *dupcnt, u32 *ranges, u32 *hashes, cudaStream_t s) {
     if (!ns) return;
-    FQZ_LAUNCH(k_rec_keys, dim3((max_records + 255) / 256, ns), 256, 0, s, rs, offs_base, keys_base);
-    FQZ_LAUNCH(k_rec_detect, dim3((max_records + ZR_DET_RECORDS - 1) / ZR_DET_RECORDS, ns), 256, 0, s, rs, offs_base, keys_base, dupcnt);
-    FQZ_LAUNCH(k_rec_match, ns, 32, 0, s, rs, ns, offs_base, keys_base, cand_base, flags, dupcnt);
+    // a segment of FQZ_ZSEG bytes takes part with at most FQZ_ZSEG / 20 records (more, i.e. shorter ones, make it ineligible)
+    const u32 per_seg = std::min<u32>(max_records, FQZ_ZSEG / 20u + 1u);
+    FQZ_LAUNCH(k_rec_ranges, (ns + 127) / 128, 128, 0, s, rs, ns, ranges);
+    FQZ_LAUNCH(k_rec_keys, dim3((per_seg + 255) / 256, ns), 256, 0, s, rs, ranges, offs_base, keys_base);
+    FQZ_LAUNCH(k_rec_detect, dim3((per_seg + ZR_DET_RECORDS - 1) / ZR_DET_RECORDS, ns), 256, 0, s, rs, ranges, offs_base, keys_base, dupcnt);
+    FQZ_LAUNCH(k_rec_match, ns, 32, 0, s, rs, ns, offs_base, keys_base, cand_base, flags, dupcnt, ranges);
     u32 threads = XX_WARPS * 32, grid = (ns * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_streams, grid, threads, XX_SMEM, s, rs, ns, flags, hashes);
 }
