@@ -401,7 +401,7 @@ def run_ours(args):
     if "zstd_enc_entropy" in stages:
         stages["zstd_enc_entropy"]["bytes"] += z_ent
     # ---- roofline of the dominant kernel (largest share of the compress step)
-    comp_stages = ["newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "xxh64", "assemble", "copy"]
+    comp_stages = ["newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "zstd_enc_dup", "xxh64", "assemble", "copy"]
     cs = {k: v for k, v in stages.items() if k in comp_stages}
     top = max(cs, key=lambda k: cs[k]["ms"]) if cs else None
     roof = None
@@ -423,6 +423,7 @@ def run_ours(args):
         stage_kernels = {
             "zstd_enc_lz": "k_zitems_parse + k_zenc<2,1> + k_zenc<2,2> (item streams: matcher, Huffman literals, FSE sequences)",
             "zstd_enc_entropy": "k_zenc_huf (packed bases, qualities: Huffman frames)",
+            "zstd_enc_dup": "k_rec_ranges + k_rec_keys + k_rec_detect + k_rec_match + k_xxh64_streams + k_lzrec_* (duplicate-record search and coding)",
             "scatter_streams": "k_scatter_streams",
             "record_meta": "k_record_meta",
             "newline_count": "k_newline_count",

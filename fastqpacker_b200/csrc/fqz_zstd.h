@@ -9,7 +9,9 @@
 #define FQZ_ZFRAME 65536u
 #define FQZ_ZFRAME_LOG 16
 // item-matcher policy: small frames, so that one 1 GiB window holds enough frames (one warp each) to fill 148 SMs
+#ifndef FQZ_ZFRAME_ITEMS
 #define FQZ_ZFRAME_ITEMS 16384u
+#endif
 // literals-only policy: frames of up to eight 16 KiB blocks sharing one Huffman tree (k_zenc_huf)
 #define FQZ_ZFRAME_ENT 131072u
 #define FQZ_ZBLOCK_ENT 16384u

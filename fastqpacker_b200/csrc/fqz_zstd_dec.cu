@@ -630,7 +630,9 @@ __global__ void __launch_bounds__(128) k_zd_offsets(ZDBlock *blocks, u32 nblocks
 }
 
 // ---------------------------------------------------------------------------------- literals
+#ifndef ZD_WARPS
 #define ZD_WARPS 4
+#endif
 struct LitScratch {
     u16 dt[1 << HUF_MAXBITS];  // nbBits << 8 | symbol
     u8 weights[256];
@@ -1207,7 +1209,9 @@ __device__ __forceinline__ void lane_copy_fwd(u8 *d, const u8 *s, u32 n) {
 // this library writes) are executed in shared memory — the dependency rounds then cost a shared-memory
 // round trip instead of one through L2 — and written out with wide coalesced stores.
 #define ZX_ENABLE 1
+#ifndef ZX_STAGE
 #define ZX_STAGE 16384u
+#endif
 #define ZX_SMEM (ZX_ENABLE ? ZD_WARPS * (ZX_STAGE + 64u) : 0u)
 __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out) {
     FQZ_DYN_SMEM(u8, smem);
