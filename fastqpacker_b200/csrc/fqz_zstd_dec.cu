@@ -1205,19 +1205,6 @@ __device__ __forceinline__ void lane_copy_fwd(u8 *d, const u8 *s, u32 n) {
     for (; k < n; k++) d[k] = s[k];
 }
 
-// Which frames k_zd_execute_ring takes (experiment, -DZG_MODE): 0 none, 1 single-block frames with sequences (the item
-// frames), 2 every frame with sequences.  The others stay with k_zd_execute.
-#ifndef ZG_MODE
-#define ZG_MODE 0
-#endif
-__device__ __forceinline__ bool zd_ring_frame(const ZDFrame &F, const ZDBlock *blocks, u32 lane) {
-    if (ZG_MODE == 0) return false;
-    if (ZG_MODE == 1 && F.nblocks != 1) return false;
-    bool any = false;
-    for (u32 b = lane; b < F.nblocks; b += 32) any |= blocks[F.first_block + b].type == 2 && blocks[F.first_block + b].nseq > 0;
-    return __any_sync(FULL, any);
-}
-
 // Frames of one block with sequences and at most ZX_STAGE bytes of content (the 16 KiB item frames
 // this library writes) are executed in shared memory — the dependency rounds then cost a shared-memory
 // round trip instead of one through L2 — and written out with wide coalesced stores.
@@ -1232,7 +1219,6 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
     u32 fi = blockIdx.x * ZD_WARPS + warp;
     if (fi >= nframes) return;
     ZDFrame F = frames[fi];
-    if (zd_ring_frame(F, blocks, lane)) return;  // k_zd_execute_ring
     u8 *const gbase = out + F.dst_off;
     u8 *base = gbase;
     const bool staged = ZX_ENABLE && F.nblocks == 1 && F.out_cap <= ZX_STAGE && blocks[F.first_block].type == 2 && blocks[F.first_block].nseq > 0;
@@ -1394,207 +1380,6 @@ __global__ void __launch_bounds__(ZD_WARPS * 32) k_zd_execute(ZDFrame *frames, u
     }
 }
 
-// ---------------------------------------------------------------------------------- execution of long frames: ring in shared memory
-// One warp per frame, like k_zd_execute, with the same 32-sequences-per-step scheme (warp scan of the lengths, all
-// literal runs at once, matches in dependency rounds) — but the step's output is produced in a ring of ZG_RING bytes
-// of shared memory that always holds the most recent output, and written to HBM once per step with coalesced stores.
-// A round of dependent copies then costs a shared-memory round trip instead of one through L2 (~10x less), which is
-// what bounds a frame whose matches mostly reach a few hundred bytes back (headers, qualities).  Sources that lie
-// before the ring are read from HBM: everything in front of the current step is final there.  A step that produces
-// more than ZG_STEP_MAX bytes (very long matches) runs in HBM as before and empties the ring.
-#ifndef ZG_RING
-#define ZG_RING 8192u
-#endif
-#define ZG_MASK (ZG_RING - 1u)
-#define ZG_STEP_MAX (ZG_RING / 4u)
-__global__ void __launch_bounds__(32) k_zd_execute_ring(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out) {
-    FQZ_DYN_SMEM(u8, ring);
-    const u32 lane = lane_id();
-    const u32 fi = blockIdx.x;
-    if (fi >= nframes) return;
-    ZDFrame F = frames[fi];
-    if (!zd_ring_frame(F, blocks, lane)) return;
-    u8 *const base = out + F.dst_off;
-    u64 o = 0;           // bytes regenerated so far in this frame
-    u64 valid_from = 0;  // ring holds [max(valid_from, o - ZG_RING), o)
-    u32 rep0 = 1, rep1 = 4, rep2 = 8;
-    u32 err = 0;
-    for (u32 b = 0; b < F.nblocks && !err; b++) {
-        ZDBlock B = blocks[F.first_block + b];
-        if (B.err) { err = 1; break; }
-        const u8 *c = (const u8 *)(uintptr_t)B.src;
-        if (B.type <= 1 && B.out_off != 0xFFFFFFFFu) {  // regenerated by k_zd_rawcopy
-            if (o + B.rsize > F.out_cap || (u64)B.out_off != o) { err = 1; break; }
-            o += B.rsize;
-            valid_from = o;
-        } else if (B.type == 0) {
-            if (o + B.rsize > F.out_cap) { err = 1; break; }
-            warp_copy(base + o, c, B.rsize, lane);
-            o += B.rsize;
-            valid_from = o;
-        } else if (B.type == 1) {
-            if (o + B.rsize > F.out_cap) { err = 1; break; }
-            u8 v = c[0];
-            for (u32 i = lane; i < B.rsize; i += 32) base[o + i] = v;
-            o += B.rsize;
-            valid_from = o;
-        } else if (B.nseq == 0) {
-            if (o + B.lit_regen > F.out_cap) { err = 1; break; }
-            if (B.out_off == 0xFFFFFFFFu) warp_copy(base + o, litbuf + B.lit_off, B.lit_regen, lane);  // else: decoded in place
-            else if ((u64)B.out_off != o) { err = 1; break; }
-            o += B.lit_regen;
-            valid_from = o;
-        } else {
-            const u8 *lit = litbuf + B.lit_off;
-            const u32 *sq = seqbuf + 3ull * B.seq_off;
-            u32 lp = 0;
-            u64 o0 = o;
-            for (u32 sb = 0; sb < B.nseq && !err; sb += 32) {
-                const u32 cn = min(32u, B.nseq - sb);
-                const bool live = lane < cn;
-                u32 ll = 0, ml = 0, ofv = 0;
-                if (live) {
-                    ll = sq[3 * (sb + lane)];
-                    ml = sq[3 * (sb + lane) + 1];
-                    ofv = sq[3 * (sb + lane) + 2];
-                }
-                // repeat offsets (RFC 8878 §3.1.1.5), uniform — unless k_zd_seq_decode resolved them already
-                u32 off = ofv;
-                if (!B.pad[0])
-                for (u32 j = 0; j < cn; j++) {
-                    u32 v = __shfl_sync(FULL, ofv, (int)j), l = __shfl_sync(FULL, ll, (int)j);
-                    u32 f;
-                    if (v > 3) {
-                        f = v - 3;
-                        rep2 = rep1; rep1 = rep0; rep0 = f;
-                    } else {
-                        u32 idx = v - 1 + (l == 0 ? 1u : 0u);
-                        if (idx == 0) f = rep0;
-                        else {
-                            f = (idx == 1) ? rep1 : (idx == 2) ? rep2 : rep0 - 1;
-                            if (idx != 1) rep2 = rep1;
-                            rep1 = rep0;
-                            rep0 = f;
-                        }
-                    }
-                    if (lane == j) off = f;
-                }
-                u32 tot = ll + ml;
-                u32 incl = group_incl_scan(tot, FULL, 32), lincl = group_incl_scan(ll, FULL, 32);
-                u32 gtot = __shfl_sync(FULL, incl, 31), gll = __shfl_sync(FULL, lincl, 31);
-                u64 lstart = o + incl - tot, mstart = lstart + ll;
-                u32 lsrc = lp + lincl - ll;
-                bool bad = live && (off == 0 || (u64)off > mstart);
-                if (__any_sync(FULL, bad) || lp + gll > B.lit_regen || o + gtot > F.out_cap) { err = 1; break; }
-                const bool in_ring = gtot <= ZG_STEP_MAX;
-                // what the ring still holds while this step writes [o, o + gtot) into it
-                const u64 ring_lo = in_ring ? max(valid_from, (o + gtot > ZG_RING) ? o + gtot - ZG_RING : 0ull) : ~0ull;
-                // byte at frame position q (q below the step: final in HBM; inside the step: in the ring)
-                auto rd = [&](u64 q) -> u8 { return q >= ring_lo ? ring[(u32)q & ZG_MASK] : base[q]; };
-                if (in_ring) {
-                    for (u32 k = 0; k < ll; k++) ring[(u32)(lstart + k) & ZG_MASK] = lit[lsrc + k];
-                } else if (live)
-                    lane_copy_fwd(base + lstart, lit + lsrc, ll);
-                __syncwarp();
-                bool done = !live || ml == 0;
-                const u64 need = (off >= ml) ? (mstart - off + ml) : mstart;  // output that must be final before this lane copies
-                for (;;) {
-                    u32 pend = __ballot_sync(FULL, !done);
-                    if (!pend) break;
-                    int hw = __ffs((int)pend) - 1;
-                    u64 hwpos = __shfl_sync(FULL, mstart, hw);  // everything below is final
-                    u32 hml = __shfl_sync(FULL, ml, hw);
-                    if (hml > 64u) {  // long match at the front: the whole warp copies it
-                        u32 hoff = __shfl_sync(FULL, off, hw);
-                        const u64 sp = hwpos - hoff;
-                        if (in_ring) {
-                            if (hoff >= hml) {
-                                for (u32 k = lane; k < hml; k += 32) ring[(u32)(hwpos + k) & ZG_MASK] = rd(sp + k);
-                            } else if (hoff >= 32u) {  // overlapping, but 32 bytes at a time never overtake the source
-                                for (u32 k0 = 0; k0 < hml; k0 += 32) {
-                                    if (k0 + lane < hml) ring[(u32)(hwpos + k0 + lane) & ZG_MASK] = rd(sp + k0 + lane);
-                                    __syncwarp();
-                                }
-                            } else {
-                                for (u32 k = lane; k < hml; k += 32) ring[(u32)(hwpos + k) & ZG_MASK] = rd(sp + k % hoff);
-                            }
-                        } else {
-                            u8 *d = base + hwpos;
-                            const u8 *s0 = d - hoff;
-                            if (hoff >= hml) {
-                                for (u32 k = lane; k < hml; k += 32) d[k] = s0[k];
-                            } else if (hoff >= 32u) {
-                                for (u32 k0 = 0; k0 < hml; k0 += 32) {
-                                    if (k0 + lane < hml) d[k0 + lane] = s0[k0 + lane];
-                                    __syncwarp();
-                                }
-                            } else {
-                                for (u32 k = lane; k < hml; k += 32) d[k] = s0[k % hoff];
-                            }
-                        }
-                        if ((int)lane == hw) done = true;
-                    } else if (!done && ml <= 64u && ((int)lane == hw || need <= hwpos)) {
-                        if (in_ring) {
-                            const u64 sp = mstart - off;
-                            for (u32 k = 0; k < ml; k++) ring[(u32)(mstart + k) & ZG_MASK] = rd(sp + k);
-                        } else {
-                            u8 *d = base + mstart;
-                            const u8 *s0 = d - off;
-                            if (off >= 4u) lane_copy_fwd(d, s0, ml);
-                            else
-                                for (u32 k = 0; k < ml; k++) d[k] = s0[k];
-                        }
-                        done = true;
-                    }
-                    __syncwarp();
-                }
-                if (in_ring) {  // the step's output to HBM: bytes up to destination alignment, then 16-byte stores
-                    u8 *g = base + o;
-                    u32 head = (u32)((16u - ((uintptr_t)g & 15u)) & 15u);
-                    if (head > gtot) head = gtot;
-                    if (lane < head) g[lane] = ring[(u32)(o + lane) & ZG_MASK];
-                    const u32 nv = (gtot - head) >> 4;
-                    const u32 r0 = (u32)(o + head) & ZG_MASK;  // 16 | ZG_RING: a vector never wraps if r0 is 4-byte aligned ... it need not be
-                    for (u32 v = lane; v < nv; v += 32) {
-                        const u32 rp = (r0 + 16u * v) & ZG_MASK;
-                        uint4 x;
-                        if ((rp & 3u) == 0 && rp + 16u <= ZG_RING) {
-                            const u32 *w = (const u32 *)(ring + rp);
-                            x = make_uint4(w[0], w[1], w[2], w[3]);
-                        } else {
-                            u32 t[4];
-                            for (u32 q = 0; q < 4; q++)
-                                t[q] = (u32)ring[(rp + 4u * q) & ZG_MASK] | ((u32)ring[(rp + 4u * q + 1u) & ZG_MASK] << 8) |
-                                       ((u32)ring[(rp + 4u * q + 2u) & ZG_MASK] << 16) | ((u32)ring[(rp + 4u * q + 3u) & ZG_MASK] << 24);
-                            x = make_uint4(t[0], t[1], t[2], t[3]);
-                        }
-                        ((uint4 *)(g + head))[v] = x;
-                    }
-                    const u32 t0 = head + 16u * nv;
-                    if (lane < gtot - t0) g[t0 + lane] = ring[(u32)(o + t0 + lane) & ZG_MASK];
-                } else
-                    valid_from = o + gtot;  // the ring missed this step
-                __syncwarp();
-                o += gtot;
-                lp += gll;
-            }
-            if (err) break;
-            u32 rest = B.lit_regen - lp;
-            if (o + rest > F.out_cap) { err = 1; break; }
-            warp_copy(base + o, lit + lp, rest, lane);
-            if (rest) valid_from = o + rest;
-            o += rest;
-            if (o - o0 > ZSTD_BLOCK_MAX) { err = 1; break; }
-        }
-        __syncwarp();
-    }
-    if (!err && F.content_size != ~0ull && o != F.content_size) err = 1;
-    if (lane == 0) {
-        frames[fi].out_size = o;
-        frames[fi].err = err;
-    }
-}
-
 // ---------------------------------------------------------------------------------- content checksum
 // see fqz_xxh64.cuh: 4 threads per frame, 8 frames per warp, frames streamed through shared memory by TMA
 __global__ void __launch_bounds__(XX_WARPS * 32) k_zd_checksum(ZDFrame *frames, u32 nframes, const u8 *out) {
@@ -1690,7 +1475,6 @@ void fqz_launch_zd_sequences(ZDBlock *blocks, const ZDFrame *frames, const u32 *
 void fqz_launch_zd_execute(ZDFrame *frames, u32 nframes, ZDBlock *blocks, const u8 *litbuf, const u32 *seqbuf, u8 *out, cudaStream_t s) {
     if (!nframes) return;
     FQZ_LAUNCH(k_zd_execute, (nframes + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, ZX_SMEM, s, frames, nframes, blocks, litbuf, seqbuf, out);
-    if (ZG_MODE) FQZ_LAUNCH(k_zd_execute_ring, nframes, 32, ZG_RING, s, frames, nframes, blocks, litbuf, seqbuf, out);
 }
 void fqz_launch_zd_rawcopy(const ZDBlock *blocks, u32 nblocks, const ZDFrame *frames, u8 *out, cudaStream_t s) {
     if (!nblocks) return;
@@ -1709,6 +1493,5 @@ int fqz_zstd_dec_init_device() {
     int e = 0;
     if (ZX_SMEM) e |= (int)cudaFuncSetAttribute(k_zd_execute, cudaFuncAttributeMaxDynamicSharedMemorySize, ZX_SMEM);
     e |= (int)cudaFuncSetAttribute(k_zd_checksum, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
-    if (ZG_RING > 48u * 1024u) e |= (int)cudaFuncSetAttribute(k_zd_execute_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, ZG_RING);
     return e;
 }
