@@ -24,11 +24,18 @@ static const int kErrOfBk[8] = {0,
 static const char *kStreamWhat[6] = {"sequences", "quality", "headers", "plus-line payload", "N positions", "lengths"};
 
 #define DEC_TABLE_CAP 1024u                  // fqz blocks per container-walk pass
-#define DEC_WINDOW_BYTES ((u64)640 << 20)    // compressed bytes per device window (device-resident calls; large windows amortise kernel tails)
+#define DEC_WINDOW_BYTES ((u64)1280 << 20)   // compressed bytes per device window (device-resident calls; large windows amortise kernel tails,
+                                             // and a reference-written file — one serial frame per stream — lasts as long as its windows are many)
 #define DEC_WINDOW_HOST ((u64)256 << 20)     // ... of the host pipeline, whose first window cannot start before it has been uploaded
 // decoded stream bytes per device window: FASTQ is at most 1.6 x the stream bytes (2 L text bytes per 1.25 L
 // of packed bases + qualities), so FASTQ offsets stay below 2^32
 #define DEC_WINDOW_OUT ((u64)2400 << 20)
+// device-resident calls: the entropy stage takes as many blocks as its 32-bit arena offsets allow; the back end then
+// runs over runs of blocks whose FASTQ stays below 2^32 bytes
+#define DEC_WINDOW_OUT_DEV ((u64)3900 << 20)
+#ifndef DEC_BACKEND_FASTQ
+#define DEC_BACKEND_FASTQ ((u64)3900 << 20)
+#endif
 
 static int backend_error(fqz_ctx *c, const std::vector<BkBlock> &blks, u64 key, u64 block_base) {
     u32 kind = (u32)(key & 0xFF);
@@ -166,7 +173,8 @@ static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, 
         }
     }
     ZDecodeOut zo;
-    int rc = fqz_zdecode_batch(c, zs, DEC_WINDOW_OUT, zo);
+    const bool chunked = d_out != nullptr && io_slot < 0;  // device output: the back end may run in several passes
+    int rc = fqz_zdecode_batch(c, zs, chunked ? DEC_WINDOW_OUT_DEV : DEC_WINDOW_OUT, zo);
     if (rc == FQZ_E_ZSTD && zo.err_stream >= 0) {
         char msg[240];
         snprintf(msg, sizeof msg, "decompressing block %llu: decompressing %s: %s", (unsigned long long)(block_base + zo.err_stream / 6),
@@ -192,7 +200,31 @@ static int decode_blocks(fqz_ctx *c, const u8 *d_fqz, const FqzBlockEntry *ent, 
         }
         B.pad2 = 0;
     }
-    return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base, io_slot);
+    if (!chunked) return backend_run(c, blks, phred64, d_out, out_cap, d_res, out_len, block_base, io_slot);
+    size_t written = 0;
+    *out_len = 0;
+    for (u32 b0 = 0; b0 < nb;) {
+        u64 est = 0;
+        u32 b1 = b0;
+        while (b1 < nb) {  // FASTQ bytes of a block <= 2 L + names + plus payloads + 4 per record
+            u64 e = 2ull * blks[b1].size[1] + blks[b1].size[2] + blks[b1].size[3] + 4ull * blks[b1].nrec;
+            if (b1 > b0 && est + e > DEC_BACKEND_FASTQ) break;
+            est += e;
+            b1++;
+        }
+        std::vector<BkBlock> part(blks.begin() + b0, blks.begin() + b1);
+        size_t wl = 0;
+        rc = backend_run(c, part, phred64, d_out + written, out_cap - written, nullptr, &wl, block_base + b0, -1);
+        if (rc == FQZ_E_NOSPACE) {  // report what the whole batch needs as far as it is known
+            *out_len = written + wl;
+            return rc;
+        }
+        if (rc != FQZ_OK) return rc;
+        written += wl;
+        b0 = b1;
+    }
+    *out_len = written;
+    return FQZ_OK;
 }
 
 struct DecState {
