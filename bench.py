@@ -240,6 +240,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = fq.context(local)
     ctx.set_option(ctx.OPT_FRONTEND, args.frontend)
+    ctx.set_option(ctx.OPT_HUF_KERNELS, args.huf_kernels)
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=local)
     nrec = args.records or FULL_RECORDS
     peak, peak_src = _peaks()
@@ -422,7 +423,7 @@ def run_ours(args):
         nl = max(1, v["launches"] // {"zstd_enc_lz": 3, "assemble": 2}.get(top, 1))
         stage_kernels = {
             "zstd_enc_lz": "k_zitems_parse + k_zenc<2,1> + k_zenc<2,2> (item streams: matcher, Huffman literals, FSE sequences)",
-            "zstd_enc_entropy": "k_zenc_huf (packed bases, qualities: Huffman frames)",
+            "zstd_enc_entropy": "k_zh_hist + k_zh_plan + k_zh_encode (packed bases, qualities: Huffman frames)",
             "zstd_enc_dup": "k_rec_ranges + k_rec_keys + k_rec_detect + k_rec_match + k_xxh64_streams + k_lzrec_* (duplicate-record search and coding)",
             "scatter_streams": "k_scatter_streams",
             "record_meta": "k_record_meta",
@@ -869,6 +870,7 @@ def main():
     ap.add_argument("--total-bytes", type=int, default=0, help="cfg5: size of the logical input (default 64e9)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 and duplicates side workloads")
     ap.add_argument("--frontend", type=int, default=0, choices=[0, 1, 2], help="A/B of the front-end kernels: see FQZ_OPT_FRONTEND")
+    ap.add_argument("--huf-kernels", type=int, default=0, choices=[0, 1], help="A/B of the literals-only frame coder: see FQZ_OPT_HUF_KERNELS")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -218,7 +218,8 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
     }
     {
         StageScope sc(c, ST_ZENC_ENTROPY, ent_bytes);
-        fqz_launch_zenc_huf(ze.d_frames, d_idx, nent, d_hash, ze.d_slots, ze.d_scan, d_lzflags, s);
+        u8 *d_zh = (nent && !c->opt_huf_single) ? (u8 *)c->arena.alloc(fqz_zenc_huf_scratch(nent)) : nullptr;
+        fqz_launch_zenc_huf(ze.d_frames, d_idx, nent, d_hash, ze.d_slots, ze.d_scan, d_lzflags, d_zh, s);
     }
     if (nrs) {
         StageScope sc(c, ST_ZENC_DUP, 0);

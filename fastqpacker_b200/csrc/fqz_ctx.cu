@@ -362,6 +362,10 @@ extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
         if (value > 2) return FQZ_E_INVALID_ARG;
         c->opt_frontend = (int)value;
         return FQZ_OK;
+    case FQZ_OPT_HUF_KERNELS:
+        if (value > 1) return FQZ_E_INVALID_ARG;
+        c->opt_huf_single = (int)value;
+        return FQZ_OK;
     case FQZ_OPT_RECORD_MATCH:
         if (value > 1) return FQZ_E_INVALID_ARG;
         c->opt_no_record_match = value ? 0 : 1;

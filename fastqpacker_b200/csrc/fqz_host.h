@@ -109,6 +109,7 @@ struct fqz_ctx {
     u64 opt_host_window_bytes = 0;  // window of the host-buffer compress calls (0 = default)
     int opt_frontend = 0;           // 0: separate kernels (count, index, metadata, scans, scatter); 1: count + index in one pass (look-back); 2: metadata + scatter fused as well
     u64 fused_windows = 0, legacy_windows = 0;
+    int opt_huf_single = 0;         // 1: literals-only frames by the single kernel (k_zenc_huf) instead of histogram / plan / encode
     int opt_no_record_match = 0;    // 1: packed bases / qualities always literals-only (no duplicate-record search)
 };
 int fqz_frontend_init_device();

@@ -60,8 +60,11 @@ void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream
 void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, const u32 *lzflags, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
 // lzflags: optional per-stream flags of fqz_launch_rec_match (frames of flagged streams are left to fqz_launch_lzrec)
+// scratch: fqz_zenc_huf_scratch(nidx) bytes -> the three-kernel version (histograms, one-warp-per-frame plan, encode);
+// nullptr -> the single kernel
+size_t fqz_zenc_huf_scratch(u32 nidx);
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
-                         cudaStream_t s);
+                         u8 *scratch, cudaStream_t s);
 // One segment (<= FQZ_ZSEG bytes) of a literals-only stream of one fqz block that carries its record boundaries
 // (packed bases, qualities): the unit of the duplicate-record search (fqz_zstd_enc.cu, "duplicated records").
 // Its frames carry pad = 1 + the segment's number in this table.

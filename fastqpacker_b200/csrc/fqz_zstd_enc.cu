@@ -2305,6 +2305,244 @@ __global__ void __launch_bounds__(ZH_THREADS) k_zenc_huf(const ZFrame *frames, c
     }
 }
 
+// ---------------------------------------------------------------------------------- literals-only frames in three kernels
+// k_zenc_huf above keeps 255 threads of a CTA waiting at barriers while one thread merges the Huffman tree, FSE-codes
+// its weights and lays the frame out (ncu: a third of its stall samples).  Split by the shape of the work instead:
+//   k_zh_hist    one CTA per frame: the 32 per-stream histograms (all warps busy), written to HBM transposed
+//   k_zh_plan    one WARP per frame: frame histogram, code (warp_huf_build), tree description, exact stream sizes,
+//                layout, every header byte of the frame — the serial steps cost one warp, not eight, and
+//                thousands of frames are planned side by side
+//   k_zh_encode  one CTA per frame: the 32 streams coded to their final places (no barrier after the first)
+// The plan of a frame (mode, stream positions, code) travels through HBM: 0.7 KB per 128 KiB frame.
+struct ZhPlan {
+    u32 mode;  // 0 raw block, 1 RLE block, 2 Huffman blocks
+    u32 total;
+    u32 sdst[32];
+    u16 hlut[256];
+};
+#define ZH_HIST_WORDS (128u * 32u + 256u)  // per frame: shist[word][stream] (two u16 counters per word), then hist[256]
+__global__ void __launch_bounds__(ZH_THREADS) k_zh_hist(const ZFrame *frames, const u32 *index, u32 nidx, u32 *out_sizes, const u32 *lzflags,
+                                                        u32 *hist_g) {
+    __shared__ u32 shist[32][128];
+    u32 tid = threadIdx.x, warp = tid >> 5;
+    u32 fi = index ? index[blockIdx.x] : blockIdx.x;
+    if (lzflags && frames[fi].pad && lzflags[frames[fi].pad - 1u]) {
+        // a segment with duplicated records is coded as ONE frame by the record matcher (k_lzrec_*), which writes
+        // its size into its first frame's entry afterwards
+        if (tid == 0) out_sizes[fi] = 0;
+        return;
+    }
+    ZFrame fr = frames[fi];
+    const u8 *src = (const u8 *)(uintptr_t)fr.src;
+    const u32 n = fr.src_len;
+    const u32 nblk = (n + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT;  // <= 8
+    for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) (&shist[0][0])[i] = 0;
+    __syncthreads();
+    if (warp < nblk) {
+        u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
+        for (u32 k = 0; k < 4; k++) {
+            u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
+            warp_stream_hist(src, a, b, shist[warp * 4 + k]);
+        }
+    }
+    __syncthreads();
+    u32 *g = hist_g + (size_t)blockIdx.x * ZH_HIST_WORDS;
+    for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) g[i] = shist[i & 31u][i >> 5];  // [word][stream]: the planner's lane = stream
+    {
+        u32 c = 0;
+        for (u32 st = 0; st < 32; st++) c += (shist[st][tid >> 1] >> (16u * (tid & 1u))) & 0xFFFFu;
+        g[32 * 128 + tid] = c;
+    }
+}
+#define ZHP_WARPS 4
+struct ZhPlanScratch {
+    u32 hist[256];
+    u16 hlut[256];
+    HufTmp huf;
+    u8 tmpsym[512];
+    short norm[64];
+    u8 tree[384];
+    u32 ssize[32], sdst[32];
+    u32 misc[4];  // 0 mode, 1 treeSize, 2 total bytes
+};
+__global__ void __launch_bounds__(ZHP_WARPS * 32) k_zh_plan(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes,
+                                                            const u32 *lzflags, const u32 *hist_g, ZhPlan *plans) {
+    __shared__ ZhPlanScratch scratch[ZHP_WARPS];
+    const u32 warp = threadIdx.x >> 5, lane = lane_id();
+    const u32 wi = blockIdx.x * ZHP_WARPS + warp;
+    if (wi >= nidx) return;
+    const u32 fi = index ? index[wi] : wi;
+    if (lzflags && frames[fi].pad && lzflags[frames[fi].pad - 1u]) return;
+    ZhPlanScratch &S = scratch[warp];
+    ZFrame fr = frames[fi];
+    const u8 *src = (const u8 *)(uintptr_t)fr.src;
+    u8 *out = slots + fr.dst_off;
+    const u32 n = fr.src_len;
+    const u32 nblk = (n + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT;
+    const u32 *g = hist_g + (size_t)wi * ZH_HIST_WORDS;
+    bool notflat = false;
+    u32 distinct = 0;
+    for (u32 i = lane; i < 256; i += 32) {
+        const u32 hc = g[32 * 128 + i];
+        S.hist[i] = hc;
+        // all 256 byte values within 25 % of n / 256 (2-bit packed random bases): a Huffman code cannot gain a percent
+        notflat |= 4u * 256u * hc > 5u * n || 4u * 256u * hc < 3u * n;
+        distinct += hc != 0;
+    }
+    __syncwarp();
+    notflat = __any_sync(FULL, notflat);
+    distinct = __reduce_add_sync(FULL, distinct);
+    u32 mode = 0, maxBits = 0, maxSym = 0;
+    if (n >= ZH_MIN_HUF && notflat) maxBits = warp_huf_build(S.hist, n, S.hlut, S.huf, &maxSym);
+    if (distinct == 1 && n > 1) mode = 1;
+    else if (maxBits) {
+        if (lane == 0) S.misc[1] = huf_write_tree(S.tree, S.huf, maxBits, maxSym, S.norm, S.tmpsym);
+        // exact size of stream `lane` = <its histogram, code lengths>
+        {
+            u32 bits = 0;
+            for (u32 w = 0; w < 128; w++) {
+                const u32 v = g[32u * w + lane];
+                bits += (v & 0xFFFFu) * S.huf.len[2 * w] + (v >> 16) * S.huf.len[2 * w + 1];
+            }
+            S.ssize[lane] = (bits + 8u) >> 3;  // + end mark, rounded up
+        }
+        __syncwarp();
+        if (lane == 0) {
+            u32 treeSize = S.misc[1];
+            u32 off = 10;
+            for (u32 k = 0; k < nblk; k++) {
+                u32 bn = min(FQZ_ZBLOCK_ENT, n - k * FQZ_ZBLOCK_ENT);
+                if (bn < ZH_MIN_HUF) {  // short tail: raw block
+                    S.sdst[4 * k] = off + 3;
+                    off += 3 + bn;
+                } else {
+                    u32 pos = off + 3 + 5 + (k == 0 ? treeSize : 0u) + 6;
+                    for (u32 q = 0; q < 4; q++) {
+                        S.sdst[4 * k + q] = pos;
+                        pos += S.ssize[4 * k + q];
+                    }
+                    off = pos + 1;
+                }
+            }
+            S.misc[2] = off + 4;
+            S.misc[0] = (treeSize != 0 && off + 4 < n + 17u) ? 2u : 0u;
+        }
+        __syncwarp();
+        mode = S.misc[0];
+    }
+    const u32 hsh = hashes[fi];
+    ZhPlan &P = plans[wi];
+    if (mode == 2) {
+        if (lane == 0) {  // frame header, block headers, literals headers, tree, jump tables
+            u32 treeSize = S.misc[1];
+            out[0] = 0x28; out[1] = 0xB5; out[2] = 0x2F; out[3] = 0xFD;
+            out[4] = 0x84;  // FCS 4 bytes, window descriptor present, content checksum, no dictionary
+            out[5] = (u8)((17 - 10) << 3);  // window = 128 KiB
+            out[6] = (u8)n; out[7] = (u8)(n >> 8); out[8] = (u8)(n >> 16); out[9] = (u8)(n >> 24);
+            for (u32 k = 0; k < nblk; k++) {
+                u32 bn = min(FQZ_ZBLOCK_ENT, n - k * FQZ_ZBLOCK_ENT);
+                u32 lastf = (k + 1 == nblk) ? 1u : 0u;
+                if (bn < ZH_MIN_HUF) {
+                    u8 *bh = out + S.sdst[4 * k] - 3;
+                    u32 h = lastf | (0u << 1) | (bn << 3);
+                    bh[0] = (u8)h; bh[1] = (u8)(h >> 8); bh[2] = (u8)(h >> 16);
+                    continue;
+                }
+                u32 tsz = (k == 0) ? treeSize : 0u;
+                u8 *bh = out + S.sdst[4 * k] - 6 - tsz - 5 - 3;
+                u32 csize = tsz + 6 + S.ssize[4 * k] + S.ssize[4 * k + 1] + S.ssize[4 * k + 2] + S.ssize[4 * k + 3];
+                u32 content = 5 + csize + 1;
+                u32 h = lastf | (2u << 1) | (content << 3);
+                bh[0] = (u8)h; bh[1] = (u8)(h >> 8); bh[2] = (u8)(h >> 16);
+                u8 *lh = bh + 3;
+                u32 lw = (k == 0 ? 2u : 3u) | (3u << 2) | (bn << 4) | (csize << 22);  // 4 streams, 18-bit sizes
+                lh[0] = (u8)lw; lh[1] = (u8)(lw >> 8); lh[2] = (u8)(lw >> 16); lh[3] = (u8)(lw >> 24);
+                lh[4] = (u8)(csize >> 10);
+                u8 *tp = lh + 5;
+                for (u32 i = 0; i < tsz; i++) tp[i] = S.tree[i];
+                u8 *jt = tp + tsz;
+                st_u16_unaligned(jt, S.ssize[4 * k]);
+                st_u16_unaligned(jt + 2, S.ssize[4 * k + 1]);
+                st_u16_unaligned(jt + 4, S.ssize[4 * k + 2]);
+                out[S.sdst[4 * k + 3] + S.ssize[4 * k + 3]] = 0;  // sequences section: none
+            }
+            u8 *ck = out + S.misc[2] - 4;
+            ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
+            out_sizes[fi] = S.misc[2];
+            P.mode = 2;
+            P.total = S.misc[2];
+        }
+        P.sdst[lane] = S.sdst[lane];
+        for (u32 i = lane; i < 256; i += 32) P.hlut[i] = S.hlut[i];
+        return;
+    }
+    // ---- raw / RLE: a single block (the raw payload is copied by k_zh_encode)
+    if (lane == 0) {
+        out[0] = 0x28; out[1] = 0xB5; out[2] = 0x2F; out[3] = 0xFD;
+        out[4] = 0x84;
+        out[5] = (u8)((17 - 10) << 3);
+        out[6] = (u8)n; out[7] = (u8)(n >> 8); out[8] = (u8)(n >> 16); out[9] = (u8)(n >> 24);
+        u32 h = 1u | (mode << 1) | (n << 3);
+        out[10] = (u8)h; out[11] = (u8)(h >> 8); out[12] = (u8)(h >> 16);
+        u32 payload = (mode == 1) ? 1u : n;
+        if (mode == 1) out[13] = src[0];
+        u8 *ck = out + 13 + payload;
+        ck[0] = (u8)hsh; ck[1] = (u8)(hsh >> 8); ck[2] = (u8)(hsh >> 16); ck[3] = (u8)(hsh >> 24);
+        out_sizes[fi] = 13 + payload + 4;
+        P.mode = mode;
+        P.total = 13 + payload + 4;
+    }
+}
+struct ZhEncShared {
+    u16 hlut[256];
+    u32 sdst[32];
+    u32 lbuf[ZH_WARPS * ZH_LANE_WORDS * 32];
+    u32 stage[ZH_WARPS][ZH_STAGE_WORDS];
+};
+__global__ void __launch_bounds__(ZH_THREADS) k_zh_encode(const ZFrame *frames, const u32 *index, u32 nidx, u8 *slots, const u32 *lzflags,
+                                                          const ZhPlan *plans) {
+    __shared__ ZhEncShared S;
+    u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    u32 fi = index ? index[blockIdx.x] : blockIdx.x;
+    if (lzflags && frames[fi].pad && lzflags[frames[fi].pad - 1u]) return;
+    ZFrame fr = frames[fi];
+    const u8 *src = (const u8 *)(uintptr_t)fr.src;
+    u8 *out = slots + fr.dst_off;
+    const u32 n = fr.src_len;
+    const u32 nblk = (n + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT;
+    const ZhPlan &P = plans[blockIdx.x];
+    const u32 mode = P.mode;
+    if (mode == 2) {
+        S.hlut[tid] = P.hlut[tid];
+        if (tid < 32) S.sdst[tid] = P.sdst[tid];
+        __syncthreads();
+        if (warp < nblk) {
+            u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
+            if (bn < ZH_MIN_HUF) {
+                u8 *d = out + S.sdst[4 * warp];
+                for (u32 i = lane; i < bn; i += 32) d[i] = src[b0 + i];
+            } else {
+                u32 *lbuf = S.lbuf + warp * (ZH_LANE_WORDS * 32u);
+                for (u32 k = 0; k < 4; k++) {
+                    u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
+                    warp_stream_encode(src, a, b, S.hlut, out + S.sdst[4 * warp + k], S.stage[warp], lbuf);
+                }
+            }
+        }
+        return;
+    }
+    if (mode == 0) {  // dst-aligned word copy of the raw block
+        u8 *d = out + 13;
+        u32 head = (u32)((4u - ((uintptr_t)d & 3u)) & 3u);
+        if (head > n) head = n;
+        if (tid < head) d[tid] = src[tid];
+        u32 nw = (n - head) >> 2;
+        for (u32 w = tid; w < nw; w += ZH_THREADS) *(u32 *)(d + head + 4u * w) = ld_u32_unaligned(src + head + 4u * w);
+        u32 t0 = head + 4u * nw;
+        if (tid < n - t0) d[t0 + tid] = src[t0 + tid];
+    }
+}
+
 // ---------------------------------------------------------------------------------- duplicated records in the literals-only streams
 // Packed bases and qualities of i.i.d. reads hold no matches worth coding (k_zenc_huf), but real runs do:
 // PCR / optical duplicates, identical test records, all-'F' quality lines.  They are looked for at RECORD
@@ -2747,10 +2985,20 @@ void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream
     u32 threads = XX_WARPS * 32, grid = (nframes * 4 + threads - 1) / threads;
     FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes);
 }
+// scratch == nullptr: the one-kernel version (k_zenc_huf); else fqz_zenc_huf_scratch(nidx) bytes for the histograms and plans
+size_t fqz_zenc_huf_scratch(u32 nidx) { return (size_t)nidx * (ZH_HIST_WORDS * sizeof(u32) + sizeof(ZhPlan)) + 256; }
 void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
-                         cudaStream_t s) {
+                         u8 *scratch, cudaStream_t s) {
     if (!nidx) return;
-    FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags);
+    if (!scratch) {
+        FQZ_LAUNCH(k_zenc_huf, nidx, ZH_THREADS, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags);
+        return;
+    }
+    u32 *hist_g = (u32 *)scratch;
+    ZhPlan *plans = (ZhPlan *)(scratch + (((size_t)nidx * ZH_HIST_WORDS * sizeof(u32) + 127) & ~(size_t)127));
+    FQZ_LAUNCH(k_zh_hist, nidx, ZH_THREADS, 0, s, frames, index, nidx, out_sizes, lzflags, hist_g);
+    FQZ_LAUNCH(k_zh_plan, (nidx + ZHP_WARPS - 1) / ZHP_WARPS, ZHP_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags, hist_g, plans);
+    FQZ_LAUNCH(k_zh_encode, nidx, ZH_THREADS, 0, s, frames, index, nidx, slots, lzflags, plans);
 }
 void fqz_launch_rec_match(const ZRStream *rs, u32 ns, u32 max_records, const u32 *offs_base, u32 *keys_base, u32 *cand_base, u32 *flags,
                           u32 *dupcnt, u32 *ranges, u32 *hashes, cudaStream_t s) {

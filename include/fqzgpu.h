@@ -67,6 +67,8 @@ int fqz_abi_version(void);
 #define FQZ_OPT_FRONTEND 4          /* front-end kernels (results identical): 0 (default) newline count, index, metadata, scans, scatter as
                                      * separate kernels; 1 count + index in one pass (look-back over the tiles); 2 metadata + scatter
                                      * fused as well.  1 and 2 read the text less often but measured slower on B200 */
+#define FQZ_OPT_HUF_KERNELS 5       /* literals-only frames: 0 (default) histogram / plan / encode kernels, 1 one kernel per frame (same format, the
+                                     * Huffman codes may differ) */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
 /* Page-locked host memory for the caller's window buffers (the Go shim reads the file into these instead of Go

@@ -88,3 +88,19 @@ def test_file_errors(emu, oracle):
 
 def test_streaming(emu, oracle):
     check_streaming(emu, oracle, nrec=300)
+
+
+def test_huf_kernel_variants(emu, oracle):
+    """FQZ_OPT_HUF_KERNELS: the one-kernel and the three-kernel coder of the literals-only frames write frames of the same
+    size that both decode (their Huffman codes may differ in tie breaks)."""
+    from tests import synth
+
+    text = synth.fastq(0, 33, 0, 4000)
+    a = emu.compress(text)
+    try:
+        emu.set_option(emu.OPT_HUF_KERNELS, 1)
+        b = emu.compress(text)
+    finally:
+        emu.set_option(emu.OPT_HUF_KERNELS, 0)
+    assert oracle.decompress(a) == text and oracle.decompress(b) == text
+    assert abs(len(a) - len(b)) <= 64
