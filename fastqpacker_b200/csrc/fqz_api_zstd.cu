@@ -179,7 +179,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
     for (u32 i : zb.idx_items) lz_bytes += zb.frames[i].src_len;
     {
         StageScope sc(c, ST_XXH64, src_bytes);
-        fqz_launch_xxh64(ze.d_frames, nf, d_hash, c->opt_huf_single ? 0 : 1, s);
+        fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
     }
     {
         StageScope sc(c, ST_ZENC_LZ, lz_bytes);

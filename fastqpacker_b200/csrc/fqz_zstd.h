@@ -55,8 +55,7 @@ struct ZFrame {
 #define ZENC_WARPS 4
 #endif
 
-// skip_ent: leave the literals-only frames to the three-kernel coder (k_zh_hist hashes a frame while it counts it)
-void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, int skip_ent, cudaStream_t s);
+void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s);
 // fills the index frames (FQZ_ZPOLICY_INDEX) from the sizes of the frames behind them
 void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_sizes, const u32 *lzflags, cudaStream_t s);
 // index: optional list of frame numbers to encode (nullptr = frames 0..nidx-1)
@@ -64,7 +63,7 @@ void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_si
 // scratch: fqz_zenc_huf_scratch(nidx) bytes -> the three-kernel version (histograms, one-warp-per-frame plan, encode);
 // nullptr -> the single kernel
 size_t fqz_zenc_huf_scratch(u32 nidx);
-void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
                          u8 *scratch, cudaStream_t s);
 // One segment (<= FQZ_ZSEG bytes) of a literals-only stream of one fqz block that carries its record boundaries
 // (packed bases, qualities): the unit of the duplicate-record search (fqz_zstd_enc.cu, "duplicated records").

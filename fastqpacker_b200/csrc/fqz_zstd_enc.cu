@@ -2321,15 +2321,9 @@ struct ZhPlan {
     u16 hlut[256];
 };
 #define ZH_HIST_WORDS (128u * 32u + 256u)  // per frame: shist[word][stream] (two u16 counters per word), then hist[256]
-// A ninth warp computes the frame's XXH64 content checksum while the eight others count: the hash is one serial
-// chain per frame (~85 us for 128 KiB, about what the histograms take), it reads the bytes the other warps are pulling
-// through L2 anyway, and the separate checksum pass over these frames (73 % of all stream bytes) goes away.
-__global__ void __launch_bounds__(ZH_THREADS + 32) k_zh_hist(const ZFrame *frames, const u32 *index, u32 nidx, u32 *out_sizes, const u32 *lzflags,
-                                                             u32 *hist_g, u32 *hashes) {
+__global__ void __launch_bounds__(ZH_THREADS) k_zh_hist(const ZFrame *frames, const u32 *index, u32 nidx, u32 *out_sizes, const u32 *lzflags,
+                                                        u32 *hist_g) {
     __shared__ u32 shist[32][128];
-    __shared__ uint4 xrows_v[(XX_STAGES * XX_ROW + 15u) / 16u];  // 16-byte aligned staging rows of the checksum warp
-    u8 *xrows = (u8 *)xrows_v;
-    __shared__ u64 xbars[XX_STAGES];
     u32 tid = threadIdx.x, warp = tid >> 5;
     u32 fi = index ? index[blockIdx.x] : blockIdx.x;
     if (lzflags && frames[fi].pad && lzflags[frames[fi].pad - 1u]) {
@@ -2342,8 +2336,7 @@ __global__ void __launch_bounds__(ZH_THREADS + 32) k_zh_hist(const ZFrame *frame
     const u8 *src = (const u8 *)(uintptr_t)fr.src;
     const u32 n = fr.src_len;
     const u32 nblk = (n + FQZ_ZBLOCK_ENT - 1) / FQZ_ZBLOCK_ENT;  // <= 8
-    if (tid < ZH_THREADS)
-        for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) (&shist[0][0])[i] = 0;
+    for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) (&shist[0][0])[i] = 0;
     __syncthreads();
     if (warp < nblk) {
         u32 b0 = warp * FQZ_ZBLOCK_ENT, bn = min(FQZ_ZBLOCK_ENT, n - b0), seg = (bn + 3u) >> 2;
@@ -2351,13 +2344,8 @@ __global__ void __launch_bounds__(ZH_THREADS + 32) k_zh_hist(const ZFrame *frame
             u32 a = b0 + min(k * seg, bn), b = (k == 3) ? b0 + bn : b0 + min((k + 1) * seg, bn);
             warp_stream_hist(src, a, b, shist[warp * 4 + k]);
         }
-    } else if (warp == ZH_WARPS) {
-        const u32 lane = tid & 31u;
-        u64 h = xxh64_quad_staged(src, (lane >> 2) == 0 ? (u64)n : 0ull, lane & 3u, group_mask(4), xrows, xbars);
-        if (lane == 0) hashes[fi] = (u32)h;
     }
     __syncthreads();
-    if (tid >= ZH_THREADS) return;
     u32 *g = hist_g + (size_t)blockIdx.x * ZH_HIST_WORDS;
     for (u32 i = tid; i < 32 * 128; i += ZH_THREADS) g[i] = shist[i & 31u][i >> 5];  // [word][stream]: the planner's lane = stream
     {
@@ -2917,8 +2905,7 @@ __global__ void __launch_bounds__(256) k_lzrec_close(const ZRStream *rs, const u
 
 // ---------------------------------------------------------------------------------- XXH64 (frame content checksum)
 // see fqz_xxh64.cuh: 4 threads per frame, 8 frames per warp, frames streamed through shared memory by TMA
-// skip_ent: the literals-only frames are hashed by k_zh_hist
-__global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *frames, u32 nframes, u32 *hashes, u32 skip_ent) {
+__global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *frames, u32 nframes, u32 *hashes) {
     FQZ_DYN_SMEM(u8, smem);
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 fi = t >> 2, q = t & 3;
@@ -2929,9 +2916,8 @@ __global__ void __launch_bounds__(XX_WARPS * 32) k_xxh64_frames(const ZFrame *fr
     u8 *rows;
     u64 *bars;
     xx_quad_smem(smem, &rows, &bars);
-    const bool mine = live && fr.policy != FQZ_ZPOLICY_INDEX && !(skip_ent && fr.policy == 1u /* FQZ_ZPOLICY_ENTROPY */);
-    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)fr.src, mine ? fr.src_len : 0u, q, gmask, rows, bars);
-    if (mine && q == 0) hashes[fi] = (u32)h;
+    u64 h = xxh64_quad_staged((const u8 *)(uintptr_t)fr.src, (live && fr.policy != FQZ_ZPOLICY_INDEX) ? fr.src_len : 0u, q, gmask, rows, bars);
+    if (live && q == 0) hashes[fi] = (u32)h;
 }
 
 // One thread per frame (see FQZ_ZPOLICY_INDEX): an index frame writes its header, every frame that is
@@ -2994,14 +2980,14 @@ void fqz_launch_zindex(const ZFrame *frames, u32 nframes, u8 *slots, u32 *out_si
     if (!nframes) return;
     FQZ_LAUNCH(k_zindex, (nframes + 127) / 128, 128, 0, s, frames, nframes, slots, out_sizes, lzflags);
 }
-void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, int skip_ent, cudaStream_t s) {
+void fqz_launch_xxh64(const ZFrame *frames, u32 nframes, u32 *hashes, cudaStream_t s) {
     if (!nframes) return;
     u32 threads = XX_WARPS * 32, grid = (nframes * 4 + threads - 1) / threads;
-    FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes, (u32)skip_ent);
+    FQZ_LAUNCH(k_xxh64_frames, grid, threads, XX_SMEM, s, frames, nframes, hashes);
 }
 // scratch == nullptr: the one-kernel version (k_zenc_huf); else fqz_zenc_huf_scratch(nidx) bytes for the histograms and plans
 size_t fqz_zenc_huf_scratch(u32 nidx) { return (size_t)nidx * (ZH_HIST_WORDS * sizeof(u32) + sizeof(ZhPlan)) + 256; }
-void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
+void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u32 *out_sizes, const u32 *lzflags,
                          u8 *scratch, cudaStream_t s) {
     if (!nidx) return;
     if (!scratch) {
@@ -3010,7 +2996,7 @@ void fqz_launch_zenc_huf(const ZFrame *frames, const u32 *index, u32 nidx, u32 *
     }
     u32 *hist_g = (u32 *)scratch;
     ZhPlan *plans = (ZhPlan *)(scratch + (((size_t)nidx * ZH_HIST_WORDS * sizeof(u32) + 127) & ~(size_t)127));
-    FQZ_LAUNCH(k_zh_hist, nidx, ZH_THREADS + 32, 0, s, frames, index, nidx, out_sizes, lzflags, hist_g, hashes);
+    FQZ_LAUNCH(k_zh_hist, nidx, ZH_THREADS, 0, s, frames, index, nidx, out_sizes, lzflags, hist_g);
     FQZ_LAUNCH(k_zh_plan, (nidx + ZHP_WARPS - 1) / ZHP_WARPS, ZHP_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, out_sizes, lzflags, hist_g, plans);
     FQZ_LAUNCH(k_zh_encode, nidx, ZH_THREADS, 0, s, frames, index, nidx, slots, lzflags, plans);
 }
