@@ -241,3 +241,47 @@ def check_shard_planning(ctx, oracle, full, to_device=None):
     whole = ctx.compress(text[:n])
     assert sharding.merge_compressed([part0, part1]) == whole
     assert oracle.decompress(whole) == text[:n].tobytes()
+
+
+def fuzz_duplicates(seed, nrec):
+    """Random mixtures for the duplicate-record coder: read lengths from 1 base to beyond the matcher's mask spans, exact and
+    near copies at short and long reach, runs of one base / one quality, N bases, reads shorter than a key."""
+    rnd = random.Random(seed)
+    lmax = rnd.choice([6, 40, 151, 300, 700, 2500])
+    lmin = rnd.choice([1, max(1, lmax // 2), lmax])
+    dup = rnd.choice([0.0, 0.1, 0.4, 0.9])
+    reach = rnd.choice([1, 30, 3000, 60000])
+    near = rnd.random() < 0.5
+    if lmax > 300:
+        nrec = max(1000, nrec // 20)  # long reads: fewer of them
+    recs, out = [], bytearray()
+    for i in range(nrec):
+        if recs and rnd.random() < dup:
+            seq, qual = recs[-1 - rnd.randrange(min(reach, len(recs)))]
+            if near and len(seq) > 4 and rnd.random() < 0.5:  # one base / one quality changed
+                k = rnd.randrange(len(seq))
+                seq = seq[:k] + rnd.choice([b"A", b"C", b"G", b"T", b"N"]) + seq[k + 1 :]
+                qual = qual[:k] + bytes([rnd.randint(35, 73)]) + qual[k + 1 :]
+        else:
+            L = rnd.randint(lmin, lmax)
+            if rnd.random() < 0.1:
+                seq = bytes([rnd.choice(b"ACGTN")]) * L
+            else:
+                seq = bytes(rnd.choices(b"ACGT", k=L))
+            if rnd.random() < 0.3:
+                qual = bytes([rnd.randint(35, 73)]) * L
+            else:
+                qual = bytes(rnd.choices(range(60, 74), k=L))
+        recs.append((seq, qual))
+        if len(recs) > 60000:
+            recs.pop(0)
+        out += b"@f%d\n" % i + seq + b"\n+\n" + qual + b"\n"
+    return bytes(out)
+
+
+def check_fuzz_duplicates(ctx, oracle, seed, nrec):
+    text = fuzz_duplicates(seed, nrec)
+    z = ctx.compress(text)
+    assert oracle.decompress(z) == text, seed
+    assert ctx.decompress(z) == text, seed
+    assert ctx.decompress(oracle.compress(text, threads=4)) == text, seed

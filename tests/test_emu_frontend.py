@@ -92,3 +92,10 @@ def test_shard_planning_calls(emu, oracle):
     from tests.fastq_cases import check_shard_planning
 
     check_shard_planning(emu, oracle, full=False)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_duplicate_coder_fuzz(emu, oracle, seed):
+    from tests.fastq_cases import check_fuzz_duplicates
+
+    check_fuzz_duplicates(emu, oracle, seed, 1500)

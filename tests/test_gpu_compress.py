@@ -277,3 +277,12 @@ def test_frontend_variants_write_the_same_file(ctx, oracle, frontend):
         ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
     assert got == want
     assert oracle.decompress(got) == text
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_duplicate_coder_fuzz(ctx, oracle, seed):
+    """Random mixtures of read lengths (1 base .. 2 500), copy rates, reaches and near copies: whatever the record matcher
+    decides, the file decodes to the input under the oracle and on the GPU."""
+    from tests.fastq_cases import check_fuzz_duplicates
+
+    check_fuzz_duplicates(ctx, oracle, 100 + seed, 40_000 if seed % 3 else 110_000)
