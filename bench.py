@@ -241,6 +241,8 @@ def run_ours(args):
     ctx = fq.context(local)
     ctx.set_option(ctx.OPT_FRONTEND, args.frontend)
     ctx.set_option(ctx.OPT_HUF_KERNELS, args.huf_kernels)
+    if args.window_bytes:
+        ctx.set_option(ctx.OPT_WINDOW_BYTES, args.window_bytes)
     lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=local)
     nrec = args.records or FULL_RECORDS
     peak, peak_src = _peaks()
@@ -870,6 +872,7 @@ def main():
     ap.add_argument("--total-bytes", type=int, default=0, help="cfg5: size of the logical input (default 64e9)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 and duplicates side workloads")
     ap.add_argument("--frontend", type=int, default=0, choices=[0, 1, 2], help="A/B of the front-end kernels: see FQZ_OPT_FRONTEND")
+    ap.add_argument("--window-bytes", type=int, default=0, help="FASTQ bytes per device pass of the compress calls (default 3e9): FQZ_OPT_WINDOW_BYTES")
     ap.add_argument("--huf-kernels", type=int, default=0, choices=[0, 1], help="A/B of the literals-only frame coder: see FQZ_OPT_HUF_KERNELS")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
