@@ -317,7 +317,7 @@ class FqzContext:
         return _DStream(self)
 
     # ---- tuning -------------------------------------------------------------------------------
-    OPT_WINDOW_BYTES, OPT_HOST_WINDOW_BYTES, OPT_RECORD_MATCH, OPT_FRONTEND, OPT_HUF_KERNELS = 1, 2, 3, 4, 5
+    OPT_WINDOW_BYTES, OPT_HOST_WINDOW_BYTES, OPT_RECORD_MATCH, OPT_FRONTEND, OPT_HUF_KERNELS, OPT_SERIAL_ENTROPY = 1, 2, 3, 4, 5, 6
 
     def set_option(self, key: int, value: int):
         self._check(self.lib.L.fqz_set_option(self.h, key, value))

@@ -181,12 +181,22 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
         StageScope sc(c, ST_XXH64, src_bytes);
         fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
     }
+    // The item-stream kernels (one warp per 16 KiB frame, ~1 ms of serial work each: every launch ends in a tail of
+    // half-empty SMs) and the literals-only coder work on different frames: run side by side on two streams, the tail
+    // of one fills with CTAs of the other.  While profiling (per-stage CUDA events on one stream) they run in order.
+    const bool fork = !c->prof.on && !c->opt_serial_entropy;
+    cudaStream_t slz = fork ? c->stream_aux : s;
+    if (fork) {
+        FQZ_CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
+        FQZ_CUDA_TRY(c, cudaStreamWaitEvent(slz, c->ev_fork, 0));
+    }
     {
         StageScope sc(c, ST_ZENC_LZ, lz_bytes);
-        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, nullptr, s);
+        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, nullptr, slz);
         fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size() + zb.idx_lz.size(), (u32)zb.idx_items.size(), d_hash, ze.d_slots, d_ws, ze.d_scan,
-                        2, d_parsed, s);
+                        2, d_parsed, slz);
     }
+    if (fork) FQZ_CUDA_TRY(c, cudaEventRecord(c->ev_join, slz));
     u32 *d_lzflags = nullptr;
     const u32 nent = (u32)zb.idx_ent.size();
     const ZRStream *d_rs = (const ZRStream *)(d_up + rs_at);
@@ -225,6 +235,7 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
         StageScope sc(c, ST_ZENC_DUP, 0);
         fqz_launch_lzrec_close(d_rs, nrs, zb.rmax_blocks, d_lzflags, d_rhash, pool_out, d_bsizes, ze.d_frames, ze.d_slots, ze.d_scan, s);
     }
+    if (fork) FQZ_CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
     {
         StageScope sc(c, ST_SCAN, 0);
         if (!zb.idx_index.empty()) fqz_launch_zindex(ze.d_frames, nf, ze.d_slots, ze.d_scan, d_lzflags, s);

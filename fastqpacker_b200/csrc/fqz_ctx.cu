@@ -273,6 +273,12 @@ extern "C" int fqz_init(int device, fqz_ctx **out) {
         return FQZ_E_CUDA;
     }
     cudaMemset(c->d_phred, 0, 256);
+    if (cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return FQZ_E_CUDA;
+    }
     // dynamic shared-memory limits are per device: set them for every context (one process may drive several GPUs)
     if (fqz_frontend_init_device() | fqz_zstd_enc_init_device() | fqz_zstd_dec_init_device()) {
         cudaGetLastError();
@@ -299,6 +305,9 @@ extern "C" void fqz_destroy(fqz_ctx *c) {
     if (c->d_phred) cudaFree(c->d_phred);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_io) cudaFreeHost(c->h_io);
+    if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -361,6 +370,10 @@ extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
     case FQZ_OPT_FRONTEND:
         if (value > 2) return FQZ_E_INVALID_ARG;
         c->opt_frontend = (int)value;
+        return FQZ_OK;
+    case FQZ_OPT_SERIAL_ENTROPY:
+        if (value > 1) return FQZ_E_INVALID_ARG;
+        c->opt_serial_entropy = (int)value;
         return FQZ_OK;
     case FQZ_OPT_HUF_KERNELS:
         if (value > 1) return FQZ_E_INVALID_ARG;

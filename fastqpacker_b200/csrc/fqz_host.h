@@ -92,6 +92,8 @@ struct IoPipe {
 struct fqz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_aux = nullptr;         // second compute stream: the item-stream kernels run beside the literals-only coder
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Arena arena;
     Profiler prof;
     std::string err;
@@ -109,6 +111,7 @@ struct fqz_ctx {
     u64 opt_host_window_bytes = 0;  // window of the host-buffer compress calls (0 = default)
     int opt_frontend = 0;           // 0: separate kernels (count, index, metadata, scans, scatter); 1: count + index in one pass (look-back); 2: metadata + scatter fused as well
     u64 fused_windows = 0, legacy_windows = 0;
+    int opt_serial_entropy = 0;     // 1: item-stream kernels and literals-only coder one after the other on one stream
     int opt_huf_single = 0;         // 1: literals-only frames by the single kernel (k_zenc_huf) instead of histogram / plan / encode
     int opt_no_record_match = 0;    // 1: packed bases / qualities always literals-only (no duplicate-record search)
 };

@@ -69,6 +69,8 @@ int fqz_abi_version(void);
                                      * fused as well.  1 and 2 read the text less often but measured slower on B200 */
 #define FQZ_OPT_HUF_KERNELS 5       /* literals-only frames: 0 (default) histogram / plan / encode kernels, 1 one kernel per frame (same format, the
                                      * Huffman codes may differ) */
+#define FQZ_OPT_SERIAL_ENTROPY 6    /* 0 (default): the item-stream kernels run on a second stream beside the literals-only coder (their launch
+                                     * tails overlap); 1: one after the other (per-stage timings are only meaningful this way) */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
 /* Page-locked host memory for the caller's window buffers (the Go shim reads the file into these instead of Go
