@@ -177,13 +177,10 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
     for (u32 i : zb.idx_ent) ent_bytes += zb.frames[i].src_len;
     for (u32 i : zb.idx_lz) lz_bytes += zb.frames[i].src_len;
     for (u32 i : zb.idx_items) lz_bytes += zb.frames[i].src_len;
-    {
-        StageScope sc(c, ST_XXH64, src_bytes);
-        fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
-    }
     // The item-stream kernels (one warp per 16 KiB frame, ~1 ms of serial work each: every launch ends in a tail of
-    // half-empty SMs) and the literals-only coder work on different frames: run side by side on two streams, the tail
-    // of one fills with CTAs of the other.  While profiling (per-stage CUDA events on one stream) they run in order.
+    // half-empty SMs) work on other frames than the literals-only coder, and only their last kernel needs the frame
+    // checksums: they run on a second stream beside the checksum pass, the duplicate search and the literals-only coder,
+    // the tail of one fills with CTAs of the other.  While profiling (per-stage CUDA events on one stream) all run in order.
     const bool fork = !c->prof.on && !c->opt_serial_entropy;
     cudaStream_t slz = fork ? c->stream_aux : s;
     if (fork) {
@@ -191,10 +188,16 @@ static int zbatch_encode(fqz_ctx *c, ZBatch &zb, ZEncoded &ze, u64 src_bytes, co
         FQZ_CUDA_TRY(c, cudaStreamWaitEvent(slz, c->ev_fork, 0));
     }
     {
+        StageScope sc(c, ST_XXH64, src_bytes);
+        fqz_launch_xxh64(ze.d_frames, nf, d_hash, s);
+    }
+    if (fork) FQZ_CUDA_TRY(c, cudaEventRecord(c->ev_hash, s));
+    {
         StageScope sc(c, ST_ZENC_LZ, lz_bytes);
-        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, nullptr, slz);
+        fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size(), (u32)zb.idx_lz.size(), d_hash, ze.d_slots, d_ws, ze.d_scan, 1, nullptr, slz,
+                        fork ? c->ev_hash : nullptr);
         fqz_launch_zenc(ze.d_frames, d_idx + zb.idx_ent.size() + zb.idx_lz.size(), (u32)zb.idx_items.size(), d_hash, ze.d_slots, d_ws, ze.d_scan,
-                        2, d_parsed, slz);
+                        2, d_parsed, slz, fork ? c->ev_hash : nullptr);
     }
     if (fork) FQZ_CUDA_TRY(c, cudaEventRecord(c->ev_join, slz));
     u32 *d_lzflags = nullptr;

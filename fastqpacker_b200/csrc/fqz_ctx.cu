@@ -275,7 +275,8 @@ extern "C" int fqz_init(int device, fqz_ctx **out) {
     cudaMemset(c->d_phred, 0, 256);
     if (cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_hash, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return FQZ_E_CUDA;
     }
@@ -308,6 +309,7 @@ extern "C" void fqz_destroy(fqz_ctx *c) {
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_hash) cudaEventDestroy(c->ev_hash);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -93,7 +93,7 @@ struct fqz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_aux = nullptr;         // second compute stream: the item-stream kernels run beside the literals-only coder
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hash = nullptr;
     Arena arena;
     Profiler prof;
     std::string err;

@@ -92,5 +92,7 @@ void fqz_launch_lzrec(const ZRStream *rs, u32 ns, const u32 *flags, const u32 *o
 void fqz_launch_lzrec_close(const ZRStream *rs, u32 ns, u32 max_blocks, const u32 *flags, const u32 *hashes, const u8 *pool_out, const u32 *bsizes,
                             const ZFrame *frames, u8 *slots, u32 *out_sizes, cudaStream_t s);
 // parsed: 2 u32 per work item, scratch between the item matcher and the entropy kernel (lz == 2 only)
+// hashes_ready: optional event the stream waits for before the kernels that read `hashes` (the checksums may still be
+// computed on another stream while the matcher and the literals run)
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
-                     u32 *parsed, cudaStream_t s);
+                     u32 *parsed, cudaStream_t s, cudaEvent_t hashes_ready = nullptr);

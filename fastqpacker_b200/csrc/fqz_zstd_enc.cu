@@ -3029,14 +3029,21 @@ void fqz_launch_lzrec_close(const ZRStream *rs, u32 ns, u32 max_blocks, const u3
                slots, out_sizes);
 }
 void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32 *hashes, u8 *slots, u8 *ws, u32 *out_sizes, int lz,
-                     u32 *parsed, cudaStream_t s) {
-    if (!nidx) return;
+                     u32 *parsed, cudaStream_t s, cudaEvent_t hashes_ready) {
+    if (!nidx) {
+        if (hashes_ready) cudaStreamWaitEvent(s, hashes_ready, 0);
+        return;
+    }
     u32 grid = (nidx + ZENC_WARPS - 1) / ZENC_WARPS;
     if (lz == 2) {
         FQZ_LAUNCH(k_zitems_parse, grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, ws, parsed);
         FQZ_LAUNCH((k_zenc<2, 1>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+        if (hashes_ready) cudaStreamWaitEvent(s, hashes_ready, 0);  // only the frame close needs the checksums
         FQZ_LAUNCH((k_zenc<2, 2>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
-    } else if (lz) FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+        return;
+    }
+    if (hashes_ready) cudaStreamWaitEvent(s, hashes_ready, 0);
+    if (lz) FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
     else FQZ_LAUNCH((k_zenc<0, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
 }
 int fqz_zstd_enc_init_device() {
