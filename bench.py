@@ -473,6 +473,9 @@ def run_ours(args):
         "roofline": roof,
         "pipeline_roofline": pipeline,
         "stages_ms_per_step": {k: round(v["ms"], 3) for k, v in stages.items()},
+        "stages_note": "per-stage device times of ONE profiled pass in which the stages run one after the other; in the timed steps the "
+                       "item-stream kernels (zstd_enc_lz) run on a second stream beside xxh64 / zstd_enc_dup / zstd_enc_entropy, so the "
+                       "stage times add up to more than ms_per_step",
         "decompress": {"value": world * n * args.steps / t_d / 1e9, "unit": UNIT, "ms_per_step": t_d / args.steps * 1e3, "e2e": e2e_d,
                        "input": "GPU-written .fqz"},
         "clocks": clocks,
