@@ -109,6 +109,11 @@ class FqzLibrary:
         self._opt(L, "fqz_decompress_begin", [vp, C.POINTER(vp)])
         self._opt(L, "fqz_decompress_feed", [vp, vp, sz, i32, vp, sz, szp, szp])
         self._opt(L, "fqz_decompress_end", [vp], restype=None)
+        self._opt(L, "fqz_is_gzip", [vp, sz])
+        self._opt(L, "fqz_gunzip_stats", [vp, C.POINTER(C.c_uint64 * 4)])
+        self._opt(L, "fqz_gunzip", [vp, vp, sz, vp, sz, szp])
+        self._opt(L, "fqz_gunzip_device", [vp, vp, sz, vp, sz, szp])
+        self._opt(L, "fqz_compress_gz", [vp, vp, sz, u32, vp, sz, szp, szp])
         self._opt(L, "fqz_synth_device", [vp, i32, C.c_uint64, C.c_uint64, C.c_uint64, vp, sz, szp])
 
     @staticmethod
@@ -252,6 +257,55 @@ class FqzContext:
             self._check(rc)
             return out[: m.value].tobytes()
 
+    # ---- gzip input (cmd/fqpack/main.go:142-174) -------------------------------------------------
+    def is_gzip(self, data) -> bool:
+        a = _as_u8(data)
+        return bool(self.lib.L.fqz_is_gzip(_ptr(a), a.size))
+
+    def gunzip(self, gz, cap: int | None = None) -> bytes:
+        """gzip file (any number of members) -> its text, inflated on the GPU."""
+        a = _as_u8(gz)
+        cap = cap or max(1 << 16, a.size * 5)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            m = C.c_size_t(0)
+            rc = self.lib.L.fqz_gunzip(self.h, _ptr(a), a.size, _ptr(out), cap, C.byref(m))
+            if rc == FQZ_E_NOSPACE:
+                cap = m.value
+                continue
+            self._check(rc)
+            return out[: m.value].tobytes()
+
+    def gunzip_stats(self) -> dict:
+        v = (C.c_uint64 * 4)()
+        self._check(self.lib.L.fqz_gunzip_stats(self.h, C.byref(v)))
+        return dict(chunks=int(v[0]), parallel=int(v[1]), dropped=int(v[2]), members=int(v[3]))
+
+    def gunzip_device(self, d_in: int, n: int, d_out: int, out_cap: int) -> int:
+        """Device buffers; returns the text length (raises FqzError(-15) with .needed set when out_cap is short)."""
+        m = C.c_size_t(0)
+        rc = self.lib.L.fqz_gunzip_device(self.h, C.c_void_p(d_in), n, C.c_void_p(d_out), out_cap, C.byref(m))
+        if rc == FQZ_E_NOSPACE:
+            e = FqzError(rc, self.lib.strerror(rc))
+            e.needed = m.value
+            raise e
+        self._check(rc)
+        return m.value
+
+    def compress_gz(self, gz, block_size: int = 0) -> bytes:
+        """gzipped FASTQ -> .fqz: the compressed bytes are uploaded, inflated and coded on the GPU."""
+        a = _as_u8(gz)
+        cap = int(self.lib.L.fqz_compress_bound(a.size * 4))
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            m, f = C.c_size_t(0), C.c_size_t(0)
+            rc = self.lib.L.fqz_compress_gz(self.h, _ptr(a), a.size, block_size, _ptr(out), cap, C.byref(m), C.byref(f))
+            if rc == FQZ_E_NOSPACE:
+                cap = m.value
+                continue
+            self._check(rc)
+            return out[: m.value].tobytes()
+
     def info(self, fqz) -> dict:
         """`fqpack info`: version, flags, blocks, records, per-stream compressed sizes (header walk only)."""
         a = _as_u8(fqz)
@@ -318,6 +372,7 @@ class FqzContext:
 
     # ---- tuning -------------------------------------------------------------------------------
     OPT_WINDOW_BYTES, OPT_HOST_WINDOW_BYTES, OPT_RECORD_MATCH, OPT_FRONTEND, OPT_HUF_KERNELS, OPT_SERIAL_ENTROPY = 1, 2, 3, 4, 5, 6
+    OPT_GZ_CHUNK_BYTES = 7
 
     def set_option(self, key: int, value: int):
         self._check(self.lib.L.fqz_set_option(self.h, key, value))

@@ -491,6 +491,22 @@ extern "C" int fqz_compress_device(fqz_ctx *c, const void *d_fastq, size_t n, ui
     return compress_device_impl(c, (const u8 *)d_fastq, n, true, st, header_block_size, (u8 *)d_out, out_cap, out_len, &used);
 }
 
+// FASTQ text that is already in device memory (inflated there by fqz_compress_gz) -> complete .fqz in HOST memory
+int fqz_compress_text_to_host(fqz_ctx *c, const u8 *d_text, u64 n, u32 header_block_size, u8 *out, size_t out_cap, size_t *out_len) {
+    const size_t ocap = fqz_compress_bound(n);
+    u8 *d_o = nullptr;
+    FQZ_TRY(fqz_io_out_acquire(c, 0, ocap, &d_o));
+    CompState st;
+    u64 used = 0;
+    size_t m = 0;
+    FQZ_TRY(compress_device_impl(c, d_text, n, true, st, header_block_size, d_o, ocap, &m, &used));
+    *out_len = m;
+    if (m > out_cap) return FQZ_E_NOSPACE;
+    if (m) FQZ_CUDA_TRY(c, cudaMemcpyAsync(out, d_o, m, cudaMemcpyDeviceToHost, c->stream));
+    FQZ_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return FQZ_OK;
+}
+
 // the device-memory twin of fqz_compress_shard: d_fastq may have any alignment (a shard starts where the plan cuts)
 extern "C" int fqz_compress_shard_device(fqz_ctx *c, const void *d_fastq, size_t n, uint32_t header_block_size, int phred64, int emit_file_header,
                                          void *d_out, size_t out_cap, size_t *out_len, int *phred64_used) {

@@ -51,7 +51,7 @@ size_t Arena::capacity() const {
 static const char *k_stage_names[ST_COUNT_] = {
     "newline_count", "newline_index", "scan", "record_meta", "scatter_streams", "zstd_enc_entropy", "zstd_enc_lz", "zstd_enc_dup", "xxh64",
     "assemble", "zstd_dec_scan", "zstd_dec_literals", "zstd_dec_sequences", "zstd_dec_execute", "prefix_walk", "record_offsets",
-    "emit_fastq", "copy"};
+    "emit_fastq", "copy", "gz_find", "gz_decode", "gz_resolve", "gz_crc"};
 
 cudaEvent_t Profiler::get() {
     if (!pool.empty()) {
@@ -304,6 +304,7 @@ extern "C" void fqz_destroy(fqz_ctx *c) {
     c->arena.release();
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_phred) cudaFree(c->d_phred);
+    if (c->gz_text) cudaFree(c->gz_text);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_io) cudaFreeHost(c->h_io);
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
@@ -335,6 +336,10 @@ extern "C" const char *fqz_strerror(int code) {
     case FQZ_E_TRUNC_NPOS: return "truncated N position data";
     case FQZ_E_NOSPACE: return "output buffer too small";
     case FQZ_E_NPOS_RANGE: return "N position beyond sequence length";
+    case FQZ_E_GZ_HEADER: return "gzip: invalid header";
+    case FQZ_E_GZ_CHECKSUM: return "gzip: invalid checksum";
+    case FQZ_E_GZ_CORRUPT: return "flate: corrupt input";
+    case FQZ_E_GZ_TRUNC: return "unexpected EOF";
     case FQZ_E_CUDA: return "CUDA error";
     case FQZ_E_NO_DEVICE: return "no CUDA device (libfqzgpu has no CPU fallback)";
     case FQZ_E_INVALID_ARG: return "invalid argument";
@@ -384,6 +389,10 @@ extern "C" int fqz_set_option(fqz_ctx *c, int key, uint64_t value) {
     case FQZ_OPT_RECORD_MATCH:
         if (value > 1) return FQZ_E_INVALID_ARG;
         c->opt_no_record_match = value ? 0 : 1;
+        return FQZ_OK;
+    case FQZ_OPT_GZ_CHUNK_BYTES:
+        if (value && (value < 256 || value > ((u64)1 << 30) || (value & 3u))) return FQZ_E_INVALID_ARG;
+        c->opt_gz_chunk_bytes = value;
         return FQZ_OK;
     default: return FQZ_E_INVALID_ARG;
     }

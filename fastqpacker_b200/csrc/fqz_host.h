@@ -53,6 +53,10 @@ enum FqzStage {
     ST_OFFSETS,
     ST_EMIT,
     ST_COPY,
+    ST_GZ_FIND,
+    ST_GZ_DECODE,
+    ST_GZ_RESOLVE,
+    ST_GZ_CRC,
     ST_COUNT_
 };
 
@@ -114,6 +118,11 @@ struct fqz_ctx {
     int opt_serial_entropy = 0;     // 1: item-stream kernels and literals-only coder one after the other on one stream
     int opt_huf_single = 0;         // 1: literals-only frames by the single kernel (k_zenc_huf) instead of histogram / plan / encode
     int opt_no_record_match = 0;    // 1: packed bases / qualities always literals-only (no duplicate-record search)
+    u64 opt_gz_chunk_bytes = 0;     // compressed bytes per warp of the gzip input stage (0 = from the input size)
+    // gzip input stage (fqz_api_gzip.cu): the inflated FASTQ text lives here between inflate and compress
+    u8 *gz_text = nullptr;
+    u64 gz_stats[4] = {0, 0, 0, 0};  // last inflate: chunks cut, chunks decoded in parallel, restart points dropped as false, members
+    size_t gz_text_cap = 0;
 };
 int fqz_frontend_init_device();
 int fqz_zstd_enc_init_device();
@@ -144,6 +153,9 @@ int fqz_io_download(fqz_ctx *c, int slot, u8 *host_dst, const u8 *dev_src, size_
 int fqz_io_finish(fqz_ctx *c);
 void fqz_io_release(fqz_ctx *c);
 int fqz_scan_excl_u32(fqz_ctx *c, u32 *d, u64 n, u64 stride, u32 narr);
+
+// ---- compress from a device-resident text into host memory (fqz_api_zstd.cu; used by fqz_compress_gz)
+int fqz_compress_text_to_host(fqz_ctx *c, const u8 *d_text, u64 n, u32 header_block_size, u8 *out, size_t out_cap, size_t *out_len);
 
 // ---- zstd decode stage (fqz_api_dec.cu)
 struct ZDStream;

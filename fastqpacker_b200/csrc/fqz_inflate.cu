@@ -1,0 +1,839 @@
+// fqz_inflate.cu — gzip / DEFLATE decoder kernels: the input side of compress mode for .gz files.
+//
+// Reference: cmd/fqpack/main.go:142-174 wraps a gzipped input in Go's compress/gzip reader (stdlib, multistream)
+// before compress.Compress parses it.  A DEFLATE stream is one serial chain (Huffman codes of unknown length,
+// matches into the previous 32 KiB), so the work is cut the way pugz / rapidgzip cut it on CPUs:
+//
+//   k_gz_find     the compressed bytes are cut into chunks; for every chunk one warp looks for the first place a
+//                 decoder can restart: a BGZF member header (byte aligned, empty window) or the header of a
+//                 non-final dynamic-Huffman block (any bit offset; the 32 KiB window in front of it is unknown).
+//   k_gz_decode   one warp per chunk decodes from its restart point to the next chunk's.  Lane 0 walks the bit
+//                 stream, 32 symbols at a time; the warp writes the literals and copies the matches.  Output is
+//                 16-bit: a byte, or 256 + i for "byte i of the window I could not see".  Runs twice: a counting
+//                 pass (sizes, member boundaries, proof that every chunk lands exactly on the next restart point —
+//                 a restart point nobody lands on was a false positive and its chunk is merged into the one in
+//                 front), then the writing pass at the final offsets.
+//   k_gz_windows  serial over the chunks (one CTA, 32 KiB per step): the window in front of chunk k is the resolved
+//                 tail of chunk k-1.
+//   k_gz_resolve  every symbol becomes a byte: out[p] = sym < 256 ? sym : window[sym - 256].  Parallel, HBM bound.
+//   k_gz_crc      CRC-32 of every member from 2 KiB pieces: a piece's raw CRC is shifted to the member's end
+//                 (multiplication by x^(8 * bytes behind it) mod P) and XORed into the member's accumulator.
+//
+// Integer / byte work only; bound by the serial Huffman chain of each chunk, not by HBM.
+#include "fqz_inflate.cuh"
+
+#define GZ_FULL 0xffffffffu
+#define GZ_WARPS 4  // warps per CTA of k_gz_decode / k_gz_find
+#define GZ_LL_BITS 10
+#define GZ_D_BITS 8
+
+static __constant__ u16 kGzLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static __constant__ u8 kGzLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static __constant__ u16 kGzDistBase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
+                                           193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static __constant__ u8 kGzDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static __constant__ u8 kGzClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// ---------------------------------------------------------------------------------- bit reader (LSB first)
+// word i of the input; bytes behind n read as zero (the caller checks the consumed position against 8 n)
+__device__ __forceinline__ u32 gz_word(const u32 *w, u64 n, u64 i) {
+    u64 b = i * 4;
+    if (b + 4 <= n) return w[i];
+    if (b >= n) return 0u;
+    return w[i] & (0xffffffffu >> (8u * (4u - (u32)(n - b))));
+}
+struct GzBits {
+    const u32 *w;
+    u64 n, wi, bb;
+    u32 bc;
+    __device__ __forceinline__ void seek(u64 bit) {
+        wi = bit >> 5;
+        u32 sh = (u32)(bit & 31u);
+        bb = (u64)gz_word(w, n, wi) >> sh;
+        bc = 32u - sh;
+        wi++;
+    }
+    // at least 33 bits afterwards
+    __device__ __forceinline__ void refill() {
+        if (bc <= 32u) {
+            bb |= (u64)gz_word(w, n, wi) << bc;
+            bc += 32u;
+            wi++;
+        }
+    }
+    __device__ __forceinline__ u32 peek(u32 k) const { return (u32)bb & ((1u << k) - 1u); }
+    __device__ __forceinline__ void drop(u32 k) {
+        bb >>= k;
+        bc -= k;
+    }
+    __device__ __forceinline__ u32 take(u32 k) {
+        u32 v = peek(k);
+        drop(k);
+        return v;
+    }
+    __device__ __forceinline__ u64 pos() const { return wi * 32u - bc; }
+};
+
+// canonical Huffman decode of one code taken LSB-first from `bits` (codes are packed starting with their most
+// significant bit).  count[l] = codes of length l, symbol[] = symbols ordered by (length, value).  -1: no code.
+__device__ __forceinline__ int gz_canon(const u32 *count, const u16 *symbol, u32 bits, u32 maxbits, u32 *len_out) {
+    int code = 0, first = 0, index = 0;
+    for (u32 len = 1; len <= maxbits; len++) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        int cnt = (int)count[len];
+        if (code - cnt < first) {
+            *len_out = len;
+            return (int)symbol[index + (code - first)];
+        }
+        index += cnt;
+        first += cnt;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// Warp-cooperative table build from code lengths.  Accepts what Go's huffmanDecoder.init accepts: an empty
+// code, a complete code, or one single code of length 1 (compress/flate/inflate.go, "degenerate single-code").
+// lut[e] = symbol << 4 | length for codes of at most lutbits bits, 0 otherwise.
+__device__ bool gz_build(const u8 *lens, u32 n, u32 *count, u32 *start, u16 *symbol, u16 *lut, u32 lutbits) {
+    const u32 lane = lane_id();
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) {
+        u32 l = lens[i];
+        if (l) atomicAdd(&count[l], 1u);
+    }
+    __syncwarp();
+    u32 ok = 1;
+    if (lane == 0) {
+        u32 kraft = 0, used = 0, off = 0;
+        for (u32 l = 1; l <= 15; l++) {
+            start[l] = off;
+            off += count[l];
+            used += count[l];
+            kraft += count[l] << (15 - l);
+        }
+        start[0] = 0;
+        ok = (used == 0 || kraft == 32768u || (used == 1 && count[1] == 1)) ? 1u : 0u;
+    }
+    ok = __shfl_sync(GZ_FULL, ok, 0);
+    if (!ok) return false;
+    __syncwarp();
+    for (u32 base = 0; base < n; base += 32) {  // symbols of equal length keep their order
+        u32 i = base + lane;
+        u32 l = i < n ? lens[i] : 0u;
+        u32 m = __match_any_sync(GZ_FULL, l);
+        u32 rank = __popc(m & ((1u << lane) - 1u));
+        if (l) symbol[start[l] + rank] = (u16)i;
+        __syncwarp();
+        if (l && rank == 0) start[l] += __popc(m);
+        __syncwarp();
+    }
+    for (u32 e = lane; e < (1u << lutbits); e += 32) {
+        u32 len = 0;
+        int s = gz_canon(count, symbol, e, lutbits, &len);
+        lut[e] = s < 0 ? (u16)0 : (u16)(((u32)s << 4) | len);
+    }
+    __syncwarp();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------- gzip member header
+// Follows compress/gzip/gunzip.go readHeader: magic 1f 8b, method 8, FEXTRA / FNAME / FCOMMENT / FHCRC; strings of
+// 512 bytes or more are ErrHeader; the header CRC (low 16 bits of the CRC-32 of everything before it) is checked.
+__device__ u32 gz_crc_bytes(u32 crc, const u8 *p, u64 n) {  // bitwise CRC-32 update (pre / post inversion by the caller)
+    for (u64 i = 0; i < n; i++) {
+        crc ^= p[i];
+        for (int k = 0; k < 8; k++) crc = (crc >> 1) ^ (0xedb88320u & (0u - (crc & 1u)));
+    }
+    return crc;
+}
+// returns 0 and *data = offset of the deflate data, or a GZ_ST_ERR_* code with *data = offset of the error
+__device__ u32 gz_member_header(const u8 *s, u64 n, u64 p, u64 *data) {
+    *data = p;
+    if (n - p < 10) {
+        *data = n;
+        return GZ_ST_ERR_TRUNC;
+    }
+    if (s[p] != 0x1f || s[p + 1] != 0x8b || s[p + 2] != 8) return GZ_ST_ERR_HEADER;
+    const u32 flg = s[p + 3];
+    u64 q = p + 10;
+    if (flg & 4u) {  // FEXTRA
+        if (n - q < 2) {
+            *data = n;
+            return GZ_ST_ERR_TRUNC;
+        }
+        u32 xlen = (u32)s[q] | ((u32)s[q + 1] << 8);
+        q += 2;
+        if (n - q < xlen) {
+            *data = n;
+            return GZ_ST_ERR_TRUNC;
+        }
+        q += xlen;
+    }
+    for (u32 bit = 8u; bit <= 16u; bit <<= 1) {  // FNAME, FCOMMENT: zero-terminated
+        if (!(flg & bit)) continue;
+        for (u32 i = 0;; i++) {
+            if (i >= 512u) {
+                *data = q;
+                return GZ_ST_ERR_HEADER;
+            }
+            if (q >= n) {
+                *data = n;
+                return GZ_ST_ERR_TRUNC;
+            }
+            if (s[q++] == 0) break;
+        }
+    }
+    if (flg & 2u) {  // FHCRC
+        if (n - q < 2) {
+            *data = n;
+            return GZ_ST_ERR_TRUNC;
+        }
+        u32 want = (u32)s[q] | ((u32)s[q + 1] << 8);
+        u32 got = ~gz_crc_bytes(0xffffffffu, s + p, q - p) & 0xffffu;
+        if (want != got) {
+            *data = q;
+            return GZ_ST_ERR_HEADER;
+        }
+        q += 2;
+    }
+    *data = q;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------- k_gz_find
+// Is `bit` the header of a non-final dynamic-Huffman block?  Every test a real header passes: BFINAL 0, BTYPE 2,
+// at most 286 / 30 codes, a complete code-length code, lengths that decode without overrun, a complete
+// literal/length code with an end-of-block symbol, a complete (or empty / single) distance code.
+__device__ bool gz_probe_dynamic(const u32 *w, u64 n, u64 bit) {
+    const u64 nbits = n * 8;
+    if (bit + 17 + 12 > nbits) return false;
+    GzBits br;
+    br.w = w;
+    br.n = n;
+    br.seek(bit);
+    br.refill();
+    u32 v = br.peek(17);
+    if ((v & 7u) != 4u) return false;
+    const u32 hlit = (v >> 3) & 31u, hdist = (v >> 8) & 31u, hclen = ((v >> 13) & 15u) + 4u;
+    if (hlit > 29u || hdist > 29u) return false;
+    br.drop(17);
+    u8 cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    u32 kraft = 0;
+    for (u32 i = 0; i < hclen; i++) {
+        br.refill();
+        u32 l = br.take(3);
+        cl[kGzClOrder[i]] = (u8)l;
+        if (l) kraft += 128u >> l;
+    }
+    if (kraft != 128u) return false;
+    // 7-bit lookup of the code-length code: length in bits 0-2, symbol in bits 3-7
+    u8 lut[128];
+    {
+        u32 code = 0;
+        for (u32 l = 1; l <= 7; l++) {
+            for (u32 s = 0; s < 19; s++) {
+                if (cl[s] != l) continue;
+                u32 r = __brev(code) >> (32 - l);
+                for (u32 e = r; e < 128u; e += 1u << l) lut[e] = (u8)((s << 3) | l);
+                code++;
+            }
+            code <<= 1;
+        }
+    }
+    const u32 nlit = hlit + 257u, nsym = nlit + hdist + 1u;
+    u32 i = 0, prev = 0, kraft_ll = 0, kraft_d = 0, nz_d = 0, one_d = 0;
+    bool eob = false;
+    while (i < nsym) {
+        br.refill();
+        u32 e = lut[br.peek(7)];
+        br.drop(e & 7u);
+        u32 s = e >> 3, len, rep;
+        if (s < 16u) {
+            len = s;
+            rep = 1;
+            prev = s;
+        } else if (s == 16u) {
+            if (i == 0) return false;
+            len = prev;
+            rep = 3u + br.take(2);
+        } else if (s == 17u) {
+            len = 0;
+            rep = 3u + br.take(3);
+            prev = 0;
+        } else {
+            len = 0;
+            rep = 11u + br.take(7);
+            prev = 0;
+        }
+        if (i + rep > nsym) return false;
+        if (len) {
+            u32 in_ll = (i < nlit) ? (min(i + rep, nlit) - i) : 0u;
+            u32 in_d = rep - in_ll;
+            kraft_ll += in_ll * (32768u >> len);
+            kraft_d += in_d * (32768u >> len);
+            nz_d += in_d;
+            if (len == 1) one_d += in_d;
+            if (i <= 256u && 256u < i + rep) eob = true;
+        }
+        i += rep;
+    }
+    if (br.pos() > nbits) return false;
+    if (kraft_ll != 32768u || !eob) return false;
+    return kraft_d == 32768u || nz_d == 0 || (nz_d == 1 && one_d == 1);
+}
+
+// BGZF member header (SAM spec 4.1): 1f 8b 08 04, XLEN 6, subfield 'B' 'C' of length 2
+__device__ __forceinline__ bool gz_probe_bgzf(const u8 *s, u64 n, u64 p) {
+    if (p + 18 > n) return false;
+    return ld_u32_unaligned(s + p) == 0x04088b1fu && ld_u16_unaligned(s + p + 10) == 6u && ld_u32_unaligned(s + p + 12) == 0x00024342u;
+}
+
+__global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_find(GzArgs a) {
+    const u32 lane = lane_id();
+    const u32 k = 1u + blockIdx.x * GZ_WARPS + (threadIdx.x >> 5);
+    if (k >= a.nchunks) return;
+    const u8 *s8 = (const u8 *)a.src;
+    const u64 lo = (u64)k * a.chunk_bytes, hi = min(a.n, lo + a.chunk_bytes);
+    u64 best = GZ_NO_TARGET;
+    u32 type = GZ_AT_NONE;
+    for (u64 base = lo; base < hi; base += 32) {  // member headers: byte aligned
+        u64 p = base + lane;
+        bool ok = p < hi && gz_probe_bgzf(s8, a.n, p);
+        u32 m = __ballot_sync(GZ_FULL, ok);
+        if (m) {
+            best = (base + (u32)(__ffs((int)m) - 1)) * 8;
+            type = GZ_AT_MEMBER;
+            break;
+        }
+    }
+    if (!a.bgzf_only) {
+        const u64 lim = min(best, hi * 8);
+        for (u64 base = lo * 8; base < lim; base += 32) {  // block headers: any bit
+            u64 p = base + lane;
+            bool ok = p < lim && gz_probe_dynamic(a.src, a.n, p);
+            u32 m = __ballot_sync(GZ_FULL, ok);
+            if (m) {
+                best = base + (u32)(__ffs((int)m) - 1);
+                type = GZ_AT_BLOCK;
+                break;
+            }
+        }
+    }
+    if (lane == 0) {
+        a.chunks[k].start_bit = best;
+        a.chunks[k].start_type = type;
+    }
+}
+
+// ---------------------------------------------------------------------------------- k_gz_decode
+struct GzSm {
+    u16 lut_ll[1u << GZ_LL_BITS];
+    u16 lut_d[1u << GZ_D_BITS];
+    u16 sym_ll[288];
+    u16 sym_d[32];
+    u32 cnt_ll[16], cnt_d[16], start[16];
+    u32 q[32];
+    u8 lens[320];
+    u8 cl[32];
+};
+
+// lane 0: the header of a dynamic block up to the code lengths of the code-length code (S.cl)
+__device__ u32 gz_dyn_counts(GzBits &br, GzSm &S, u32 *nlit, u32 *ndist) {
+    br.refill();
+    *nlit = br.take(5) + 257u;
+    *ndist = br.take(5) + 1u;
+    u32 hclen = br.take(4) + 4u;
+    if (*nlit > 286u || *ndist > 30u) return GZ_ST_ERR_CORRUPT;
+    for (u32 i = 0; i < 19; i++) S.cl[i] = 0;
+    for (u32 i = 0; i < hclen; i++) {
+        br.refill();
+        S.cl[kGzClOrder[i]] = (u8)br.take(3);
+    }
+    return 0;
+}
+// lane 0: the nlit + ndist code lengths, coded with the code-length code whose tables sit in the distance slots
+__device__ u32 gz_dyn_lengths(GzBits &br, GzSm &S, u32 total) {
+    u32 i = 0;
+    while (i < total) {
+        br.refill();
+        u32 e = S.lut_d[br.peek(7)];
+        if (!e) return GZ_ST_ERR_CORRUPT;
+        br.drop(e & 15u);
+        u32 s = e >> 4;
+        if (s < 16u) {
+            S.lens[i++] = (u8)s;
+            continue;
+        }
+        u32 rep, val = 0;
+        if (s == 16u) {
+            if (i == 0) return GZ_ST_ERR_CORRUPT;
+            rep = 3u + br.take(2);
+            val = S.lens[i - 1];
+        } else if (s == 17u)
+            rep = 3u + br.take(3);
+        else
+            rep = 11u + br.take(7);
+        if (i + rep > total) return GZ_ST_ERR_CORRUPT;
+        for (u32 k = 0; k < rep; k++) S.lens[i++] = (u8)val;
+    }
+    return 0;
+}
+
+// lane 0: up to 32 symbols of a compressed block into S.q (literal: value; match: length << 16 | distance).
+// avail = bytes a match may reach back.  Returns the count; *flags bit 0 = end of block, bits 8.. = error status.
+__device__ u32 gz_symbols(GzBits &br, GzSm &S, u64 nbits, u64 avail, u32 *bytes, u32 *flags) {
+    u32 cnt = 0, produced = 0, fl = 0;
+    while (cnt < 32u) {
+        br.refill();
+        u32 e = S.lut_ll[br.peek(GZ_LL_BITS)], sym, len;
+        if (e) {
+            sym = e >> 4;
+            len = e & 15u;
+        } else {
+            int s = gz_canon(S.cnt_ll, S.sym_ll, br.peek(15), 15, &len);
+            if (s < 0) {
+                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
+                break;
+            }
+            sym = (u32)s;
+        }
+        br.drop(len);
+        if (sym < 256u) {
+            S.q[cnt++] = sym;
+            produced++;
+        } else if (sym == 256u) {
+            fl = 1;
+            if (br.pos() > nbits) fl = GZ_ST_ERR_TRUNC << 8;
+            break;
+        } else {
+            if (sym >= 286u) {
+                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
+                break;
+            }
+            u32 ml = kGzLenBase[sym - 257u] + br.take(kGzLenExtra[sym - 257u]);
+            br.refill();
+            u32 d = S.lut_d[br.peek(GZ_D_BITS)], ds, dl;
+            if (d) {
+                ds = d >> 4;
+                dl = d & 15u;
+            } else {
+                int s = gz_canon(S.cnt_d, S.sym_d, br.peek(15), 15, &dl);
+                if (s < 0) {
+                    fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
+                    break;
+                }
+                ds = (u32)s;
+            }
+            br.drop(dl);
+            if (ds >= 30u) {
+                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
+                break;
+            }
+            u32 dist = kGzDistBase[ds] + br.take(kGzDistExtra[ds]);
+            if (br.pos() > nbits) {
+                fl = GZ_ST_ERR_TRUNC << 8;
+                break;
+            }
+            if ((u64)dist > avail + produced) {  // reaches in front of the member (Go: dist > histSize)
+                fl = GZ_ST_ERR_CORRUPT << 8;
+                break;
+            }
+            S.q[cnt++] = (ml << 16) | dist;
+            produced += ml;
+        }
+        if (br.pos() > nbits) {
+            fl = GZ_ST_ERR_TRUNC << 8;
+            break;
+        }
+    }
+    *bytes = produced;
+    *flags = fl;
+    return cnt;
+}
+
+template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_decode(GzArgs a) {
+    __shared__ GzSm smem[GZ_WARPS];
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const u32 li = blockIdx.x * GZ_WARPS + wid;
+    if (li >= a.nlist) return;
+    GzSm &S = smem[wid];
+    GzChunk &C = a.chunks[a.list[li]];
+    const u8 *s8 = (const u8 *)a.src;
+    const u64 n = a.n, nbits = a.n * 8;
+    const u64 target = C.target_bit;
+    const u32 target_type = C.target_type;
+    u16 *out = WRITE ? a.sym + C.out_off : nullptr;
+    GzMember *mem = WRITE ? a.members + C.member_base : nullptr;
+    const u64 out_off = C.out_off;
+
+    GzBits br;
+    br.w = a.src;
+    br.n = n;
+    br.wi = 0;
+    br.bb = 0;
+    br.bc = 0;
+    u64 pos = C.start_bit;  // bit position at member / block boundaries, the same in every lane
+    u64 produced = 0;       // bytes decoded by this chunk
+    bool known = false;     // the window in front of the current position lies inside this chunk's own output
+    u64 member_from = 0;    // ... and starts here
+    bool at_header = C.start_type == GZ_AT_MEMBER;
+    u32 nmem = 0, status = 0;
+    u64 errbit = 0;
+    if (!at_header && lane == 0) br.seek(pos);
+
+    for (;;) {
+        if (pos > target) {
+            status = GZ_ST_OVERSHOOT;
+            break;
+        }
+        if (at_header) {
+            if (pos == target && target_type == GZ_AT_MEMBER) {
+                status = GZ_ST_REACHED;
+                break;
+            }
+            if ((pos >> 3) == n) {
+                status = GZ_ST_END;
+                break;
+            }
+            u32 rc = 0;
+            u64 data = 0;
+            if (lane == 0) rc = gz_member_header(s8, n, pos >> 3, &data);
+            rc = __shfl_sync(GZ_FULL, rc, 0);
+            data = __shfl_sync(GZ_FULL, data, 0);
+            if (rc) {
+                status = rc;
+                errbit = data * 8;
+                break;
+            }
+            known = true;
+            member_from = produced;
+            pos = data * 8;
+            if (lane == 0) br.seek(pos);
+            at_header = false;
+            continue;
+        }
+        if (pos == target && target_type == GZ_AT_BLOCK) {
+            status = GZ_ST_REACHED;
+            break;
+        }
+        // ---- block header
+        u32 hdr = 0;
+        if (lane == 0) {
+            br.refill();
+            hdr = br.take(3);
+            if (br.pos() > nbits) hdr = 0x100u;
+        }
+        hdr = __shfl_sync(GZ_FULL, hdr, 0);
+        if (hdr & 0x100u) {
+            status = GZ_ST_ERR_TRUNC;
+            errbit = nbits;
+            break;
+        }
+        const u32 bfinal = hdr & 1u, btype = hdr >> 1;
+        if (btype == 3u) {
+            status = GZ_ST_ERR_CORRUPT;
+            errbit = pos;
+            break;
+        }
+        if (btype == 0u) {  // stored: LEN, ~LEN, bytes
+            u64 at = 0;
+            if (lane == 0) at = (br.pos() + 7u) >> 3;
+            at = __shfl_sync(GZ_FULL, at, 0);
+            if (at + 4 > n) {
+                status = GZ_ST_ERR_TRUNC;
+                errbit = nbits;
+                break;
+            }
+            const u32 len = (u32)s8[at] | ((u32)s8[at + 1] << 8), nlen = (u32)s8[at + 2] | ((u32)s8[at + 3] << 8);
+            if ((len ^ nlen) != 0xffffu) {
+                status = GZ_ST_ERR_CORRUPT;
+                errbit = at * 8;
+                break;
+            }
+            if (at + 4 + len > n) {
+                status = GZ_ST_ERR_TRUNC;
+                errbit = nbits;
+                break;
+            }
+            if (WRITE)
+                for (u32 t = lane; t < len; t += 32) out[produced + t] = (u16)s8[at + 4 + t];
+            produced += len;
+            pos = (at + 4 + len) * 8;
+            if (lane == 0) br.seek(pos);
+            __syncwarp();
+        } else {
+            // ---- code tables
+            u32 rc = 0, nlit = 288, ndist = 32;
+            if (btype == 1u) {
+                for (u32 i = lane; i < 288u; i += 32) S.lens[i] = (u8)(i < 144u ? 8 : (i < 256u ? 9 : (i < 280u ? 7 : 8)));
+                S.lens[288u + lane] = 5;
+                __syncwarp();
+            } else {
+                if (lane == 0) {
+                    rc = gz_dyn_counts(br, S, &nlit, &ndist);
+                    if (br.pos() > nbits) rc = GZ_ST_ERR_TRUNC;
+                }
+                rc = __shfl_sync(GZ_FULL, rc, 0);
+                nlit = __shfl_sync(GZ_FULL, nlit, 0);
+                ndist = __shfl_sync(GZ_FULL, ndist, 0);
+                if (!rc && !gz_build(S.cl, 19, S.cnt_d, S.start, S.sym_d, S.lut_d, 7)) rc = GZ_ST_ERR_CORRUPT;
+                if (!rc) {
+                    if (lane == 0) {
+                        rc = gz_dyn_lengths(br, S, nlit + ndist);
+                        if (br.pos() > nbits) rc = GZ_ST_ERR_TRUNC;
+                    }
+                    rc = __shfl_sync(GZ_FULL, rc, 0);
+                }
+            }
+            if (!rc && !gz_build(S.lens, nlit, S.cnt_ll, S.start, S.sym_ll, S.lut_ll, GZ_LL_BITS)) rc = GZ_ST_ERR_CORRUPT;
+            if (!rc && !gz_build(S.lens + nlit, ndist, S.cnt_d, S.start, S.sym_d, S.lut_d, GZ_D_BITS)) rc = GZ_ST_ERR_CORRUPT;
+            if (rc) {
+                status = rc;
+                errbit = rc == GZ_ST_ERR_TRUNC ? nbits : pos;
+                break;
+            }
+            // ---- symbols, 32 at a time
+            for (;;) {
+                u32 cnt = 0, bytes = 0, fl = 0;
+                if (lane == 0) cnt = gz_symbols(br, S, nbits, known ? produced - member_from : produced + GZ_WINDOW, &bytes, &fl);
+                __syncwarp();
+                cnt = __shfl_sync(GZ_FULL, cnt, 0);
+                bytes = __shfl_sync(GZ_FULL, bytes, 0);
+                fl = __shfl_sync(GZ_FULL, fl, 0);
+                if (WRITE) {
+                    const u32 e = lane < cnt ? S.q[lane] : 0u;
+                    const u32 mlen = e >> 16;
+                    const u32 len = lane < cnt ? (mlen ? mlen : 1u) : 0u;
+                    const u32 o = group_incl_scan(len, GZ_FULL, 32) - len;
+                    if (lane < cnt && !mlen) out[produced + o] = (u16)e;
+                    __syncwarp();
+                    u32 mm = __ballot_sync(GZ_FULL, mlen != 0u);
+                    while (mm) {
+                        const int j = __ffs((int)mm) - 1;
+                        mm &= mm - 1u;
+                        const u32 L = __shfl_sync(GZ_FULL, mlen, j), D = __shfl_sync(GZ_FULL, e & 0xffffu, j);
+                        const u64 dst = produced + __shfl_sync(GZ_FULL, o, j);
+                        for (u32 t = lane; t < L; t += 32) {
+                            const u32 tt = t < D ? t : t % D;  // overlapping matches repeat with period D
+                            const long long src = (long long)dst + (long long)tt - (long long)D;
+                            out[dst + t] = src >= 0 ? out[src] : (u16)(256 + (long long)GZ_WINDOW + src);
+                        }
+                        __syncwarp();
+                    }
+                }
+                produced += bytes;
+                if (fl >> 8) {
+                    status = fl >> 8;
+                    break;
+                }
+                if (fl & 1u) break;
+            }
+            if (status) {
+                u64 p = 0;
+                if (lane == 0) p = br.pos();
+                errbit = status == GZ_ST_ERR_TRUNC ? nbits : __shfl_sync(GZ_FULL, p, 0);
+                break;
+            }
+            u64 p = 0;
+            if (lane == 0) p = br.pos();
+            pos = __shfl_sync(GZ_FULL, p, 0);
+        }
+        if (bfinal) {  // trailer: CRC-32, ISIZE
+            const u64 at = (pos + 7u) >> 3;
+            if (at + 8 > n) {
+                status = GZ_ST_ERR_TRUNC;
+                errbit = nbits;
+                break;
+            }
+            if (WRITE && lane == 0) {
+                GzMember m;
+                m.out_end = out_off + produced;
+                m.trailer_byte = at;
+                m.crc = (u32)s8[at] | ((u32)s8[at + 1] << 8) | ((u32)s8[at + 2] << 16) | ((u32)s8[at + 3] << 24);
+                m.isize = (u32)s8[at + 4] | ((u32)s8[at + 5] << 8) | ((u32)s8[at + 6] << 16) | ((u32)s8[at + 7] << 24);
+                m.crc_acc = 0;
+                m.pad = 0;
+                mem[nmem] = m;
+            }
+            nmem++;
+            pos = (at + 8) * 8;
+            at_header = true;
+            known = false;
+        }
+    }
+    if (lane == 0) {
+        if (WRITE) {
+            if (status < 16u && (produced != C.out_len || nmem != C.members || pos != C.end_bit)) {
+                status = GZ_ST_ERR_INTERNAL;
+                errbit = C.start_bit;
+            }
+            if (status >= 16u) atomicMin(a.err, (unsigned long long)((errbit << 8) | status));
+        } else {
+            C.out_len = produced;
+            C.end_bit = pos;
+            C.err_bit = errbit;
+            C.members = nmem;
+            C.after_member = known ? produced - member_from : ~0ull;
+            C.status = status;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- k_gz_windows
+// One CTA, chunk after chunk in stream order: the window of a chunk that starts at a block header is the last
+// 32 KiB in front of it = the tail of the previous chunk (its markers resolved through ITS window) behind what is
+// left of that window.
+__global__ void __launch_bounds__(1024) k_gz_windows(GzArgs a) {
+    for (u32 i = 1; i < a.nlist; i++) {
+        const GzChunk &C = a.chunks[a.list[i]];
+        if (C.start_type != GZ_AT_BLOCK) continue;
+        const GzChunk &P = a.chunks[a.list[i - 1]];
+        u8 *win = a.win + (size_t)C.win_slot * GZ_WINDOW;
+        const u8 *pwin = a.win + (size_t)P.win_slot * GZ_WINDOW;
+        const u16 *psym = a.sym + P.out_off;
+        const u64 plen = P.out_len;
+        for (u32 t = threadIdx.x; t < GZ_WINDOW; t += blockDim.x) {
+            u8 v;
+            if (plen >= GZ_WINDOW) {
+                u16 s = psym[plen - GZ_WINDOW + t];
+                v = s < 256u ? (u8)s : pwin[s - 256u];
+            } else {
+                const u32 keep = GZ_WINDOW - (u32)plen;  // bytes of the previous window still in reach
+                if (t < keep)
+                    v = pwin[t + (u32)plen];
+                else {
+                    u16 s = psym[t - keep];
+                    v = s < 256u ? (u8)s : pwin[s - 256u];
+                }
+            }
+            win[t] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------- k_gz_resolve
+__global__ void __launch_bounds__(256) k_gz_resolve(GzArgs a) {
+    const GzChunk &C = a.chunks[a.list[blockIdx.y]];
+    const u16 *sym = a.sym + C.out_off;
+    u8 *out = a.out + C.out_off;
+    const u8 *win = a.win + (size_t)C.win_slot * GZ_WINDOW;
+    const u32 first_valid = GZ_WINDOW - C.window_valid;
+    const bool has_window = C.start_type == GZ_AT_BLOCK;
+    bool bad = false;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < C.out_len; p += (u64)gridDim.x * blockDim.x) {
+        u32 s = sym[p];
+        if (s >= 256u) {
+            s -= 256u;
+            if (!has_window || s < first_valid) bad = true;  // a match that reaches in front of its member
+            s = win[s];
+        }
+        out[p] = (u8)s;
+    }
+    if (bad) atomicMin(a.err, (unsigned long long)((C.start_bit << 8) | (has_window ? GZ_ST_ERR_CORRUPT : GZ_ST_ERR_INTERNAL)));
+}
+
+// ---------------------------------------------------------------------------------- k_gz_crc
+// reflected CRC-32 arithmetic: bit 31 is x^0 (zlib's multmodp)
+__device__ __forceinline__ u32 gz_mulmod(u32 a, u32 b) {
+    u32 p = 0;
+    for (int i = 31; i >= 0; i--) {
+        if (a & (1u << i)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ 0xedb88320u : b >> 1;
+    }
+    return p;
+}
+// x^(8 * bytes) mod P
+__device__ __forceinline__ u32 gz_xpow8(const u32 *pw, u64 bytes) {
+    u32 r = 0x80000000u;
+    for (u32 k = 0; bytes; k++, bytes >>= 1)
+        if (bytes & 1u) r = gz_mulmod(pw[k], r);
+    return r;
+}
+#define GZ_CRC_PIECE 2048u
+__global__ void __launch_bounds__(128) k_gz_crc(GzArgs a, u64 out_len) {
+    __shared__ u32 T[256];
+    for (u32 i = threadIdx.x; i < 256u; i += blockDim.x) {
+        u32 c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xedb88320u & (0u - (c & 1u)));
+        T[i] = c;
+    }
+    __syncthreads();
+    const u64 piece = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 lo = piece * GZ_CRC_PIECE;
+    if (lo >= out_len) return;
+    const u64 hi = min(out_len, lo + GZ_CRC_PIECE);
+    // first member that ends behind lo
+    u32 m = 0, r = a.nmembers;
+    while (m < r) {
+        u32 mid = (m + r) >> 1;
+        if (a.members[mid].out_end > lo)
+            r = mid;
+        else
+            m = mid + 1;
+    }
+    while (lo < hi && m < a.nmembers) {
+        const u64 mend = a.members[m].out_end;
+        const u64 se = min(hi, mend);
+        u32 c = 0;
+        u64 p = lo;
+        for (; p < se && (p & 3u); p++) c = T[(c ^ a.out[p]) & 0xffu] ^ (c >> 8);
+        for (; p + 4 <= se; p += 4) {
+            c ^= *(const u32 *)(a.out + p);
+            c = T[c & 0xffu] ^ (c >> 8);
+            c = T[c & 0xffu] ^ (c >> 8);
+            c = T[c & 0xffu] ^ (c >> 8);
+            c = T[c & 0xffu] ^ (c >> 8);
+        }
+        for (; p < se; p++) c = T[(c ^ a.out[p]) & 0xffu] ^ (c >> 8);
+        if (c) atomicXor(&a.members[m].crc_acc, gz_mulmod(gz_xpow8(a.pw, mend - se), c));
+        lo = se;
+        if (lo < hi) {
+            m++;
+            while (m < a.nmembers && a.members[m].out_end <= lo) m++;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_gz_verify(GzArgs a) {
+    const u32 m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= a.nmembers) return;
+    const GzMember &M = a.members[m];
+    const u64 from = m ? a.members[m - 1].out_end : 0ull, len = M.out_end - from;
+    const u32 crc = ~(gz_mulmod(gz_xpow8(a.pw, len), 0xffffffffu) ^ M.crc_acc);
+    if (crc != M.crc || (u32)len != M.isize) atomicMin(a.err, (unsigned long long)(((M.trailer_byte * 8) << 8) | GZ_ST_ERR_CHECKSUM));
+}
+
+// ---------------------------------------------------------------------------------- launchers
+void fqz_launch_gz_find(const GzArgs &a, cudaStream_t s) {
+    if (a.nchunks < 2) return;
+    u32 grid = (a.nchunks - 1 + GZ_WARPS - 1) / GZ_WARPS;
+    FQZ_LAUNCH(k_gz_find, grid, GZ_WARPS * 32, 0, s, a);
+}
+void fqz_launch_gz_decode(const GzArgs &a, bool write, cudaStream_t s) {
+    if (!a.nlist) return;
+    u32 grid = (a.nlist + GZ_WARPS - 1) / GZ_WARPS;
+    if (write)
+        FQZ_LAUNCH(k_gz_decode<true>, grid, GZ_WARPS * 32, 0, s, a);
+    else
+        FQZ_LAUNCH(k_gz_decode<false>, grid, GZ_WARPS * 32, 0, s, a);
+}
+void fqz_launch_gz_windows(const GzArgs &a, cudaStream_t s) {
+    if (a.nlist < 2) return;
+    FQZ_LAUNCH(k_gz_windows, 1, 1024, 0, s, a);
+}
+void fqz_launch_gz_resolve(const GzArgs &a, cudaStream_t s) {
+    if (!a.nlist) return;
+    FQZ_LAUNCH(k_gz_resolve, dim3(16, a.nlist), 256, 0, s, a);
+}
+void fqz_launch_gz_crc(const GzArgs &a, u64 out_len, cudaStream_t s) {
+    if (out_len) {
+        u64 pieces = (out_len + GZ_CRC_PIECE - 1) / GZ_CRC_PIECE;
+        FQZ_LAUNCH(k_gz_crc, (u32)((pieces + 127) / 128), 128, 0, s, a, out_len);
+    }
+    if (a.nmembers) FQZ_LAUNCH(k_gz_verify, (a.nmembers + 255) / 256, 256, 0, s, a);
+}

@@ -38,6 +38,10 @@ extern "C" {
 #define FQZ_E_TRUNC_LEN (-13)   /* "truncated length data"             compress.go:1048 */
 #define FQZ_E_TRUNC_NPOS (-14)  /* "truncated N position data"         compress.go:1057 */
 #define FQZ_E_NOSPACE (-15)     /* output buffer too small; *out_len = bytes required, nothing consumed */
+#define FQZ_E_GZ_HEADER (-18)   /* "gzip: invalid header"    Go compress/gzip ErrHeader, reached through cmd/fqpack/main.go:151-156 */
+#define FQZ_E_GZ_CHECKSUM (-19) /* "gzip: invalid checksum"  ErrChecksum: CRC-32 or ISIZE of a member */
+#define FQZ_E_GZ_CORRUPT (-20)  /* "flate: corrupt input before offset %d"  compress/flate CorruptInputError */
+#define FQZ_E_GZ_TRUNC (-21)    /* "unexpected EOF" inside a gzip member ("EOF" for an empty input) */
 #define FQZ_E_NPOS_RANGE (-17)  /* N position >= sequence length (the reference panics: encoder/sequence.go:218-220) */
 #define FQZ_E_CUDA (-32)        /* CUDA runtime failure; text in fqz_last_error() */
 #define FQZ_E_NO_DEVICE (-33)   /* no usable CUDA device: there is no CPU fallback */
@@ -71,6 +75,8 @@ int fqz_abi_version(void);
                                      * Huffman codes may differ) */
 #define FQZ_OPT_SERIAL_ENTROPY 6    /* 0 (default): the item-stream kernels run on a second stream beside the literals-only coder (their launch
                                      * tails overlap); 1: one after the other (per-stage timings are only meaningful this way) */
+#define FQZ_OPT_GZ_CHUNK_BYTES 7    /* gzip input: compressed bytes decoded by one warp (default: input size / (16 x SMs), 64 KiB .. 4 MiB;
+                                     * multiple of 4, >= 256).  Results do not depend on it */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
 /* Page-locked host memory for the caller's window buffers (the Go shim reads the file into these instead of Go
@@ -102,6 +108,24 @@ typedef struct fqz_file_info {
 } fqz_file_info;
 int fqz_info(fqz_ctx *ctx, const uint8_t *fqz, size_t n, fqz_file_info *out);
 int fqz_check(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t *records, uint64_t *fastq_bytes);
+
+/* ---- gzip input (cmd/fqpack/main.go:123-174).  In compress mode fqpack reads an input whose name ends in ".gz" or that
+ * starts with 1f 8b through Go's compress/gzip: concatenated members (BGZF, pigz -i, cat a.gz b.gz) decode as one
+ * stream, every member's CRC-32 and ISIZE are verified, bytes behind the last member that are not a gzip header are
+ * "gzip: invalid header".  fqz_is_gzip = inputHasGzipMagic (main.go:164-174).  fqz_gunzip: gzip file in host memory ->
+ * text in host memory (FQZ_E_NOSPACE: *out_len = bytes needed).  fqz_gunzip_device: the same between device buffers
+ * (16-byte aligned, FQZ_DEVICE_SLACK readable bytes behind the input).  fqz_compress_gz = gzip.NewReader + compress.Compress:
+ * the COMPRESSED bytes cross PCIe, the text is inflated and coded in HBM; *fastq_len (optional) = bytes of FASTQ.
+ * DEFLATE is decoded in parallel from restart points found in the compressed stream (BGZF member headers,
+ * dynamic-block headers), proven by the decoder in front landing exactly on them. */
+int fqz_is_gzip(const uint8_t *buf, size_t n);
+/* how the last gzip input of this context was cut: [0] chunks, [1] chunks decoded side by side (restart points proven),
+ * [2] restart points dropped as false positives, [3] gzip members */
+int fqz_gunzip_stats(fqz_ctx *ctx, uint64_t out[4]);
+int fqz_gunzip(fqz_ctx *ctx, const uint8_t *gz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
+int fqz_gunzip_device(fqz_ctx *ctx, const void *d_gz, size_t n, void *d_out, size_t out_cap, size_t *out_len);
+int fqz_compress_gz(fqz_ctx *ctx, const uint8_t *gz, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap, size_t *out_len,
+                    size_t *fastq_len);
 
 /* One shard of a file that is split across GPUs on block boundaries (blocks are independent,
  * compress.go:523-528).  phred64: -1 = detect on this shard's first block (the shard
