@@ -48,6 +48,7 @@ UNIT = "GB/s"
 FULL_RECORDS = 25_000_000  # BASELINE config 2: ~9 GB of 150 bp Phred+33 reads
 CFG4_RECORDS = 2_000_000  # BASELINE config 4
 CFG4_SEED = 0x5EED0004
+GZIP_RECORDS = 1_000_000  # gzip input side workload (row f3)
 DUP_RECORDS = 3_000_000
 CFG5_BYTES = 64_000_000_000  # BASELINE config 5
 WORKLOAD = "synthetic Illumina 150 bp Phred+33 reads shaped like ERR532393_1 (BASELINE config 2), compress at 1 B200 per rank"
@@ -379,6 +380,10 @@ def run_ours(args):
                                        "synthetic Phred+64, N-heavy (5 % N), '+' payloads, 50-300 bp (BASELINE config 4)")
         extras["duplicates"] = side_workload(ctx, torch, 2, SEED, min(DUP_RECORDS, nrec), 372, timed, os.cpu_count() or 1,
                                              "config-2 reads of which 35 % are exact copies of one of the 400 reads in front (generator kind 2)")
+        try:
+            extras["gzip_input"] = gzip_workload(ctx, torch, d_in, min(GZIP_RECORDS, nrec), timed)
+        except Exception as e:  # the side workload must never cost the headline line
+            extras["gzip_input"] = {"error": repr(e)[:300]}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -823,6 +828,80 @@ def reference_written(args, ctx, torch, dist, rank, world, nrec, d_in, n, d_back
             "records": total_records, "fastq_bytes": int(total), "blocks": len(blocks), "scaling": "strong (one file, block runs per rank)",
             "input": "oracle-written .fqz of the whole workload (reference-shaped: one libzstd-1 frame per stream and block)"}
     return (refw, cb) if rank == 0 else (None, None)
+
+
+def gzip_workload(ctx, torch, d_in, nrec, timed):
+    """SURVEY 8 row f3 (cmd/fqpack/main.go:142-174): the first `nrec` records of the workload as .fq.gz — one zlib level-1
+    member (what `gzip -1` / pigz write) and BGZF (what bgzip writes) — inflated on the GPU.  Reports GB/s of TEXT:
+    device-resident fqz_gunzip_device, end to end fqz_compress_gz (compressed bytes up, .fqz down, pinned), and zlib's
+    inflate on one host core beside them."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    # cut at a record boundary: config-2 records are 4 lines
+    probe = d_in[: nrec * 372 + 4096].cpu().numpy()
+    nl = np.flatnonzero(probe == 10)
+    n = int(nl[4 * nrec - 1]) + 1
+    text = probe[:n].tobytes()
+    del probe, nl
+
+    def member(t):
+        c = zlib.compressobj(1, zlib.DEFLATED, -15)
+        return b"\x1f\x8b\x08\0\0\0\0\0\0\xff" + c.compress(t) + c.flush() + struct.pack("<II", zlib.crc32(t), len(t) & 0xFFFFFFFF)
+
+    def bgzf_block(p):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        raw = c.compress(p) + c.flush()
+        return b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", 25 + len(raw)) + raw + struct.pack("<II", zlib.crc32(p), len(p))
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        fut = ex.submit(member, text)
+        blocks = list(ex.map(bgzf_block, [text[i : i + 65280] for i in range(0, n, 65280)] + [b""]))
+        files = {"gzip_level1": fut.result(), "bgzf": b"".join(blocks)}
+    t_make = time.perf_counter() - t0
+    out = {"workload": "first %d records of the config-2 input as .fq.gz" % nrec, "records": nrec, "fastq_bytes": n, "unit": UNIT,
+           "made_in_s": t_make}
+    d_text = torch.empty(n + 4096, dtype=torch.uint8, device="cuda")
+    for name, gz in files.items():
+        g = np.frombuffer(gz, dtype=np.uint8)
+        d_gz = torch.zeros(g.size + 64, dtype=torch.uint8, device="cuda")
+        d_gz[: g.size] = torch.from_numpy(g.copy()).cuda()
+        res = {}
+
+        def dev():
+            res["n"] = ctx.gunzip_device(d_gz.data_ptr(), g.size, d_text.data_ptr(), n)
+
+        t = timed(dev, 3, 1)
+        ok = res["n"] == n and bool(torch.equal(d_text[:n].cpu(), torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy())))
+        st = ctx.gunzip_stats()
+        h_gz = torch.from_numpy(g.copy()).pin_memory()
+        h_out = torch.empty(n // 2 + (1 << 20), dtype=torch.uint8).pin_memory()
+        import ctypes as C
+
+        def e2e():
+            m, f = C.c_size_t(0), C.c_size_t(0)
+            rc = ctx.lib.L.fqz_compress_gz(ctx.h, C.c_void_p(h_gz.data_ptr()), g.size, 0, C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(m), C.byref(f))
+            assert rc == 0 and f.value == n, (rc, f.value)
+            res["m"] = m.value
+
+        e2e()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            e2e()
+        t_e = (time.perf_counter() - t0) / 2
+        t0 = time.perf_counter()
+        d = zlib.decompressobj(31)
+        cpu_bytes = len(d.decompress(gz[: 1 << 26]))  # one host core over the first 64 MiB of the file
+        t_cpu = time.perf_counter() - t0
+        out[name] = {"gz_bytes": g.size, "gunzip_device": {"value": 3 * n / t / 1e9, "unit": UNIT, "bit_exact": ok},
+                     "compress_gz_e2e": {"value": n / t_e / 1e9, "unit": UNIT, "h2d_bytes": g.size, "d2h_bytes": res["m"], "fqz_bytes": res["m"]},
+                     "cpu_zlib_inflate_1core": {"value": cpu_bytes / t_cpu / 1e9, "unit": UNIT},
+                     "chunks": st}
+    return out
 
 
 def side_workload(ctx, torch, kind, seed, nrec, per_record, timed, cpu_threads, what):

@@ -45,20 +45,22 @@ __device__ __forceinline__ u32 gz_word(const u32 *w, u64 n, u64 i) {
 struct GzBits {
     const u32 *w;
     u64 n, wi, bb;
-    u32 bc;
+    u32 bc, nxt;  // nxt = word wi, loaded one refill ahead so that its latency hides behind the symbols in between
     __device__ __forceinline__ void seek(u64 bit) {
         wi = bit >> 5;
         u32 sh = (u32)(bit & 31u);
         bb = (u64)gz_word(w, n, wi) >> sh;
         bc = 32u - sh;
         wi++;
+        nxt = gz_word(w, n, wi);
     }
     // at least 33 bits afterwards
     __device__ __forceinline__ void refill() {
         if (bc <= 32u) {
-            bb |= (u64)gz_word(w, n, wi) << bc;
+            bb |= (u64)nxt << bc;
             bc += 32u;
             wi++;
+            nxt = gz_word(w, n, wi);
         }
     }
     __device__ __forceinline__ u32 peek(u32 k) const { return (u32)bb & ((1u << k) - 1u); }
@@ -477,6 +479,7 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
     br.wi = 0;
     br.bb = 0;
     br.bc = 0;
+    br.nxt = 0;
     u64 pos = C.start_bit;  // bit position at member / block boundaries, the same in every lane
     u64 produced = 0;       // bytes decoded by this chunk
     bool known = false;     // the window in front of the current position lies inside this chunk's own output
@@ -611,12 +614,31 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                     const u32 len = lane < cnt ? (mlen ? mlen : 1u) : 0u;
                     const u32 o = group_incl_scan(len, GZ_FULL, 32) - len;
                     if (lane < cnt && !mlen) out[produced + o] = (u16)e;
+                    // short matches whose source lies in front of this batch do not depend on anything the batch
+                    // writes: every lane copies its own, four loads in flight per round trip to L2
+                    const u32 dist = e & 0xffffu;
+                    const bool indep = mlen != 0u && mlen <= 32u && dist >= o + mlen;
+                    if (indep) {
+                        const long long s0 = (long long)(produced + o) - (long long)dist;
+                        u16 *dp = out + produced + o;
+                        for (u32 t = 0; t < mlen; t += 4) {
+                            u16 v[4];
+#pragma unroll
+                            for (u32 k = 0; k < 4; k++) {
+                                const long long s = s0 + t + k;
+                                v[k] = (t + k < mlen) ? (s >= 0 ? out[s] : (u16)(256 + (long long)GZ_WINDOW + s)) : (u16)0;
+                            }
+#pragma unroll
+                            for (u32 k = 0; k < 4; k++)
+                                if (t + k < mlen) dp[t + k] = v[k];
+                        }
+                    }
                     __syncwarp();
-                    u32 mm = __ballot_sync(GZ_FULL, mlen != 0u);
+                    u32 mm = __ballot_sync(GZ_FULL, mlen != 0u && !indep);
                     while (mm) {
                         const int j = __ffs((int)mm) - 1;
                         mm &= mm - 1u;
-                        const u32 L = __shfl_sync(GZ_FULL, mlen, j), D = __shfl_sync(GZ_FULL, e & 0xffffu, j);
+                        const u32 L = __shfl_sync(GZ_FULL, mlen, j), D = __shfl_sync(GZ_FULL, dist, j);
                         const u64 dst = produced + __shfl_sync(GZ_FULL, o, j);
                         for (u32 t = lane; t < L; t += 32) {
                             const u32 tt = t < D ? t : t % D;  // overlapping matches repeat with period D

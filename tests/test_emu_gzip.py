@@ -1,0 +1,50 @@
+"""Runs the gzip input kernels (restart-point search, parallel DEFLATE decode, window resolution, CRC-32) through the
+CPU emulation (tests/emu) against the gunzip oracle.  The parity tests proper are the -m gpu ones
+(tests/test_gpu_gzip.py), which reuse these cases at full size."""
+import pytest
+
+from tests.gzip_cases import bad_cases, check_bad, check_compress_gz, check_good, good_cases
+
+SCALE = 0.3
+CASES = good_cases(SCALE)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.emu_lib import emu_context
+
+    return emu_context()
+
+
+@pytest.fixture(scope="module")
+def gunzip_oracle():
+    from oracle import gunzip_oracle
+
+    return gunzip_oracle
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gunzip(emu, gunzip_oracle, name):
+    check_good(emu, gunzip_oracle, name, CASES, chunks=(0, 1024))
+
+
+@pytest.mark.parametrize("name", sorted(bad_cases()))
+def test_gunzip_errors(emu, gunzip_oracle, name):
+    check_bad(emu, gunzip_oracle, name, chunks=(0, 1024))
+
+
+def test_restart_points_are_used_and_false_ones_dropped(emu, gunzip_oracle):
+    stats = check_good(emu, gunzip_oracle, "small_blocks", CASES, chunks=(512,))[0]
+    assert stats["parallel"] > 4 and stats["members"] == 1
+    stats = check_good(emu, gunzip_oracle, "bgzf", CASES, chunks=(1024,))[0]
+    assert stats["parallel"] > 4 and stats["members"] > 4
+    stats = check_good(emu, gunzip_oracle, "gz_in_stored", CASES, chunks=(512,))[0]
+    assert stats["dropped"] > 0
+
+
+def test_compress_gz(emu, oracle, sample_fq):
+    from tests.fastq_cases import rand_fastq
+
+    check_compress_gz(emu, oracle, sample_fq)
+    check_compress_gz(emu, oracle, rand_fastq(150, 9, lmin=30, lmax=120), chunk=1024)
+    check_compress_gz(emu, oracle, rand_fastq(150, 10, lmin=30, lmax=120), bgzf_block=2000, chunk=1024)
