@@ -68,9 +68,10 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     }
     u64 ch = c->opt_gz_chunk_bytes;
     if (!ch) {
-        ch = n / ((u64)c->sm_count * 16u);
+        // a warp decodes one chunk; restart points only exist at block boundaries (every 20-60 KB of a zlib stream)
+        ch = n / ((u64)c->sm_count * 32u);
         ch = (ch + 4095u) & ~(u64)4095u;
-        ch = std::min<u64>(std::max<u64>(ch, 65536u), (u64)4 << 20);
+        ch = std::min<u64>(std::max<u64>(ch, 32768u), (u64)4 << 20);
     }
     while ((n + ch - 1) / ch > 32768u) ch *= 2;
     if (ch >= ((u64)1 << 31)) return FQZ_E_TOO_LARGE;

@@ -314,13 +314,40 @@ __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_find(GzArgs a) {
         }
     }
     if (!a.bgzf_only) {
+        // block headers: any bit.  1024 positions per step, 32 contiguous ones per lane: first the 13 header bits that
+        // every lane can test without diverging (BFINAL 0, BTYPE 2, HLIT <= 29, HDIST <= 29: one position in nine
+        // survives), then the full probe of the survivors
         const u64 lim = min(best, hi * 8);
-        for (u64 base = lo * 8; base < lim; base += 32) {  // block headers: any bit
-            u64 p = base + lane;
-            bool ok = p < lim && gz_probe_dynamic(a.src, a.n, p);
-            u32 m = __ballot_sync(GZ_FULL, ok);
-            if (m) {
-                best = base + (u32)(__ffs((int)m) - 1);
+        for (u64 base = lo * 8; base < lim; base += 1024) {
+            const u64 p0 = base + (u64)lane * 32u;
+            const u64 wi = p0 >> 5;
+            const u32 sh = (u32)(p0 & 31u);
+            const u32 w0 = gz_word(a.src, a.n, wi), w1 = gz_word(a.src, a.n, wi + 1), w2 = gz_word(a.src, a.n, wi + 2);
+            const u64 v = ((u64)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);  // bits p0 .. p0 + 63
+            u32 cand = 0;
+#pragma unroll
+            for (u32 j = 0; j < 32; j++) {
+                const u32 x = (u32)(v >> j);
+                const bool ok = (x & 7u) == 4u && ((x >> 3) & 31u) <= 29u && ((x >> 8) & 31u) <= 29u;
+                cand |= (ok ? 1u : 0u) << j;
+            }
+            if (p0 >= lim)
+                cand = 0;
+            else if (lim - p0 < 32)
+                cand &= (1u << (u32)(lim - p0)) - 1u;
+            u32 hit = 32;
+            while (cand) {
+                const u32 j = (u32)__ffs((int)cand) - 1u;
+                cand &= cand - 1u;
+                if (gz_probe_dynamic(a.src, a.n, p0 + j)) {
+                    hit = j;
+                    break;
+                }
+            }
+            const u32 m = __ballot_sync(GZ_FULL, hit < 32u);
+            if (m) {  // lanes hold ascending positions: the first lane with a hit holds the first header
+                const int l = __ffs((int)m) - 1;
+                best = base + (u64)l * 32u + __shfl_sync(GZ_FULL, hit, l);
                 type = GZ_AT_BLOCK;
                 break;
             }
@@ -710,30 +737,49 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
 // One CTA, chunk after chunk in stream order: the window of a chunk that starts at a block header is the last
 // 32 KiB in front of it = the tail of the previous chunk (its markers resolved through ITS window) behind what is
 // left of that window.
-__global__ void __launch_bounds__(1024) k_gz_windows(GzArgs a) {
+struct GzWinStep {
+    u32 type, slot, pslot;
+    u64 poff, plen;
+};
+__device__ __forceinline__ GzWinStep gz_win_step(const GzArgs &a, u32 i) {
+    const GzChunk &C = a.chunks[a.list[i]];
+    const GzChunk &P = a.chunks[a.list[i - 1]];
+    GzWinStep s;
+    s.type = C.start_type;
+    s.slot = C.win_slot;
+    s.pslot = P.win_slot;
+    s.poff = P.out_off;
+    s.plen = P.out_len;
+    return s;
+}
+#define GZ_WIN_THREADS 1024u
+#define GZ_WIN_BATCH 8u
+__global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_windows(GzArgs a) {
+    // the steps form one serial chain: the descriptor of the next step is loaded while this one runs, and every
+    // thread keeps eight of its 32 elements in flight per round trip to L2
+    GzWinStep nx = gz_win_step(a, 1);
     for (u32 i = 1; i < a.nlist; i++) {
-        const GzChunk &C = a.chunks[a.list[i]];
-        if (C.start_type != GZ_AT_BLOCK) continue;
-        const GzChunk &P = a.chunks[a.list[i - 1]];
-        u8 *win = a.win + (size_t)C.win_slot * GZ_WINDOW;
-        const u8 *pwin = a.win + (size_t)P.win_slot * GZ_WINDOW;
-        const u16 *psym = a.sym + P.out_off;
-        const u64 plen = P.out_len;
-        for (u32 t = threadIdx.x; t < GZ_WINDOW; t += blockDim.x) {
-            u8 v;
-            if (plen >= GZ_WINDOW) {
-                u16 s = psym[plen - GZ_WINDOW + t];
-                v = s < 256u ? (u8)s : pwin[s - 256u];
-            } else {
-                const u32 keep = GZ_WINDOW - (u32)plen;  // bytes of the previous window still in reach
-                if (t < keep)
-                    v = pwin[t + (u32)plen];
-                else {
-                    u16 s = psym[t - keep];
-                    v = s < 256u ? (u8)s : pwin[s - 256u];
-                }
+        const GzWinStep cur = nx;
+        if (i + 1 < a.nlist) nx = gz_win_step(a, i + 1);
+        if (cur.type != GZ_AT_BLOCK) continue;
+        u8 *win = a.win + (size_t)cur.slot * GZ_WINDOW;
+        const u8 *pwin = a.win + (size_t)cur.pslot * GZ_WINDOW;
+        const u16 *psym = a.sym + cur.poff;
+        const u64 plen = cur.plen;
+        const u32 keep = plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)plen;  // bytes of the previous window still in reach
+        const u16 *tail = psym + (plen >= GZ_WINDOW ? plen - GZ_WINDOW : 0u);
+        for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
+            u32 s[GZ_WIN_BATCH];
+#pragma unroll
+            for (u32 k = 0; k < GZ_WIN_BATCH; k++) {
+                const u32 t = b + k * GZ_WIN_THREADS + threadIdx.x;
+                s[k] = t < keep ? 256u + t + (u32)plen : (u32)tail[t - keep];
             }
-            win[t] = v;
+#pragma unroll
+            for (u32 k = 0; k < GZ_WIN_BATCH; k++)
+                if (s[k] >= 256u) s[k] = pwin[s[k] - 256u];
+#pragma unroll
+            for (u32 k = 0; k < GZ_WIN_BATCH; k++) win[b + k * GZ_WIN_THREADS + threadIdx.x] = (u8)s[k];
         }
         __syncthreads();
     }
@@ -846,7 +892,7 @@ void fqz_launch_gz_decode(const GzArgs &a, bool write, cudaStream_t s) {
 }
 void fqz_launch_gz_windows(const GzArgs &a, cudaStream_t s) {
     if (a.nlist < 2) return;
-    FQZ_LAUNCH(k_gz_windows, 1, 1024, 0, s, a);
+    FQZ_LAUNCH(k_gz_windows, 1, GZ_WIN_THREADS, 0, s, a);
 }
 void fqz_launch_gz_resolve(const GzArgs &a, cudaStream_t s) {
     if (!a.nlist) return;
