@@ -208,14 +208,21 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     }
     if (d_text) *d_text = out;
     u16 *d_sym = (u16 *)c->arena.alloc((size_t)total * 2 + 64);
-    u8 *d_win = (u8 *)c->arena.alloc((size_t)slots * GZ_WINDOW);
+    // windows: groups of ~sqrt(chunks) chunks (fqz_inflate.cu, k_gz_maps)
+    u32 gsize = 1;
+    while ((u64)gsize * gsize < chain.size()) gsize++;
+    const u32 ngroups = (u32)((chain.size() + gsize - 1) / gsize);
+    u8 *d_win = (u8 *)c->arena.alloc((size_t)ngroups * GZ_WINDOW);
+    u16 *d_maps = slots > 1 ? (u16 *)c->arena.alloc((size_t)chain.size() * GZ_WINDOW * sizeof(u16)) : nullptr;
     GzMember *d_mem = (GzMember *)c->arena.alloc(((size_t)nm + 1) * sizeof(GzMember));
-    if (!d_sym || !d_win || !d_mem) {
+    if (!d_sym || !d_win || !d_mem || (slots > 1 && !d_maps)) {
         c->err = "arena: out of device memory (gzip output)";
         return FQZ_E_CUDA;
     }
     a.sym = d_sym;
     a.win = d_win;
+    a.maps = d_maps;
+    a.gsize = gsize;
     a.out = out;
     a.members = d_mem;
     a.nmembers = nm;
@@ -225,7 +232,6 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     FQZ_TRY(fqz_pin_copy(c, d_chunks, h, chunks_b));
     FQZ_TRY(fqz_pin_copy(c, d_list, hlist, chain.size() * sizeof(u32)));
     FQZ_TRY(fqz_pin_copy(c, d_err, herr, sizeof(unsigned long long)));
-    FQZ_CUDA_TRY(c, cudaMemsetAsync(d_win, 0, GZ_WINDOW, s));
     {
         StageScope sc(c, ST_GZ_DECODE, n + 2 * total);
         fqz_launch_gz_decode(a, true, s);

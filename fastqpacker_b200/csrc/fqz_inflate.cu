@@ -7,14 +7,16 @@
 //   k_gz_find     the compressed bytes are cut into chunks; for every chunk one warp looks for the first place a
 //                 decoder can restart: a BGZF member header (byte aligned, empty window) or the header of a
 //                 non-final dynamic-Huffman block (any bit offset; the 32 KiB window in front of it is unknown).
-//   k_gz_decode   one warp per chunk decodes from its restart point to the next chunk's.  Lane 0 walks the bit
-//                 stream, 32 symbols at a time; the warp writes the literals and copies the matches.  Output is
+//   k_gz_decode   one warp per chunk decodes from its restart point to the next chunk's.  The bit stream is walked by
+//                 the whole warp (every lane decodes the token that would start at its bit, the chain through them
+//                 is followed with shuffles), up to 32 tokens per step; the warp writes the literals and copies the
+//                 matches.  Output is
 //                 16-bit: a byte, or 256 + i for "byte i of the window I could not see".  Runs twice: a counting
 //                 pass (sizes, member boundaries, proof that every chunk lands exactly on the next restart point —
 //                 a restart point nobody lands on was a false positive and its chunk is merged into the one in
 //                 front), then the writing pass at the final offsets.
-//   k_gz_windows  serial over the chunks (one CTA, 32 KiB per step): the window in front of chunk k is the resolved
-//                 tail of chunk k-1.
+//   k_gz_maps,    the window in front of chunk k is the resolved tail of chunk k-1: a serial chain, cut into
+//   k_gz_bases    ~sqrt(chunks) groups (windows as maps of the group's base window, then the base windows in order).
 //   k_gz_resolve  every symbol becomes a byte: out[p] = sym < 256 ? sym : window[sym - 256].  Parallel, HBM bound.
 //   k_gz_crc      CRC-32 of every member from 2 KiB pieces: a piece's raw CRC is shifted to the member's end
 //                 (multiplication by x^(8 * bytes behind it) mod P) and XORed into the member's accumulator.
@@ -27,11 +29,6 @@
 #define GZ_LL_BITS 10
 #define GZ_D_BITS 8
 
-static __constant__ u16 kGzLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-static __constant__ u8 kGzLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-static __constant__ u16 kGzDistBase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
-                                           193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-static __constant__ u8 kGzDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static __constant__ u8 kGzClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // ---------------------------------------------------------------------------------- bit reader (LSB first)
@@ -413,74 +410,105 @@ __device__ u32 gz_dyn_lengths(GzBits &br, GzSm &S, u32 total) {
     return 0;
 }
 
-// lane 0: up to 32 symbols of a compressed block into S.q (literal: value; match: length << 16 | distance).
-// avail = bytes a match may reach back.  Returns the count; *flags bit 0 = end of block, bits 8.. = error status.
-__device__ u32 gz_symbols(GzBits &br, GzSm &S, u64 nbits, u64 avail, u32 *bytes, u32 *flags) {
-    u32 cnt = 0, produced = 0, fl = 0;
-    while (cnt < 32u) {
-        br.refill();
-        u32 e = S.lut_ll[br.peek(GZ_LL_BITS)], sym, len;
-        if (e) {
-            sym = e >> 4;
-            len = e & 15u;
-        } else {
-            int s = gz_canon(S.cnt_ll, S.sym_ll, br.peek(15), 15, &len);
-            if (s < 0) {
-                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
-                break;
-            }
-            sym = (u32)s;
-        }
-        br.drop(len);
-        if (sym < 256u) {
-            S.q[cnt++] = sym;
-            produced++;
-        } else if (sym == 256u) {
-            fl = 1;
-            if (br.pos() > nbits) fl = GZ_ST_ERR_TRUNC << 8;
-            break;
-        } else {
-            if (sym >= 286u) {
-                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
-                break;
-            }
-            u32 ml = kGzLenBase[sym - 257u] + br.take(kGzLenExtra[sym - 257u]);
-            br.refill();
-            u32 d = S.lut_d[br.peek(GZ_D_BITS)], ds, dl;
-            if (d) {
-                ds = d >> 4;
-                dl = d & 15u;
+// Whole warp: up to 32 tokens of a compressed block from bit *pos on into S.q (literal: value; match: length << 16 |
+// distance).  A single thread walks a DEFLATE stream at ~400 cycles per token on this machine, so the walk is spread
+// over the lanes: lane i decodes the complete token that WOULD start at bit *pos + i (literal/length code, extra
+// bits, distance code, extra bits: at most 48 bits), then the real chain is followed through the 32 candidates with
+// one shuffle per token — the lanes that were not token starts decoded garbage that nobody reads.
+// Returns the count; *flags bit 0 = end of block, bits 8.. = error status; *pos is moved behind what was taken.
+__device__ u32 gz_tokens(const u32 *w, u64 n, GzSm &S, u64 nbits, u64 *pos, u32 *flags) {
+    const u32 lane = lane_id();
+    u64 P = *pos;
+    u32 cnt = 0, fl = 0;
+    while (cnt < 32u && !fl) {
+        const u64 off = P + lane;
+        const u64 wi = off >> 5;
+        const u32 sh = (u32)(off & 31u);
+        const u32 w0 = gz_word(w, n, wi), w1 = gz_word(w, n, wi + 1), w2 = gz_word(w, n, wi + 2);
+        u64 v = ((u64)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);  // bits off .. off + 63
+        u32 used, tok = 0, kind = 0;  // kind: 0 literal / match, 1 end of block, 2 no such code
+        {
+            u32 e = S.lut_ll[(u32)v & ((1u << GZ_LL_BITS) - 1u)], sym = 0, len = 0;
+            if (e) {
+                sym = e >> 4;
+                len = e & 15u;
             } else {
-                int s = gz_canon(S.cnt_d, S.sym_d, br.peek(15), 15, &dl);
-                if (s < 0) {
-                    fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
-                    break;
+                int c = gz_canon(S.cnt_ll, S.sym_ll, (u32)v & 0x7fffu, 15, &len);
+                if (c < 0) {
+                    kind = 2;
+                    len = 1;
+                } else
+                    sym = (u32)c;
+            }
+            v >>= len;
+            used = len;
+            if (kind == 0) {
+                if (sym < 256u)
+                    tok = sym;
+                else if (sym == 256u)
+                    kind = 1;
+                else if (sym >= 286u)
+                    kind = 2;
+                else {
+                    // length: 257..264 -> 3..10; 265..284 -> groups of four with 1..5 extra bits; 285 -> 258
+                    u32 eb = 0, ml = sym - 254u;
+                    if (sym == 285u)
+                        ml = 258u;
+                    else if (sym >= 265u) {
+                        eb = (sym - 261u) >> 2;
+                        ml = ((4u + ((sym - 261u) & 3u)) << eb) + 3u + ((u32)v & ((1u << eb) - 1u));
+                    }
+                    v >>= eb;
+                    used += eb;
+                    u32 d = S.lut_d[(u32)v & ((1u << GZ_D_BITS) - 1u)], ds = 0, dl = 0;
+                    if (d) {
+                        ds = d >> 4;
+                        dl = d & 15u;
+                    } else {
+                        int c = gz_canon(S.cnt_d, S.sym_d, (u32)v & 0x7fffu, 15, &dl);
+                        if (c < 0) {
+                            kind = 2;
+                            dl = 1;
+                        } else
+                            ds = (u32)c;
+                    }
+                    v >>= dl;
+                    used += dl;
+                    if (ds >= 30u) kind = 2;
+                    // distance: 0..3 -> 1..4; then pairs with 1..13 extra bits
+                    u32 de = 0, dist = ds + 1u;
+                    if (ds >= 4u && ds < 30u) {
+                        de = (ds >> 1) - 1u;
+                        dist = ((2u + (ds & 1u)) << de) + 1u + ((u32)v & ((1u << de) - 1u));
+                    }
+                    used += de;
+                    tok = (ml << 16) | dist;
                 }
-                ds = (u32)s;
             }
-            br.drop(dl);
-            if (ds >= 30u) {
-                fl = (br.pos() > nbits ? GZ_ST_ERR_TRUNC : GZ_ST_ERR_CORRUPT) << 8;
-                break;
-            }
-            u32 dist = kGzDistBase[ds] + br.take(kGzDistExtra[ds]);
-            if (br.pos() > nbits) {
+        }
+        u32 cur = 0;  // the same in every lane
+        while (cur < 32u && cnt < 32u) {
+            const u32 u = __shfl_sync(GZ_FULL, used, (int)cur), k = __shfl_sync(GZ_FULL, kind, (int)cur);
+            if (P + cur + u > nbits) {  // Go runs out of input before it can see what the zero padding decodes to
                 fl = GZ_ST_ERR_TRUNC << 8;
                 break;
             }
-            if ((u64)dist > avail + produced) {  // reaches in front of the member (Go: dist > histSize)
+            if (k == 2u) {
                 fl = GZ_ST_ERR_CORRUPT << 8;
                 break;
             }
-            S.q[cnt++] = (ml << 16) | dist;
-            produced += ml;
+            if (k == 1u) {
+                cur += u;
+                fl = 1;
+                break;
+            }
+            if (lane == cur) S.q[cnt] = tok;
+            cnt++;
+            cur += u;
         }
-        if (br.pos() > nbits) {
-            fl = GZ_ST_ERR_TRUNC << 8;
-            break;
-        }
+        P += cur;
     }
-    *bytes = produced;
+    *pos = P;
     *flags = fl;
     return cnt;
 }
@@ -627,23 +655,39 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                 errbit = rc == GZ_ST_ERR_TRUNC ? nbits : pos;
                 break;
             }
-            // ---- symbols, 32 at a time
+            // ---- tokens, up to 32 at a time
+            {
+                u64 p = 0;
+                if (lane == 0) p = br.pos();
+                pos = __shfl_sync(GZ_FULL, p, 0);
+            }
             for (;;) {
-                u32 cnt = 0, bytes = 0, fl = 0;
-                if (lane == 0) cnt = gz_symbols(br, S, nbits, known ? produced - member_from : produced + GZ_WINDOW, &bytes, &fl);
+                u32 fl = 0;
+                u32 cnt = gz_tokens(a.src, n, S, nbits, &pos, &fl);
                 __syncwarp();
-                cnt = __shfl_sync(GZ_FULL, cnt, 0);
-                bytes = __shfl_sync(GZ_FULL, bytes, 0);
-                fl = __shfl_sync(GZ_FULL, fl, 0);
+                const u32 e = lane < cnt ? S.q[lane] : 0u;
+                u32 mlen = e >> 16;
+                const u32 dist = e & 0xffffu;
+                u32 len = lane < cnt ? (mlen ? mlen : 1u) : 0u;
+                u32 incl = group_incl_scan(len, GZ_FULL, 32);
+                const u32 o = incl - len;
+                // a match that reaches in front of its member (Go: dist > histSize): the step ends in front of it
+                const u64 avail = known ? produced - member_from : produced + GZ_WINDOW;
+                const u32 bad = __ballot_sync(GZ_FULL, mlen != 0u && (u64)dist > avail + o);
+                if (bad) {
+                    cnt = (u32)__ffs((int)bad) - 1u;
+                    fl = GZ_ST_ERR_CORRUPT << 8;
+                    if (lane >= cnt) {
+                        len = 0;
+                        mlen = 0;
+                    }
+                    incl = group_incl_scan(len, GZ_FULL, 32);
+                }
+                const u32 bytes = __shfl_sync(GZ_FULL, incl, 31);
                 if (WRITE) {
-                    const u32 e = lane < cnt ? S.q[lane] : 0u;
-                    const u32 mlen = e >> 16;
-                    const u32 len = lane < cnt ? (mlen ? mlen : 1u) : 0u;
-                    const u32 o = group_incl_scan(len, GZ_FULL, 32) - len;
                     if (lane < cnt && !mlen) out[produced + o] = (u16)e;
-                    // short matches whose source lies in front of this batch do not depend on anything the batch
+                    // short matches whose source lies in front of this step do not depend on anything the step
                     // writes: every lane copies its own, four loads in flight per round trip to L2
-                    const u32 dist = e & 0xffffu;
                     const bool indep = mlen != 0u && mlen <= 32u && dist >= o + mlen;
                     if (indep) {
                         const long long s0 = (long long)(produced + o) - (long long)dist;
@@ -675,6 +719,7 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                         __syncwarp();
                     }
                 }
+                __syncwarp();  // S.q is rewritten by the next step
                 produced += bytes;
                 if (fl >> 8) {
                     status = fl >> 8;
@@ -683,14 +728,10 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                 if (fl & 1u) break;
             }
             if (status) {
-                u64 p = 0;
-                if (lane == 0) p = br.pos();
-                errbit = status == GZ_ST_ERR_TRUNC ? nbits : __shfl_sync(GZ_FULL, p, 0);
+                errbit = status == GZ_ST_ERR_TRUNC ? nbits : pos;
                 break;
             }
-            u64 p = 0;
-            if (lane == 0) p = br.pos();
-            pos = __shfl_sync(GZ_FULL, p, 0);
+            if (lane == 0) br.seek(pos);
         }
         if (bfinal) {  // trailer: CRC-32, ISIZE
             const u64 at = (pos + 7u) >> 3;
@@ -733,73 +774,117 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
     }
 }
 
-// ---------------------------------------------------------------------------------- k_gz_windows
-// One CTA, chunk after chunk in stream order: the window of a chunk that starts at a block header is the last
-// 32 KiB in front of it = the tail of the previous chunk (its markers resolved through ITS window) behind what is
-// left of that window.
+// ---------------------------------------------------------------------------------- k_gz_maps, k_gz_bases, k_gz_resolve
+// The window in front of a chunk that starts at a block header is the last 32 KiB in front of it: the tail of the
+// previous chunk, with ITS markers resolved through ITS window, behind what is left of that window — one serial chain
+// over all chunks.  It is cut into groups of ~sqrt(chunks): inside a group every window is kept as a MAP of the
+// group's base window (entry < 256: a byte; else 256 + index into the base window), built chunk after chunk by one CTA
+// per group (k_gz_maps); the base windows are then resolved group after group by one CTA (k_gz_bases); k_gz_resolve
+// looks a marker up through its chunk's map and its group's base window.  2 sqrt(chunks) serial steps instead of chunks.
+#define GZ_WIN_THREADS 1024u
+#define GZ_WIN_BATCH 8u
 struct GzWinStep {
-    u32 type, slot, pslot;
+    u32 type;
     u64 poff, plen;
 };
 __device__ __forceinline__ GzWinStep gz_win_step(const GzArgs &a, u32 i) {
-    const GzChunk &C = a.chunks[a.list[i]];
-    const GzChunk &P = a.chunks[a.list[i - 1]];
     GzWinStep s;
-    s.type = C.start_type;
-    s.slot = C.win_slot;
-    s.pslot = P.win_slot;
+    s.type = a.chunks[a.list[i]].start_type;
+    const GzChunk &P = a.chunks[a.list[i ? i - 1 : 0]];
     s.poff = P.out_off;
     s.plen = P.out_len;
     return s;
 }
-#define GZ_WIN_THREADS 1024u
-#define GZ_WIN_BATCH 8u
-__global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_windows(GzArgs a) {
-    // the steps form one serial chain: the descriptor of the next step is loaded while this one runs, and every
-    // thread keeps eight of its 32 elements in flight per round trip to L2
-    GzWinStep nx = gz_win_step(a, 1);
-    for (u32 i = 1; i < a.nlist; i++) {
+// element t of the window behind the previous chunk (tail = its last symbols, plen of them if fewer than 32 Ki):
+// a symbol of that chunk, or — 256 + index — a byte of the previous chunk's own window
+__device__ __forceinline__ u32 gz_win_src(const u16 *tail, u32 keep, u32 plen, u32 t) {
+    return t < keep ? 256u + t + plen : (u32)tail[t - keep];
+}
+__global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_maps(GzArgs a) {
+    const u32 first = blockIdx.x * a.gsize, last = min(a.nlist, first + a.gsize);
+    GzWinStep nx = gz_win_step(a, first);
+    for (u32 i = first; i < last; i++) {
         const GzWinStep cur = nx;
-        if (i + 1 < a.nlist) nx = gz_win_step(a, i + 1);
-        if (cur.type != GZ_AT_BLOCK) continue;
-        u8 *win = a.win + (size_t)cur.slot * GZ_WINDOW;
-        const u8 *pwin = a.win + (size_t)cur.pslot * GZ_WINDOW;
-        const u16 *psym = a.sym + cur.poff;
-        const u64 plen = cur.plen;
-        const u32 keep = plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)plen;  // bytes of the previous window still in reach
-        const u16 *tail = psym + (plen >= GZ_WINDOW ? plen - GZ_WINDOW : 0u);
-        for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
-            u32 s[GZ_WIN_BATCH];
+        if (i + 1 < last) nx = gz_win_step(a, i + 1);
+        u16 *M = a.maps + (size_t)i * GZ_WINDOW;
+        if (cur.type != GZ_AT_BLOCK) {  // starts at a member header: nothing in front of it can be referenced
+            for (u32 t = threadIdx.x; t < GZ_WINDOW; t += GZ_WIN_THREADS) M[t] = 0;
+        } else if (i == first) {  // its window IS the group's base window
+            for (u32 t = threadIdx.x; t < GZ_WINDOW; t += GZ_WIN_THREADS) M[t] = (u16)(256u + t);
+        } else {
+            const u16 *Mp = M - GZ_WINDOW;
+            const u32 keep = cur.plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)cur.plen;
+            const u16 *tail = a.sym + cur.poff + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
+            for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
+                u32 s[GZ_WIN_BATCH];
 #pragma unroll
-            for (u32 k = 0; k < GZ_WIN_BATCH; k++) {
-                const u32 t = b + k * GZ_WIN_THREADS + threadIdx.x;
-                s[k] = t < keep ? 256u + t + (u32)plen : (u32)tail[t - keep];
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++) s[k] = gz_win_src(tail, keep, (u32)min(cur.plen, (u64)GZ_WINDOW), b + k * GZ_WIN_THREADS + threadIdx.x);
+#pragma unroll
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++)
+                    if (s[k] >= 256u) s[k] = Mp[s[k] - 256u];
+#pragma unroll
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++) M[b + k * GZ_WIN_THREADS + threadIdx.x] = (u16)s[k];
             }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_bases(GzArgs a) {
+    const u32 ngroups = (a.nlist + a.gsize - 1) / a.gsize;
+    for (u32 t = threadIdx.x; t < GZ_WINDOW; t += GZ_WIN_THREADS) a.win[t] = 0;  // group 0 starts the file
+    __syncthreads();
+    GzWinStep nx = gz_win_step(a, min(a.gsize, a.nlist - 1));
+    for (u32 g = 1; g < ngroups; g++) {
+        const u32 first = g * a.gsize;
+        const GzWinStep cur = nx;
+        if (g + 1 < ngroups) nx = gz_win_step(a, first + a.gsize);
+        u8 *B = a.win + (size_t)g * GZ_WINDOW;
+        if (cur.type != GZ_AT_BLOCK) {
+            for (u32 t = threadIdx.x; t < GZ_WINDOW; t += GZ_WIN_THREADS) B[t] = 0;
+        } else {
+            const u8 *Bp = B - GZ_WINDOW;
+            const u16 *Mp = a.maps + (size_t)(first - 1) * GZ_WINDOW;
+            const u32 keep = cur.plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)cur.plen;
+            const u16 *tail = a.sym + cur.poff + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
+            for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
+                u32 s[GZ_WIN_BATCH];
 #pragma unroll
-            for (u32 k = 0; k < GZ_WIN_BATCH; k++)
-                if (s[k] >= 256u) s[k] = pwin[s[k] - 256u];
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++) s[k] = gz_win_src(tail, keep, (u32)min(cur.plen, (u64)GZ_WINDOW), b + k * GZ_WIN_THREADS + threadIdx.x);
 #pragma unroll
-            for (u32 k = 0; k < GZ_WIN_BATCH; k++) win[b + k * GZ_WIN_THREADS + threadIdx.x] = (u8)s[k];
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++)
+                    if (s[k] >= 256u) s[k] = Mp[s[k] - 256u];
+#pragma unroll
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++)
+                    if (s[k] >= 256u) s[k] = Bp[s[k] - 256u];
+#pragma unroll
+                for (u32 k = 0; k < GZ_WIN_BATCH; k++) B[b + k * GZ_WIN_THREADS + threadIdx.x] = (u8)s[k];
+            }
         }
         __syncthreads();
     }
 }
 
-// ---------------------------------------------------------------------------------- k_gz_resolve
 __global__ void __launch_bounds__(256) k_gz_resolve(GzArgs a) {
-    const GzChunk &C = a.chunks[a.list[blockIdx.y]];
+    const u32 i = blockIdx.y;
+    const GzChunk &C = a.chunks[a.list[i]];
     const u16 *sym = a.sym + C.out_off;
     u8 *out = a.out + C.out_off;
-    const u8 *win = a.win + (size_t)C.win_slot * GZ_WINDOW;
-    const u32 first_valid = GZ_WINDOW - C.window_valid;
     const bool has_window = C.start_type == GZ_AT_BLOCK;
+    const u16 *M = has_window ? a.maps + (size_t)i * GZ_WINDOW : nullptr;
+    const u8 *B = has_window ? a.win + (size_t)(i / a.gsize) * GZ_WINDOW : nullptr;
+    const u32 first_valid = GZ_WINDOW - C.window_valid;
     bool bad = false;
     for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < C.out_len; p += (u64)gridDim.x * blockDim.x) {
         u32 s = sym[p];
         if (s >= 256u) {
             s -= 256u;
-            if (!has_window || s < first_valid) bad = true;  // a match that reaches in front of its member
-            s = win[s];
+            if (!has_window || s < first_valid) {  // a match that reaches in front of its member
+                bad = true;
+                s = 0;
+            } else {
+                s = M[s];
+                if (s >= 256u) s = B[s - 256u];
+            }
         }
         out[p] = (u8)s;
     }
@@ -891,8 +976,10 @@ void fqz_launch_gz_decode(const GzArgs &a, bool write, cudaStream_t s) {
         FQZ_LAUNCH(k_gz_decode<false>, grid, GZ_WARPS * 32, 0, s, a);
 }
 void fqz_launch_gz_windows(const GzArgs &a, cudaStream_t s) {
-    if (a.nlist < 2) return;
-    FQZ_LAUNCH(k_gz_windows, 1, GZ_WIN_THREADS, 0, s, a);
+    if (!a.maps) return;  // no chunk starts at a block header: nothing to resolve
+    const u32 ngroups = (a.nlist + a.gsize - 1) / a.gsize;
+    FQZ_LAUNCH(k_gz_maps, ngroups, GZ_WIN_THREADS, 0, s, a);
+    FQZ_LAUNCH(k_gz_bases, 1, GZ_WIN_THREADS, 0, s, a);
 }
 void fqz_launch_gz_resolve(const GzArgs &a, cudaStream_t s) {
     if (!a.nlist) return;

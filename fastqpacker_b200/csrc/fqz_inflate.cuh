@@ -43,7 +43,7 @@ struct GzChunk {
     u32 member_base;   // index of its first member record
     u32 window_valid;  // bytes of the 32 KiB window in front of the chunk that belong to the same member
     u32 prev;          // previous chunk of the chain
-    u32 win_slot;      // index of its window in the window table
+    u32 win_slot;      // (unused)
 };
 
 struct GzMember {
@@ -64,7 +64,9 @@ struct GzArgs {
     u32 nlist;
     u32 bgzf_only;    // k_gz_find: look for BGZF member headers only
     u16 *sym;         // decoded symbols: < 256 a byte, else 256 + index into the chunk's window
-    u8 *win;          // window table, GZ_WINDOW bytes per slot
+    u8 *win;          // base window of every group of chunks, GZ_WINDOW bytes each
+    u16 *maps;        // per chunk of the chain: its window as a map of the group's base window (nullptr: no chunk needs one)
+    u32 gsize;        // chunks per group
     u8 *out;
     GzMember *members;
     u32 nmembers;
