@@ -424,8 +424,19 @@ __device__ u32 gz_tokens(const u32 *w, u64 n, GzSm &S, u64 nbits, u64 *pos, u32 
         const u64 off = P + lane;
         const u64 wi = off >> 5;
         const u32 sh = (u32)(off & 31u);
-        const u32 w0 = gz_word(w, n, wi), w1 = gz_word(w, n, wi + 1), w2 = gz_word(w, n, wi + 2);
+        u32 w0, w1, w2;
+        if ((P >> 3) + 20 <= n) {  // the words of every lane lie inside the input (the same test in all lanes)
+            w0 = w[wi];
+            w1 = w[wi + 1];
+            w2 = w[wi + 2];
+        } else {
+            w0 = gz_word(w, n, wi);
+            w1 = gz_word(w, n, wi + 1);
+            w2 = gz_word(w, n, wi + 2);
+        }
         u64 v = ((u64)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);  // bits off .. off + 63
+        const u64 left = nbits > P ? nbits - P : 0ull;
+        const u32 room = left > 0xffffu ? 0xffffu : (u32)left;  // bits of input behind P, as far as this step can care
         u32 used, tok = 0, kind = 0;  // kind: 0 literal / match, 1 end of block, 2 no such code
         {
             u32 e = S.lut_ll[(u32)v & ((1u << GZ_LL_BITS) - 1u)], sym = 0, len = 0;
@@ -489,7 +500,7 @@ __device__ u32 gz_tokens(const u32 *w, u64 n, GzSm &S, u64 nbits, u64 *pos, u32 
         u32 cur = 0;  // the same in every lane
         while (cur < 32u && cnt < 32u) {
             const u32 u = __shfl_sync(GZ_FULL, used, (int)cur), k = __shfl_sync(GZ_FULL, kind, (int)cur);
-            if (P + cur + u > nbits) {  // Go runs out of input before it can see what the zero padding decodes to
+            if (cur + u > room) {  // Go runs out of input before it can see what the zero padding decodes to
                 fl = GZ_ST_ERR_TRUNC << 8;
                 break;
             }

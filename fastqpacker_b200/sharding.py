@@ -91,8 +91,10 @@ def slice_bounds(n: int, world: int) -> List[Tuple[int, int]]:
     return [(n * r // world, n * (r + 1) // world) for r in range(world)]
 
 
-def plan_compress(newline_positions_per_slice: Sequence[Sequence[int]], n: int, world: int) -> List[Tuple[int, int]]:
-    """Block-aligned byte ranges per rank.
+def plan_compress(newline_positions_per_slice: Sequence[Sequence[int]], n: int, world: int,
+                  bounds: Sequence[Tuple[int, int]] | None = None) -> List[Tuple[int, int]]:
+    """Block-aligned byte ranges per rank.  `bounds`: the slices the ranks hold when they are not the even ones
+    of `slice_bounds` (a BGZF input is cut on member boundaries, `plan_bgzf`).
 
     newline_positions_per_slice[r] holds, for slice r, the absolute offsets of the newlines that end a
     block (every 400 000th newline of the file), which rank r can compute from its local count and the
@@ -102,7 +104,7 @@ def plan_compress(newline_positions_per_slice: Sequence[Sequence[int]], n: int, 
     cuts = sorted(p + 1 for ps in newline_positions_per_slice for p in ps)  # first byte after each full block
     cuts = [c for c in cuts if c < n]
     starts = [0] + cuts  # block starts
-    bounds = slice_bounds(n, world)
+    bounds = list(bounds) if bounds is not None else slice_bounds(n, world)
     plan = []
     for r, (a, b) in enumerate(bounds):
         mine = [s for s in starts if a <= s < b]
@@ -124,6 +126,74 @@ def block_cut_candidates(local_newlines: Sequence[int], lines_before: int) -> Li
     while k <= len(local_newlines):
         out.append(local_newlines[k - 1])
         k += LINES_PER_BLOCK
+    return out
+
+
+# ---------------------------------------------------------------------------------- gzip input over several GPUs
+# A plain gzip member is one serial chain and goes to ONE GPU whole (fqz_compress_gz).  A BGZF file (bgzip, the
+# usual container of large FASTQ) is a sequence of independent members that each say how large they are (BSIZE in
+# the 'BC' extra field) and how much text they hold (ISIZE in the trailer): it can be cut between members and the
+# text offset of every cut is known without inflating anything.  Every rank inflates its run of members on its GPU
+# (fqz_gunzip_device) and owns that slice of the text; from there on the flow is the one of a plain-text input
+# (newline counts, block cuts, plan_compress with these slices as `bounds`).
+@dataclass
+class BgzfMember:
+    offset: int  # of the member header in the file
+    size: int  # BSIZE + 1
+    text_offset: int  # of its first byte in the inflated text
+    text_size: int  # ISIZE
+
+
+def walk_bgzf(gz: bytes) -> List[BgzfMember]:
+    """Members of a BGZF file, hopping from header to header (SAM spec 4.1).  ValueError for anything else."""
+    out, pos, text = [], 0, 0
+    n = len(gz)
+    while pos < n:
+        if n - pos < 18 or gz[pos : pos + 4] != b"\x1f\x8b\x08\x04":
+            raise ValueError(f"not a BGZF member at offset {pos}")
+        xlen = gz[pos + 10] | (gz[pos + 11] << 8)
+        q, end, bsize = pos + 12, pos + 12 + xlen, None
+        while q + 4 <= end:
+            slen = gz[q + 2] | (gz[q + 3] << 8)
+            if gz[q : q + 2] == b"BC" and slen == 2:
+                bsize = gz[q + 4] | (gz[q + 5] << 8)
+            q += 4 + slen
+        if bsize is None or pos + bsize + 1 > n or bsize + 1 < 12 + xlen + 8:
+            raise ValueError(f"not a BGZF member at offset {pos}")
+        size = bsize + 1
+        isize = struct.unpack_from("<I", gz, pos + size - 4)[0]
+        out.append(BgzfMember(pos, size, text, isize))
+        pos += size
+        text += isize
+    return out
+
+
+def plan_bgzf(members: Sequence[BgzfMember], world: int) -> List[Tuple[int, int]]:
+    """Contiguous [first, last) member ranges per rank, balanced by bytes of TEXT."""
+    total = sum(m.text_size for m in members)
+    plan, first, acc = [], 0, 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        last = first
+        while last < len(members) and (acc + members[last].text_size / 2 <= target or r == world - 1):
+            acc += members[last].text_size
+            last += 1
+        plan.append((first, last))
+        first = last
+    return plan
+
+
+def bgzf_slices(members: Sequence[BgzfMember], plan: Sequence[Tuple[int, int]]) -> List[Tuple[Tuple[int, int], Tuple[int, int]]]:
+    """Per rank: (byte range of its members in the file, byte range of their text)."""
+    out = []
+    end_file = members[-1].offset + members[-1].size if members else 0
+    end_text = members[-1].text_offset + members[-1].text_size if members else 0
+    for first, last in plan:
+        fa = members[first].offset if first < len(members) else end_file
+        ta = members[first].text_offset if first < len(members) else end_text
+        fb = members[last].offset if last < len(members) else end_file
+        tb = members[last].text_offset if last < len(members) else end_text
+        out.append(((fa, fb), (ta, tb)))
     return out
 
 

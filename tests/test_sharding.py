@@ -94,3 +94,80 @@ def test_plan_decompress_balances_and_covers():
         sharding.walk_container(b"FQX\x00" + fqz[4:])
     with pytest.raises(ValueError):
         sharding.walk_container(fqz[:-5])
+
+
+def _bgzf_worker(rank, world, port, tmp):
+    """One BGZF input over two ranks: members are cut between ranks from their headers alone, every rank inflates its
+    own run (gunzip oracle here, fqz_gunzip_device on the GPU) and the block planning runs on those slices."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import fqz_oracle as oracle
+    from oracle import gunzip_oracle
+    from tests.gzip_cases import bgzf
+
+    text = _text().tobytes()
+    n = len(text)
+    gz = bgzf(text, block=65280, level=1)
+    members = sharding.walk_bgzf(gz)
+    assert sum(m.text_size for m in members) == n and members[-1].text_size == 0  # the EOF block
+    plan_m = sharding.plan_bgzf(members, world)
+    slices = sharding.bgzf_slices(members, plan_m)
+    (fa, fb), (a, b) = slices[rank]
+    mine = gunzip_oracle.gunzip(gz[fa:fb]) if fb > fa else b""  # this rank's members only
+    assert mine == text[a:b]
+    local = (np.flatnonzero(np.frombuffer(mine, dtype=np.uint8) == 10) + a).tolist()
+    counts = [None] * world
+    dist.all_gather_object(counts, len(local))
+    cand = sharding.block_cut_candidates(local, sum(counts[:rank]))
+    allc = [None] * world
+    dist.all_gather_object(allc, cand)
+    plan = sharding.plan_compress(allc, n, world, bounds=[s[1] for s in slices])
+    lo, hi = plan[rank]
+    # the bytes in front of a rank's first block finish the last block of the rank before it
+    heads = [None] * world
+    dist.all_gather_object(heads, mine[: max(lo, a) - a] if hi > lo else mine)
+    if hi > lo:
+        chunk = mine[lo - a :]
+        r = rank + 1
+        while len(chunk) < hi - lo and r < world:
+            chunk += heads[r]
+            r += 1
+        assert len(chunk) == hi - lo and chunk == text[lo:hi]
+    flag = [None]
+    if rank == 0:
+        flag[0] = int(oracle.encode_streams(text[lo:hi], max_records=100000)["phred64"])
+    dist.broadcast_object_list(flag, src=0)
+    part = oracle.compress(text[lo:hi], threads=2) if hi > lo else b""
+    if rank > 0 and part:
+        part = part[10:]
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    if rank == 0:
+        assert sharding.merge_compressed(parts) == oracle.compress(text, threads=2)
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bgzf_input(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_bgzf_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_walk_bgzf_rejects_plain_gzip():
+    import gzip
+
+    from tests.gzip_cases import bgzf
+
+    gz = bgzf(b"@r\nACGT\n+\nIIII\n" * 5000, block=4000)
+    members = sharding.walk_bgzf(gz)
+    assert len(members) == (5000 * 15 + 3999) // 4000 + 1 and members[1].text_offset == 4000
+    for world in (1, 2, 3, 8, 64):
+        plan = sharding.plan_bgzf(members, world)
+        assert plan[0][0] == 0 and plan[-1][1] == len(members) and all(plan[i][1] == plan[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        sharding.walk_bgzf(gzip.compress(b"plain gzip has no BC field"))
+    with pytest.raises(ValueError):
+        sharding.walk_bgzf(gz[:-5])
