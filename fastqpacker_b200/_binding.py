@@ -110,7 +110,7 @@ class FqzLibrary:
         self._opt(L, "fqz_decompress_feed", [vp, vp, sz, i32, vp, sz, szp, szp])
         self._opt(L, "fqz_decompress_end", [vp], restype=None)
         self._opt(L, "fqz_is_gzip", [vp, sz])
-        self._opt(L, "fqz_gunzip_stats", [vp, C.POINTER(C.c_uint64 * 4)])
+        self._opt(L, "fqz_gunzip_stats", [vp, C.POINTER(C.c_uint64 * 5)])
         self._opt(L, "fqz_gunzip", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_gunzip_device", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_compress_gz", [vp, vp, sz, u32, vp, sz, szp, szp])
@@ -277,9 +277,9 @@ class FqzContext:
             return out[: m.value].tobytes()
 
     def gunzip_stats(self) -> dict:
-        v = (C.c_uint64 * 4)()
+        v = (C.c_uint64 * 5)()
         self._check(self.lib.L.fqz_gunzip_stats(self.h, C.byref(v)))
-        return dict(chunks=int(v[0]), parallel=int(v[1]), dropped=int(v[2]), members=int(v[3]))
+        return dict(chunks=int(v[0]), parallel=int(v[1]), dropped=int(v[2]), members=int(v[3]), decoded_twice=int(v[4]))
 
     def gunzip_device(self, d_in: int, n: int, d_out: int, out_cap: int) -> int:
         """Device buffers; returns the text length (raises FqzError(-15) with .needed set when out_cap is short)."""

@@ -131,7 +131,28 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     };
     for (size_t i = 0; i < chain.size(); i++) retarget(i);
 
-    // ---- counting pass; every chunk must land exactly on the next restart point
+    // ---- speculative pass: every chunk decodes into scratch room of GZ_SPEC_RATIO symbols per compressed byte (FASTQ
+    //      inflates 3-5x) and a few member records; what it finds out — sizes, member ends, whether it lands exactly on
+    //      the next restart point — is all the counting pass of a two-pass design would give, and the symbols come with it.
+    //      A chunk that runs out of room keeps counting and is decoded again below, at its exact size.  Without the
+    //      memory for the scratch the pass only counts (room 0) and every chunk is decoded again.
+    const u64 GZ_SPEC_RATIO = 6;
+    u64 spec_cap = GZ_SPEC_RATIO * ch;
+    const u32 spec_mcap = (u32)(ch / 512u) + 8u;
+    u16 *d_spec = (u16 *)c->arena.alloc((size_t)K * spec_cap * sizeof(u16));
+    GzMember *d_smem = (GzMember *)c->arena.alloc((size_t)K * spec_mcap * sizeof(GzMember));
+    if (!d_smem) {
+        c->err = "arena: out of device memory (gzip members)";
+        return FQZ_E_CUDA;
+    }
+    if (!d_spec) spec_cap = 0;
+    for (u32 k = 0; k < K; k++) {
+        h[k].sym_ptr = (u64)(uintptr_t)(d_spec + (size_t)k * spec_cap);
+        h[k].sym_cap = spec_cap;
+        h[k].mem_ptr = (u64)(uintptr_t)(d_smem + (size_t)k * spec_mcap);
+        h[k].mem_cap = spec_mcap;
+    }
+    a.spec = 1;
     std::vector<u32> dirty = chain;
     size_t proven = 0;
     int reruns = 0;
@@ -142,7 +163,7 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
         a.nlist = (u32)dirty.size();
         {
             StageScope sc(c, ST_GZ_DECODE, n);
-            fqz_launch_gz_decode(a, false, s);
+            fqz_launch_gz_decode(a, true, s);
         }
         FQZ_TRY(fqz_pin_copy(c, h, d_chunks, chunks_b));
         FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
@@ -176,16 +197,21 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     }
 
     // ---- places
-    u64 total = 0;
-    u32 nm = 0, slots = 1;
+    u64 total = 0, over_sym = 0;
+    u32 nm = 0, over_mem = 0, nblock = 0;
+    std::vector<u32> redo;
     for (size_t i = 0; i < chain.size(); i++) {
         GzChunk &C = h[chain[i]];
         C.out_off = total;
         C.member_base = nm;
         total += C.out_len;
         nm += C.members;
-        C.prev = i ? chain[i - 1] : 0u;
-        C.win_slot = C.start_type == GZ_AT_BLOCK ? slots++ : 0u;
+        if (C.start_type == GZ_AT_BLOCK) nblock++;
+        if (C.overflow) {
+            redo.push_back(chain[i]);
+            over_sym += C.out_len;
+            over_mem += C.members;
+        }
         if (i == 0)
             C.window_valid = 0;
         else {
@@ -207,37 +233,57 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
         out = c->gz_text;
     }
     if (d_text) *d_text = out;
-    u16 *d_sym = (u16 *)c->arena.alloc((size_t)total * 2 + 64);
     // windows: groups of ~sqrt(chunks) chunks (fqz_inflate.cu, k_gz_maps)
     u32 gsize = 1;
     while ((u64)gsize * gsize < chain.size()) gsize++;
     const u32 ngroups = (u32)((chain.size() + gsize - 1) / gsize);
     u8 *d_win = (u8 *)c->arena.alloc((size_t)ngroups * GZ_WINDOW);
-    u16 *d_maps = slots > 1 ? (u16 *)c->arena.alloc((size_t)chain.size() * GZ_WINDOW * sizeof(u16)) : nullptr;
+    u16 *d_maps = nblock ? (u16 *)c->arena.alloc((size_t)chain.size() * GZ_WINDOW * sizeof(u16)) : nullptr;
     GzMember *d_mem = (GzMember *)c->arena.alloc(((size_t)nm + 1) * sizeof(GzMember));
-    if (!d_sym || !d_win || !d_mem || (slots > 1 && !d_maps)) {
+    u16 *d_osym = redo.empty() ? nullptr : (u16 *)c->arena.alloc((size_t)over_sym * sizeof(u16) + 64);
+    GzMember *d_omem = redo.empty() ? nullptr : (GzMember *)c->arena.alloc(((size_t)over_mem + 1) * sizeof(GzMember));
+    if (!d_win || !d_mem || (nblock && !d_maps) || (!redo.empty() && (!d_osym || !d_omem))) {
         c->err = "arena: out of device memory (gzip output)";
         return FQZ_E_CUDA;
     }
-    a.sym = d_sym;
+    {
+        u64 so = 0;
+        u32 mo = 0;
+        for (u32 k : redo) {  // exact room for the chunks that ran out of it
+            h[k].sym_ptr = (u64)(uintptr_t)(d_osym + so);
+            h[k].sym_cap = h[k].out_len;
+            h[k].mem_ptr = (u64)(uintptr_t)(d_omem + mo);
+            h[k].mem_cap = h[k].members;
+            so += h[k].out_len;
+            mo += h[k].members;
+        }
+    }
     a.win = d_win;
     a.maps = d_maps;
     a.gsize = gsize;
     a.out = out;
     a.members = d_mem;
     a.nmembers = nm;
-    a.nlist = (u32)chain.size();
-    memcpy(hlist, chain.data(), chain.size() * sizeof(u32));
     *herr = ~0ull;
     FQZ_TRY(fqz_pin_copy(c, d_chunks, h, chunks_b));
-    FQZ_TRY(fqz_pin_copy(c, d_list, hlist, chain.size() * sizeof(u32)));
     FQZ_TRY(fqz_pin_copy(c, d_err, herr, sizeof(unsigned long long)));
-    {
-        StageScope sc(c, ST_GZ_DECODE, n + 2 * total);
+    c->gz_stats[4] = redo.size();
+    if (!redo.empty()) {
+        memcpy(hlist, redo.data(), redo.size() * sizeof(u32));
+        FQZ_TRY(fqz_pin_copy(c, d_list, hlist, redo.size() * sizeof(u32)));
+        a.nlist = (u32)redo.size();
+        a.spec = 0;
+        StageScope sc(c, ST_GZ_DECODE, n + 2 * over_sym);
         fqz_launch_gz_decode(a, true, s);
+        // hlist is read by the copy kernel when it runs: it must have run before the chain is written over it
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
     }
+    memcpy(hlist, chain.data(), chain.size() * sizeof(u32));
+    FQZ_TRY(fqz_pin_copy(c, d_list, hlist, chain.size() * sizeof(u32)));
+    a.nlist = (u32)chain.size();
     {
         StageScope sc(c, ST_GZ_RESOLVE, 3 * total);
+        fqz_launch_gz_members(a, s);
         fqz_launch_gz_windows(a, s);
         fqz_launch_gz_resolve(a, s);
     }
@@ -253,9 +299,9 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     return FQZ_OK;
 }
 
-extern "C" int fqz_gunzip_stats(fqz_ctx *c, uint64_t out[4]) {
+extern "C" int fqz_gunzip_stats(fqz_ctx *c, uint64_t out[5]) {
     if (!c || !out) return FQZ_E_INVALID_ARG;
-    for (int i = 0; i < 4; i++) out[i] = c->gz_stats[i];
+    for (int i = 0; i < 5; i++) out[i] = c->gz_stats[i];
     return FQZ_OK;
 }
 

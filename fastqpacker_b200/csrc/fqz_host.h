@@ -121,7 +121,7 @@ struct fqz_ctx {
     u64 opt_gz_chunk_bytes = 0;     // compressed bytes per warp of the gzip input stage (0 = from the input size)
     // gzip input stage (fqz_api_gzip.cu): the inflated FASTQ text lives here between inflate and compress
     u8 *gz_text = nullptr;
-    u64 gz_stats[4] = {0, 0, 0, 0};  // last inflate: chunks cut, chunks decoded in parallel, restart points dropped as false, members
+    u64 gz_stats[5] = {0, 0, 0, 0, 0};  // last inflate: chunks cut, chunks decoded in parallel, restart points dropped as false, members, chunks decoded twice
     size_t gz_text_cap = 0;
 };
 int fqz_frontend_init_device();

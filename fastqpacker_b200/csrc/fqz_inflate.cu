@@ -11,10 +11,11 @@
 //                 the whole warp (every lane decodes the token that would start at its bit, the chain through them
 //                 is followed with shuffles), up to 32 tokens per step; the warp writes the literals and copies the
 //                 matches.  Output is
-//                 16-bit: a byte, or 256 + i for "byte i of the window I could not see".  Runs twice: a counting
-//                 pass (sizes, member boundaries, proof that every chunk lands exactly on the next restart point —
-//                 a restart point nobody lands on was a false positive and its chunk is merged into the one in
-//                 front), then the writing pass at the final offsets.
+//                 16-bit: a byte, or 256 + i for "byte i of the window I could not see".  One speculative pass into
+//                 scratch room of six symbols per compressed byte gives the symbols, the sizes, the member
+//                 boundaries and the proof that every chunk lands exactly on the next restart point (a restart point
+//                 nobody lands on was a false positive and its chunk is merged into the one in front); only chunks
+//                 that ran out of room are decoded again, at exact sizes.
 //   k_gz_maps,    the window in front of chunk k is the resolved tail of chunk k-1: a serial chain, cut into
 //   k_gz_bases    ~sqrt(chunks) groups (windows as maps of the group's base window, then the base windows in order).
 //   k_gz_resolve  every symbol becomes a byte: out[p] = sym < 256 ? sym : window[sym - 256].  Parallel, HBM bound.
@@ -535,9 +536,11 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
     const u64 n = a.n, nbits = a.n * 8;
     const u64 target = C.target_bit;
     const u32 target_type = C.target_type;
-    u16 *out = WRITE ? a.sym + C.out_off : nullptr;
-    GzMember *mem = WRITE ? a.members + C.member_base : nullptr;
-    const u64 out_off = C.out_off;
+    u16 *out = WRITE ? (u16 *)(uintptr_t)C.sym_ptr : nullptr;
+    GzMember *mem = WRITE ? (GzMember *)(uintptr_t)C.mem_ptr : nullptr;
+    const u64 sym_cap = C.sym_cap;
+    const u32 mem_cap = C.mem_cap;
+    bool over = false;  // out of room (speculative pass): counting goes on, writing stops
 
     GzBits br;
     br.w = a.src;
@@ -629,7 +632,8 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                 errbit = nbits;
                 break;
             }
-            if (WRITE)
+            if (WRITE && produced + len > sym_cap) over = true;
+            if (WRITE && !over)
                 for (u32 t = lane; t < len; t += 32) out[produced + t] = (u16)s8[at + 4 + t];
             produced += len;
             pos = (at + 4 + len) * 8;
@@ -695,7 +699,8 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                     incl = group_incl_scan(len, GZ_FULL, 32);
                 }
                 const u32 bytes = __shfl_sync(GZ_FULL, incl, 31);
-                if (WRITE) {
+                if (WRITE && produced + bytes > sym_cap) over = true;
+                if (WRITE && !over) {
                     if (lane < cnt && !mlen) out[produced + o] = (u16)e;
                     // short matches whose source lies in front of this step do not depend on anything the step
                     // writes: every lane copies its own, four loads in flight per round trip to L2
@@ -751,9 +756,10 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
                 errbit = nbits;
                 break;
             }
-            if (WRITE && lane == 0) {
+            if (WRITE && nmem >= mem_cap) over = true;
+            if (WRITE && !over && lane == 0) {
                 GzMember m;
-                m.out_end = out_off + produced;
+                m.out_end = produced;  // relative to the chunk; k_gz_members adds its place
                 m.trailer_byte = at;
                 m.crc = (u32)s8[at] | ((u32)s8[at + 1] << 8) | ((u32)s8[at + 2] << 16) | ((u32)s8[at + 3] << 24);
                 m.isize = (u32)s8[at + 4] | ((u32)s8[at + 5] << 8) | ((u32)s8[at + 6] << 16) | ((u32)s8[at + 7] << 24);
@@ -768,13 +774,14 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
         }
     }
     if (lane == 0) {
-        if (WRITE) {
-            if (status < 16u && (produced != C.out_len || nmem != C.members || pos != C.end_bit)) {
+        if (WRITE && !a.spec) {
+            if (status < 16u && (over || produced != C.out_len || nmem != C.members || pos != C.end_bit)) {
                 status = GZ_ST_ERR_INTERNAL;
                 errbit = C.start_bit;
             }
             if (status >= 16u) atomicMin(a.err, (unsigned long long)((errbit << 8) | status));
         } else {
+            C.overflow = over ? 1u : 0u;
             C.out_len = produced;
             C.end_bit = pos;
             C.err_bit = errbit;
@@ -796,13 +803,13 @@ template <bool WRITE> __global__ void __launch_bounds__(GZ_WARPS * 32) k_gz_deco
 #define GZ_WIN_BATCH 8u
 struct GzWinStep {
     u32 type;
-    u64 poff, plen;
+    u64 psym, plen;
 };
 __device__ __forceinline__ GzWinStep gz_win_step(const GzArgs &a, u32 i) {
     GzWinStep s;
     s.type = a.chunks[a.list[i]].start_type;
     const GzChunk &P = a.chunks[a.list[i ? i - 1 : 0]];
-    s.poff = P.out_off;
+    s.psym = P.sym_ptr;
     s.plen = P.out_len;
     return s;
 }
@@ -825,7 +832,7 @@ __global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_maps(GzArgs a) {
         } else {
             const u16 *Mp = M - GZ_WINDOW;
             const u32 keep = cur.plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)cur.plen;
-            const u16 *tail = a.sym + cur.poff + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
+            const u16 *tail = (const u16 *)(uintptr_t)cur.psym + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
             for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
                 u32 s[GZ_WIN_BATCH];
 #pragma unroll
@@ -856,7 +863,7 @@ __global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_bases(GzArgs a) {
             const u8 *Bp = B - GZ_WINDOW;
             const u16 *Mp = a.maps + (size_t)(first - 1) * GZ_WINDOW;
             const u32 keep = cur.plen >= GZ_WINDOW ? 0u : GZ_WINDOW - (u32)cur.plen;
-            const u16 *tail = a.sym + cur.poff + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
+            const u16 *tail = (const u16 *)(uintptr_t)cur.psym + (cur.plen >= GZ_WINDOW ? cur.plen - GZ_WINDOW : 0u);
             for (u32 b = 0; b < GZ_WINDOW; b += GZ_WIN_BATCH * GZ_WIN_THREADS) {
                 u32 s[GZ_WIN_BATCH];
 #pragma unroll
@@ -878,7 +885,7 @@ __global__ void __launch_bounds__(GZ_WIN_THREADS) k_gz_bases(GzArgs a) {
 __global__ void __launch_bounds__(256) k_gz_resolve(GzArgs a) {
     const u32 i = blockIdx.y;
     const GzChunk &C = a.chunks[a.list[i]];
-    const u16 *sym = a.sym + C.out_off;
+    const u16 *sym = (const u16 *)(uintptr_t)C.sym_ptr;
     u8 *out = a.out + C.out_off;
     const bool has_window = C.start_type == GZ_AT_BLOCK;
     const u16 *M = has_window ? a.maps + (size_t)i * GZ_WINDOW : nullptr;
@@ -900,6 +907,20 @@ __global__ void __launch_bounds__(256) k_gz_resolve(GzArgs a) {
         out[p] = (u8)s;
     }
     if (bad) atomicMin(a.err, (unsigned long long)((C.start_bit << 8) | (has_window ? GZ_ST_ERR_CORRUPT : GZ_ST_ERR_INTERNAL)));
+}
+
+// ---------------------------------------------------------------------------------- k_gz_members
+// the member records of every chunk, in stream order, into the file-wide table (out_end made absolute)
+__global__ void __launch_bounds__(128) k_gz_members(GzArgs a) {
+    const u32 i = blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (i >= a.nlist) return;
+    const GzChunk &C = a.chunks[a.list[i]];
+    const GzMember *src = (const GzMember *)(uintptr_t)C.mem_ptr;
+    for (u32 j = lane_id(); j < C.members; j += 32) {
+        GzMember m = src[j];
+        m.out_end += C.out_off;
+        a.members[C.member_base + j] = m;
+    }
 }
 
 // ---------------------------------------------------------------------------------- k_gz_crc
@@ -985,6 +1006,9 @@ void fqz_launch_gz_decode(const GzArgs &a, bool write, cudaStream_t s) {
         FQZ_LAUNCH(k_gz_decode<true>, grid, GZ_WARPS * 32, 0, s, a);
     else
         FQZ_LAUNCH(k_gz_decode<false>, grid, GZ_WARPS * 32, 0, s, a);
+}
+void fqz_launch_gz_members(const GzArgs &a, cudaStream_t s) {
+    if (a.nlist && a.nmembers) FQZ_LAUNCH(k_gz_members, (a.nlist + 3) / 4, 128, 0, s, a);
 }
 void fqz_launch_gz_windows(const GzArgs &a, cudaStream_t s) {
     if (!a.maps) return;  // no chunk starts at a block header: nothing to resolve

@@ -38,12 +38,18 @@ struct GzChunk {
     u64 after_member;  // bytes decoded since the last member header met inside the chunk; ~0 = none met
     u32 status;
     u32 members;       // members whose trailer lies inside the chunk
-    // filled by the host between the passes
-    u64 out_off;       // place of the chunk's output
-    u32 member_base;   // index of its first member record
+    u32 overflow;      // the speculative pass ran out of symbol or member room: the chunk is decoded again at exact sizes
+    u32 pad0;
+    // places: provisional ones for the speculative pass, exact ones for a chunk that is decoded again
+    u64 sym_ptr;       // device address of the chunk's symbols (u16)
+    u64 sym_cap;       // symbols there is room for
+    u64 mem_ptr;       // device address of its member records (out_end relative to the chunk)
+    u32 mem_cap;
+    // filled by the host once every chunk's size is known
+    u32 member_base;   // index of its first member in the file-wide member table
+    u64 out_off;       // place of the chunk's text
     u32 window_valid;  // bytes of the 32 KiB window in front of the chunk that belong to the same member
-    u32 prev;          // previous chunk of the chain
-    u32 win_slot;      // (unused)
+    u32 pad1;
 };
 
 struct GzMember {
@@ -63,7 +69,7 @@ struct GzArgs {
     const u32 *list;  // chunks to run
     u32 nlist;
     u32 bgzf_only;    // k_gz_find: look for BGZF member headers only
-    u16 *sym;         // decoded symbols: < 256 a byte, else 256 + index into the chunk's window
+    u32 spec;         // k_gz_decode<write>: 1 = speculative pass (room may run out, results recorded), 0 = exact places (results verified)
     u8 *win;          // base window of every group of chunks, GZ_WINDOW bytes each
     u16 *maps;        // per chunk of the chain: its window as a map of the group's base window (nullptr: no chunk needs one)
     u32 gsize;        // chunks per group
@@ -76,6 +82,7 @@ struct GzArgs {
 
 void fqz_launch_gz_find(const GzArgs &a, cudaStream_t s);
 void fqz_launch_gz_decode(const GzArgs &a, bool write, cudaStream_t s);
+void fqz_launch_gz_members(const GzArgs &a, cudaStream_t s);
 void fqz_launch_gz_windows(const GzArgs &a, cudaStream_t s);
 void fqz_launch_gz_resolve(const GzArgs &a, cudaStream_t s);
 void fqz_launch_gz_crc(const GzArgs &a, u64 out_len, cudaStream_t s);

@@ -120,8 +120,9 @@ int fqz_check(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t *records, uin
  * dynamic-block headers), proven by the decoder in front landing exactly on them. */
 int fqz_is_gzip(const uint8_t *buf, size_t n);
 /* how the last gzip input of this context was cut: [0] chunks, [1] chunks decoded side by side (restart points proven),
- * [2] restart points dropped as false positives, [3] gzip members */
-int fqz_gunzip_stats(fqz_ctx *ctx, uint64_t out[4]);
+ * [2] restart points dropped as false positives, [3] gzip members, [4] chunks that outgrew the scratch room of the
+ * speculative pass (more than 6 bytes of text per compressed byte) and were decoded a second time */
+int fqz_gunzip_stats(fqz_ctx *ctx, uint64_t out[5]);
 int fqz_gunzip(fqz_ctx *ctx, const uint8_t *gz, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
 int fqz_gunzip_device(fqz_ctx *ctx, const void *d_gz, size_t n, void *d_out, size_t out_cap, size_t *out_len);
 int fqz_compress_gz(fqz_ctx *ctx, const uint8_t *gz, size_t n, uint32_t header_block_size, uint8_t *out, size_t out_cap, size_t *out_len,

@@ -44,6 +44,11 @@ def test_restart_points_are_used_and_false_ones_dropped(ctx, gunzip_oracle):
     assert stats["parallel"] > 4 and stats["members"] > 4
     stats = check_good(ctx, gunzip_oracle, "gz_in_stored", CASES, chunks=(512,))[0]
     assert stats["dropped"] > 0
+    # the speculative pass has room for 6 bytes of text per compressed byte: FASTQ fits, runs of one byte do not
+    st = check_good(ctx, gunzip_oracle, "small_blocks", CASES, chunks=(512,))[0]
+    assert st["decoded_twice"] < st["parallel"] // 2, st
+    assert check_good(ctx, gunzip_oracle, "newline_only", CASES, chunks=(256,))[0]["decoded_twice"] == 1
+    assert check_good(ctx, gunzip_oracle, "identical_records", CASES, chunks=(512,))[0]["decoded_twice"] > 0
 
 
 def test_compress_gz_configs(ctx, oracle, sample_fq):
