@@ -229,6 +229,7 @@ __device__ bool gz_probe_dynamic(const u32 *w, u64 n, u64 bit) {
         u32 l = br.take(3);
         cl[kGzClOrder[i]] = (u8)l;
         if (l) kraft += 128u >> l;
+        if (kraft > 128u) return false;  // over-subscribed already
     }
     if (kraft != 128u) return false;
     // 7-bit lookup of the code-length code: length in bits 0-2, symbol in bits 3-7
