@@ -69,7 +69,7 @@ static int gz_inflate(fqz_ctx *c, const u8 *d_gz, u64 n, u8 *d_out, u64 out_cap,
     u64 ch = c->opt_gz_chunk_bytes;
     if (!ch) {
         // a warp decodes one chunk; restart points only exist at block boundaries (every 20-60 KB of a zlib stream)
-        ch = n / ((u64)c->sm_count * 32u);
+        ch = n / ((u64)c->sm_count * 36u);  // 36 warps of k_gz_decode are resident per SM (registers, shared memory): one wave
         ch = (ch + 4095u) & ~(u64)4095u;
         ch = std::min<u64>(std::max<u64>(ch, 32768u), (u64)4 << 20);
     }

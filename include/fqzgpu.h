@@ -75,7 +75,7 @@ int fqz_abi_version(void);
                                      * Huffman codes may differ) */
 #define FQZ_OPT_SERIAL_ENTROPY 6    /* 0 (default): the item-stream kernels run on a second stream beside the literals-only coder (their launch
                                      * tails overlap); 1: one after the other (per-stage timings are only meaningful this way) */
-#define FQZ_OPT_GZ_CHUNK_BYTES 7    /* gzip input: compressed bytes decoded by one warp (default: input size / (32 x SMs), 32 KiB .. 4 MiB;
+#define FQZ_OPT_GZ_CHUNK_BYTES 7    /* gzip input: compressed bytes decoded by one warp (default: input size / (36 x SMs), 32 KiB .. 4 MiB;
                                      * multiple of 4, >= 256).  Results do not depend on it */
 int fqz_set_option(fqz_ctx *ctx, int key, uint64_t value);
 
