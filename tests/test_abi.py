@@ -30,7 +30,8 @@ def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for name in ("fqz_init", "fqz_compress", "fqz_decompress", "fqz_compress_feed", "fqz_decompress_feed", "fqz_compress_shard",
                  "fqz_encode_streams", "fqz_decode_streams", "fqz_zstd_compress", "fqz_zstd_decompress", "fqz_compress_device",
-                 "fqz_decompress_device"):
+                 "fqz_decompress_device", "fqz_is_gzip", "fqz_gunzip", "fqz_gunzip_device", "fqz_compress_gz", "fqz_gunzip_stats", "fqz_info",
+                 "fqz_check"):
         assert name in syms
 
 
@@ -51,6 +52,11 @@ def test_abi_version_and_error_texts(lib):
     assert lib.fqz_strerror(-5) == b"invalid magic bytes: not an FQZ file"
     assert lib.fqz_strerror(-9) == b"truncated header data"
     assert lib.fqz_strerror(-14) == b"truncated N position data"
+    # Go's compress/gzip and compress/flate texts for a gzipped input (cmd/fqpack/main.go:142-174)
+    assert lib.fqz_strerror(-18) == b"gzip: invalid header"
+    assert lib.fqz_strerror(-19) == b"gzip: invalid checksum"
+    assert lib.fqz_strerror(-20).startswith(b"flate: corrupt input")
+    assert lib.fqz_strerror(-21) == b"unexpected EOF"
 
 
 def test_no_cpu_fallback(lib):
