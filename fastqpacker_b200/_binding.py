@@ -65,6 +65,18 @@ class _FileInfo(C.Structure):
     ]
 
 
+class _BlockRef(C.Structure):
+    _fields_ = [
+        ("offset", C.c_uint64),
+        ("size", C.c_uint64),
+        ("first_record", C.c_uint64),
+        ("records", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("original_seq", C.c_uint64),
+        ("original_qual", C.c_uint64),
+    ]
+
+
 class FqzLibrary:
     def __init__(self, path: str):
         self.path = path
@@ -100,6 +112,8 @@ class FqzLibrary:
         self._opt(L, "fqz_decompress_device", [vp, vp, sz, vp, sz, szp])
         self._opt(L, "fqz_info", [vp, vp, sz, C.POINTER(_FileInfo)])
         self._opt(L, "fqz_check", [vp, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+        self._opt(L, "fqz_block_index", [vp, sz, C.POINTER(_BlockRef), sz, szp])
+        self._opt(L, "fqz_decompress_blocks", [vp, vp, sz, C.c_uint64, C.c_uint64, vp, sz, szp])
         self._opt(L, "fqz_compress_bound", [sz], restype=sz)
         self._opt(L, "fqz_host_alloc", [sz], restype=vp)
         self._opt(L, "fqz_host_free", [vp], restype=None)
@@ -125,6 +139,21 @@ class FqzLibrary:
 
     def strerror(self, code: int) -> str:
         return self.L.fqz_strerror(code).decode()
+
+    def block_index(self, fqz) -> list:
+        """Side-table index of a .fqz (one hop over the block headers, host only: needs no context and no GPU):
+        a dict(offset, size, first_record, records, original_seq, original_qual) per block."""
+        a = _as_u8(fqz)
+        n = C.c_size_t(0)
+        rc = self.L.fqz_block_index(_ptr(a), a.size, None, 0, C.byref(n))
+        if rc not in (FQZ_OK, FQZ_E_NOSPACE):
+            raise FqzError(rc, self.strerror(rc), f"after {n.value} whole blocks")
+        tab = (_BlockRef * max(1, n.value))()
+        rc = self.L.fqz_block_index(_ptr(a), a.size, tab, n.value, C.byref(n))
+        if rc != FQZ_OK:
+            raise FqzError(rc, self.strerror(rc))
+        return [dict(offset=int(t.offset), size=int(t.size), first_record=int(t.first_record), records=int(t.records),
+                     original_seq=int(t.original_seq), original_qual=int(t.original_qual)) for t in tab[: n.value]]
 
     def context(self, device: int = 0) -> "FqzContext":
         return FqzContext(self, device)
@@ -251,6 +280,23 @@ class FqzContext:
             out = np.empty(cap, dtype=np.uint8)
             m = C.c_size_t(0)
             rc = self.lib.L.fqz_decompress(self.h, _ptr(a), a.size, _ptr(out), cap, C.byref(m))
+            if rc == FQZ_E_NOSPACE:
+                cap = max(m.value, cap * 2)
+                continue
+            self._check(rc)
+            return out[: m.value].tobytes()
+
+    def block_index(self, fqz) -> list:
+        return self.lib.block_index(fqz)
+
+    def decompress_blocks(self, fqz, first_block: int, num_blocks: int, cap: int | None = None) -> bytes:
+        """FASTQ of blocks [first_block, first_block + num_blocks) alone (random access through the block index)."""
+        a = _as_u8(fqz)
+        cap = cap or max(1 << 16, a.size * 6)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            m = C.c_size_t(0)
+            rc = self.lib.L.fqz_decompress_blocks(self.h, _ptr(a), a.size, first_block, num_blocks, _ptr(out), cap, C.byref(m))
             if rc == FQZ_E_NOSPACE:
                 cap = max(m.value, cap * 2)
                 continue

@@ -441,6 +441,86 @@ extern "C" int fqz_info(fqz_ctx *c, const uint8_t *fqz, size_t n, fqz_file_info 
     return FQZ_OK;
 }
 
+// fqz_block_index: the index the container does not carry (compress.go:721-736 reads header after header), built as a
+// side table from one hop over the block headers.  Host arithmetic, no context: usable without a GPU.
+extern "C" int fqz_block_index(const uint8_t *fqz, size_t n, fqz_block_ref *out, size_t cap, size_t *count) {
+    if (!count || (!fqz && n) || (!out && cap)) return FQZ_E_INVALID_ARG;
+    *count = 0;
+    if (n < 4) return FQZ_E_TRUNC_FILE;
+    if (!(fqz[0] == 'F' && fqz[1] == 'Q' && fqz[2] == 'Z' && fqz[3] == 0)) return FQZ_E_MAGIC;
+    if (n < 10) return FQZ_E_TRUNC_FILE;
+    const u32 version = fqz[4];
+    if (version != 1 && version != 2) return FQZ_E_VERSION;
+    const size_t hsz = version == 1 ? 32 : 36;
+    const int ns = version == 1 ? 5 : 6;
+    size_t pos = 10, nb = 0;
+    u64 first = 0;
+    while (pos < n) {
+        if (n - pos < hsz) return FQZ_E_TRUNC_FILE;
+        u32 v[9];
+        for (size_t i = 0; i < hsz / 4; i++) v[i] = (u32)fqz[pos + 4 * i] | ((u32)fqz[pos + 4 * i + 1] << 8) | ((u32)fqz[pos + 4 * i + 2] << 16) | ((u32)fqz[pos + 4 * i + 3] << 24);
+        u64 payload = 0;
+        for (int a = 0; a < ns; a++) payload += v[1 + a];
+        if (n - pos - hsz < payload) return FQZ_E_TRUNC_FILE;
+        if (nb < cap) {
+            fqz_block_ref &r = out[nb];
+            r.offset = pos;
+            r.size = hsz + payload;
+            r.first_record = first;
+            r.records = v[0];
+            r.reserved = 0;
+            r.original_seq = v[1 + ns];
+            r.original_qual = v[2 + ns];
+        }
+        nb++;
+        *count = nb;
+        first += v[0];
+        pos += hsz + payload;
+    }
+    return nb > cap ? FQZ_E_NOSPACE : FQZ_OK;
+}
+
+// fqz_decompress_blocks: random access through the index — the bytes of blocks [first_block, first_block + num_blocks)
+// are uploaded and decoded like a file that starts there (decompress_blocks with pos0 = 0); version and Phred flag come
+// from the file header.
+extern "C" int fqz_decompress_blocks(fqz_ctx *c, const uint8_t *fqz, size_t n, uint64_t first_block, uint64_t num_blocks, uint8_t *out,
+                                     size_t out_cap, size_t *out_len) {
+    if (!c || !out_len || (!fqz && n) || (!out && out_cap)) return FQZ_E_INVALID_ARG;
+    cudaSetDevice(c->device);
+    c->err.clear();
+    *out_len = 0;
+    DecState st;
+    FQZ_TRY(parse_file_header(c, fqz, n, st));
+    size_t nb = 0;
+    int rc = fqz_block_index(fqz, n, nullptr, 0, &nb);
+    if (rc != FQZ_OK && rc != FQZ_E_NOSPACE) {
+        if (rc == FQZ_E_TRUNC_FILE) c->err = "reading block: unexpected EOF";
+        return rc;
+    }
+    if (first_block > nb || num_blocks > nb - first_block) {
+        c->err = "block range reaches past the last block of the file";
+        return FQZ_E_INVALID_ARG;
+    }
+    if (num_blocks == 0) return FQZ_OK;
+    std::vector<fqz_block_ref> idx(nb);
+    FQZ_TRY(fqz_block_index(fqz, n, idx.data(), nb, &nb));
+    const u64 lo = idx[first_block].offset;
+    const u64 hi = idx[first_block + num_blocks - 1].offset + idx[first_block + num_blocks - 1].size;
+    st.block_base = first_block;  // error texts name the block's index in the file
+    rc = fqz_io_upload(c, fqz + lo, (size_t)(hi - lo));
+    size_t m = 0;
+    if (rc == FQZ_OK) {
+        u64 used = 0;
+        static u8 dummy;
+        rc = decompress_blocks(c, c->io.d_in, hi - lo, 0, true, false, st, nullptr, out ? out : &dummy, out_cap, &m, &used, true);
+    }
+    int rc2 = fqz_io_finish(c);
+    if (rc == FQZ_OK) rc = rc2;
+    if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *out_len = m;
+    if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
+    return rc;
+}
+
 // fqz_check: what `fqpack check` would do — walk the container, decode every stream of every block (frame checksums
 // verified), rebuild every record, and report pass / fail without writing the FASTQ anywhere: the text of each
 // device window is produced in HBM and dropped, so the check runs at the device-resident decompress rate plus

@@ -109,6 +109,29 @@ typedef struct fqz_file_info {
 int fqz_info(fqz_ctx *ctx, const uint8_t *fqz, size_t n, fqz_file_info *out);
 int fqz_check(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t *records, uint64_t *fastq_bytes);
 
+/* ---- block index and random access.  The container has no index (a reader must hop from block header to block header,
+ * compress.go:690-758; ROADMAP.md lists one as future work), so this library builds it on demand as a SIDE TABLE that
+ * costs one hop over the headers and can be stored beside the archive: no format change, every .fqz the reference
+ * writes has one.
+ * fqz_block_index: one entry per block, in file order.  Host arithmetic only, needs no context and no GPU.  *count = blocks
+ *   in the file, also when cap is too small (FQZ_E_NOSPACE then; out may be NULL with cap 0 to size the table).  Errors
+ *   as fqz_info: FQZ_E_MAGIC, FQZ_E_VERSION, FQZ_E_TRUNC_FILE (*count = whole blocks in front of the cut).
+ * fqz_decompress_blocks: the FASTQ of blocks [first_block, first_block + num_blocks) alone = records
+ *   [index[first_block].first_record, ...): only those blocks' bytes cross PCIe.  Blocks are independent
+ *   (compress.go:523-528), which is also what lets several GPUs share a file (fastqpacker_b200/sharding.py).
+ *   FQZ_E_INVALID_ARG when the range reaches past the last block. */
+typedef struct fqz_block_ref {
+    uint64_t offset;        /* of the block header from the start of the file */
+    uint64_t size;          /* block header + its payloads */
+    uint64_t first_record;  /* records in the blocks in front of this one */
+    uint32_t records;       /* NumRecords (container.go:84) */
+    uint32_t reserved;
+    uint64_t original_seq, original_qual; /* OriginalSeqSize / OriginalQualSize: bases and quality bytes of the block */
+} fqz_block_ref;
+int fqz_block_index(const uint8_t *fqz, size_t n, fqz_block_ref *out, size_t cap, size_t *count);
+int fqz_decompress_blocks(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t first_block, uint64_t num_blocks, uint8_t *out,
+                          size_t out_cap, size_t *out_len);
+
 /* ---- gzip input (cmd/fqpack/main.go:123-174).  In compress mode fqpack reads an input whose name ends in ".gz" or that
  * starts with 1f 8b through Go's compress/gzip: concatenated members (BGZF, pigz -i, cat a.gz b.gz) decode as one
  * stream, every member's CRC-32 and ISIZE are verified, bytes behind the last member that are not a gzip header are

@@ -404,3 +404,82 @@ def check_streaming(ctx, oracle, nrec=300, chunk=None):
             break
     ds.close()
     assert res == want
+
+
+def multi_block_file(oracle, version=2, gpu_ctx=None):
+    """A container of several small blocks (any NumRecords <= 100 000 per block is a valid file: the reader takes
+    the count from each block header, compress.go:738-758) and the text of every block: reference-shaped blocks
+    from the oracle, and one written by the GPU coder when a context is given."""
+    from fastqpacker_b200.sharding import merge_compressed
+    from tests.fastq_cases import GOOD_CASES, rand_fastq
+
+    texts = [GOOD_CASES["rand_small"], GOOD_CASES["three"], rand_fastq(700, 21, lmin=1, lmax=40), rand_fastq(300, 23, plus_payload=True),
+             GOOD_CASES["nbases"], rand_fastq(150, 22, lmin=100, lmax=400, n_rate=0.1)]
+    # the text a block decodes to (the codec is lossy where the reference is: N bases keep quality 0 only, v1 drops
+    # plus-line payloads)
+    texts = [oracle.decompress(oracle.compress(t, version=version)) for t in texts]
+    parts = [oracle.compress(t, version=version) for t in texts]
+    if gpu_ctx is not None and version == 2:
+        raw = rand_fastq(250, 24, lmin=30, lmax=90)
+        texts.append(oracle.decompress(oracle.compress(raw)))
+        parts.append(gpu_ctx.compress(raw))
+        assert oracle.decompress(parts[-1]) == texts[-1]
+    assert all(p[9] == parts[0][9] for p in parts)  # the Phred flag is file-global (compress.go:146-164): blocks of one file share it
+    return merge_compressed(parts), texts
+
+
+def check_block_index(lib, oracle):
+    """fqz_block_index against the Python header walk (sharding.walk_container) and the oracle; needs no GPU."""
+    from fastqpacker_b200._binding import FqzError
+    from fastqpacker_b200.sharding import walk_container
+
+    for version in (2, 1):
+        fqz, texts = multi_block_file(oracle, version)
+        assert oracle.decompress(fqz) == b"".join(texts)
+        idx = lib.block_index(fqz)
+        _, _, want = walk_container(fqz)
+        assert [(e["offset"], e["size"], e["records"]) for e in idx] == [(b.offset, b.size, b.records) for b in want]
+        first = 0
+        for e, t in zip(idx, texts):
+            assert e["first_record"] == first and e["records"] == t.count(b"\n") // 4
+            assert e["original_seq"] == e["original_qual"] == sum(len(l) for l in t.split(b"\n")[1::4])
+            first += e["records"]
+        assert idx[-1]["offset"] + idx[-1]["size"] == len(fqz)
+        assert lib.block_index(fqz[:10]) == []
+        for blob, code in ((b"FQX\x00" + fqz[4:], -5), (fqz[:3], -7), (fqz[:8], -7), (fqz[:4] + b"\x07" + fqz[5:], -6),
+                           (fqz[: idx[2]["offset"] + 11], -7), (fqz[:-1], -7)):
+            with pytest.raises(FqzError) as e:
+                lib.block_index(blob)
+            assert e.value.code == code
+    return fqz
+
+
+def check_decompress_blocks(ctx, oracle, dense=True):
+    """Random access: every block range of a multi-block file decodes to exactly those blocks' text."""
+    from fastqpacker_b200._binding import FqzError
+
+    for version in (2, 1):
+        fqz, texts = multi_block_file(oracle, version, gpu_ctx=ctx)
+        nb = len(texts)
+        assert len(ctx.block_index(fqz)) == nb
+        assert ctx.decompress(fqz) == b"".join(texts)
+        for first in range(nb) if dense else (0, 2, nb - 1):
+            for count in (1, 2, nb - first) if dense else (1, nb - first):
+                if first + count <= nb:
+                    assert ctx.decompress_blocks(fqz, first, count) == b"".join(texts[first : first + count]), (version, first, count)
+        assert ctx.decompress_blocks(fqz, nb, 0) == b"" and ctx.decompress_blocks(fqz, 2, 0) == b""
+        for first, count in ((0, nb + 1), (nb, 1), (nb + 5, 0)):
+            with pytest.raises(FqzError) as e:
+                ctx.decompress_blocks(fqz, first, count)
+            assert e.value.code == -34
+        # a damaged block is only met by the ranges that hold it, and the error names its index in the file
+        idx = ctx.block_index(fqz)
+        bad = bytearray(fqz)
+        hsz = 32 if version == 1 else 36
+        bad[idx[3]["offset"] + hsz + 5] ^= 0x40
+        bad = bytes(bad)
+        assert ctx.decompress_blocks(bad, 0, 3) == b"".join(texts[:3])
+        assert ctx.decompress_blocks(bad, 4, nb - 4) == b"".join(texts[4:])
+        with pytest.raises(FqzError) as e:
+            ctx.decompress_blocks(bad, 2, 3)
+        assert e.value.code == -8 and "block 3" in str(e.value), str(e.value)

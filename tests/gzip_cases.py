@@ -225,3 +225,63 @@ def check_compress_gz(ctx, oracle, text, level=6, chunk=4096, bgzf_block=0):
     assert fqz == ctx.compress(text)
     assert oracle.decompress(fqz) == oracle.decompress(oracle.compress(text))
     return len(gz), len(fqz)
+
+
+def fuzz_file(seed: int, max_text=20000):
+    """A random gzip file (1-3 members, random zlib parameters, flush points, header fields) and, for odd seeds, a random
+    corruption of it (bit flips or a cut).  Returns (bytes, chunk option)."""
+    rnd = random.Random(0xF00D + seed)
+    kinds = ("fastq", "random", "repeat", "runs", "mixed")
+    gz = b""
+    for _ in range(rnd.randint(1, 3)):
+        n = rnd.randint(0, max_text)
+        kind = rnd.choice(kinds)
+        if kind == "fastq":
+            t = rand_fastq(max(1, n // 200), rnd.randrange(1 << 20), lmin=20, lmax=150)[:n]
+        elif kind == "random":
+            t = bytes(rnd.randrange(256) for _ in range(n))
+        elif kind == "repeat":
+            unit = bytes(rnd.randrange(256) for _ in range(rnd.randint(1, 600)))
+            t = (unit * (n // len(unit) + 1))[:n]
+        elif kind == "runs":
+            t = b"".join(bytes([rnd.randrange(65, 70)]) * rnd.randint(1, 400) for _ in range(n // 100 + 1))[:n]
+        else:
+            t = (rand_fastq(max(1, n // 400), 3, lmin=20, lmax=150) + bytes(rnd.randrange(256) for _ in range(n // 2)))[:n]
+        flg = rnd.choice((0, 0, 8, 4, 2, 2 | 8 | 16))
+        gz += _member(t, level=rnd.randint(0, 9), mem_level=rnd.randint(1, 9),
+                      strategy=rnd.choice((zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED)),
+                      flush_every=rnd.choice((0, 0, 997, 5000)), flush_mode=rnd.choice((zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH)), flg=flg,
+                      extra=b"xy\x02\0ab", name=b"f.fq", comment=b"c")
+    if seed & 1:
+        if rnd.random() < 0.3 and len(gz) > 1:
+            gz = gz[: rnd.randrange(1, len(gz))]
+        else:
+            b = bytearray(gz)
+            for _ in range(rnd.randint(1, 3)):
+                p = rnd.randrange(len(b))
+                b[p] ^= 1 << rnd.randrange(8)
+            gz = bytes(b)
+    return gz, rnd.choice((0, 256, 512, 1024, 4096))
+
+
+def check_fuzz(ctx, gunzip_oracle, seed, max_text=20000):
+    """Same verdict as the oracle: the same text, or an error where it reports one (the class must match for cuts:
+    `unexpected EOF`; for flipped bits zlib and Go's flate may name different symptoms of the same damage)."""
+    from fastqpacker_b200._binding import FqzError
+
+    gz, chunk = fuzz_file(seed, max_text)
+    try:
+        want, kind = gunzip_oracle.gunzip(gz), None
+    except gunzip_oracle.GunzipError as e:
+        want, kind = None, e.kind
+    ctx.set_option(ctx.OPT_GZ_CHUNK_BYTES, chunk)
+    try:
+        got, code = ctx.gunzip(gz), 0
+    except FqzError as e:
+        got, code = None, e.code
+    finally:
+        ctx.set_option(ctx.OPT_GZ_CHUNK_BYTES, 0)
+    if kind is None:
+        assert code == 0 and got == want, (seed, chunk, code)
+    else:
+        assert code in (-18, -19, -20, -21), (seed, chunk, kind, code)

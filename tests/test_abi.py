@@ -31,7 +31,7 @@ def test_header_declares_the_expected_surface():
     for name in ("fqz_init", "fqz_compress", "fqz_decompress", "fqz_compress_feed", "fqz_decompress_feed", "fqz_compress_shard",
                  "fqz_encode_streams", "fqz_decode_streams", "fqz_zstd_compress", "fqz_zstd_decompress", "fqz_compress_device",
                  "fqz_decompress_device", "fqz_is_gzip", "fqz_gunzip", "fqz_gunzip_device", "fqz_compress_gz", "fqz_gunzip_stats", "fqz_info",
-                 "fqz_check"):
+                 "fqz_check", "fqz_block_index", "fqz_decompress_blocks"):
         assert name in syms
 
 
@@ -77,3 +77,12 @@ def test_product_package_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "fqz_oracle" not in src and "libfqzoracle" not in src and "from oracle" not in src, f
+
+
+def test_block_index_runs_without_a_gpu(lib, oracle):
+    """fqz_block_index is header arithmetic on the host: it needs neither a context nor a device, so the real library's
+    version is checked here against the Python header walk and the oracle."""
+    from fastqpacker_b200._binding import FqzLibrary
+    from tests.decode_cases import check_block_index
+
+    check_block_index(FqzLibrary(LIB), oracle)

@@ -9,6 +9,8 @@ from tests.decode_cases import (
     check_back_end,
     check_decode_errors,
     check_decompress_reference_written,
+    check_block_index,
+    check_decompress_blocks,
     check_file_errors,
     check_round_trip,
     check_streaming,
@@ -84,6 +86,13 @@ def test_decode_errors(emu, oracle):
 
 def test_file_errors(emu, oracle):
     check_file_errors(emu, oracle)
+
+
+def test_block_index_and_random_access(emu, oracle):
+    """fqz_block_index / fqz_decompress_blocks: the side-table index and the decode of any block range (v2, v1,
+    reference-shaped and GPU-written blocks in one file)."""
+    check_block_index(emu.lib, oracle)
+    check_decompress_blocks(emu, oracle, dense=False)
 
 
 def test_streaming(emu, oracle):

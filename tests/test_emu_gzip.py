@@ -58,3 +58,11 @@ def test_compress_gz(emu, oracle, sample_fq):
     check_compress_gz(emu, oracle, sample_fq)
     check_compress_gz(emu, oracle, rand_fastq(150, 9, lmin=30, lmax=120), chunk=1024)
     check_compress_gz(emu, oracle, rand_fastq(150, 10, lmin=30, lmax=120), bgzf_block=2000, chunk=1024)
+
+
+def test_gunzip_fuzz(emu, gunzip_oracle):
+    """Random gzip files and random damage (tests/gzip_cases.fuzz_file); the GPU suite runs more seeds."""
+    from tests.gzip_cases import check_fuzz
+
+    for seed in range(40, 70):
+        check_fuzz(emu, gunzip_oracle, seed, 8000)

@@ -98,3 +98,13 @@ def test_gunzip_bgzf_large(ctx, gunzip_oracle):
     assert ctx.gunzip(gz) == text
     st = ctx.gunzip_stats()
     assert st["members"] == (len(text) + 65279) // 65280 + 1
+
+
+@pytest.mark.parametrize("first", range(40, 160, 20))
+def test_gunzip_fuzz(ctx, gunzip_oracle, first):
+    """Random gzip files (1-3 members, random zlib level / memLevel / strategy, flush points, optional header fields, random
+    chunk size) and random damage to every second one: the same text as the oracle, or an error where it reports one."""
+    from tests.gzip_cases import check_fuzz
+
+    for seed in range(first, first + 20):
+        check_fuzz(ctx, gunzip_oracle, seed, 8000)
