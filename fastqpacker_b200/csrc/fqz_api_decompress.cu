@@ -533,7 +533,11 @@ extern "C" int fqz_check(fqz_ctx *c, const uint8_t *fqz, size_t n, uint64_t *rec
     if (records) *records = 0;
     if (fastq_bytes) *fastq_bytes = 0;
     fqz_file_info fi;
-    FQZ_TRY(fqz_info(c, fqz, n, &fi));
+    // a cut file is reported by the decode below, which meets the damage in file order like fqz_decompress does (a corrupt
+    // frame in an earlier block comes first)
+    const int rc_info = fqz_info(c, fqz, n, &fi);
+    if (rc_info != FQZ_OK && rc_info != FQZ_E_TRUNC_FILE) return rc_info;
+    const std::string info_err = c->err;
     DecState st;
     FQZ_TRY(parse_file_header(c, fqz, n, st));
     int rc = fqz_io_upload(c, fqz, n);
@@ -546,6 +550,10 @@ extern "C" int fqz_check(fqz_ctx *c, const uint8_t *fqz, size_t n, uint64_t *rec
     if (rc == FQZ_OK) rc = rc2;
     if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
     if (rc != FQZ_OK) return rc;
+    if (rc_info != FQZ_OK) {
+        c->err = info_err;
+        return rc_info;
+    }
     if (records) *records = fi.records;
     if (fastq_bytes) *fastq_bytes = m;
     return FQZ_OK;

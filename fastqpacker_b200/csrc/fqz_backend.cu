@@ -159,8 +159,17 @@ __device__ static void walk_chain(const u8 *p, u32 size, u32 kind, u32 pos, u32 
                 u32 acc = min(total, nrec - r);
                 for (u32 j = 0; j < k; j++)
                     if (ex + j < acc) offs[r + ex + j] = cbase + (u32)cl[32u * j];
-                int lastl = 31 - __clz((int)havem);
-                pos = __shfl_sync(0xffffffffu, last_next, lastl);
+                if (acc < total) {
+                    // the chain ends inside this chunk (NumRecords counts fewer items than the stream holds: the reference
+                    // reads NumRecords of them and ignores the rest, compress.go:944-985): stop at the start of candidate acc
+                    bool mine = acc >= ex && acc < ex + k;
+                    u32 mm = __ballot_sync(0xffffffffu, mine);
+                    u32 v = mine ? cbase + (u32)cl[32u * (acc - ex)] : 0u;
+                    pos = __shfl_sync(0xffffffffu, v, __ffs((int)mm) - 1);
+                } else {
+                    int lastl = 31 - __clz((int)havem);
+                    pos = __shfl_sync(0xffffffffu, last_next, lastl);
+                }
                 r += acc;
                 continue;  // (when acc < total the loop ends: r == nrec)
             }

@@ -483,3 +483,101 @@ def check_decompress_blocks(ctx, oracle, dense=True):
         with pytest.raises(FqzError) as e:
             ctx.decompress_blocks(bad, 2, 3)
         assert e.value.code == -8 and "block 3" in str(e.value), str(e.value)
+
+
+def check_block_header_fields(ctx, oracle, nrec=1500, quick=False):
+    """Block headers that disagree with their streams (ROADMAP.md PR-005, `compress.go:738-758,944-1078`): NumRecords below
+    what the streams hold decodes exactly that many records and ignores the rest, above it is `truncated ... data` at the
+    first missing record however large the claim (no allocation follows the claim), and OriginalSeqSize / OriginalQualSize
+    are not used by the reader at all.  Reference-shaped and GPU-written blocks, same verdict as the oracle."""
+    from fastqpacker_b200._binding import FqzError
+    from tests.fastq_cases import rand_fastq
+
+    text = rand_fastq(nrec, 31, lmin=20, lmax=120, plus_payload=True)
+    for fqz in (oracle.compress(text), ctx.compress(text)):
+        hdr = list(struct.unpack("<9I", fqz[10:46]))
+        assert hdr[0] == nrec
+
+        def verdict(fn, blob):
+            try:
+                return fn(blob)
+            except (FqzError, oracle.OracleError) as e:
+                return e.code
+
+        fields = ((0, (0, 1, 2, 31, 32, 33, 150, 151, nrec // 2, nrec - 1, nrec + 1, 100_001, 0x7FFFFFFF, 0xFFFFFFFF)),
+                  (7, (0, 1, hdr[7] + 1, 0xFFFFFFFF)), (8, (0, hdr[8] - 1, 0xFFFFFFFF)))
+        if quick:  # the CPU emulation of the kernels is slow
+            fields = ((0, (1, 33, nrec - 1, nrec + 1, 0xFFFFFFFF)), (7, (0xFFFFFFFF,)), (8, (0,)))
+        for field, values in fields:
+            for v in values:
+                h = list(hdr)
+                h[field] = v
+                blob = fqz[:10] + struct.pack("<9I", *h) + fqz[46:]
+                want = verdict(oracle.decompress, blob)
+                assert verdict(ctx.decompress, blob) == want, (field, v)
+                chk = verdict(ctx.check, blob)
+                assert chk == want if isinstance(want, int) else chk == (v if field == 0 else nrec, len(want)), (field, v)
+
+
+def fuzz_fqz(ctx, oracle, seed: int):
+    """A small .fqz (reference-shaped or GPU-written, v2 or v1, one or several blocks) with random damage: flipped bits,
+    bytes replaced / dropped / inserted, the tail cut — anywhere: file header, block headers, frame headers, entropy
+    tables, bit streams, checksums."""
+    from fastqpacker_b200.sharding import merge_compressed
+    from tests.fastq_cases import rand_fastq
+
+    rnd = random.Random(0xF02 + seed)
+    version = rnd.choice((2, 2, 1))
+    parts = []
+    for _ in range(rnd.choice((1, 1, 2, 3))):
+        text = rand_fastq(rnd.randint(1, 120), rnd.randrange(1 << 20), lmin=1, lmax=rnd.choice((8, 60, 300)), plus_payload=rnd.random() < 0.3,
+                          n_rate=rnd.choice((0.0, 0.05)))
+        if rnd.random() < 0.3:
+            text = text * rnd.randint(2, 6)  # repeated records: match sequences in every stream
+        parts.append(ctx.compress(text) if version == 2 and rnd.random() < 0.5 else oracle.compress(text, version=version))
+    b = bytearray(merge_compressed(parts))
+    for _ in range(rnd.choice((0, 1, 1, 1, 2, 3))):
+        op = rnd.randrange(5)
+        p = rnd.randrange(len(b))
+        if rnd.random() < 0.35:  # aim at the headers
+            p = min(len(b) - 1, rnd.randrange(0, 10 + 36 + 24))
+        if op == 0:
+            b[p] ^= 1 << rnd.randrange(8)
+        elif op == 1:
+            b[p] = rnd.choice((0, 1, 0x7F, 0x80, 0xFF, rnd.randrange(256)))
+        elif op == 2:
+            del b[p]
+        elif op == 3:
+            b.insert(p, rnd.randrange(256))
+        else:
+            del b[p:]
+    return bytes(b)
+
+
+def check_fuzz_fqz(ctx, oracle, seed):
+    """Damaged archives (ROADMAP.md PR-006): where the oracle decodes the file the GPU gives the same text, where it rejects
+    it so does the GPU — with the same code unless the damage sits inside a zstd frame (libzstd and the GPU decoder may
+    trip over different symptoms of it) — and `fqz_check` agrees with `fqz_decompress`."""
+    from fastqpacker_b200._binding import FqzError
+
+    blob = fuzz_fqz(ctx, oracle, seed)
+    try:
+        want = oracle.decompress(blob)
+    except oracle.OracleError as e:
+        want = e.code
+    try:
+        got = ctx.decompress(blob)
+    except FqzError as e:
+        got = e.code
+    try:
+        chk = ctx.check(blob)[1]
+    except FqzError as e:
+        chk = e.code
+    if isinstance(want, int):
+        assert isinstance(got, int) and got < 0, (seed, want, len(got) if not isinstance(got, int) else got)
+        # -17: an N position beyond its read, where the reference panics (sequence.go:218-220)
+        assert got == want or -8 in (got, want) or -17 in (got, want), (seed, want, got)
+        assert chk == got, (seed, chk, got)
+    else:
+        assert got == want, (seed, got if isinstance(got, int) else len(got), len(want))
+        assert chk == len(want), (seed, chk)

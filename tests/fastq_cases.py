@@ -1,6 +1,7 @@
 """FASTQ inputs shared by the oracle, emulation and GPU parity tests (mirrors the inputs of the
 reference's own tests, internal/compress/compress_test.go and internal/fqparser/parser_test.go)."""
 import random
+import re
 
 
 def rand_fastq(nrec, seed, lmin=1, lmax=300, phred=33, n_rate=0.02, plus_payload=False, crlf=False, lower=False):
@@ -285,3 +286,69 @@ def check_fuzz_duplicates(ctx, oracle, seed, nrec):
     assert oracle.decompress(z) == text, seed
     assert ctx.decompress(z) == text, seed
     assert ctx.decompress(oracle.compress(text, threads=4)) == text, seed
+
+
+def fuzz_fastq(seed: int, max_rec=60):
+    """A small FASTQ text (LF or CRLF, Phred+33 or +64, N bases, plus payloads, short and empty reads) with a few random
+    edits that a parser must either reject or read the way the reference does: bytes dropped, inserted or replaced (biased
+    to the bytes the grammar cares about), lines dropped or doubled, the tail cut."""
+    rnd = random.Random(0xFA57 + seed)
+    lmin = rnd.choice((0, 1, 20))
+    text = bytearray(rand_fastq(rnd.randint(1, max_rec), rnd.randrange(1 << 20), lmin=lmin, lmax=lmin + rnd.choice((4, 40, 150)),
+                                crlf=rnd.random() < 0.2, plus_payload=rnd.random() < 0.3, phred=rnd.choice((33, 33, 64)),
+                                n_rate=rnd.choice((0.0, 0.05, 0.5)), lower=rnd.random() < 0.1))
+    special = b"\n\n\n\r@+N \x00\xff!~;@Ih"
+    for _ in range(rnd.choice((0, 1, 1, 2, 3))):
+        if not text:
+            break
+        op = rnd.randrange(6)
+        p = rnd.randrange(len(text))
+        if op == 0:
+            del text[p]
+        elif op == 1:
+            text.insert(p, rnd.choice(special))
+        elif op == 2:
+            text[p] = rnd.choice(special) if rnd.random() < 0.7 else rnd.randrange(256)
+        elif op == 3:  # drop the line p lies in
+            a = text.rfind(b"\n", 0, p) + 1
+            b = text.find(b"\n", p)
+            del text[a : (b + 1 if b >= 0 else len(text))]
+        elif op == 4:  # double it
+            a = text.rfind(b"\n", 0, p) + 1
+            b = text.find(b"\n", p)
+            text[a:a] = text[a : (b + 1 if b >= 0 else len(text))]
+        else:
+            del text[p:]
+    return bytes(text)
+
+
+def check_fuzz_fastq(ctx, oracle, seed, max_rec=60):
+    """Same verdict as the oracle on an edited FASTQ: the same six streams and block fields, or the same error code at the
+    same record (parser.go:136-243, compress.go:474-520); the whole-file call agrees with the block-level one."""
+    from fastqpacker_b200._binding import FqzError
+
+    text = fuzz_fastq(seed, max_rec)
+    try:
+        want, werr = oracle.encode_streams(text), None
+    except oracle.OracleError as e:
+        want, werr = None, (e.code, int(re.search(r"record (\d+)", str(e)).group(1)))
+    try:
+        got, gerr = ctx.encode_streams(text), None
+    except FqzError as e:
+        got, gerr = None, (e.code, e.record)
+    assert gerr == werr, (seed, gerr, werr)
+    if want is not None:
+        for k in ("nrec", "phred64", "orig_seq", "orig_qual", "consumed"):
+            assert got[k] == want[k], (seed, k)
+        assert got["streams"] == want["streams"], seed
+    try:
+        ref = oracle.decompress(oracle.compress(text))
+    except oracle.OracleError as e:
+        ref = e.code
+    try:
+        fqz = ctx.compress(text)
+        mine = oracle.decompress(fqz)
+        assert ctx.decompress(fqz) == mine, seed
+    except FqzError as e:
+        mine = e.code
+    assert mine == ref, (seed, mine if isinstance(mine, int) else len(mine), ref if isinstance(ref, int) else len(ref))

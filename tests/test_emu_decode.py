@@ -9,6 +9,7 @@ from tests.decode_cases import (
     check_back_end,
     check_decode_errors,
     check_decompress_reference_written,
+    check_block_header_fields,
     check_block_index,
     check_decompress_blocks,
     check_file_errors,
@@ -88,6 +89,10 @@ def test_file_errors(emu, oracle):
     check_file_errors(emu, oracle)
 
 
+def test_block_header_fields(emu, oracle):
+    check_block_header_fields(emu, oracle, nrec=400, quick=True)
+
+
 def test_block_index_and_random_access(emu, oracle):
     """fqz_block_index / fqz_decompress_blocks: the side-table index and the decode of any block range (v2, v1,
     reference-shaped and GPU-written blocks in one file)."""
@@ -113,3 +118,11 @@ def test_huf_kernel_variants(emu, oracle):
         emu.set_option(emu.OPT_HUF_KERNELS, 0)
     assert oracle.decompress(a) == text and oracle.decompress(b) == text
     assert abs(len(a) - len(b)) <= 64
+
+
+def test_archive_fuzz(emu, oracle):
+    """Damaged .fqz files (tests/decode_cases.fuzz_fqz): the oracle's verdict; the GPU suite runs more seeds."""
+    from tests.decode_cases import check_fuzz_fqz
+
+    for seed in range(0, 40):
+        check_fuzz_fqz(emu, oracle, seed)

@@ -99,3 +99,12 @@ def test_duplicate_coder_fuzz(emu, oracle, seed):
     from tests.fastq_cases import check_fuzz_duplicates
 
     check_fuzz_duplicates(emu, oracle, seed, 1500)
+
+
+def test_fastq_parser_fuzz(emu, oracle):
+    """Edited FASTQ texts (tests/fastq_cases.fuzz_fastq): the oracle's verdict, record index included; the GPU suite runs
+    more seeds."""
+    from tests.fastq_cases import check_fuzz_fastq
+
+    for seed in range(0, 60):
+        check_fuzz_fastq(emu, oracle, seed)

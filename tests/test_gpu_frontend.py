@@ -83,3 +83,13 @@ def test_synth_block_matches_oracle(ctx, oracle, kind, count):
     assert got["consumed"] == want["consumed"] and got["phred64"] == want["phred64"] == kind
     for nm, a, b in zip(oracle.STREAM_NAMES, got["streams"], want["streams"]):
         assert a == b, nm
+
+
+@pytest.mark.parametrize("first", range(0, 400, 100))
+def test_fastq_parser_fuzz(ctx, oracle, first):
+    """Edited FASTQ texts (bytes dropped / inserted / replaced, lines dropped or doubled, the tail cut): the same six streams
+    or the same error at the same record as the oracle (the fuzz target of the reference's ROADMAP.md PR-006)."""
+    from tests.fastq_cases import check_fuzz_fastq
+
+    for seed in range(first, first + 100):
+        check_fuzz_fastq(ctx, oracle, seed)
