@@ -589,20 +589,23 @@ extern "C" int fqz_decompress_feed(fqz_dstream *s, const uint8_t *fqz, size_t n,
     }
     u64 pos = 0;
     if (!s->st.have_header && n < 10 && !is_last) return FQZ_E_NEED_MORE;
-    if (!s->st.have_header) {
-        FQZ_TRY(parse_file_header(c, fqz, n, s->st));  // read on the host; the payload streams to the device
+    DecState trial = s->st;  // committed only when the call succeeds: FQZ_E_NOSPACE consumes nothing, not even the file header
+    if (!trial.have_header) {
+        FQZ_TRY(parse_file_header(c, fqz, n, trial));  // read on the host; the payload streams to the device
         pos = 10;
-        *consumed = 10;
     }
     u64 used = pos;
     static u8 dummy;
     int rc = fqz_io_upload(c, fqz, n);
-    if (rc == FQZ_OK) rc = decompress_blocks(c, c->io.d_in, n, pos, is_last != 0, true, s->st, nullptr, out ? out : &dummy, out_cap, out_len, &used, true);
+    if (rc == FQZ_OK) rc = decompress_blocks(c, c->io.d_in, n, pos, is_last != 0, true, trial, nullptr, out ? out : &dummy, out_cap, out_len, &used, true);
     int rc2 = fqz_io_finish(c);  // never return while a copy still reads or writes the caller's memory
     if (rc == FQZ_OK) rc = rc2;
     if (rc == FQZ_E_CUDA && c->err.empty()) c->err = cudaGetErrorString(cudaGetLastError());
-    if (rc == FQZ_OK || rc == FQZ_E_NOSPACE) *consumed = (size_t)used;
-    if (rc == FQZ_OK && !is_last && used == pos && pos < n && *out_len == 0 && *consumed == 0) return FQZ_E_NEED_MORE;
+    if (rc == FQZ_OK) {
+        s->st = trial;
+        *consumed = (size_t)used;
+    }
+    if (rc == FQZ_OK && !is_last && used == 0 && n && *out_len == 0) return FQZ_E_NEED_MORE;
     return rc;
 }
 

@@ -581,3 +581,112 @@ def check_fuzz_fqz(ctx, oracle, seed):
     else:
         assert got == want, (seed, got if isinstance(got, int) else len(got), len(want))
         assert chk == len(want), (seed, chk)
+
+
+def fuzz_bytes(rnd, n):
+    """n bytes built from pieces a compressor treats differently: noise, small alphabets, runs, repeats at random reach,
+    near-copies, counters, text."""
+    out = bytearray()
+    while len(out) < n:
+        kind = rnd.randrange(8)
+        m = rnd.choice((1, 3, 17, 200, 3000, 40000))
+        m = rnd.randint(1, m)
+        if kind == 0:
+            out += rnd.randbytes(m)
+        elif kind == 1:
+            k = rnd.randint(1, 9)
+            out += bytes(rnd.randrange(k) for _ in range(min(m, 5000)))
+        elif kind == 2:
+            out += bytes([rnd.randrange(256)]) * m
+        elif kind == 3 and out:  # copy from anywhere behind (overlapping when the reach is short)
+            reach = rnd.randint(1, min(len(out), rnd.choice((1, 2, 3, 8, 300, 70000, 1 << 20))))
+            for _ in range(min(m, 20000)):
+                out.append(out[-reach])
+        elif kind == 4 and out:  # a near-copy: a few bytes changed
+            reach = rnd.randint(1, len(out))
+            piece = bytearray(out[len(out) - reach : len(out) - reach + m])
+            for _ in range(len(piece) // 50 + 1):
+                piece[rnd.randrange(len(piece))] = rnd.randrange(256)
+            out += piece
+        elif kind == 5:
+            out += b"".join(struct.pack("<I", 100 + (i % rnd.randint(1, 9))) for i in range(min(m, 4000)))
+        elif kind == 6:
+            out += b"".join(b"\x17\x00read%d/1 some:%d:text" % (i, rnd.randrange(99999)) for i in range(min(m, 500)))
+        else:
+            out += b"ACGTTGCA"[rnd.randrange(8) :] * (m // 4 + 1)
+    return bytes(out[:n])
+
+
+def check_fuzz_zstd(ctx, oracle, seed, max_bytes=400_000):
+    """Entropy stage against libzstd both ways on random structured data: frames libzstd writes at a random level (fast
+    negative levels to 19), window, checksum and content-size setting decode bit-exact on the device, several frames back
+    to back; what the device writes under either policy decodes under libzstd."""
+    rnd = random.Random(0x25D + seed)
+    n = rnd.choice((0, 1, 5, 100, 3000, 70000, max_bytes))
+    n = rnd.randint(0, n)
+    data = fuzz_bytes(rnd, n)
+    level = rnd.choice((-5, -1, 1, 1, 2, 3, 5, 7, 9, 12, 16, 19))
+    if rnd.random() < 0.5:
+        z = oracle.zstd_compress(data, level)
+    else:
+        z = oracle.zstd_compress_adv(data, level, window_log=rnd.choice((0, 10, 14, 17, 20, 22)), content_size=rnd.choice((-1, 0, 1)),
+                                     checksum=rnd.choice((-1, 0, 1)))
+    assert oracle.zstd_decompress(z, cap=len(data) + 64) == data
+    assert ctx.zstd_decompress(z) == data, (seed, "decode", level, n)
+    if rnd.random() < 0.3:
+        more = fuzz_bytes(rnd, rnd.randint(0, 5000))
+        assert ctx.zstd_decompress(z + oracle.zstd_compress(more, 3)) == data + more, (seed, "two frames")
+    for policy in (0, 1):
+        mine = ctx.zstd_compress(data, policy)
+        assert oracle.zstd_decompress(mine, cap=len(data) + 64) == data, (seed, "encode", policy, n)
+        assert ctx.zstd_decompress(mine) == data, (seed, "round trip", policy, n)
+
+
+def check_fuzz_feed(ctx, oracle, seed):
+    """fqz_decompress_feed with windows and output room of random size (a byte at a time near the file header, windows that
+    end inside block headers and payloads, room for less than one block): every call consumes whole blocks only, the
+    pieces concatenate to the text of the whole-buffer call.  Same for fqz_compress_feed on the text."""
+    import numpy as np
+
+    from fastqpacker_b200.sharding import merge_compressed
+    from tests.fastq_cases import rand_fastq
+
+    rnd = random.Random(0xFEED + seed)
+    version = rnd.choice((2, 2, 1))
+    texts = [rand_fastq(rnd.randint(1, 200), rnd.randrange(1 << 20), lmin=1, lmax=rnd.choice((8, 60, 300))) for _ in range(rnd.randint(1, 6))]
+    parts = [ctx.compress(t) if version == 2 and rnd.random() < 0.5 else oracle.compress(t, version=version) for t in texts]
+    if any(p[9] != parts[0][9] for p in parts):
+        parts = parts[:1]
+    fqz = merge_compressed(parts)
+    want = oracle.decompress(fqz)
+    assert ctx.decompress(fqz) == want
+    ds = ctx.decompress_stream()
+    room = np.empty(rnd.choice((len(want) + 64, max(1, len(want) // 3), 1000)), dtype=np.uint8)
+    res, pos, window, calls = b"", 0, b"", 0
+    while True:
+        step = rnd.choice((1, 3, 9, 37, 1000, len(fqz) // 3 + 1, len(fqz)))
+        window += fqz[pos : pos + step]
+        pos += step
+        last = pos >= len(fqz)
+        while True:
+            calls += 1
+            assert calls < 100_000
+            try:
+                m, used = ds.feed(window, last, room)
+            except Exception as e:
+                assert getattr(e, "code", 0) == -35 and not last, (seed, getattr(e, "code", 0), str(e))
+                break
+            if m < 0:  # FQZ_E_NOSPACE: -m bytes are needed for the next block; nothing was consumed
+                assert -m > room.size
+                room = np.empty(-m, dtype=np.uint8)
+                continue
+            res += room[:m].tobytes()
+            window = window[used:]
+            if not (last and window):  # with is_last the caller keeps calling until the window is empty
+                break
+            assert used > 0
+        if last:
+            assert not window
+            break
+    ds.close()
+    assert res == want, (seed, len(res), len(want))

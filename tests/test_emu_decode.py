@@ -126,3 +126,19 @@ def test_archive_fuzz(emu, oracle):
 
     for seed in range(0, 40):
         check_fuzz_fqz(emu, oracle, seed)
+
+
+def test_feed_fuzz(emu, oracle):
+    """fqz_decompress_feed with random window and output sizes (tests/decode_cases.check_fuzz_feed)."""
+    from tests.decode_cases import check_fuzz_feed
+
+    for seed in (0, 13, 16, 22):  # 13, 16, 22: no room for the first block on the call that reads the file header
+        check_fuzz_feed(emu, oracle, seed)
+
+
+def test_zstd_fuzz(emu, oracle):
+    """Entropy stage against libzstd both ways on random structured data (tests/decode_cases.check_fuzz_zstd)."""
+    from tests.decode_cases import check_fuzz_zstd
+
+    for seed in range(0, 25):
+        check_fuzz_zstd(emu, oracle, seed, 100_000)

@@ -165,3 +165,23 @@ def test_archive_fuzz(ctx, oracle, first):
 
     for seed in range(first, first + 100):
         check_fuzz_fqz(ctx, oracle, seed)
+
+
+@pytest.mark.parametrize("first", range(0, 60, 20))
+def test_feed_fuzz(ctx, oracle, first):
+    """fqz_decompress_feed with windows and output room of random size: whole blocks only, nothing consumed on FQZ_E_NOSPACE
+    (not even the file header), the pieces concatenate to the whole-buffer result."""
+    from tests.decode_cases import check_fuzz_feed
+
+    for seed in range(first, first + 20):
+        check_fuzz_feed(ctx, oracle, seed)
+
+
+@pytest.mark.parametrize("first", range(0, 300, 100))
+def test_zstd_fuzz(ctx, oracle, first):
+    """Entropy stage against libzstd both ways on random structured data: libzstd frames of random level / window / checksum
+    / content-size setting decode bit-exact, device-written frames of either policy decode under libzstd."""
+    from tests.decode_cases import check_fuzz_zstd
+
+    for seed in range(first, first + 100):
+        check_fuzz_zstd(ctx, oracle, seed, 300_000 if seed >= 30 else 100_000)
