@@ -113,22 +113,20 @@ static int backend_run(fqz_ctx *c, std::vector<BkBlock> &blks, u32 phred64, u8 *
     FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
     FQZ_TRY(fqz_pin_copy(c, htot, d_tot, tot_b));
     FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
-    if (hst2->err_key != ~0ull) {
-        // a sequence / quality stream may run short at an earlier record than the failure seen so far
-        bool wrap = false;
-        for (u32 b = 0; b < nb; b++) wrap |= htot[b].packed >= (1ull << 32) || htot[b].bases >= (1ull << 32);
-        if (!wrap) {
-            FQZ_TRY(fqz_scan_excl_u32(c, d_sz, R + 1, stride, 3));
-            fqz_launch_check_seq_qual(d_blks, nb, max_nrec, d_sz, stride, d_st, s);
-            FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
-            FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
-        }
-        return backend_error(c, blks, hst2->err_key, block_base);
+    // Streams that cannot hold what the lengths add up to: the emit pass would find the record, but its 32-bit offsets are
+    // only good when the sums are (a damaged length stream may add up to anything)
+    bool short_any = false;
+    for (u32 b = 0; b < nb; b++) short_any |= htot[b].packed > blks[b].size[0] || htot[b].bases > blks[b].size[1];
+    if (hst2->err_key != ~0ull || short_any) {
+        // a sequence / quality stream may run short, or an N position may lie beyond its read, at an earlier point of the
+        // reference's record order than the failure seen so far
+        fqz_launch_first_error(d_blks, nb, d_offs, hst2->err_key, d_st, s);
+        FQZ_TRY(fqz_pin_copy(c, hst2, d_st, sizeof(FqzDecStatus)));
+        FQZ_CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (hst2->err_key != ~0ull) return backend_error(c, blks, hst2->err_key, block_base);
     }
     u64 total = 0, stream_bytes = 0;
     for (u32 b = 0; b < nb; b++) {
-        if (htot[b].packed >= (1ull << 32) || htot[b].bases >= (1ull << 32))  // cannot fit any real stream
-            return backend_error(c, blks, (blks[b].rec_base << 8) | BK_E_TRUNC_SEQ, block_base);
         total += htot[b].fastq;
         for (int a = 0; a < 6; a++) stream_bytes += blks[b].size[a];
     }

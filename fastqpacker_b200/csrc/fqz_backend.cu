@@ -212,6 +212,7 @@ __device__ static void walk_chain(const u8 *p, u32 size, u32 kind, u32 pos, u32 
         r += run;
         pos += run * isz;
     }
+    if (err && r < nrec && lane == 0) offs[r] = pos;  // the end of the last whole item (k_first_error reads item r - 1)
     wait(0);  // no bulk copy may still be in flight when the CTA's shared memory is released
     wait(1);
     __syncwarp();
@@ -374,19 +375,58 @@ k_record_sizes(const BkBlock *blks, u32 nblocks, const u32 *offs_base, u32 *sz, 
     }
 }
 
-// Error path only: the sequence / quality truncation checks of k_emit_fastq without the emit, so
-// that the first failure in the reference's record order is reported when several streams are short.
-__global__ void __launch_bounds__(256) k_check_seq_qual(const BkBlock *blks, u32 nblocks, const u32 *sc, u64 stride, FqzDecStatus *st) {
-    u32 b = blockIdx.y;
+// Error path only.  The walks and k_record_sizes have found a failure (a chain or the length stream runs short at some
+// record); a sequence or quality stream that runs short, or an N position beyond its read, at an EARLIER point of the
+// reference's record order must win (compress.go:944-1078 stops at the first).  One warp per block goes through the
+// records in order, 32 at a time, with 64-bit running offsets (lengths of a damaged stream may add up to anything), up to
+// the record of the failure known so far, and at that record only through the checks that come before the known one.
+// limit_key: the failure known when the kernel was launched (~0: none; then every record is checked).
+__global__ void __launch_bounds__(128) k_first_error(const BkBlock *blks, u32 nblocks, const u32 *offs_base, u64 limit_key, FqzDecStatus *st) {
+    u32 b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
+    if (b >= nblocks) return;
     BkBlock B = blks[b];
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B.nrec) return;
-    u64 R = B.rec_base + r;
-    u32 L = sc[2 * stride + R + 1] - sc[2 * stride + R];
-    u32 o_seq = sc[0 * stride + R] - sc[0 * stride + B.rec_base];
-    u32 o_qual = sc[2 * stride + R] - sc[2 * stride + B.rec_base];
-    if ((u64)o_seq + ((L + 3u) >> 2) > B.size[0]) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_SEQ);
-    else if ((u64)o_qual + L > B.size[1]) atomicMin(&st->err_key, (R << 8) | BK_E_TRUNC_QUAL);
+    const u64 lim_rec = limit_key >> 8;
+    const u32 lim_code = limit_key == ~0ull ? 8u : (u32)(limit_key & 0xFF);
+    if (B.rec_base > lim_rec) return;
+    const u32 *on = offs_base + 3ull * B.rec_base + 3ull * b + 2ull * (B.nrec + 1);  // N-position items (kind 2)
+    const u8 *lens = (const u8 *)(uintptr_t)B.stream[5];
+    const u8 *nps = (const u8 *)(uintptr_t)B.stream[4];
+    u64 so = 0, qo = 0;  // bytes of packed bases / qualities in front of the 32 records at hand
+    for (u32 base = 0; base < B.nrec; base += 32) {
+        u32 r = base + lane;
+        u64 R = B.rec_base + r;
+        bool live = r < B.nrec && R <= lim_rec;
+        u32 cap = (live && R == lim_rec) ? lim_code : 8u;  // checks with a kind below cap come first in this record
+        if (cap <= BK_E_TRUNC_SEQ) live = false;           // length, N-position or header failure: nothing of ours in front
+        u64 L = live ? (u64) * (const u32 *)(lens + 4ull * r) : 0ull;
+        u64 pk = (L + 3u) >> 2;
+        u64 ipk = pk, iL = L;  // inclusive sums over the lanes
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t0 = __shfl_up_sync(0xffffffffu, ipk, (unsigned)d), t1 = __shfl_up_sync(0xffffffffu, iL, (unsigned)d);
+            if (lane >= (u32)d) {
+                ipk += t0;
+                iL += t1;
+            }
+        }
+        u32 code = 0;
+        if (live) {
+            if (so + ipk > B.size[0]) code = BK_E_TRUNC_SEQ;
+            else if (cap > BK_E_NPOS_RANGE) {
+                u32 a = on[r], nn = (on[r + 1] - a - 2) >> 1;
+                for (u32 k = 0; k < nn && !code; k++)
+                    if (((u32)nps[a + 2 + 2 * k] | ((u32)nps[a + 3 + 2 * k] << 8)) >= L) code = BK_E_NPOS_RANGE;
+            }
+            if (!code && cap > BK_E_TRUNC_QUAL && qo + iL > B.size[1]) code = BK_E_TRUNC_QUAL;
+        }
+        u32 hit = __ballot_sync(0xffffffffu, code != 0);
+        if (hit) {  // the lowest record decides; a sequence stream short at a later record is short at every one behind it
+            if (lane == (u32)__ffs((int)hit) - 1u) atomicMin(&st->err_key, (R << 8) | code);
+            return;
+        }
+        so += __shfl_sync(0xffffffffu, ipk, 31);
+        qo += __shfl_sync(0xffffffffu, iL, 31);
+        if (B.rec_base + base + 31 >= lim_rec) return;
+    }
 }
 
 // ---------------------------------------------------------------------------------- emit
@@ -574,9 +614,9 @@ void fqz_launch_record_sizes(const BkBlock *blks, u32 nblocks, u32 max_nrec, con
     if (!nblocks || !max_nrec) return;
     FQZ_LAUNCH(k_record_sizes, dim3((max_nrec + 255) / 256, nblocks), 256, 0, s, blks, nblocks, offs, sz, stride, tot, st);
 }
-void fqz_launch_check_seq_qual(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *sc, u64 stride, FqzDecStatus *st, cudaStream_t s) {
-    if (!nblocks || !max_nrec) return;
-    FQZ_LAUNCH(k_check_seq_qual, dim3((max_nrec + 255) / 256, nblocks), 256, 0, s, blks, nblocks, sc, stride, st);
+void fqz_launch_first_error(const BkBlock *blks, u32 nblocks, const u32 *offs, u64 limit_key, FqzDecStatus *st, cudaStream_t s) {
+    if (!nblocks) return;
+    FQZ_LAUNCH(k_first_error, (nblocks + 3) / 4, 128, 0, s, blks, nblocks, offs, limit_key, st);
 }
 void fqz_launch_emit(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, const u32 *sc, u64 stride, u32 phred64, u8 *out,
                      FqzDecStatus *st, cudaStream_t s) {

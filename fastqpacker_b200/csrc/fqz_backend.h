@@ -60,6 +60,7 @@ void fqz_launch_walk_container(const u8 *fqz, u64 n, u64 pos, u32 version, FqzBl
 void fqz_launch_walk_prefixes(const BkBlock *blks, u32 nblocks, u32 max_segments, u32 *offs, u32 *ok, FqzDecStatus *st, cudaStream_t s);
 void fqz_launch_record_sizes(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, u32 *sz, u64 stride, BkTotals *tot,
                              FqzDecStatus *st, cudaStream_t s);
-void fqz_launch_check_seq_qual(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *sc, u64 stride, FqzDecStatus *st, cudaStream_t s);
+// error path: first sequence / quality truncation or out-of-range N position in front of the failure `limit_key` (~0: none known)
+void fqz_launch_first_error(const BkBlock *blks, u32 nblocks, const u32 *offs, u64 limit_key, FqzDecStatus *st, cudaStream_t s);
 void fqz_launch_emit(const BkBlock *blks, u32 nblocks, u32 max_nrec, const u32 *offs, const u32 *sc, u64 stride, u32 phred64, u8 *out,
                      FqzDecStatus *st, cudaStream_t s);

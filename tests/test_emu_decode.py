@@ -142,3 +142,11 @@ def test_zstd_fuzz(emu, oracle):
 
     for seed in range(0, 25):
         check_fuzz_zstd(emu, oracle, seed, 100_000)
+
+
+def test_streams_fuzz(emu, oracle):
+    """Back end on damaged decoded streams (tests/decode_cases.check_fuzz_streams): the oracle's text or its first error."""
+    from tests.decode_cases import check_fuzz_streams
+
+    for seed in range(0, 150):
+        check_fuzz_streams(emu, oracle, seed)

@@ -185,3 +185,15 @@ def test_zstd_fuzz(ctx, oracle, first):
 
     for seed in range(first, first + 100):
         check_fuzz_zstd(ctx, oracle, seed, 300_000 if seed >= 30 else 100_000)
+
+
+@pytest.mark.parametrize("first", range(0, 1500, 500))
+def test_streams_fuzz(ctx, oracle, first):
+    """Back end alone on six decoded streams with random damage (lengths, N counts and positions, length prefixes, cuts,
+    NumRecords off by a few): the text the oracle builds, or the FIRST error in the reference's record order
+    (compress.go:944-1078) — also when several streams are damaged, when lengths add up past 2^32, and -17 where the
+    reference would panic."""
+    from tests.decode_cases import check_fuzz_streams
+
+    for seed in range(first, first + 500):
+        check_fuzz_streams(ctx, oracle, seed)
