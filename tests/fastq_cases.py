@@ -328,12 +328,13 @@ def check_fuzz_fastq(ctx, oracle, seed, max_rec=60):
     from fastqpacker_b200._binding import FqzError
 
     text = fuzz_fastq(seed, max_rec)
+    phred = (-1, -1, 0, 1)[seed % 4]  # detected (quality.go:22-49) or forced by the caller
     try:
-        want, werr = oracle.encode_streams(text), None
+        want, werr = oracle.encode_streams(text, phred64=phred), None
     except oracle.OracleError as e:
         want, werr = None, (e.code, int(re.search(r"record (\d+)", str(e)).group(1)))
     try:
-        got, gerr = ctx.encode_streams(text), None
+        got, gerr = ctx.encode_streams(text, phred), None
     except FqzError as e:
         got, gerr = None, (e.code, e.record)
     assert gerr == werr, (seed, gerr, werr)

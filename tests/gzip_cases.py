@@ -285,3 +285,35 @@ def check_fuzz(ctx, gunzip_oracle, seed, max_text=20000):
         assert code == 0 and got == want, (seed, chunk, code)
     else:
         assert code in (-18, -19, -20, -21), (seed, chunk, kind, code)
+
+
+def check_fuzz_compress_gz(ctx, gunzip_oracle, seed, max_text=8000):
+    """fqz_compress_gz = gzip.NewReader in front of compress.Compress (main.go:142-174): on any input the verdict of
+    inflating first and compressing the text — the same .fqz bytes, the gzip error, or the FASTQ error."""
+    from fastqpacker_b200._binding import FqzError
+
+    gz, chunk = fuzz_file(seed, max_text)
+    if seed % 4 >= 2:  # the generator's texts are rarely FASTQ: put a member of real records in front
+        gz = _member(rand_fastq(30, seed, lmin=20, lmax=150), level=1 + seed % 9) + gz
+
+    def verdict(fn):
+        try:
+            return fn()
+        except FqzError as e:
+            return e.code
+
+    ctx.set_option(ctx.OPT_GZ_CHUNK_BYTES, chunk)
+    try:
+        got = verdict(lambda: ctx.compress_gz(gz))
+        text = verdict(lambda: ctx.gunzip(gz))
+    finally:
+        ctx.set_option(ctx.OPT_GZ_CHUNK_BYTES, 0)
+    try:
+        want_text = gunzip_oracle.gunzip(gz)
+    except gunzip_oracle.GunzipError:
+        want_text = None
+    if want_text is None:
+        assert isinstance(text, int) and got == text, (seed, got, text)
+    else:
+        assert text == want_text
+        assert got == verdict(lambda: ctx.compress(want_text)), (seed, got if isinstance(got, int) else len(got))

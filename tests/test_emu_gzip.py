@@ -66,3 +66,10 @@ def test_gunzip_fuzz(emu, gunzip_oracle):
 
     for seed in range(40, 70):
         check_fuzz(emu, gunzip_oracle, seed, 8000)
+
+
+def test_compress_gz_fuzz(emu, gunzip_oracle):
+    from tests.gzip_cases import check_fuzz_compress_gz
+
+    for seed in range(0, 12):
+        check_fuzz_compress_gz(emu, gunzip_oracle, seed)

@@ -108,3 +108,12 @@ def test_gunzip_fuzz(ctx, gunzip_oracle, first):
 
     for seed in range(first, first + 20):
         check_fuzz(ctx, gunzip_oracle, seed, 8000)
+
+
+@pytest.mark.parametrize("first", range(0, 200, 50))
+def test_compress_gz_fuzz(ctx, gunzip_oracle, first):
+    """fqz_compress_gz on random and damaged gzip files: the verdict of inflating first and compressing the text."""
+    from tests.gzip_cases import check_fuzz_compress_gz
+
+    for seed in range(first, first + 50):
+        check_fuzz_compress_gz(ctx, gunzip_oracle, seed)
