@@ -490,18 +490,17 @@ extern "C" int fqz_decompress_blocks(fqz_ctx *c, const uint8_t *fqz, size_t n, u
     DecState st;
     FQZ_TRY(parse_file_header(c, fqz, n, st));
     size_t nb = 0;
-    int rc = fqz_block_index(fqz, n, nullptr, 0, &nb);
-    if (rc != FQZ_OK && rc != FQZ_E_NOSPACE) {
-        if (rc == FQZ_E_TRUNC_FILE) c->err = "reading block: unexpected EOF";
-        return rc;
-    }
+    int rc = fqz_block_index(fqz, n, nullptr, 0, &nb);  // a cut file: nb = the whole blocks in front of the cut, which still decode
+    const bool cut = rc == FQZ_E_TRUNC_FILE;
+    if (rc != FQZ_OK && rc != FQZ_E_NOSPACE && !cut) return rc;
     if (first_block > nb || num_blocks > nb - first_block) {
-        c->err = "block range reaches past the last block of the file";
-        return FQZ_E_INVALID_ARG;
+        c->err = cut ? "reading block: unexpected EOF" : "block range reaches past the last block of the file";
+        return cut ? FQZ_E_TRUNC_FILE : FQZ_E_INVALID_ARG;
     }
     if (num_blocks == 0) return FQZ_OK;
     std::vector<fqz_block_ref> idx(nb);
-    FQZ_TRY(fqz_block_index(fqz, n, idx.data(), nb, &nb));
+    rc = fqz_block_index(fqz, n, idx.data(), nb, &nb);
+    if (rc != FQZ_OK && rc != FQZ_E_TRUNC_FILE) return rc;
     const u64 lo = idx[first_block].offset;
     const u64 hi = idx[first_block + num_blocks - 1].offset + idx[first_block + num_blocks - 1].size;
     st.block_base = first_block;  // error texts name the block's index in the file

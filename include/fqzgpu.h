@@ -119,7 +119,8 @@ int fqz_check(fqz_ctx *ctx, const uint8_t *fqz, size_t n, uint64_t *records, uin
  * fqz_decompress_blocks: the FASTQ of blocks [first_block, first_block + num_blocks) alone = records
  *   [index[first_block].first_record, ...): only those blocks' bytes cross PCIe.  Blocks are independent
  *   (compress.go:523-528), which is also what lets several GPUs share a file (fastqpacker_b200/sharding.py).
- *   FQZ_E_INVALID_ARG when the range reaches past the last block. */
+ *   FQZ_E_INVALID_ARG when the range reaches past the last block.  Of a file that was cut, the whole blocks in front of the
+ *   cut still decode (FQZ_E_TRUNC_FILE for a range that reaches into it). */
 typedef struct fqz_block_ref {
     uint64_t offset;        /* of the block header from the start of the file */
     uint64_t size;          /* block header + its payloads */

@@ -472,6 +472,14 @@ def check_decompress_blocks(ctx, oracle, dense=True):
             with pytest.raises(FqzError) as e:
                 ctx.decompress_blocks(fqz, first, count)
             assert e.value.code == -34
+        # a cut file: the whole blocks in front of the cut still decode
+        idx = ctx.block_index(fqz)
+        cutf = fqz[: idx[4]["offset"] + 20]
+        assert ctx.decompress_blocks(cutf, 1, 3) == b"".join(texts[1:4])
+        for first, count in ((3, 2), (4, 1), (5, 1)):
+            with pytest.raises(FqzError) as e:
+                ctx.decompress_blocks(cutf, first, count)
+            assert e.value.code == -7
         # a damaged block is only met by the ranges that hold it, and the error names its index in the file
         idx = ctx.block_index(fqz)
         bad = bytearray(fqz)

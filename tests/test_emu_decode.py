@@ -55,7 +55,7 @@ def test_zstd_frame_shapes(emu, oracle):
 
 
 def test_item_hints(emu, oracle):
-    check_item_hints(emu, oracle)
+    check_item_hints(emu, oracle, nrec=2200)  # the GPU suite runs 3000
 
 
 def test_zstd_index_frame(emu, oracle):

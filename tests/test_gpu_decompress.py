@@ -167,7 +167,7 @@ def test_archive_fuzz(ctx, oracle, first):
         check_fuzz_fqz(ctx, oracle, seed)
 
 
-@pytest.mark.parametrize("first", range(0, 60, 20))
+@pytest.mark.parametrize("first", range(0, 40, 20))
 def test_feed_fuzz(ctx, oracle, first):
     """fqz_decompress_feed with windows and output room of random size: whole blocks only, nothing consumed on FQZ_E_NOSPACE
     (not even the file header), the pieces concatenate to the whole-buffer result."""
@@ -177,7 +177,7 @@ def test_feed_fuzz(ctx, oracle, first):
         check_fuzz_feed(ctx, oracle, seed)
 
 
-@pytest.mark.parametrize("first", range(0, 300, 100))
+@pytest.mark.parametrize("first", range(0, 200, 100))
 def test_zstd_fuzz(ctx, oracle, first):
     """Entropy stage against libzstd both ways on random structured data: libzstd frames of random level / window / checksum
     / content-size setting decode bit-exact, device-written frames of either policy decode under libzstd."""
