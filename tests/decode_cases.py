@@ -739,3 +739,93 @@ def check_fuzz_streams(ctx, oracle, seed):
     except FqzError as e:
         got = e.code
     assert got == want, (seed, got if isinstance(got, int) else len(got), want if isinstance(want, int) else len(want))
+
+
+def check_fuzz_hints(ctx, oracle, seed, nrec=2500, _cache={}):
+    """Damage inside the index frames (skippable frames in front of the header / plus / N-position streams of a GPU-written
+    block): any zstd reader skips their content, so the file still decodes to the same text unless the
+    damage hits the frame's own magic or size — the hints may only ever cost the parallel walk, never change the result."""
+    import struct
+
+    from fastqpacker_b200._binding import FqzError
+    from tests import synth
+
+    key = (id(ctx), nrec)
+    if key not in _cache:
+        text = synth.fastq(1, 77, 0, nrec)
+        _cache[key] = (text, ctx.compress(text))
+    text, fqz = _cache[key]
+    rnd = random.Random(0x41D7 + seed)
+    hdr = struct.unpack_from("<9I", fqz, 10)
+    pos = 10 + 36 + hdr[1] + hdr[2]
+    spans = []
+    for a in (2, 3, 4):
+        if fqz[pos : pos + 4] == b"\x5e\x2a\x4d\x18":
+            spans.append((pos, 8 + struct.unpack_from("<I", fqz, pos + 4)[0]))
+        pos += hdr[1 + a]
+    assert spans
+    b = bytearray(fqz)
+    for _ in range(rnd.choice((1, 1, 2, 4))):
+        at, ln = rnd.choice(spans)
+        p = at + (rnd.randrange(ln) if rnd.random() < 0.8 else rnd.randrange(min(ln, 24)))
+        op = rnd.randrange(3)
+        if op == 0:
+            b[p] ^= 1 << rnd.randrange(8)
+        elif op == 1:
+            b[p] = rnd.choice((0, 1, 0xFF, rnd.randrange(256)))
+        else:
+            b[p : p + 2] = struct.pack("<H", rnd.choice((0, 1, 0x3FFF, 0x4000, 0xFFFF, rnd.randrange(65536))))
+    blob = bytes(b)
+    try:
+        want = oracle.decompress(blob)
+    except oracle.OracleError as e:
+        want = e.code
+    try:
+        got = ctx.decompress(blob)
+    except FqzError as e:
+        got = e.code
+    if isinstance(want, int):
+        assert isinstance(got, int) and got < 0, (seed, want)
+    else:
+        assert want == text and got == want, (seed, got if isinstance(got, int) else len(got))
+
+
+def check_fuzz_zstd_index(ctx, oracle, seed, _cache={}):
+    """Damage inside the index frame of a device-written zstd stream (a skippable frame any reader steps over): the same
+    bytes as libzstd decodes, or an error where libzstd reports one — the index may only cost the parallel frame walk."""
+    import struct
+
+    from fastqpacker_b200._binding import FqzError
+
+    rnd = random.Random(0x1DE + seed)
+    policy = seed & 1
+    if policy not in _cache:  # (one context per test session)
+        r2 = random.Random(policy)
+        data = fuzz_bytes(r2, 3 * 131072 + 333)
+        _cache[policy] = (data, ctx.zstd_compress(data, policy))
+    data, z = _cache[policy]
+    assert z[:4] == b"\x5e\x2a\x4d\x18", "no index frame in front of a multi-frame stream"
+    ln = 8 + struct.unpack_from("<I", z, 4)[0]
+    b = bytearray(z)
+    for _ in range(rnd.choice((1, 1, 2, 4))):
+        p = rnd.randrange(ln) if rnd.random() < 0.8 else rnd.randrange(min(ln, 24))
+        op = rnd.randrange(3)
+        if op == 0:
+            b[p] ^= 1 << rnd.randrange(8)
+        elif op == 1:
+            b[p] = rnd.choice((0, 1, 0xFF, rnd.randrange(256)))
+        else:
+            b[p : p + 4] = struct.pack("<I", rnd.choice((0, 1, 0xFFFF, 0x10000, len(z), 0xFFFFFFFF, rnd.randrange(1 << 32))))
+    blob = bytes(b[: len(z)])
+    try:
+        want = oracle.zstd_decompress(blob, cap=len(data) + 64)
+    except oracle.OracleError as e:
+        want = e.code
+    try:
+        got = ctx.zstd_decompress(blob)
+    except FqzError as e:
+        got = e.code
+    if isinstance(want, int):
+        assert isinstance(got, int) and got < 0, (seed, want)
+    else:
+        assert got == want, (seed, got if isinstance(got, int) else len(got), len(want))

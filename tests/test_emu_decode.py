@@ -150,3 +150,13 @@ def test_streams_fuzz(emu, oracle):
 
     for seed in range(0, 150):
         check_fuzz_streams(emu, oracle, seed)
+
+
+def test_index_frame_fuzz(emu, oracle):
+    """Damage inside the index frames (item hints of a block, frame index of a zstd stream): never a different result."""
+    from tests.decode_cases import check_fuzz_hints, check_fuzz_zstd_index
+
+    for seed in range(0, 6):
+        check_fuzz_hints(emu, oracle, seed, nrec=2200)
+    for seed in range(0, 8):
+        check_fuzz_zstd_index(emu, oracle, seed)

@@ -197,3 +197,16 @@ def test_streams_fuzz(ctx, oracle, first):
 
     for seed in range(first, first + 500):
         check_fuzz_streams(ctx, oracle, seed)
+
+
+def test_index_frame_fuzz(ctx, oracle):
+    """Damage inside the skippable index frames the GPU coder writes (item hints in front of the header / plus / N-position
+    streams, the frame index of a multi-frame zstd stream): libzstd steps over them, so the result must not change — the
+    index may only cost the parallel walk — unless the damage hits the skippable frame's own magic or size, where both
+    readers report an error."""
+    from tests.decode_cases import check_fuzz_hints, check_fuzz_zstd_index
+
+    for seed in range(0, 200):
+        check_fuzz_hints(ctx, oracle, seed)
+    for seed in range(0, 200):
+        check_fuzz_zstd_index(ctx, oracle, seed)
