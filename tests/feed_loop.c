@@ -76,11 +76,11 @@ static int do_compress(fqz_ctx *ctx, FILE *r, FILE *w, size_t window, size_t *ni
     return ret;
 }
 
-static int do_decompress(fqz_ctx *ctx, FILE *r, FILE *w, size_t window, size_t *nin, size_t *nout, unsigned *calls) {
+static int do_decompress(fqz_ctx *ctx, FILE *r, FILE *w, size_t window, size_t room, size_t *nin, size_t *nout, unsigned *calls) {
     fqz_dstream *s = NULL;
     int rc = fqz_decompress_begin(ctx, &s);
     if (rc != FQZ_OK) return fail(ctx, rc, "");
-    size_t cap = window, len = 0, ocap = 6 * window + (1u << 20);
+    size_t cap = window, len = 0, ocap = room ? room : 6 * window + (1u << 20);  /* room: output bytes to start with (tests: too few) */
     uint8_t *in = (uint8_t *)fqz_host_alloc(cap), *out = (uint8_t *)fqz_host_alloc(ocap);
     if (!in || !out) return fail(ctx, FQZ_E_CUDA, "allocating window buffers");
     int eof = 0, ret = 0;
@@ -127,10 +127,11 @@ static int do_decompress(fqz_ctx *ctx, FILE *r, FILE *w, size_t window, size_t *
 
 int main(int argc, char **argv) {
     if (argc < 4 || (argv[1][0] != 'c' && argv[1][0] != 'd')) {
-        fprintf(stderr, "usage: feed_loop c|d <in> <out> [window_bytes]\n");
+        fprintf(stderr, "usage: feed_loop c|d <in> <out> [window_bytes [output_bytes]]\n");
         return 2;
     }
     size_t window = argc > 4 ? (size_t)strtoull(argv[4], NULL, 10) : ((size_t)512 << 20);
+    size_t room = argc > 5 ? (size_t)strtoull(argv[5], NULL, 10) : 0;
     FILE *r = fopen(argv[2], "rb"), *w = fopen(argv[3], "wb");
     if (!r || !w) {
         perror("open");
@@ -142,7 +143,7 @@ int main(int argc, char **argv) {
     size_t nin = 0, nout = 0;
     unsigned calls = 0;
     double t0 = now();
-    int ret = argv[1][0] == 'c' ? do_compress(ctx, r, w, window, &nin, &nout, &calls) : do_decompress(ctx, r, w, window, &nin, &nout, &calls);
+    int ret = argv[1][0] == 'c' ? do_compress(ctx, r, w, window, &nin, &nout, &calls) : do_decompress(ctx, r, w, window, room, &nin, &nout, &calls);
     double dt = now() - t0;
     fqz_destroy(ctx);
     fclose(r);
