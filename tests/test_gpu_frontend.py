@@ -91,5 +91,9 @@ def test_fastq_parser_fuzz(ctx, oracle, first):
     or the same error at the same record as the oracle (the fuzz target of the reference's ROADMAP.md PR-006)."""
     from tests.fastq_cases import check_fuzz_fastq
 
-    for seed in range(first, first + 100):
-        check_fuzz_fastq(ctx, oracle, seed)
+    try:
+        ctx.set_option(ctx.OPT_FRONTEND, (first // 100) % 3)  # the three sets of front-end kernels give the same verdicts
+        for seed in range(first, first + 100):
+            check_fuzz_fastq(ctx, oracle, seed)
+    finally:
+        ctx.set_option(ctx.OPT_FRONTEND, 0)
