@@ -166,7 +166,10 @@ int fqz_compress_shard(fqz_ctx *ctx, const uint8_t *fastq, size_t n, uint32_t he
  *      collectAndWriteResults, compress.go:240-403, and their decompress twins :630-719).
  *      feed() consumes a whole number of blocks; the caller re-presents the unconsumed tail in
  *      front of the next window.  The first compress feed also emits the file header; Phred is
- *      decided on the first block only (compress.go:146-164). */
+ *      decided on the first block only (compress.go:146-164).  A feed that does not return FQZ_OK
+ *      (FQZ_E_NEED_MORE: no whole block in the window yet; FQZ_E_NOSPACE: *out_len = room the next
+ *      block needs) leaves the stream as it was and consumes nothing — not even the file header —
+ *      so the caller grows its buffer and presents the same window again. */
 typedef struct fqz_cstream fqz_cstream;
 typedef struct fqz_dstream fqz_dstream;
 int fqz_compress_begin(fqz_ctx *ctx, uint32_t header_block_size, fqz_cstream **s);
