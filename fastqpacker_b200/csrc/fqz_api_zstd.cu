@@ -312,7 +312,11 @@ int fqz_compress_window(fqz_ctx *c, const u8 *d_text, u64 n, bool is_last, u64 r
             size_t o0 = fo.blk_off[a][b], o1 = fo.blk_off[a][b + 1];
             if (kStreamPolicy[a] == FQZ_ZPOLICY_ITEMS) {
                 // headers / plus lines / N positions: item starts = the scanned per-record offsets; lengths: 4-byte items
-                if (a < 5) zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride, (u32)o0, (u32)fo.R + 1);
+                // (the block's own slice of the offsets: items[0] is the stream start, so that the first item has no predecessor and
+                // a block is coded the same whether or not other blocks share its device window)
+                if (a < 5)
+                    zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride + (size_t)b * FQZ_BLOCK_RECORDS, (u32)o0,
+                                  nrec[b] + 1);
                 else zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], nullptr, 0, 4);
             } else  // packed bases / qualities: literals-only, with the record boundaries for the duplicate search
                 zb.add_stream(fo.d_streams[a] + o0, o1 - o0, kStreamPolicy[a], fo.d_offs + a * fo.offs_stride, (u32)o0, (u32)fo.R + 1,

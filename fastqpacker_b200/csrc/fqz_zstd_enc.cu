@@ -1704,7 +1704,8 @@ __device__ __forceinline__ void write_block_header(u8 *o, u32 type, u32 size) {
     o[0] = (u8)h; o[1] = (u8)(h >> 8); o[2] = (u8)(h >> 16);
 }
 
-// MODE 0: literals-only (legacy, superseded by k_zenc_huf), 1: hash-table LZ77, 2: item matcher
+// MODE 1: hash-table LZ77, 2: item matcher (MODE 0, a literals-only variant, is no longer instantiated: k_zenc_huf and the
+// three-kernel coder took its place)
 // The item matcher runs as its own kernel in front of k_zenc<2> (which then only entropy-codes what it
 // finds in the workspace): two kernels of half the code each instead of one whose 240 KB of instructions
 // thrashed the instruction cache (15 % of its stalls were instruction fetch).
@@ -3043,8 +3044,8 @@ void fqz_launch_zenc(const ZFrame *frames, const u32 *index, u32 nidx, const u32
         return;
     }
     if (hashes_ready) cudaStreamWaitEvent(s, hashes_ready, 0);
-    if (lz) FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
-    else FQZ_LAUNCH((k_zenc<0, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
+    // lz == 1: generic data; literals-only frames go through k_zenc_huf / the three-kernel coder, never through here
+    FQZ_LAUNCH((k_zenc<1, 0>), grid, ZENC_WARPS * 32, 0, s, frames, index, nidx, hashes, slots, ws, out_sizes, parsed);
 }
 int fqz_zstd_enc_init_device() {
     cudaError_t e = cudaFuncSetAttribute(k_xxh64_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, XX_SMEM);
