@@ -192,6 +192,7 @@ def test_window_hand_over_short_reads(ctx, oracle):
         ctx.set_option(ctx.OPT_HOST_WINDOW_BYTES, 0)
     assert oracle.decompress(cut) == text
     assert ctx.decompress(cut) == text
+    assert cut == ctx.compress(text)  # a block's bytes do not depend on which blocks share its device window
 
 
 @pytest.mark.parametrize("name", sorted(__import__("tests.fastq_cases", fromlist=["x"]).REPETITIVE_CASES))
